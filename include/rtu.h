@@ -1,0 +1,260 @@
+/*
+ * rtu.h -- C ABI of the B200-native render path for RayTracer-Utah scenes.
+ *
+ * This is the drop-in boundary for ONE path of the reference: the per-pixel render loop
+ *   Render -> Trace/ShadowTrace -> Object::IntersectRay -> Material::Shade -> Light::Illuminate
+ * (RenderFunctions.cpp:55-240, objFunctions.cpp:15-522, mtlFunctions.cpp:120-298,
+ *  lightFunctions.cpp:27-84).  Everything is extern "C", plain pointers and sizes; no C++,
+ * CUDA or torch types appear in a signature.  All functions return 0 on success and a
+ * non-zero rtu_status otherwise; rtu_last_error() gives the message (the reference's render
+ * path has no error reporting at all: void functions on detached threads, main.cpp:29-64).
+ *
+ * The host-side scene description below is a flattened, read-only mirror of the reference's
+ * scene globals (main.cpp:17-27): what LoadScene() (xmlload.cpp:64) leaves in rootNode,
+ * camera, materials, lights, objList, background, environment, textureList.  A reference
+ * maintainer fills it by walking those globals (INTEGRATION.md shows the stub); our own
+ * loader (rtu_host_load_xml) fills it from the same XML/OBJ/PNG files.
+ *
+ * Matrices are column-major float[9] exactly as cyMatrix3f::data (cyMatrix.h:290-294).
+ */
+#ifndef RTU_H_INCLUDED
+#define RTU_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTU_BIGFLOAT 1.0e30f /* scene.h:55 */
+
+typedef enum {
+    RTU_OK = 0,
+    RTU_ERR_INVALID = 1,   /* bad argument / malformed scene description */
+    RTU_ERR_CUDA = 2,      /* CUDA runtime error (message has the cudaError string) */
+    RTU_ERR_IO = 3,        /* file missing / unreadable / unparsable */
+    RTU_ERR_NO_DEVICE = 4, /* no CUDA device: there is NO CPU fallback */
+    RTU_ERR_UNSUPPORTED = 5
+} rtu_status;
+
+/* ------------------------------------------------------------------ scene description */
+
+/* Object kinds: the closed world xmlload.cpp:193-199 can create. */
+enum { RTU_OBJ_NONE = 0, RTU_OBJ_SPHERE = 1, RTU_OBJ_PLANE = 2, RTU_OBJ_MESH = 3 };
+
+/* One scene-graph Node (scene.h:437-513).  Nodes are stored in PRE-ORDER, which is the order
+ * Trace() visits them (RenderFunctions.cpp:181-213); node 0 is rootNode. */
+typedef struct rtu_node {
+    float tm[9];      /* Transformation::tm  (scene.h:226) */
+    float itm[9];     /* Transformation::itm (scene.h:228) */
+    float pos[3];     /* Transformation::pos (scene.h:227) */
+    int32_t parent;   /* index of the parent node, -1 for the root */
+    int32_t kind;     /* RTU_OBJ_* of Node::obj (scene.h:442) */
+    int32_t mesh;     /* index into meshes[] when kind==RTU_OBJ_MESH, else -1 */
+    int32_t material; /* index into materials[] of Node::mtl, -1 if none */
+} rtu_node;
+
+/* One TriObj (objects.h:46-66): cyTriMesh arrays (cyTriMesh.h:106-119) + its cyBVH
+ * (cyBVH.h:187-203) exactly as built by bvh.SetMesh(this,4) (objects.h:58). */
+typedef struct rtu_mesh {
+    const float *v;     uint32_t nv;  /* 3 floats per vertex */
+    const float *vn;    uint32_t nvn;
+    const float *vt;    uint32_t nvt;
+    const uint32_t *f;                /* nf x 3 vertex indices */
+    const uint32_t *fn;               /* nf x 3 normal indices */
+    const uint32_t *ft;               /* nf x 3 texture-vertex indices (may be NULL) */
+    uint32_t nf;
+    const float *bvh_boxes;           /* bvh_nodes x 6 (min xyz, max xyz); node 0 unused, root = 1 */
+    const uint32_t *bvh_data;         /* bvh_nodes packed words: leaf bit 31, count-1 bits 28..30, offset / child index */
+    uint32_t bvh_nodes;               /* number of entries INCLUDING the unused node 0 */
+    const uint32_t *bvh_elements;     /* nf face ids in leaf order */
+    float bound_min[3], bound_max[3]; /* cyTriMesh::boundMin/Max */
+} rtu_mesh;
+
+enum { RTU_TEX_NULL = 0, RTU_TEX_CHECKER = 1, RTU_TEX_FILE = 2 };
+
+/* A TextureMap (scene.h:375-397) together with the Texture it points at
+ * (texture.h:20-45).  RTU_TEX_NULL is a map whose texture failed to load: it samples black
+ * (scene.h:382). */
+typedef struct rtu_texmap {
+    int32_t kind;
+    float itm[9];       /* Transformation of the map: Sample() uses itm*(uvw-pos) (scene.h:235,382) */
+    float pos[3];
+    float color1[3];    /* TextureChecker */
+    float color2[3];
+    const uint8_t *rgb8; /* TextureFile::data, width*height*3, row 0 first */
+    int32_t width, height;
+} rtu_texmap;
+
+/* TexturedColor (scene.h:405-433): colour, optionally multiplied by a texture map. */
+typedef struct rtu_texcolor {
+    float color[3];
+    int32_t texmap; /* index into texmaps[], -1 when TexturedColor::map == NULL */
+} rtu_texcolor;
+
+/* MtlBlinn (materials.h:20-57).  A MultiMtl is represented by its sub-material 0, which is
+ * the only one the reference can ever shade with (hInfo.mtlID is never set: SURVEY A-9). */
+typedef struct rtu_material {
+    rtu_texcolor diffuse, specular, reflection, refraction, emission;
+    float glossiness;
+    float absorption[3];
+    float ior;
+    float reflection_glossiness, refraction_glossiness;
+} rtu_material;
+
+enum { RTU_LIGHT_AMBIENT = 0, RTU_LIGHT_DIRECT = 1, RTU_LIGHT_POINT = 2 };
+
+/* AmbientLight / DirectLight / PointLight (lights.h:28-99). */
+typedef struct rtu_light {
+    int32_t kind;
+    float intensity[3];
+    float v[3]; /* DirectLight::direction (normalised) or PointLight::position */
+    float size; /* PointLight::size (soft shadow disk radius) */
+} rtu_light;
+
+/* Camera (scene.h:517-535) after LoadScene's fix-up (xmlload.cpp:109-126). */
+typedef struct rtu_camera {
+    float pos[3], dir[3], up[3];
+    float fov, focaldist, dof;
+    int32_t width, height;
+} rtu_camera;
+
+typedef struct rtu_scene_desc {
+    rtu_camera camera;
+    const rtu_node *nodes;         int32_t n_nodes;
+    const rtu_mesh *meshes;        int32_t n_meshes;
+    const rtu_material *materials; int32_t n_materials;
+    const rtu_light *lights;       int32_t n_lights;
+    const rtu_texmap *texmaps;     int32_t n_texmaps;
+    rtu_texcolor background;       /* scene.h global `background`  */
+    rtu_texcolor environment;      /* scene.h global `environment` */
+} rtu_scene_desc;
+
+/* ------------------------------------------------------------------ batched operator I/O */
+
+/* Ray (scene.h:59-68). */
+typedef struct rtu_ray { float p[3]; float dir[3]; } rtu_ray;
+
+/* HitInfo (scene.h:150-163) with the node pointer replaced by the pre-order node index and
+ * the winning face id added (the reference does not record it). */
+typedef struct rtu_hit {
+    float z;
+    float p[3];
+    float N[3];
+    float uvw[3];
+    int32_t node;  /* -1 = no hit (then z == RTU_BIGFLOAT) */
+    int32_t face;  /* winning triangle of a mesh hit, else -1 */
+    int32_t front; /* HitInfo::front */
+} rtu_hit;
+
+/* ------------------------------------------------------------------ frame parameters */
+
+enum {
+    RTU_MODE_PRIMARY = 0, /* one Trace() per pixel centre: node/face ids + z only */
+    RTU_MODE_WHITTED = 1, /* Trace + Shade(ray,h,lights,shade_bounces): RenderFunctions.cpp:135 alone */
+    RTU_MODE_PATH = 2     /* HEAD estimator: MonteCarlo GI list + lights (RenderFunctions.cpp:132-135) */
+};
+enum {
+    RTU_PATTERN_CENTER = 0,   /* pixel centre (0.5,0.5); spp must be 1 */
+    RTU_PATTERN_REFERENCE = 1 /* s/spp + Halton(s,4), s/spp + Halton(s,5) (RenderFunctions.cpp:81-85,96) */
+};
+enum {
+    RTU_FLAG_CULL_NULL_SHADOW_RAYS = 1 /* skip shadow rays whose contribution is exactly 0 (the reference traces them) */
+};
+
+typedef struct rtu_params {
+    int32_t width, height;        /* 0 = use the scene camera's (xml <width>/<height>) */
+    int32_t spp;                  /* samples per pixel; the reference hard-codes 1024 (RenderFunctions.cpp:27) */
+    int32_t sample_begin;         /* this call renders samples [sample_begin, sample_end) of the spp ... */
+    int32_t sample_end;           /* ... (spp-sliced multi-GPU); 0,0 = all */
+    int32_t pattern;              /* RTU_PATTERN_* */
+    int32_t mode;                 /* RTU_MODE_* */
+    int32_t shade_bounces;        /* bounceCount passed to Shade; the reference hard-codes 5 (RenderFunctions.cpp:134) */
+    int32_t gi_bounces;           /* monteCarloBounces = 4 (RenderFunctions.cpp:31) */
+    int32_t row_begin, row_end;   /* image rows rendered by this call (tile-sliced multi-GPU); 0,0 = all */
+    uint32_t flags;               /* RTU_FLAG_* */
+    uint64_t seed;                /* counter-based RNG key (soft shadows, glossy, DOF, GI) */
+} rtu_params;
+
+/* Host output buffers of one frame; any pointer may be NULL. */
+typedef struct rtu_image {
+    uint8_t *rgb8;    /* W*H*3  Result.png pixels: gamma 1/2.2 then Color24 (RenderFunctions.cpp:152-159) */
+    float *rgb;       /* W*H*3  linear mean radiance (parity buffer, not in the reference) */
+    float *z;         /* W*H    pixel-centre primary z, RTU_BIGFLOAT on miss (SURVEY A-3) */
+    uint8_t *z8;      /* W*H    ZBuffer.png greys (RenderImage::ComputeZBufferImage, scene.h:590-612) */
+    int32_t *node_id; /* W*H    primary hit node (pre-order index), -1 on miss */
+    int32_t *face_id; /* W*H    primary hit face, -1 if not a mesh */
+} rtu_image;
+
+/* Counters of the last render/trace call.  A "ray" is one root-level Trace or ShadowTrace
+ * (SURVEY section 8d); box/tri/node counts feed the algorithmic-bytes roofline figure
+ * 28*box_tests + 52*tri_tests + 48*node_visits. */
+typedef struct rtu_stats {
+    uint64_t trace_rays;
+    uint64_t shadow_rays;
+    uint64_t box_tests;
+    uint64_t tri_tests;
+    uint64_t node_visits;
+    uint64_t kernel_launches;
+    double device_ms;      /* CUDA-event time of the device work of the last call */
+    double trace_kernel_ms;  /* time inside the closest-hit/shade wave kernels */
+    double shadow_kernel_ms; /* time inside the any-hit kernels */
+} rtu_stats;
+
+typedef struct rtu_context rtu_context; /* one per GPU / host thread */
+typedef struct rtu_scene rtu_scene;     /* device-resident scene, owned by a context */
+typedef struct rtu_host_scene rtu_host_scene; /* result of our XML/OBJ/PNG loader (host memory) */
+
+const char *rtu_last_error(void);
+int rtu_version(void);
+
+/* ------------------------------------------------------------------ scene front-end (host only, no CUDA)
+ * Replaces LoadScene(const char*) (xmlload.cpp:64-131) + TriObj::Load (objects.h:52-60)
+ * + TextureFile::Load (texture.cpp:57-91).  asset_root is prepended to relative object /
+ * texture paths (the reference resolves them against the CWD). */
+int rtu_host_load_xml(const char *xml_path, const char *asset_root, rtu_host_scene **out);
+const rtu_scene_desc *rtu_host_scene_desc(const rtu_host_scene *hs);
+void rtu_host_scene_destroy(rtu_host_scene *hs);
+/* cyBVH build (cyBVH.h:122-142, BVHTriMesh 339-379) on caller arrays; fills caller-provided
+ * boxes[(2*nf)*6], data[2*nf], elements[nf]; *n_nodes gets the entry count incl. node 0. */
+int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t nf,
+                       uint32_t max_per_leaf, float *boxes, uint32_t *data, uint32_t *elements,
+                       uint32_t *n_nodes);
+/* Result.png / ZBuffer.png writers (RenderImage::SaveImage/SaveZImage, scene.h:638-654). */
+int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels);
+
+/* ------------------------------------------------------------------ device path
+ * stream: a cudaStream_t cast to void* (NULL = legacy default stream). */
+int rtu_context_create(int32_t device, void *stream, rtu_context **out);
+void rtu_context_destroy(rtu_context *ctx);
+
+/* Pack + upload (H2D) a scene: flattens instances, re-lays the BVH out as 64-byte node
+ * pairs and 64-byte triangle records, copies materials/lights/textures. */
+int rtu_scene_upload(rtu_context *ctx, const rtu_scene_desc *desc, rtu_scene **out);
+void rtu_scene_destroy(rtu_scene *scene);
+
+/* Batched operators with HOST buffers (copies inside):
+ *   rtu_trace        == Trace(ray, &rootNode, hInfo) with a fresh HitInfo   (RenderFunctions.cpp:181)
+ *   rtu_shadow_trace == GenLight::Shadow's ShadowTrace with h.z = t_max     (lightFunctions.cpp:27-37)
+ *   rtu_shade        == hit.node->GetMaterial()->Shade(ray, hit, lights, bounces) (mtlFunctions.cpp:120) */
+int rtu_trace(rtu_scene *scene, const rtu_ray *rays, int64_t n, rtu_hit *hits);
+int rtu_shadow_trace(rtu_scene *scene, const rtu_ray *rays, const float *t_max, int64_t n, uint8_t *occluded);
+int rtu_shade(rtu_scene *scene, const rtu_ray *rays, const rtu_hit *hits, int64_t n, int32_t bounces, float *rgb);
+
+/* Frame level.  rtu_render: the whole Render() job with HOST output buffers (the e2e path).
+ * rtu_render_device: same work, result left in device memory (accum: W*H float4 = sum of
+ * radiance over the rendered samples, .w = sample count); accum may be a caller-owned device
+ * pointer (e.g. a torch tensor, so that NCCL can reduce it) or NULL for the internal one.
+ * rtu_resolve: accum -> mean, gamma, Color24, z image; writes HOST buffers. */
+void rtu_params_default(rtu_params *p);
+int rtu_render(rtu_scene *scene, const rtu_params *params, rtu_image *out);
+int rtu_render_device(rtu_scene *scene, const rtu_params *params, float *d_accum, int32_t clear_accum);
+int rtu_resolve(rtu_scene *scene, const rtu_params *params, const float *d_accum, rtu_image *out);
+int rtu_get_stats(const rtu_scene *scene, rtu_stats *out);
+int rtu_synchronize(rtu_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTU_H_INCLUDED */

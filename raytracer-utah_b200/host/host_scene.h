@@ -1,0 +1,62 @@
+// Owning host-side containers behind the POD rtu_scene_desc of include/rtu.h.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/rtu.h"
+
+namespace rtu {
+
+// cyTriMesh arrays + cyBVH arrays of one TriObj (objects.h:46-66)
+struct HostMesh {
+    std::string name;
+    std::vector<float> v, vn, vt;        // xyz triples
+    std::vector<uint32_t> f, fn, ft;     // index triples
+    std::vector<float> bvh_boxes;        // (n_nodes) x 6, node 0 unused
+    std::vector<uint32_t> bvh_data;
+    std::vector<uint32_t> bvh_elements;
+    float bound_min[3] = {1, 1, 1}, bound_max[3] = {0, 0, 0}; // cyTriMesh.h:128 "not ready" box
+    uint32_t nf() const { return (uint32_t)(f.size() / 3); }
+};
+
+struct HostTexture {
+    std::string name;
+    int kind = RTU_TEX_NULL;
+    float color1[3] = {0, 0, 0}, color2[3] = {1, 1, 1};
+    std::vector<uint8_t> rgb8;
+    int width = 0, height = 0;
+};
+
+// Loads an OBJ with the parsing rules of cyTriMesh::LoadFromFileObj (cyTriMesh.h:263-547),
+// then TriObj::Load's post-steps (objects.h:52-60): ComputeNormals if none, bounding box,
+// BVH with max 4 elements per leaf.  Returns false if the file cannot be opened.
+bool load_obj_mesh(const char *path, HostMesh *out, std::string *err);
+void compute_vertex_normals(HostMesh *m);
+void compute_bounds(HostMesh *m);
+// cyBVH::Build (cyBVH.h:122-142) + BVHTriMesh element callbacks (:356-375)
+void build_bvh(const float *v, const uint32_t *f, uint32_t nf, uint32_t max_per_leaf,
+               std::vector<float> *boxes, std::vector<uint32_t> *data, std::vector<uint32_t> *elements);
+
+bool decode_png_rgb8(const char *path, std::vector<uint8_t> *rgb, int *w, int *h, std::string *err);
+bool encode_png(const char *path, const uint8_t *px, int w, int h, int channels, std::string *err);
+
+void set_error(const std::string &msg);
+const std::string &last_error();
+
+} // namespace rtu
+
+struct rtu_host_scene {
+    rtu_scene_desc desc;
+    std::vector<rtu_node> nodes;
+    std::vector<std::string> node_names;
+    std::vector<std::unique_ptr<rtu::HostMesh>> meshes;
+    std::vector<rtu_mesh> mesh_descs;
+    std::vector<rtu_material> materials;
+    std::vector<std::string> material_names;
+    std::vector<rtu_light> lights;
+    std::vector<std::unique_ptr<rtu::HostTexture>> textures; // TextureList (scene.h:368)
+    std::vector<rtu_texmap> texmaps;
+    void finalize(); // points desc at the vectors
+};

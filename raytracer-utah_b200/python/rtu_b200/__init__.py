@@ -1,0 +1,357 @@
+"""ctypes binding of include/rtu.h (librtu_b200.so) for the tests and bench.py.
+
+Not the product: the product is the C ABI.  This module only mirrors the structs and wraps
+the calls with numpy buffers so that the Python parity tests read like calls into the
+reference (Trace / ShadowTrace / Shade / Render).  It never computes anything itself and
+fails loudly if the shared library is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))          # raytracer-utah_b200/
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.path.join(PKG_ROOT, "librtu_b200.so")
+SCENES = os.path.join(REPO_ROOT, "scenes")
+BIGFLOAT = np.float32(1.0e30)
+
+OBJ_NONE, OBJ_SPHERE, OBJ_PLANE, OBJ_MESH = 0, 1, 2, 3
+TEX_NULL, TEX_CHECKER, TEX_FILE = 0, 1, 2
+LIGHT_AMBIENT, LIGHT_DIRECT, LIGHT_POINT = 0, 1, 2
+MODE_PRIMARY, MODE_WHITTED, MODE_PATH = 0, 1, 2
+PATTERN_CENTER, PATTERN_REFERENCE = 0, 1
+FLAG_CULL_NULL_SHADOW_RAYS = 1
+
+f32, i32, u32, u8 = C.c_float, C.c_int32, C.c_uint32, C.c_uint8
+PF, PU, PB = C.POINTER(f32), C.POINTER(u32), C.POINTER(u8)
+
+
+class Node(C.Structure):
+    _fields_ = [("tm", f32 * 9), ("itm", f32 * 9), ("pos", f32 * 3), ("parent", i32),
+                ("kind", i32), ("mesh", i32), ("material", i32)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("v", PF), ("nv", u32), ("vn", PF), ("nvn", u32), ("vt", PF), ("nvt", u32),
+                ("f", PU), ("fn", PU), ("ft", PU), ("nf", u32),
+                ("bvh_boxes", PF), ("bvh_data", PU), ("bvh_nodes", u32), ("bvh_elements", PU),
+                ("bound_min", f32 * 3), ("bound_max", f32 * 3)]
+
+
+class TexMap(C.Structure):
+    _fields_ = [("kind", i32), ("itm", f32 * 9), ("pos", f32 * 3), ("color1", f32 * 3),
+                ("color2", f32 * 3), ("rgb8", PB), ("width", i32), ("height", i32)]
+
+
+class TexColor(C.Structure):
+    _fields_ = [("color", f32 * 3), ("texmap", i32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("diffuse", TexColor), ("specular", TexColor), ("reflection", TexColor),
+                ("refraction", TexColor), ("emission", TexColor), ("glossiness", f32),
+                ("absorption", f32 * 3), ("ior", f32), ("reflection_glossiness", f32),
+                ("refraction_glossiness", f32)]
+
+
+class Light(C.Structure):
+    _fields_ = [("kind", i32), ("intensity", f32 * 3), ("v", f32 * 3), ("size", f32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("pos", f32 * 3), ("dir", f32 * 3), ("up", f32 * 3), ("fov", f32),
+                ("focaldist", f32), ("dof", f32), ("width", i32), ("height", i32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("camera", Camera),
+                ("nodes", C.POINTER(Node)), ("n_nodes", i32),
+                ("meshes", C.POINTER(Mesh)), ("n_meshes", i32),
+                ("materials", C.POINTER(Material)), ("n_materials", i32),
+                ("lights", C.POINTER(Light)), ("n_lights", i32),
+                ("texmaps", C.POINTER(TexMap)), ("n_texmaps", i32),
+                ("background", TexColor), ("environment", TexColor)]
+
+
+class Params(C.Structure):
+    _fields_ = [("width", i32), ("height", i32), ("spp", i32), ("sample_begin", i32),
+                ("sample_end", i32), ("pattern", i32), ("mode", i32), ("shade_bounces", i32),
+                ("gi_bounces", i32), ("row_begin", i32), ("row_end", i32), ("flags", u32),
+                ("seed", C.c_uint64)]
+
+
+class Image(C.Structure):
+    _fields_ = [("rgb8", PB), ("rgb", PF), ("z", PF), ("z8", PB),
+                ("node_id", C.POINTER(i32)), ("face_id", C.POINTER(i32))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("trace_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("box_tests", C.c_uint64),
+                ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("device_ms", C.c_double), ("trace_kernel_ms", C.c_double), ("shadow_kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+RAY_DTYPE = np.dtype([("p", "<f4", 3), ("dir", "<f4", 3)])
+HIT_DTYPE = np.dtype([("z", "<f4"), ("p", "<f4", 3), ("N", "<f4", 3), ("uvw", "<f4", 3),
+                      ("node", "<i4"), ("face", "<i4"), ("front", "<i4")])
+
+_lib = None
+
+
+class RtuError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads librtu_b200.so; there is no fallback of any kind."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RtuError("librtu_b200.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.rtu_last_error.restype = C.c_char_p
+        L.rtu_host_scene_desc.restype = C.POINTER(SceneDesc)
+        L.rtu_host_scene_desc.argtypes = [C.c_void_p]
+        L.rtu_host_load_xml.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.rtu_host_scene_destroy.argtypes = [C.c_void_p]
+        L.rtu_host_scene_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RtuError("%s failed (status %d): %s" % (what, rc, lib().rtu_last_error().decode("utf-8", "replace")))
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+class HostScene:
+    """rtu_host_load_xml: our replacement for LoadScene(const char*) (xmlload.cpp:64)."""
+
+    def __init__(self, xml_path, asset_root=None):
+        L = lib()
+        self._h = C.c_void_p()
+        root = asset_root if asset_root is not None else SCENES
+        _check(L.rtu_host_load_xml(os.fsencode(xml_path), os.fsencode(root), C.byref(self._h)), "rtu_host_load_xml")
+        self.warnings = L.rtu_last_error().decode("utf-8", "replace")
+        self.desc = L.rtu_host_scene_desc(self._h).contents
+
+    def close(self):
+        if self._h:
+            lib().rtu_host_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # numpy views for the loader-parity tests
+    def nodes(self):
+        d = self.desc
+        n = d.n_nodes
+        out = {"tm": np.zeros((n, 9), "f4"), "itm": np.zeros((n, 9), "f4"), "pos": np.zeros((n, 3), "f4"),
+               "meta": np.zeros((n, 4), "i4")}
+        for i in range(n):
+            nd = d.nodes[i]
+            out["tm"][i] = np.frombuffer(nd.tm, "f4")
+            out["itm"][i] = np.frombuffer(nd.itm, "f4")
+            out["pos"][i] = np.frombuffer(nd.pos, "f4")
+            out["meta"][i] = (nd.parent, nd.kind, nd.mesh, nd.material)
+        return out
+
+    def mesh(self, i):
+        m = self.desc.meshes[i]
+
+        def arr(p, n, dt):
+            if not p or n == 0:
+                return np.zeros((0, 3), dt)
+            return np.ctypeslib.as_array(p, shape=(n * 3,)).view(dt).reshape(n, 3).copy()
+
+        return {"v": arr(m.v, m.nv, "f4"), "vn": arr(m.vn, m.nvn, "f4"), "vt": arr(m.vt, m.nvt, "f4"),
+                "f": arr(m.f, m.nf, "u4"), "fn": arr(m.fn, m.nf, "u4"), "ft": arr(m.ft, m.nf, "u4"),
+                "bvh_boxes": np.ctypeslib.as_array(m.bvh_boxes, shape=(m.bvh_nodes * 6,)).reshape(-1, 6).copy(),
+                "bvh_data": np.ctypeslib.as_array(m.bvh_data, shape=(m.bvh_nodes,)).copy(),
+                "bvh_elements": np.ctypeslib.as_array(m.bvh_elements, shape=(m.nf,)).copy(),
+                "bound": np.concatenate([np.frombuffer(m.bound_min, "f4"), np.frombuffer(m.bound_max, "f4")])}
+
+    def camera(self):
+        c = self.desc.camera
+        return np.array(list(c.pos) + list(c.dir) + list(c.up) + [c.fov, c.focaldist, c.dof, c.width, c.height], "f4")
+
+    def materials(self):
+        d = self.desc
+        out = np.zeros((d.n_materials, 22), "f4")
+        for i in range(d.n_materials):
+            m = d.materials[i]
+            out[i] = (list(m.diffuse.color) + list(m.specular.color) + list(m.reflection.color) +
+                      list(m.refraction.color) + list(m.emission.color) + list(m.absorption) +
+                      [m.glossiness, m.ior, m.reflection_glossiness, m.refraction_glossiness])
+        return out
+
+    def lights(self):
+        d = self.desc
+        out = np.zeros((d.n_lights, 8), "f4")
+        for i in range(d.n_lights):
+            l = d.lights[i]
+            out[i] = [l.kind] + list(l.intensity) + list(l.v) + [l.size]
+        return out
+
+
+def default_params(**kw):
+    p = Params()
+    lib().rtu_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        L = lib()
+        self._h = C.c_void_p()
+        L.rtu_context_create.argtypes = [i32, C.c_void_p, C.POINTER(C.c_void_p)]
+        _check(L.rtu_context_create(device, C.c_void_p(stream or 0), C.byref(self._h)), "rtu_context_create")
+
+    def synchronize(self):
+        L = lib()
+        L.rtu_synchronize.argtypes = [C.c_void_p]
+        _check(L.rtu_synchronize(self._h), "rtu_synchronize")
+
+    def close(self):
+        if self._h:
+            L = lib()
+            L.rtu_context_destroy.argtypes = [C.c_void_p]
+            L.rtu_context_destroy.restype = None
+            L.rtu_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Scene:
+    """Device-resident scene (rtu_scene_upload) with the batched operator calls."""
+
+    def __init__(self, ctx, desc):
+        L = lib()
+        self.ctx = ctx
+        self.desc = desc
+        self._h = C.c_void_p()
+        L.rtu_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+        _check(L.rtu_scene_upload(ctx._h, C.byref(desc), C.byref(self._h)), "rtu_scene_upload")
+
+    def close(self):
+        if self._h:
+            L = lib()
+            L.rtu_scene_destroy.argtypes = [C.c_void_p]
+            L.rtu_scene_destroy.restype = None
+            L.rtu_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def trace(self, rays):
+        """Trace(ray, &rootNode, HitInfo()) for every ray (RenderFunctions.cpp:181)."""
+        L = lib()
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], HIT_DTYPE)
+        L.rtu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _check(L.rtu_trace(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data), "rtu_trace")
+        return hits
+
+    def shadow_trace(self, rays, t_max):
+        """GenLight::Shadow's ShadowTrace with h.z = t_max (lightFunctions.cpp:27-37)."""
+        L = lib()
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        t_max = np.ascontiguousarray(t_max, "f4")
+        occ = np.zeros(rays.shape[0], "u1")
+        L.rtu_shadow_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _check(L.rtu_shadow_trace(self._h, rays.ctypes.data, t_max.ctypes.data, rays.shape[0], occ.ctypes.data), "rtu_shadow_trace")
+        return occ
+
+    def shade(self, rays, hits, bounces=5):
+        """hit.node->GetMaterial()->Shade(ray, hit, lights, bounces) (mtlFunctions.cpp:120)."""
+        L = lib()
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.ascontiguousarray(hits, HIT_DTYPE)
+        rgb = np.zeros((rays.shape[0], 3), "f4")
+        L.rtu_shade.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, i32, C.c_void_p]
+        _check(L.rtu_shade(self._h, rays.ctypes.data, hits.ctypes.data, rays.shape[0], bounces, rgb.ctypes.data), "rtu_shade")
+        return rgb
+
+    def _dims(self, params):
+        w = params.width or self.desc.camera.width
+        h = params.height or self.desc.camera.height
+        return w, h
+
+    def render(self, params, want=("rgb8", "rgb", "z", "z8", "node_id", "face_id")):
+        """rtu_render: whole frame, host buffers out (the e2e path)."""
+        L = lib()
+        w, h = self._dims(params)
+        bufs = {}
+        img = Image()
+        spec = {"rgb8": ((h, w, 3), "u1", u8), "rgb": ((h, w, 3), "f4", f32), "z": ((h, w), "f4", f32),
+                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
+        for k in want:
+            shp, dt, ct = spec[k]
+            bufs[k] = np.zeros(shp, dt)
+            setattr(img, k, _ptr(bufs[k], ct))
+        L.rtu_render.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Image)]
+        _check(L.rtu_render(self._h, C.byref(params), C.byref(img)), "rtu_render")
+        return bufs
+
+    def render_device(self, params, d_accum=0, clear=True):
+        L = lib()
+        L.rtu_render_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, i32]
+        _check(L.rtu_render_device(self._h, C.byref(params), C.c_void_p(d_accum), 1 if clear else 0), "rtu_render_device")
+
+    def resolve(self, params, d_accum=0, want=("rgb8", "rgb")):
+        L = lib()
+        w, h = self._dims(params)
+        bufs = {}
+        img = Image()
+        spec = {"rgb8": ((h, w, 3), "u1", u8), "rgb": ((h, w, 3), "f4", f32), "z": ((h, w), "f4", f32),
+                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
+        for k in want:
+            shp, dt, ct = spec[k]
+            bufs[k] = np.zeros(shp, dt)
+            setattr(img, k, _ptr(bufs[k], ct))
+        L.rtu_resolve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(Image)]
+        _check(L.rtu_resolve(self._h, C.byref(params), C.c_void_p(d_accum), C.byref(img)), "rtu_resolve")
+        return bufs
+
+    def stats(self):
+        L = lib()
+        s = Stats()
+        L.rtu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        _check(L.rtu_get_stats(self._h, C.byref(s)), "rtu_get_stats")
+        return s.as_dict()
+
+
+def build_bvh(v, f, max_per_leaf=4):
+    """rtu_host_build_bvh: cyBVH::Build on caller arrays."""
+    L = lib()
+    v = np.ascontiguousarray(v, "f4")
+    f = np.ascontiguousarray(f, "u4")
+    nf = f.shape[0]
+    boxes = np.zeros((max(2 * nf, 2), 6), "f4")
+    data = np.zeros(max(2 * nf, 2), "u4")
+    elem = np.zeros(max(nf, 1), "u4")
+    n = u32(0)
+    L.rtu_host_build_bvh.argtypes = [C.c_void_p, u32, C.c_void_p, u32, u32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(u32)]
+    _check(L.rtu_host_build_bvh(v.ctypes.data, v.shape[0], f.ctypes.data, nf, max_per_leaf,
+                                boxes.ctypes.data, data.ctypes.data, elem.ctypes.data, C.byref(n)), "rtu_host_build_bvh")
+    return boxes[:n.value].copy(), data[:n.value].copy(), elem[:nf].copy()
+
+
+def write_png(path, pixels):
+    L = lib()
+    px = np.ascontiguousarray(pixels, "u1")
+    ch = 1 if px.ndim == 2 else px.shape[2]
+    L.rtu_write_png.argtypes = [C.c_char_p, C.c_void_p, i32, i32, i32]
+    _check(L.rtu_write_png(os.fsencode(path), px.ctypes.data, px.shape[1], px.shape[0], ch), "rtu_write_png")
