@@ -160,7 +160,8 @@ enum {
     RTU_PATTERN_REFERENCE = 1 /* s/spp + Halton(s,4), s/spp + Halton(s,5) (RenderFunctions.cpp:81-85,96) */
 };
 enum {
-    RTU_FLAG_CULL_NULL_SHADOW_RAYS = 1 /* skip shadow rays whose contribution is exactly 0 (the reference traces them) */
+    RTU_FLAG_CULL_NULL_SHADOW_RAYS = 1, /* skip shadow rays whose contribution is exactly 0 (the reference traces them) */
+    RTU_FLAG_CULL_ZERO_WEIGHT_RAYS = 2  /* skip secondary rays whose throughput is exactly 0 (e.g. absorbed TIR; the reference traces them) */
 };
 
 typedef struct rtu_params {
@@ -241,6 +242,9 @@ void rtu_scene_destroy(rtu_scene *scene);
 int rtu_trace(rtu_scene *scene, const rtu_ray *rays, int64_t n, rtu_hit *hits);
 int rtu_shadow_trace(rtu_scene *scene, const rtu_ray *rays, const float *t_max, int64_t n, uint8_t *occluded);
 int rtu_shade(rtu_scene *scene, const rtu_ray *rays, const rtu_hit *hits, int64_t n, int32_t bounces, float *rgb);
+/* The camera ray Render() builds for sample `sample` of every pixel (RenderFunctions.cpp:78-97),
+ * rays[x + width*y]; lens offsets are 0 (dof is ignored here). */
+int rtu_camera_rays(rtu_scene *scene, const rtu_params *params, int32_t sample, rtu_ray *rays);
 
 /* Frame level.  rtu_render: the whole Render() job with HOST output buffers (the e2e path).
  * rtu_render_device: same work, result left in device memory (accum: W*H float4 = sum of

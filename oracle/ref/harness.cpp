@@ -326,6 +326,7 @@ static void DumpHits(const std::string &pre, int n, const std::vector<float> &ra
 static void ModeKat(const Opts &o)
 {
     int n = o.n;
+    Node idn;   // identity transform
     g_rng = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)o.seed;
     // ---- sphere / plane: rays aimed near the unit primitive, some with axis-aligned or zero components
     for (int kind = 1; kind <= 2; kind++) {
@@ -346,7 +347,10 @@ static void ModeKat(const Opts &o)
             HitInfo h;
             if (i % 3 == 0) h.z = Rnd() * 4;                 // a nearer hit already found / shadow t_max
             zin[i] = h.z;
-            bool res = kind == 1 ? theSphere.IntersectRay(r, h) : thePlane.IntersectRay(r, h);
+            // through two identity nodes (rootNode + object node), exactly as Trace() would reach the object
+            Ray lr = idn.ToNodeCoords(idn.ToNodeCoords(r));
+            bool res = kind == 1 ? theSphere.IntersectRay(lr, h) : thePlane.IntersectRay(lr, h);
+            if (res) { idn.FromNodeCoords(h); idn.FromNodeCoords(h); }
             hit[i] = res; hs[i] = h;
             for (int k = 0; k < 3; k++) { rays[i * 6 + k] = p[k]; rays[i * 6 + 3 + k] = d[k]; }
         }
@@ -400,11 +404,13 @@ static void ModeKat(const Opts &o)
             HitInfo h;
             if (i % 3 == 0) h.z = Rnd() * 2;
             zin[i] = h.z;
-            hit[i] = t->IntersectRay(r, h);
+            Ray lr = idn.ToNodeCoords(idn.ToNodeCoords(r));
+            hit[i] = t->IntersectRay(lr, h);
+            if (hit[i]) { idn.FromNodeCoords(h); idn.FromNodeCoords(h); }
             hs[i] = h;
             // WinningFace starts from z=BIGFLOAT; the winner is the same whenever the mesh hit at all,
             // because the closest triangle also passes the tighter initial-z gate
-            face[i] = hit[i] ? WinningFace(t, r) : -1;
+            face[i] = hit[i] ? WinningFace(t, lr) : -1;
             for (int k = 0; k < 3; k++) { rays[i * 6 + k] = p[k]; rays[i * 6 + 3 + k] = d[k]; }
         }
         DumpHits(o.out + "_mesh", n, rays, zin, hit, hs, &face);

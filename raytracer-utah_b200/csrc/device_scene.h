@@ -1,0 +1,157 @@
+// Device-side scene layout (HBM), shared by the packer (rtu_api.cu) and the kernels.
+//
+// Everything the traversal loop touches is a 16-byte-aligned record read with 128-bit loads:
+//   DNode     (112 B)  one scene-graph node in pre-order: the "to" transform (itm,pos) used by
+//                      Node::ToNodeCoords and the "from" transform (tm, itm^T) used by FromNodeCoords
+//   BvhPair   ( 64 B)  the two adjacent children of one internal cyBVH node: both boxes + both
+//                      child words, so one pop of an internal node costs exactly one 64-byte fetch
+//                      (the reference reads 2 x 28 B nodes + the parent's child index)
+//   TriRec    ( 48 B)  one triangle in LEAF order with everything ray-independent pre-evaluated on
+//                      the host with the reference's float op order (unit normal, projection axis,
+//                      projected edges, projected area): objFunctions.cpp:259-300
+//   TriShade  (112 B)  the 3 positions / normals / texture vertices of the same slot, fetched only
+//                      for the winning triangle (objFunctions.cpp:317-320)
+#pragma once
+#include <stdint.h>
+
+#define RTU_MAX_DEPTH 8          // scene-graph nesting handled by the generic (non-flat) path
+#define RTU_STACK 64             // BVH traversal stack entries (reference: 100; depth-first needs depth+1)
+#define RTU_KIND_BITS 3
+
+struct __align__(16) DNode {
+    float itm[9];   // ToNodeCoords:   p' = itm*(p-pos)                  scene.h:235,501-507
+    float pos[3];
+    float tm[9];    // FromNodeCoords: p  = tm*p + pos; N = norm(itm^T N) scene.h:236,242,508-512
+    int32_t parent; // pre-order index, -1 root
+    int32_t depth;  // 0 root
+    int32_t kind;   // RTU_OBJ_*
+    int32_t mesh;
+    int32_t material;
+    int32_t pad[2];
+};
+
+// child word: bit31 = leaf; leaf: bits 28..30 = count-1, bits 0..27 = first triangle slot
+//             internal: index of that child's BvhPair
+struct __align__(16) BvhPair {
+    float b1[6];    // child 1 box: min xyz, max xyz
+    float b2[6];    // child 2 box
+    uint32_t c1, c2;
+    uint32_t pad[2];
+};
+
+struct __align__(16) TriRec {
+    float nx, ny, nz, ax;       // unit geometric normal, A.x
+    float ay, az, area, fbits;  // A.y, A.z, projected area of ABC (already /2), face id | axis<<30 as int bits
+    float cau, cav, bau, bav;   // projected C-A and B-A
+};
+
+struct __align__(16) TriShade {
+    float v[9];   // A, B, C
+    float vn[9];  // normals at A, B, C
+    float vt[9];  // texture vertices at A, B, C
+    float pad;
+};
+
+struct DMesh {
+    const BvhPair *pairs;
+    const TriRec *tris;
+    const TriShade *shade;
+    uint32_t root;       // child word of the root node (leaf meshes have no pairs)
+    uint32_t n_pairs;
+    uint32_t n_tris;
+    float bmin[3], bmax[3];
+    uint32_t empty;      // no faces: cyTriMesh's "not ready" box never intersects
+};
+
+struct DTexMap {
+    int32_t kind;
+    float itm[9];
+    float pos[3];
+    float c1[3], c2[3];
+    const uint8_t *rgb8;
+    int32_t width, height;
+};
+
+struct DTexColor {
+    float c[3];
+    int32_t map; // -1 none
+};
+
+struct DMaterial {
+    DTexColor diffuse, specular, reflection, refraction;
+    float glossiness;
+    float absorption[3];
+    float ior;
+    float refl_gloss, refr_gloss;
+};
+
+struct DLight {
+    int32_t kind;
+    float I[3];
+    float v[3];
+    float size;
+};
+
+// camera frame pre-evaluated on the host exactly like CalculateImageOrigin / CalculateCurrentPoint
+// (RenderFunctions.cpp:243-269)
+struct DCamera {
+    float pos[3];
+    float origin[3]; // top-left corner of the image plane
+    float u[3], v[3]; // one-pixel steps
+    float lens_x[3], lens_y[3]; // thin-lens basis (RenderFunctions.cpp:93)
+    float dof;
+    int32_t width, height;
+    float inv_w, inv_h; // not used for parity-critical math
+};
+
+struct DScene {
+    const DNode *nodes;
+    int32_t n_nodes;
+    int32_t flat;        // 1: every object node hangs directly off the root
+    const DMesh *meshes;
+    const DMaterial *materials;
+    int32_t n_materials;
+    const DLight *lights;
+    int32_t n_lights;
+    const DTexMap *texmaps;
+    DTexColor background, environment;
+    float cam_pos[3];    // Shade uses camera.pos for the view vector (mtlFunctions.cpp:137)
+};
+
+// --- wavefront queues (structure of float4 arrays: every lane's 16-byte store is contiguous with its neighbour's)
+struct RayQueue {        // closest-hit rays of the next wave
+    float4 *o;  // origin.xyz, pixel (int bits)
+    float4 *d;  // dir.xyz, meta (int bits): kind | bounce<<3 | material<<8
+    float4 *w;  // throughput rgb, aux index (int bits, -1 none)
+    uint32_t *path; // RNG path word of the ray
+    uint32_t *count;
+    uint32_t cap;
+};
+struct AuxPool {         // extra payload of refracted / Fresnel rays
+    float4 *a;  // Kt.rgb, Schlick F
+    float4 *b;  // mirror direction at the parent hit, unused
+    uint32_t *count;
+    uint32_t cap;
+};
+struct ShadowQueue {     // any-hit rays
+    float4 *o;  // origin.xyz, pixel
+    float4 *d;  // dir.xyz, t_max
+    float4 *c;  // contribution rgb if unoccluded
+    uint32_t *count;
+    uint32_t cap;
+};
+
+enum RayKind {
+    RK_PRIMARY = 0,
+    RK_REFRACT = 1,  // refracted ray: miss -> env(dir); hit -> Beer * Kt * (1-F), then spawns RK_FRESNEL
+    RK_FRESNEL = 2,  // mirror ray spawned only after the refracted ray hit (mtlFunctions.cpp:234-251)
+    RK_TIR = 3,      // total internal reflection: miss adds nothing (mtlFunctions.cpp:205-222)
+    RK_REFLECT = 4,  // Kr mirror ray: miss -> env(dir)*Kr colour (mtlFunctions.cpp:273-290)
+    RK_GI = 5        // cosine-hemisphere bounce of MonteCarlo() (RenderFunctions.cpp:561-575)
+};
+
+struct DCounters {
+    unsigned long long trace_rays, shadow_rays, box_tests, tri_tests, node_visits;
+    uint32_t overflow;
+    uint32_t pad;
+};

@@ -1,0 +1,900 @@
+// C ABI (include/rtu.h) device side: context, scene packing + upload, wave orchestration.
+// There is no CPU fallback: every entry point that renders or traces needs a CUDA device and
+// returns RTU_ERR_NO_DEVICE / RTU_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/hmath.h"
+#include "../host/host_scene.h"
+#include "rtu_internal.h"
+
+using rtu::V3;
+
+namespace {
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            rtu::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+            return e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RTU_ERR_NO_DEVICE : RTU_ERR_CUDA; \
+        }                                                                                               \
+    } while (0)
+
+template <class T> int dev_upload(const std::vector<T> &h, T **d, cudaStream_t st, std::vector<void *> &owned)
+{
+    *d = nullptr;
+    if (h.empty()) return RTU_OK;
+    CU(cudaMalloc((void **)d, h.size() * sizeof(T)));
+    owned.push_back(*d);
+    CU(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return RTU_OK;
+}
+
+} // namespace
+
+struct rtu_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    LaunchCfg cfg;
+    size_t chunk_rays = 1u << 22;
+    // scratch (lazily sized)
+    WaveBuffers wb;
+    size_t q_cap = 0, shadow_cap = 0;
+    std::vector<void *> scratch;
+    unsigned *work = nullptr;
+    size_t work_n = 0;
+    unsigned *zmm = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct rtu_scene {
+    rtu_context *ctx = nullptr;
+    DScene S;
+    rtu_camera cam;
+    std::vector<void *> owned;
+    int n_shadow_lights = 0;
+    // frame buffers
+    float4 *accum = nullptr;
+    size_t accum_n = 0;
+    float *d_rgb = nullptr;
+    unsigned char *d_rgb8 = nullptr;
+    float *d_z = nullptr;
+    unsigned char *d_z8 = nullptr;
+    int *d_node = nullptr, *d_face = nullptr;
+    size_t img_n = 0;
+    float2 *d_offsets = nullptr;
+    size_t offsets_n = 0;
+    uint64_t launches = 0;
+    bool timed = false;
+};
+
+namespace {
+
+int free_list(std::vector<void *> &v)
+{
+    for (void *p : v) cudaFree(p);
+    v.clear();
+    return 0;
+}
+
+int ensure_scratch(rtu_context *c, size_t q_cap, size_t shadow_cap)
+{
+    if (q_cap <= c->q_cap && shadow_cap <= c->shadow_cap) return RTU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    free_list(c->scratch);
+    c->q_cap = c->shadow_cap = 0;
+    auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) c->scratch.push_back(*p);
+        return e;
+    };
+    unsigned *counts = nullptr;
+    CU(alloc((void **)&counts, 8 * sizeof(unsigned)));
+    CU(cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned), c->stream));
+    for (int i = 0; i < 2; i++) {
+        CU(alloc((void **)&c->wb.q[i].o, q_cap * sizeof(float4)));
+        CU(alloc((void **)&c->wb.q[i].d, q_cap * sizeof(float4)));
+        CU(alloc((void **)&c->wb.q[i].w, q_cap * sizeof(float4)));
+        CU(alloc((void **)&c->wb.q[i].path, q_cap * sizeof(uint32_t)));
+        c->wb.q[i].count = counts + i;
+        c->wb.q[i].cap = (uint32_t)q_cap;
+        CU(alloc((void **)&c->wb.aux[i].a, q_cap * sizeof(float4)));
+        CU(alloc((void **)&c->wb.aux[i].b, q_cap * sizeof(float4)));
+        c->wb.aux[i].count = counts + 2 + i;
+        c->wb.aux[i].cap = (uint32_t)q_cap;
+    }
+    CU(alloc((void **)&c->wb.shadow.o, shadow_cap * sizeof(float4)));
+    CU(alloc((void **)&c->wb.shadow.d, shadow_cap * sizeof(float4)));
+    CU(alloc((void **)&c->wb.shadow.c, shadow_cap * sizeof(float4)));
+    c->wb.shadow.count = counts + 4;
+    c->wb.shadow.cap = (uint32_t)shadow_cap;
+    CU(alloc((void **)&c->wb.counters, sizeof(DCounters)));
+    CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
+    c->q_cap = q_cap;
+    c->shadow_cap = shadow_cap;
+    return RTU_OK;
+}
+
+int ensure_work(rtu_context *c, size_t n)
+{
+    if (n > c->work_n) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->work) cudaFree(c->work);
+        c->work = nullptr;
+        CU(cudaMalloc((void **)&c->work, n * sizeof(unsigned)));
+        c->work_n = n;
+    }
+    CU(cudaMemsetAsync(c->work, 0, c->work_n * sizeof(unsigned), c->stream));
+    return RTU_OK;
+}
+
+// ---- camera frame: CalculateImageOrigin / CalculateCurrentPoint (RenderFunctions.cpp:243-269)
+void make_camera(const rtu_camera &c, int W, int H, DCamera *out)
+{
+    V3 pos(c.pos[0], c.pos[1], c.pos[2]), dir(c.dir[0], c.dir[1], c.dir[2]), up(c.up[0], c.up[1], c.up[2]);
+    float d = c.focaldist;
+    float actualHeight = (float)(tan((c.fov / 2) * M_PI / 180.0) * 2 * d);
+    float actualWidth = ((float)W / (float)H) * actualHeight;
+    V3 nd = rtu::normalized(dir), nu = rtu::normalized(up);
+    V3 right = rtu::normalized(rtu::cross(nd, nu));
+    V3 topCenter = pos + d * nd + (actualHeight / 2) * nu;
+    V3 origin = topCenter - (actualWidth / 2) * right;
+    V3 u = right * (actualWidth / (float)W);
+    V3 v = (-1.0f * nu) * (actualHeight / (float)H);
+    for (int k = 0; k < 3; k++) {
+        out->pos[k] = pos[k]; out->origin[k] = origin[k]; out->u[k] = u[k]; out->v[k] = v[k];
+        out->lens_x[k] = right[k]; out->lens_y[k] = up[k];
+    }
+    out->dof = c.dof;
+    out->width = W;
+    out->height = H;
+    out->inv_w = 1.0f / W;
+    out->inv_h = 1.0f / H;
+}
+
+float halton(int index, int base) // scene.h:130-139
+{
+    float r = 0;
+    float f = 1.0f / (float)base;
+    for (int i = index; i > 0; i /= base) {
+        r += f * (i % base);
+        f /= (float)base;
+    }
+    return r;
+}
+
+// ---- mesh packing
+int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *> &owned)
+{
+    memset(out, 0, sizeof *out);
+    for (int k = 0; k < 3; k++) { out->bmin[k] = m.bound_min[k]; out->bmax[k] = m.bound_max[k]; }
+    if (m.nf == 0 || m.bvh_nodes < 2) { out->empty = 1; return RTU_OK; }
+    if (!m.v || !m.f || !m.vn || !m.fn || !m.bvh_boxes || !m.bvh_data || !m.bvh_elements) {
+        rtu::set_error("rtu_scene_upload: mesh with missing arrays");
+        return RTU_ERR_INVALID;
+    }
+    const uint32_t LEAF = 0x80000000u;
+    // BFS numbering of internal nodes -> pair records; top levels end up first (smem staging)
+    std::vector<uint32_t> pair_of(m.bvh_nodes, 0xffffffffu), order;
+    auto check_node = [&](uint32_t n) { return n >= 1 && n < m.bvh_nodes; };
+    if (!(m.bvh_data[1] & LEAF)) { pair_of[1] = 0; order.push_back(1); }
+    for (size_t h = 0; h < order.size(); h++) {
+        uint32_t n = order[h];
+        uint32_t c1 = m.bvh_data[n] & 0x7fffffffu;
+        if (!check_node(c1) || !check_node(c1 + 1)) { rtu::set_error("rtu_scene_upload: BVH child index out of range"); return RTU_ERR_INVALID; }
+        for (uint32_t c = c1; c <= c1 + 1; c++)
+            if (!(m.bvh_data[c] & LEAF)) {
+                if (pair_of[c] != 0xffffffffu) { rtu::set_error("rtu_scene_upload: BVH is not a tree"); return RTU_ERR_INVALID; }
+                pair_of[c] = (uint32_t)order.size();
+                order.push_back(c);
+            }
+    }
+    auto child_word = [&](uint32_t c, uint32_t *w) -> bool {
+        uint32_t dw = m.bvh_data[c];
+        if (dw & LEAF) {
+            uint32_t off = dw & 0x0fffffffu, cnt = ((dw >> 28) & 7u) + 1u;
+            if ((uint64_t)off + cnt > m.nf) return false;
+            *w = dw;
+        } else {
+            *w = pair_of[c];
+        }
+        return true;
+    };
+    std::vector<BvhPair> pairs(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        uint32_t c1 = m.bvh_data[order[i]] & 0x7fffffffu;
+        BvhPair &P = pairs[i];
+        memcpy(P.b1, m.bvh_boxes + (size_t)c1 * 6, 6 * sizeof(float));
+        memcpy(P.b2, m.bvh_boxes + (size_t)(c1 + 1) * 6, 6 * sizeof(float));
+        if (!child_word(c1, &P.c1) || !child_word(c1 + 1, &P.c2)) { rtu::set_error("rtu_scene_upload: BVH leaf range out of bounds"); return RTU_ERR_INVALID; }
+        P.pad[0] = P.pad[1] = 0;
+    }
+    if (!child_word(1, &out->root)) { rtu::set_error("rtu_scene_upload: BVH root leaf out of bounds"); return RTU_ERR_INVALID; }
+    // depth bound for the traversal stack (depth-first, both children pushed: depth+1 entries)
+    {
+        std::vector<std::pair<uint32_t, int>> st2;
+        st2.push_back({1u, 1});
+        int maxd = 1;
+        while (!st2.empty()) {
+            auto [n, dpt] = st2.back();
+            st2.pop_back();
+            maxd = std::max(maxd, dpt);
+            if (!(m.bvh_data[n] & LEAF)) {
+                uint32_t c1 = m.bvh_data[n] & 0x7fffffffu;
+                st2.push_back({c1, dpt + 1});
+                st2.push_back({c1 + 1, dpt + 1});
+            }
+        }
+        if (maxd + 2 > RTU_STACK) { rtu::set_error("rtu_scene_upload: BVH deeper than the traversal stack"); return RTU_ERR_UNSUPPORTED; }
+    }
+    auto P3 = [&](const float *a, uint32_t i) { return V3(a[(size_t)i * 3], a[(size_t)i * 3 + 1], a[(size_t)i * 3 + 2]); };
+    std::vector<TriRec> tris(m.nf);
+    std::vector<TriShade> shade(m.nf);
+    for (uint32_t s = 0; s < m.nf; s++) {
+        uint32_t face = m.bvh_elements[s];
+        if (face >= m.nf) { rtu::set_error("rtu_scene_upload: BVH element out of range"); return RTU_ERR_INVALID; }
+        uint32_t i0 = m.f[face * 3], i1 = m.f[face * 3 + 1], i2 = m.f[face * 3 + 2];
+        if (i0 >= m.nv || i1 >= m.nv || i2 >= m.nv) { rtu::set_error("rtu_scene_upload: vertex index out of range"); return RTU_ERR_INVALID; }
+        V3 A = P3(m.v, i0), B = P3(m.v, i1), C = P3(m.v, i2);
+        V3 N = rtu::normalized(rtu::cross(B - A, C - A));                       // objFunctions.cpp:263
+        float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z);
+        float mxy = (ax < ay) ? ay : ax;                                        // std::max (:274)
+        float mx = (mxy < az) ? az : mxy;
+        unsigned axis = mx == ax ? 0u : (mx == ay ? 1u : (mx == az ? 2u : 3u)); // :278-295
+        float Au, Av, Bu, Bv, Cu, Cv;
+        if (axis == 0) { Au = A.y; Av = A.z; Bu = B.y; Bv = B.z; Cu = C.y; Cv = C.z; }
+        else if (axis == 1) { Au = A.x; Av = A.z; Bu = B.x; Bv = B.z; Cu = C.x; Cv = C.z; }
+        else { Au = A.x; Av = A.y; Bu = B.x; Bv = B.y; Cu = C.x; Cv = C.y; }
+        TriRec &T = tris[s];
+        T.nx = N.x; T.ny = N.y; T.nz = N.z;
+        T.ax = A.x; T.ay = A.y; T.az = A.z;
+        T.cau = Cu - Au; T.cav = Cv - Av; T.bau = Bu - Au; T.bav = Bv - Av;
+        float cr = (-T.cav) * T.bau + T.cau * T.bav;                            // Point2::Cross (cyPoint.h:248)
+        T.area = (float)((double)cr / 2.0);                                     // :298
+        uint32_t fb = (face & 0x3fffffffu) | (axis << 30);
+        memcpy(&T.fbits, &fb, 4);
+        TriShade &Sh = shade[s];
+        memset(&Sh, 0, sizeof Sh);
+        for (int k = 0; k < 3; k++) {
+            uint32_t vi = m.f[face * 3 + k];
+            uint32_t ni = m.fn[face * 3 + k];
+            if (ni >= m.nvn) { rtu::set_error("rtu_scene_upload: normal index out of range"); return RTU_ERR_INVALID; }
+            for (int c = 0; c < 3; c++) { Sh.v[k * 3 + c] = m.v[(size_t)vi * 3 + c]; Sh.vn[k * 3 + c] = m.vn[(size_t)ni * 3 + c]; }
+            if (m.ft && m.vt) {
+                uint32_t ti = m.ft[face * 3 + k];
+                if (ti >= m.nvt) { rtu::set_error("rtu_scene_upload: texture index out of range"); return RTU_ERR_INVALID; }
+                for (int c = 0; c < 3; c++) Sh.vt[k * 3 + c] = m.vt[(size_t)ti * 3 + c];
+            }
+        }
+    }
+    BvhPair *dp = nullptr;
+    TriRec *dt = nullptr;
+    TriShade *ds = nullptr;
+    int rc;
+    if ((rc = dev_upload(pairs, &dp, st, owned))) return rc;
+    if ((rc = dev_upload(tris, &dt, st, owned))) return rc;
+    if ((rc = dev_upload(shade, &ds, st, owned))) return rc;
+    CU(cudaStreamSynchronize(st)); // host vectors go out of scope
+    out->pairs = dp;
+    out->tris = dt;
+    out->shade = ds;
+    out->n_pairs = (uint32_t)pairs.size();
+    out->n_tris = m.nf;
+    return RTU_OK;
+}
+
+DTexColor pack_tc(const rtu_texcolor &t, int n_texmaps)
+{
+    DTexColor d;
+    d.c[0] = t.color[0]; d.c[1] = t.color[1]; d.c[2] = t.color[2];
+    d.map = (t.texmap >= 0 && t.texmap < n_texmaps) ? t.texmap : -1;
+    return d;
+}
+
+} // namespace
+
+extern "C" {
+
+void rtu_params_default(rtu_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->spp = 1;
+    p->pattern = RTU_PATTERN_CENTER;
+    p->mode = RTU_MODE_WHITTED;
+    p->shade_bounces = 5; // RenderFunctions.cpp:134
+    p->gi_bounces = 4;    // RenderFunctions.cpp:31
+}
+
+int rtu_context_create(int32_t device, void *stream, rtu_context **out)
+{
+    if (!out) { rtu::set_error("rtu_context_create: null out"); return RTU_ERR_INVALID; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        rtu::set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+        return RTU_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { rtu::set_error("rtu_context_create: bad device index"); return RTU_ERR_INVALID; }
+    CU(cudaSetDevice(device));
+    rtu_context *c = new rtu_context;
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->cfg.sm_count = prop.multiProcessorCount;
+    c->cfg.blocks_per_sm = 2;
+    c->cfg.threads = 256;
+    if (const char *s = getenv("RTU_CHUNK_RAYS")) { long long v = atoll(s); if (v >= 1024) c->chunk_rays = (size_t)v; }
+    if (const char *s = getenv("RTU_BLOCKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= 8) c->cfg.blocks_per_sm = v; }
+    memset(&c->wb, 0, sizeof c->wb);
+    CU(cudaMalloc((void **)&c->zmm, 2 * sizeof(unsigned)));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    *out = c;
+    return RTU_OK;
+}
+
+void rtu_context_destroy(rtu_context *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_list(c->scratch);
+    if (c->work) cudaFree(c->work);
+    if (c->zmm) cudaFree(c->zmm);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+int rtu_synchronize(rtu_context *c)
+{
+    if (!c) { rtu::set_error("rtu_synchronize: null context"); return RTU_ERR_INVALID; }
+    CU(cudaStreamSynchronize(c->stream));
+    return RTU_OK;
+}
+
+int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
+{
+    if (!c || !d || !out) { rtu::set_error("rtu_scene_upload: null argument"); return RTU_ERR_INVALID; }
+    if (d->n_nodes < 1 || !d->nodes) { rtu::set_error("rtu_scene_upload: scene has no root node"); return RTU_ERR_INVALID; }
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<rtu_scene> sc(new rtu_scene);
+    sc->ctx = c;
+    sc->cam = d->camera;
+    memset(&sc->S, 0, sizeof sc->S);
+    int rc;
+    auto fail = [&](int code) { free_list(sc->owned); return code; };
+
+    // nodes
+    std::vector<DNode> nodes(d->n_nodes);
+    int flat = 1;
+    for (int i = 0; i < d->n_nodes; i++) {
+        const rtu_node &n = d->nodes[i];
+        DNode &o = nodes[i];
+        memset(&o, 0, sizeof o);
+        memcpy(o.itm, n.itm, sizeof o.itm);
+        memcpy(o.pos, n.pos, sizeof o.pos);
+        memcpy(o.tm, n.tm, sizeof o.tm);
+        if ((i == 0) != (n.parent < 0) || n.parent >= i) { rtu::set_error("rtu_scene_upload: nodes must be in pre-order with node 0 as the only root"); return fail(RTU_ERR_INVALID); }
+        o.parent = n.parent;
+        o.depth = i == 0 ? 0 : nodes[n.parent].depth + 1;
+        if (o.depth >= RTU_MAX_DEPTH) { rtu::set_error("rtu_scene_upload: scene graph deeper than RTU_MAX_DEPTH"); return fail(RTU_ERR_UNSUPPORTED); }
+        if (i > 0 && n.parent != 0) flat = 0;
+        o.kind = n.kind;
+        o.mesh = n.mesh;
+        o.material = (n.material >= 0 && n.material < d->n_materials) ? n.material : -1;
+        if (n.kind == RTU_OBJ_MESH && (n.mesh < 0 || n.mesh >= d->n_meshes)) { rtu::set_error("rtu_scene_upload: bad mesh index"); return fail(RTU_ERR_INVALID); }
+        if (n.kind < 0 || n.kind > 3) { rtu::set_error("rtu_scene_upload: bad object kind"); return fail(RTU_ERR_INVALID); }
+    }
+    DNode *dn = nullptr;
+    if ((rc = dev_upload(nodes, &dn, c->stream, sc->owned))) return fail(rc);
+    // meshes
+    std::vector<DMesh> meshes(d->n_meshes);
+    for (int i = 0; i < d->n_meshes; i++)
+        if ((rc = pack_mesh(d->meshes[i], &meshes[i], c->stream, sc->owned))) return fail(rc);
+    DMesh *dm = nullptr;
+    if ((rc = dev_upload(meshes, &dm, c->stream, sc->owned))) return fail(rc);
+    // textures (pixel arrays de-duplicated by host pointer)
+    std::vector<DTexMap> tms(d->n_texmaps);
+    std::vector<std::pair<const uint8_t *, uint8_t *>> pix;
+    for (int i = 0; i < d->n_texmaps; i++) {
+        const rtu_texmap &t = d->texmaps[i];
+        DTexMap &o = tms[i];
+        memset(&o, 0, sizeof o);
+        o.kind = t.kind;
+        memcpy(o.itm, t.itm, sizeof o.itm);
+        memcpy(o.pos, t.pos, sizeof o.pos);
+        memcpy(o.c1, t.color1, sizeof o.c1);
+        memcpy(o.c2, t.color2, sizeof o.c2);
+        o.width = t.width;
+        o.height = t.height;
+        if (t.kind == RTU_TEX_FILE) {
+            if (!t.rgb8 || t.width <= 0 || t.height <= 0) { o.width = o.height = 0; o.rgb8 = nullptr; continue; }
+            uint8_t *dp = nullptr;
+            for (auto &pr : pix) if (pr.first == t.rgb8) dp = pr.second;
+            if (!dp) {
+                size_t bytes = (size_t)t.width * t.height * 3;
+                CU(cudaMalloc((void **)&dp, bytes));
+                sc->owned.push_back(dp);
+                CU(cudaMemcpyAsync(dp, t.rgb8, bytes, cudaMemcpyHostToDevice, c->stream));
+                pix.push_back({t.rgb8, dp});
+            }
+            o.rgb8 = dp;
+        }
+    }
+    DTexMap *dt = nullptr;
+    if ((rc = dev_upload(tms, &dt, c->stream, sc->owned))) return fail(rc);
+    // materials
+    std::vector<DMaterial> mats(d->n_materials);
+    for (int i = 0; i < d->n_materials; i++) {
+        const rtu_material &m = d->materials[i];
+        DMaterial &o = mats[i];
+        o.diffuse = pack_tc(m.diffuse, d->n_texmaps);
+        o.specular = pack_tc(m.specular, d->n_texmaps);
+        o.reflection = pack_tc(m.reflection, d->n_texmaps);
+        o.refraction = pack_tc(m.refraction, d->n_texmaps);
+        o.glossiness = m.glossiness;
+        memcpy(o.absorption, m.absorption, sizeof o.absorption);
+        o.ior = m.ior;
+        o.refl_gloss = m.reflection_glossiness;
+        o.refr_gloss = m.refraction_glossiness;
+    }
+    DMaterial *dmt = nullptr;
+    if ((rc = dev_upload(mats, &dmt, c->stream, sc->owned))) return fail(rc);
+    // lights
+    std::vector<DLight> lts(d->n_lights);
+    sc->n_shadow_lights = 0;
+    for (int i = 0; i < d->n_lights; i++) {
+        const rtu_light &l = d->lights[i];
+        DLight &o = lts[i];
+        o.kind = l.kind;
+        memcpy(o.I, l.intensity, sizeof o.I);
+        memcpy(o.v, l.v, sizeof o.v);
+        o.size = l.size;
+        if (l.kind != RTU_LIGHT_AMBIENT) sc->n_shadow_lights++;
+    }
+    DLight *dl = nullptr;
+    if ((rc = dev_upload(lts, &dl, c->stream, sc->owned))) return fail(rc);
+    CU(cudaStreamSynchronize(c->stream));
+
+    DScene &S = sc->S;
+    S.nodes = dn;
+    S.n_nodes = d->n_nodes;
+    S.flat = flat;
+    S.meshes = dm;
+    S.materials = dmt;
+    S.n_materials = d->n_materials;
+    S.lights = dl;
+    S.n_lights = d->n_lights;
+    S.texmaps = dt;
+    S.background = pack_tc(d->background, d->n_texmaps);
+    S.environment = pack_tc(d->environment, d->n_texmaps);
+    memcpy(S.cam_pos, d->camera.pos, sizeof S.cam_pos);
+    *out = sc.release();
+    return RTU_OK;
+}
+
+void rtu_scene_destroy(rtu_scene *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    free_list(s->owned);
+    if (s->accum) cudaFree(s->accum);
+    if (s->d_rgb) cudaFree(s->d_rgb);
+    if (s->d_rgb8) cudaFree(s->d_rgb8);
+    if (s->d_z) cudaFree(s->d_z);
+    if (s->d_z8) cudaFree(s->d_z8);
+    if (s->d_node) cudaFree(s->d_node);
+    if (s->d_face) cudaFree(s->d_face);
+    if (s->d_offsets) cudaFree(s->d_offsets);
+    delete s;
+}
+
+} // extern "C"
+
+namespace {
+
+int frame_dims(const rtu_scene *s, const rtu_params *p, int *W, int *H)
+{
+    if (p->width < 0 || p->height < 0) { rtu::set_error("negative image size"); return RTU_ERR_INVALID; }
+    *W = p->width > 0 ? p->width : s->cam.width;
+    *H = p->height > 0 ? p->height : s->cam.height;
+    if (*W <= 0 || *H <= 0 || (long long)*W * *H > (1ll << 28)) { rtu::set_error("bad image size"); return RTU_ERR_INVALID; }
+    return RTU_OK;
+}
+
+int ensure_image(rtu_scene *s, size_t npix)
+{
+    if (npix <= s->img_n) return RTU_OK;
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    if (s->d_rgb) cudaFree(s->d_rgb);
+    if (s->d_rgb8) cudaFree(s->d_rgb8);
+    if (s->d_z) cudaFree(s->d_z);
+    if (s->d_z8) cudaFree(s->d_z8);
+    if (s->d_node) cudaFree(s->d_node);
+    if (s->d_face) cudaFree(s->d_face);
+    s->d_rgb = nullptr; s->d_rgb8 = nullptr; s->d_z = nullptr; s->d_z8 = nullptr; s->d_node = nullptr; s->d_face = nullptr;
+    s->img_n = 0;
+    CU(cudaMalloc((void **)&s->d_rgb, npix * 3 * sizeof(float)));
+    CU(cudaMalloc((void **)&s->d_rgb8, npix * 3));
+    CU(cudaMalloc((void **)&s->d_z, npix * sizeof(float)));
+    CU(cudaMalloc((void **)&s->d_z8, npix));
+    CU(cudaMalloc((void **)&s->d_node, npix * sizeof(int)));
+    CU(cudaMalloc((void **)&s->d_face, npix * sizeof(int)));
+    s->img_n = npix;
+    return RTU_OK;
+}
+
+int ensure_accum(rtu_scene *s, size_t npix)
+{
+    if (npix <= s->accum_n) return RTU_OK;
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    if (s->accum) cudaFree(s->accum);
+    s->accum = nullptr;
+    s->accum_n = 0;
+    CU(cudaMalloc((void **)&s->accum, npix * sizeof(float4)));
+    s->accum_n = npix;
+    return RTU_OK;
+}
+
+int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, int *s_end)
+{
+    int W, H, rc;
+    if ((rc = frame_dims(s, p, &W, &H))) return rc;
+    if (p->spp < 1 || p->spp > (1 << 20)) { rtu::set_error("bad spp"); return RTU_ERR_INVALID; }
+    if (p->pattern == RTU_PATTERN_CENTER && p->spp != 1) { rtu::set_error("RTU_PATTERN_CENTER needs spp == 1"); return RTU_ERR_INVALID; }
+    if (p->mode == RTU_MODE_PATH) { rtu::set_error("RTU_MODE_PATH is not implemented yet"); return RTU_ERR_UNSUPPORTED; }
+    if (p->shade_bounces < 0 || p->shade_bounces > 15) { rtu::set_error("shade_bounces out of range"); return RTU_ERR_INVALID; }
+    make_camera(s->cam, W, H, &F->cam);
+    F->spp = p->spp;
+    F->row_begin = 0;
+    F->row_end = H;
+    if (p->row_begin != 0 || p->row_end != 0) { F->row_begin = p->row_begin; F->row_end = p->row_end; }
+    if (F->row_begin < 0 || F->row_end > H || F->row_begin >= F->row_end) { rtu::set_error("bad row range"); return RTU_ERR_INVALID; }
+    *s_begin = 0;
+    *s_end = p->spp;
+    if (p->sample_begin != 0 || p->sample_end != 0) { *s_begin = p->sample_begin; *s_end = p->sample_end; }
+    if (*s_begin < 0 || *s_end > p->spp || *s_begin >= *s_end) { rtu::set_error("bad sample range"); return RTU_ERR_INVALID; }
+    F->mode = p->mode;
+    F->shade_bounces = p->shade_bounces;
+    F->gi_bounces = p->gi_bounces;
+    F->flags = p->flags;
+    F->seed = make_uint2((unsigned)(p->seed & 0xffffffffu), (unsigned)(p->seed >> 32));
+    // sub-pixel offsets of every sample (RenderFunctions.cpp:71,81-85,96)
+    std::vector<float2> off(p->spp);
+    if (p->pattern == RTU_PATTERN_CENTER) {
+        off[0] = make_float2(0.5f, 0.5f);
+    } else {
+        float pixelIncrement = 1.0 / p->spp;
+        for (int i = 0; i < p->spp; i++) {
+            float cur = i * pixelIncrement;
+            off[i] = make_float2(cur + halton(i, 4), cur + halton(i, 5));
+        }
+    }
+    if ((size_t)p->spp > s->offsets_n) {
+        CU(cudaStreamSynchronize(s->ctx->stream));
+        if (s->d_offsets) cudaFree(s->d_offsets);
+        s->d_offsets = nullptr;
+        CU(cudaMalloc((void **)&s->d_offsets, (size_t)p->spp * sizeof(float2)));
+        s->offsets_n = p->spp;
+    }
+    CU(cudaMemcpyAsync(s->d_offsets, off.data(), off.size() * sizeof(float2), cudaMemcpyHostToDevice, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream)); // `off` is a local
+    F->sample_offsets = s->d_offsets;
+    return RTU_OK;
+}
+
+// the waves that follow a first wave whose output is in q[out_q]
+int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_t *work_i)
+{
+    rtu_context *c = s->ctx;
+    int n_waves = 2 * F.shade_bounces + 1; // a Fresnel ray starts one wave after its sibling at every level
+    launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
+    s->launches++;
+    int in_q = out_q;
+    for (int w = 0; w < n_waves; w++) {
+        launch_reset_counts(c->stream, c->wb.q[1 - in_q].count, c->wb.aux[1 - in_q].count, c->wb.shadow.count, nullptr);
+        launch_wave_queue(c->cfg, c->stream, s->S, F, c->wb, in_q, accum, c->work + (*work_i)++);
+        launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
+        s->launches += 3;
+        in_q = 1 - in_q;
+    }
+    CU(cudaGetLastError());
+    return RTU_OK;
+}
+
+int check_overflow(rtu_scene *s, DCounters *host)
+{
+    rtu_context *c = s->ctx;
+    CU(cudaMemcpyAsync(host, c->wb.counters, sizeof(DCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (host->overflow) {
+        rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS");
+        return RTU_ERR_UNSUPPORTED;
+    }
+    return RTU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
+{
+    if (!s || !p) { rtu::set_error("rtu_render_device: null argument"); return RTU_ERR_INVALID; }
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    FrameSetup F;
+    int s0, s1, rc;
+    if ((rc = setup_frame(s, p, &F, &s0, &s1))) return rc;
+    int W = F.cam.width, H = F.cam.height;
+    size_t npix = (size_t)W * H;
+    float4 *accum = (float4 *)d_accum;
+    if (!accum) {
+        if ((rc = ensure_accum(s, npix))) return rc;
+        accum = s->accum;
+    }
+    int rows = F.row_end - F.row_begin;
+    size_t per_sample = (size_t)((W + 7) / 8) * ((rows + 3) / 4) * 32;
+    size_t chunk_samples = std::max<size_t>(1, c->chunk_rays / per_sample);
+    size_t chunk_cap = std::max(per_sample, chunk_samples * per_sample);
+    if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
+    size_t q_cap = chunk_cap * 2;
+    size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
+    if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
+    size_t n_chunks = ((size_t)(s1 - s0) + chunk_samples - 1) / chunk_samples;
+    size_t launches_per_chunk = 2 + 2 * (size_t)(2 * F.shade_bounces + 1);
+    if ((rc = ensure_work(c, n_chunks * launches_per_chunk + 8))) return rc;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
+    if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * sizeof(float4), c->stream));
+    s->launches = 0;
+    size_t wi = 0;
+    for (int a = s0; a < s1; a += (int)chunk_samples) {
+        int b = std::min<int>(s1, a + (int)chunk_samples);
+        launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, nullptr);
+        launch_wave_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, 0, accum, c->work + wi++);
+        s->launches += 2;
+        if ((rc = run_waves(s, F, accum, 0, &wi))) return rc;
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    s->timed = true;
+    CU(cudaGetLastError());
+    return RTU_OK;
+}
+
+int rtu_resolve(rtu_scene *s, const rtu_params *p, const float *d_accum, rtu_image *out)
+{
+    if (!s || !p || !out) { rtu::set_error("rtu_resolve: null argument"); return RTU_ERR_INVALID; }
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    int W, H, rc;
+    if ((rc = frame_dims(s, p, &W, &H))) return rc;
+    size_t npix = (size_t)W * H;
+    if ((rc = ensure_image(s, npix))) return rc;
+    const float4 *accum = d_accum ? (const float4 *)d_accum : s->accum;
+    if (out->rgb || out->rgb8) {
+        if (!accum) { rtu::set_error("rtu_resolve: nothing rendered yet"); return RTU_ERR_INVALID; }
+        launch_resolve(c->stream, accum, (int)npix, 0.f, p->spp, out->rgb ? s->d_rgb : nullptr, out->rgb8 ? s->d_rgb8 : nullptr);
+        if (out->rgb) CU(cudaMemcpyAsync(out->rgb, s->d_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, s->d_rgb8, npix * 3, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (out->z || out->z8 || out->node_id || out->face_id) {
+        DCamera cam;
+        make_camera(s->cam, W, H, &cam);
+        // visibility at pixel centres: the z the reference meant to store (SURVEY A-3)
+        if (!c->wb.counters) { if ((rc = ensure_scratch(c, 1024, 1024))) return rc; }
+        launch_primary_ids(c->cfg, c->stream, s->S, cam, s->d_z, s->d_node, s->d_face, c->wb.counters);
+        if (out->z8) launch_zimage(c->stream, s->d_z, (int)npix, c->zmm, s->d_z8);
+        if (out->z) CU(cudaMemcpyAsync(out->z, s->d_z, npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->z8) CU(cudaMemcpyAsync(out->z8, s->d_z8, npix, cudaMemcpyDeviceToHost, c->stream));
+        if (out->node_id) CU(cudaMemcpyAsync(out->node_id, s->d_node, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (out->face_id) CU(cudaMemcpyAsync(out->face_id, s->d_face, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return RTU_OK;
+}
+
+int rtu_render(rtu_scene *s, const rtu_params *p, rtu_image *out)
+{
+    if (!s || !p || !out) { rtu::set_error("rtu_render: null argument"); return RTU_ERR_INVALID; }
+    int rc;
+    if (p->mode == RTU_MODE_PRIMARY) {
+        rtu_image o = *out;
+        o.rgb = nullptr;
+        o.rgb8 = nullptr;
+        if ((rc = ensure_scratch(s->ctx, 1024, 1024))) return rc;
+        CU(cudaMemsetAsync(s->ctx->wb.counters, 0, sizeof(DCounters), s->ctx->stream));
+        CU(cudaEventRecord(s->ctx->ev0, s->ctx->stream));
+        rc = rtu_resolve(s, p, nullptr, &o);
+        CU(cudaEventRecord(s->ctx->ev1, s->ctx->stream));
+        s->timed = true;
+        return rc;
+    }
+    if ((rc = rtu_render_device(s, p, nullptr, 1))) return rc;
+    DCounters hc;
+    if ((rc = check_overflow(s, &hc))) return rc;
+    return rtu_resolve(s, p, nullptr, out);
+}
+
+int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
+{
+    if (!s || !out) { rtu::set_error("rtu_get_stats: null argument"); return RTU_ERR_INVALID; }
+    rtu_context *c = s->ctx;
+    memset(out, 0, sizeof *out);
+    if (!c->wb.counters) return RTU_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    DCounters hc;
+    CU(cudaMemcpy(&hc, c->wb.counters, sizeof hc, cudaMemcpyDeviceToHost));
+    out->trace_rays = hc.trace_rays;
+    out->shadow_rays = hc.shadow_rays;
+    out->box_tests = hc.box_tests;
+    out->tri_tests = hc.tri_tests;
+    out->node_visits = hc.node_visits;
+    out->kernel_launches = s->launches;
+    if (s->timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->device_ms = ms;
+    }
+    if (hc.overflow) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS"); return RTU_ERR_UNSUPPORTED; }
+    return RTU_OK;
+}
+
+int rtu_trace(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
+{
+    if (!s || (n > 0 && (!rays || !hits)) || n < 0) { rtu::set_error("rtu_trace: bad argument"); return RTU_ERR_INVALID; }
+    if (n == 0) return RTU_OK;
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_scratch(c, std::max<size_t>(c->q_cap, 1024), std::max<size_t>(c->shadow_cap, 1024)))) return rc;
+    rtu_ray *dr = nullptr;
+    rtu_hit *dh = nullptr;
+    CU(cudaMalloc((void **)&dr, n * sizeof(rtu_ray)));
+    cudaError_t e = cudaMalloc((void **)&dh, n * sizeof(rtu_hit));
+    if (e != cudaSuccess) { cudaFree(dr); CU(e); }
+    e = cudaMemcpyAsync(dr, rays, n * sizeof(rtu_ray), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream);
+    if (e == cudaSuccess) {
+        cudaEventRecord(c->ev0, c->stream);
+        launch_trace_batch(c->cfg, c->stream, s->S, dr, n, dh, c->wb.counters);
+        cudaEventRecord(c->ev1, c->stream);
+        s->timed = true;
+        s->launches = 1;
+        e = cudaMemcpyAsync(hits, dh, n * sizeof(rtu_hit), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(dr);
+    cudaFree(dh);
+    CU(e);
+    return RTU_OK;
+}
+
+int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int64_t n, uint8_t *occluded)
+{
+    if (!s || (n > 0 && (!rays || !t_max || !occluded)) || n < 0) { rtu::set_error("rtu_shadow_trace: bad argument"); return RTU_ERR_INVALID; }
+    if (n == 0) return RTU_OK;
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_scratch(c, std::max<size_t>(c->q_cap, 1024), std::max<size_t>(c->shadow_cap, 1024)))) return rc;
+    rtu_ray *dr = nullptr;
+    float *dt = nullptr;
+    unsigned char *docc = nullptr;
+    CU(cudaMalloc((void **)&dr, n * sizeof(rtu_ray)));
+    cudaError_t e = cudaMalloc((void **)&dt, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&docc, n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dr, rays, n * sizeof(rtu_ray), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dt, t_max, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream);
+    if (e == cudaSuccess) {
+        cudaEventRecord(c->ev0, c->stream);
+        launch_shadow_batch(c->cfg, c->stream, s->S, dr, dt, n, docc, c->wb.counters);
+        cudaEventRecord(c->ev1, c->stream);
+        s->timed = true;
+        s->launches = 1;
+        e = cudaMemcpyAsync(occluded, docc, n, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(dr);
+    if (dt) cudaFree(dt);
+    if (docc) cudaFree(docc);
+    CU(e);
+    return RTU_OK;
+}
+
+int rtu_camera_rays(rtu_scene *s, const rtu_params *p, int32_t sample, rtu_ray *rays)
+{
+    if (!s || !p || !rays) { rtu::set_error("rtu_camera_rays: null argument"); return RTU_ERR_INVALID; }
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    int W, H, rc;
+    if ((rc = frame_dims(s, p, &W, &H))) return rc;
+    if (sample < 0 || sample >= p->spp) { rtu::set_error("rtu_camera_rays: bad sample index"); return RTU_ERR_INVALID; }
+    float ox = 0.5f, oy = 0.5f;
+    if (p->pattern == RTU_PATTERN_REFERENCE) {
+        float pixelIncrement = 1.0 / p->spp;
+        float cur = sample * pixelIncrement;
+        ox = cur + halton(sample, 4);
+        oy = cur + halton(sample, 5);
+    }
+    DCamera cam;
+    make_camera(s->cam, W, H, &cam);
+    size_t n = (size_t)W * H;
+    rtu_ray *dr = nullptr;
+    CU(cudaMalloc((void **)&dr, n * sizeof(rtu_ray)));
+    launch_camera_rays(c->stream, cam, ox, oy, dr);
+    cudaError_t e = cudaMemcpyAsync(rays, dr, n * sizeof(rtu_ray), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(dr);
+    CU(e);
+    return RTU_OK;
+}
+
+int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n, int32_t bounces, float *rgb)
+{
+    if (!s || (n > 0 && (!rays || !hits || !rgb)) || n < 0 || bounces < 0 || bounces > 15) { rtu::set_error("rtu_shade: bad argument"); return RTU_ERR_INVALID; }
+    if (n == 0) return RTU_OK;
+    if (n >= (1ll << 27)) { rtu::set_error("rtu_shade: batch too large"); return RTU_ERR_UNSUPPORTED; }
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    int rc;
+    size_t q_cap = std::max<size_t>((size_t)n * 2, 1024);
+    size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
+    if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
+    if ((rc = ensure_work(c, 2 + 2 * (size_t)(2 * bounces + 1) + 8))) return rc;
+    FrameSetup F;
+    memset(&F, 0, sizeof F);
+    F.cam.width = (int)n;
+    F.cam.height = 1;
+    F.spp = 1;
+    F.shade_bounces = bounces;
+    F.row_end = 1;
+    F.mode = RTU_MODE_WHITTED;
+    rtu_ray *dr = nullptr;
+    rtu_hit *dh = nullptr;
+    float4 *acc = nullptr;
+    std::vector<float4> host_acc((size_t)n);
+    CU(cudaMalloc((void **)&dr, n * sizeof(rtu_ray)));
+    cudaError_t e = cudaMalloc((void **)&dh, n * sizeof(rtu_hit));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&acc, n * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dr, rays, n * sizeof(rtu_ray), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dh, hits, n * sizeof(rtu_hit), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(acc, 0, n * sizeof(float4), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream);
+    rc = RTU_OK;
+    if (e == cudaSuccess) {
+        size_t wi = 0;
+        s->launches = 2;
+        launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, nullptr);
+        launch_shade_batch(c->cfg, c->stream, s->S, F, dr, dh, n, c->wb, 0, acc);
+        rc = run_waves(s, F, acc, 0, &wi);
+        if (rc == RTU_OK) e = cudaMemcpyAsync(host_acc.data(), acc, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(dr);
+    if (dh) cudaFree(dh);
+    if (acc) cudaFree(acc);
+    if (rc) return rc;
+    CU(e);
+    for (int64_t i = 0; i < n; i++) { rgb[i * 3] = host_acc[i].x; rgb[i * 3 + 1] = host_acc[i].y; rgb[i * 3 + 2] = host_acc[i].z; }
+    DCounters hc;
+    return check_overflow(s, &hc);
+}
+
+} // extern "C"

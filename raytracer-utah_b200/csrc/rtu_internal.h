@@ -1,0 +1,60 @@
+// Launch wrappers implemented in rtu_kernels.cu and used by rtu_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/rtu.h"
+#include "device_scene.h"
+
+struct FrameSetup {
+    DCamera cam;
+    int spp;             // total samples per pixel of the frame (defines the reference pattern)
+    const float2 *sample_offsets; // device, spp entries: pixel offsets of sample s
+    int row_begin, row_end;
+    int mode;
+    int shade_bounces;
+    int gi_bounces;
+    unsigned flags;
+    uint2 seed;
+};
+
+struct LaunchCfg {
+    int sm_count;
+    int blocks_per_sm;
+    int threads;
+};
+
+struct WaveBuffers {
+    RayQueue q[2];
+    AuxPool aux[2];
+    ShadowQueue shadow;
+    unsigned *work;       // device work-fetch counters (one per launch slot)
+    DCounters *counters;
+};
+
+// one closest-hit + shade wave over generated primary rays: samples [s0,s1) of rows [row_begin,row_end)
+void launch_wave_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
+                         const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter);
+// one wave over queue q[in_q] -> q[1-in_q]
+void launch_wave_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
+                       int in_q, float4 *accum, unsigned *work_counter);
+// any-hit over the shadow queue, adds unoccluded contributions to accum
+void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
+                        unsigned *work_counter);
+void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d);
+
+// pixel-centre primary visibility: z / node / face per pixel (RTU_MODE_PRIMARY, ZBuffer.png)
+void launch_primary_ids(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const DCamera &cam, float *z, int *node,
+                        int *face, DCounters *counters);
+// batched operators
+void launch_trace_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, long long n,
+                        rtu_hit *hits, DCounters *counters);
+void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
+                         long long n, unsigned char *occ, DCounters *counters);
+// Shade(ray, hit, lights, bounces) for caller-provided hits: first step, then the usual waves
+void launch_shade_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const rtu_ray *rays,
+                        const rtu_hit *hits, long long n, const WaveBuffers &B, int out_q, float4 *accum);
+void launch_camera_rays(cudaStream_t st, const DCamera &cam, float ox, float oy, rtu_ray *rays);
+// accum -> mean, gamma 1/2.2, Color24 (RenderFunctions.cpp:152-159)
+void launch_resolve(cudaStream_t st, const float4 *accum, int npix, float inv_unused, int spp, float *rgb, unsigned char *rgb8);
+// RenderImage::ComputeZBufferImage (scene.h:590-612)
+void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8);

@@ -1,0 +1,454 @@
+// sm_100a kernels of the render path.
+//
+//   k_wave<true>    persistent threads; generates camera rays of a chunk of (sample, pixel)
+//                   work items on the fly, closest-hit + shade, appends shadow / secondary rays
+//   k_wave<false>   same, but the rays come from the previous wave's queue
+//   k_shadow_wave   persistent threads; any-hit over the shadow queue, adds unoccluded radiance
+//   k_primary_ids   pixel-centre visibility (ids + z)        k_trace_batch / k_shadow_batch /
+//   k_shade_first   batched operator entry points            k_resolve / k_zminmax / k_zimage
+//
+// Work distribution replaces PixelIterator's atomic ticket counter (PixelIterator.h:25-38):
+// each warp takes 32 consecutive tickets from a global counter until the wave is drained.
+// Grids are SM-count multiples (148 x blocks/SM), CTAs stay resident for the whole wave.
+#include <cstdio>
+
+#include "rtu_internal.h"
+#include "shade.cuh"
+
+#define WAVE_THREADS 256
+#define WAVE_MIN_BLOCKS 2
+
+__device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *c)
+{
+    unsigned t = tl.trace, s = tl.shadow, b = tl.box, r = tl.tri, n = tl.node;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (t) atomicAdd(&c->trace_rays, (unsigned long long)t);
+        if (s) atomicAdd(&c->shadow_rays, (unsigned long long)s);
+        if (b) atomicAdd(&c->box_tests, (unsigned long long)b);
+        if (r) atomicAdd(&c->tri_tests, (unsigned long long)r);
+        if (n) atomicAdd(&c->node_visits, (unsigned long long)n);
+    }
+}
+
+// Camera ray of pixel (x,y) with sub-pixel offset (ox,oy): RenderFunctions.cpp:88-97, 258-269
+__device__ __forceinline__ Ray camera_ray(const DCamera &C, int x, int y, float ox, float oy, Rng *rng)
+{
+    float fi = (float)x + ox, fj = (float)y + oy;
+    float cx = (C.origin[0] + fi * C.u[0]) + fj * C.v[0];
+    float cy = (C.origin[1] + fi * C.u[1]) + fj * C.v[1];
+    float cz = (C.origin[2] + fi * C.u[2]) + fj * C.v[2];
+    Ray r;
+    r.px = C.pos[0]; r.py = C.pos[1]; r.pz = C.pos[2];
+    if (C.dof > 0.f && rng) {
+        float4 u = rng->next4();
+        float th = u.y * 6.283185307179586f;
+        float rad = sqrtf(u.x * C.dof * C.dof);
+        float lx = rad * cosf(th), ly = rad * sinf(th);
+        r.px = (C.pos[0] + C.lens_y[0] * ly) + C.lens_x[0] * lx;
+        r.py = (C.pos[1] + C.lens_y[1] * ly) + C.lens_x[1] * lx;
+        r.pz = (C.pos[2] + C.lens_y[2] * ly) + C.lens_x[2] * lx;
+    }
+    r.dx = cx - r.px; r.dy = cy - r.py; r.dz = cz - r.pz;
+    norm3(r.dx, r.dy, r.dz);
+    return r;
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+k_wave(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, WaveOut O, unsigned *work)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u;
+    const int W = F.cam.width;
+    const int rows = F.row_end - F.row_begin;
+    const int tilesX = (W + 7) >> 3, tilesY = (rows + 3) >> 2;
+    const unsigned perSample = (unsigned)(tilesX * tilesY) * 32u;
+    unsigned total;
+    if (PRIMARY) total = perSample * (unsigned)(s1 - s0);
+    else { total = *in.count; if (total > in.cap) total = in.cap; }
+    ShadeParams SP;
+    SP.flags = F.flags;
+    SP.seed = F.seed;
+
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        unsigned idx = base + lane;
+        if (idx >= total) continue;
+
+        Ray ray;
+        Col Wt;
+        int pixel, kind, bounce, mtl, aux;
+        unsigned path;
+        if (PRIMARY) {
+            unsigned sl = idx / perSample, t = idx - sl * perSample;
+            int s = s0 + (int)sl;
+            unsigned tile = t >> 5, in5 = t & 31u;
+            int tx = (int)(tile % (unsigned)tilesX), ty = (int)(tile / (unsigned)tilesX);
+            int x = tx * 8 + (int)(in5 & 7u), y = F.row_begin + ty * 4 + (int)(in5 >> 3);
+            if (x >= W || y >= F.row_end) continue;
+            pixel = y * W + x;
+            float2 off = __ldg(&F.sample_offsets[s]);
+            path = (unsigned)s;
+            Rng rng;
+            rng.key = F.seed; rng.pixel = (unsigned)pixel; rng.path = path; rng.dim = 1000u;
+            ray = camera_ray(F.cam, x, y, off.x, off.y, &rng);
+            Wt = mk(1.f, 1.f, 1.f);
+            kind = RK_PRIMARY; bounce = F.shade_bounces; mtl = 0; aux = -1;
+        } else {
+            float4 o = in.o[idx], d = in.d[idx], w = in.w[idx];
+            path = in.path[idx];
+            ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+            ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+            pixel = __float_as_int(o.w);
+            unsigned meta = __float_as_uint(d.w);
+            kind = (int)(meta & 7u); bounce = (int)((meta >> 3) & 31u); mtl = (int)(meta >> 8);
+            Wt = mk(w.x, w.y, w.z);
+            aux = __float_as_int(w.w);
+        }
+
+        Best B;
+        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        tl.trace++;
+        scene_hit<false>(S, ray, B, tl);
+
+        if (B.node < 0) {
+            // what the recursion adds when Trace() misses
+            Col c = mk(0, 0, 0);
+            if (kind == RK_PRIMARY) {
+                int py = pixel / W, px = pixel - py * W;
+                c = Wt * background_sample(S, px, py, W, F.cam.height);            // RenderFunctions.cpp:145
+            } else if (kind == RK_REFRACT) {
+                c = Wt * environment_sample(S, ray.dx, ray.dy, ray.dz);           // mtlFunctions.cpp:267
+            } else if (kind == RK_REFLECT || kind == RK_FRESNEL) {
+                Col wm = Wt;
+                if (aux >= 0) { float4 a = inaux.a[aux]; wm = mk(a.x, a.y, a.z); }
+                c = wm * environment_sample(S, ray.dx, ray.dy, ray.dz);           // :250, :289
+            }
+            accum_add(O.accum, pixel, c);
+            continue;
+        }
+        HitRec H;
+        finalize_hit(S, ray, B, H);
+        if (kind == RK_REFRACT) {
+            float4 a = inaux.a[aux], b = inaux.b[aux];
+            Col Kt = mk(a.x, a.y, a.z);
+            float Fr = a.w;
+            Col ab = mk(1.f, 1.f, 1.f);
+            if (!H.front) {                                                        // Beer absorption on exit (:258-262)
+                const DMaterial &PM = S.materials[mtl];
+                ab = mk(expf((-H.z) * PM.absorption[0]), expf((-H.z) * PM.absorption[1]), expf((-H.z) * PM.absorption[2]));
+            }
+            Col Wh = (Wt * (ab * Kt)) * (float)(1.0 - (double)Fr);                 // :264
+            // Fresnel mirror ray exists only because the refracted ray hit (:234-251)
+            Col Wf = Wt * Fr;
+            Col WfKt = Wf * Kt;
+            if (!((F.flags & 2u) && !nonblack(Wf))) {
+                unsigned na = warp_alloc(O.aux.count, true);
+                if (na >= O.aux.cap) O.counters->overflow = 1;
+                else {
+                    O.aux.a[na] = make_float4(Wf.r, Wf.g, Wf.b, 0.f);
+                    O.aux.b[na] = make_float4(0, 0, 0, 0);
+                    push_ray(O, ray.px, ray.py, ray.pz, b.x, b.y, b.z, WfKt, pixel, pack_meta(RK_FRESNEL, bounce, mtl), (int)na,
+                             child_path(path, 4u));
+                }
+            }
+            if (!((F.flags & 2u) && !nonblack(Wh)))
+                shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wh, bounce, pixel, path);
+        } else {
+            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wt, bounce, pixel, path);
+        }
+    }
+    flush_tally(tl, O.counters);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned total = *Q.count;
+    if (total > Q.cap) total = Q.cap;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        unsigned idx = base + lane;
+        if (idx >= total) continue;
+        float4 o = Q.o[idx], d = Q.d[idx], c = Q.c[idx];
+        Ray ray;
+        ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+        ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+        Best B;
+        B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
+        tl.shadow++;
+        bool occ = scene_hit<true>(S, ray, B, tl);
+        if (occ && B.z > 0.0f) continue;                                                // :31-35
+        accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
+    }
+    flush_tally(tl, counters);
+}
+
+__global__ void k_reset_counts(unsigned *a, unsigned *b, unsigned *c, unsigned *d)
+{
+    if (a) *a = 0;
+    if (b) *b = 0;
+    if (c) *c = 0;
+    if (d) *d = 0;
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+k_primary_ids(DScene S, DCamera C, float *z, int *node, int *face, DCounters *counters)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    int npix = C.width * C.height;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        int y = p / C.width, x = p - y * C.width;
+        Ray ray = camera_ray(C, x, y, 0.5f, 0.5f, nullptr);
+        Best B;
+        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        tl.trace++;
+        scene_hit<false>(S, ray, B, tl);
+        if (z) z[p] = B.z;
+        if (node) node[p] = B.node;
+        if (face) {
+            int f = -1;
+            if (B.node >= 0 && S.nodes[B.node].kind == 3) {
+                const DMesh &M = S.meshes[S.nodes[B.node].mesh];
+                f = (int)(((unsigned)__float_as_int(M.tris[B.slot].fbits)) & 0x3fffffffu);
+            }
+            face[p] = f;
+        }
+    }
+    flush_tally(tl, counters);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+k_trace_batch(DScene S, const rtu_ray *rays, long long n, rtu_hit *hits, DCounters *counters)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.px = rays[i].p[0]; ray.py = rays[i].p[1]; ray.pz = rays[i].p[2];
+        ray.dx = rays[i].dir[0]; ray.dy = rays[i].dir[1]; ray.dz = rays[i].dir[2];
+        Best B;
+        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        tl.trace++;
+        scene_hit<false>(S, ray, B, tl);
+        HitRec H;
+        finalize_hit(S, ray, B, H);
+        rtu_hit o;
+        o.z = H.z;
+        o.p[0] = H.px; o.p[1] = H.py; o.p[2] = H.pz;
+        o.N[0] = H.nx; o.N[1] = H.ny; o.N[2] = H.nz;
+        o.uvw[0] = H.u; o.uvw[1] = H.v; o.uvw[2] = H.w;
+        o.node = H.node; o.face = H.face; o.front = H.front;
+        hits[i] = o;
+    }
+    flush_tally(tl, counters);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+k_shadow_batch(DScene S, const rtu_ray *rays, const float *tmax, long long n, unsigned char *occ, DCounters *counters)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.px = rays[i].p[0]; ray.py = rays[i].p[1]; ray.pz = rays[i].p[2];
+        ray.dx = rays[i].dir[0]; ray.dy = rays[i].dir[1]; ray.dz = rays[i].dir[2];
+        Best B;
+        B.z = tmax[i]; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        tl.shadow++;
+        bool h = scene_hit<true>(S, ray, B, tl);
+        occ[i] = (h && B.z > 0.0f) ? 1 : 0;
+    }
+    flush_tally(tl, counters);
+}
+
+// First Shade() step on caller-provided hits (rtu_shade); pixel index = ray index.
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+k_shade_first(DScene S, FrameSetup F, const rtu_ray *rays, const rtu_hit *hits, long long n, WaveOut O)
+{
+    ShadeParams SP;
+    SP.flags = F.flags;
+    SP.seed = F.seed;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        rtu_hit h = hits[i];
+        if (h.node < 0 || h.node >= S.n_nodes) continue;
+        HitRec H;
+        H.z = h.z;
+        H.px = h.p[0]; H.py = h.p[1]; H.pz = h.p[2];
+        H.nx = h.N[0]; H.ny = h.N[1]; H.nz = h.N[2];
+        H.u = h.uvw[0]; H.v = h.uvw[1]; H.w = h.uvw[2];
+        H.node = h.node; H.face = h.face; H.front = h.front;
+        H.material = S.nodes[h.node].material;
+        shade_hit(S, SP, O, rays[i].dir[0], rays[i].dir[1], rays[i].dir[2], H, mk(1.f, 1.f, 1.f), F.shade_bounces, (int)i, 0u);
+    }
+}
+
+__global__ void k_camera_rays(DCamera C, float ox, float oy, rtu_ray *rays)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= C.width * C.height) return;
+    int y = p / C.width, x = p - y * C.width;
+    Ray r = camera_ray(C, x, y, ox, oy, nullptr);
+    rtu_ray o;
+    o.p[0] = r.px; o.p[1] = r.py; o.p[2] = r.pz;
+    o.dir[0] = r.dx; o.dir[1] = r.dy; o.dir[2] = r.dz;
+    rays[p] = o;
+}
+
+__global__ void k_resolve(const float4 *accum, int npix, int spp, float *rgb, unsigned char *rgb8)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float4 a = accum[p];
+    float n = (float)spp;
+    float r = a.x / n, g = a.y / n, b = a.z / n; // pixelValuesSum /= (float)maxSampleSize (RenderFunctions.cpp:152)
+    if (rgb) { rgb[p * 3] = r; rgb[p * 3 + 1] = g; rgb[p * 3 + 2] = b; }
+    if (rgb8) {
+        float c[3] = {r, g, b};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float gmm = (float)pow((double)c[k], 1 / 2.2); // :155-157
+            float s = gmm * 255;                           // Color24::FloatToByte (cyColor.h:245-246)
+            int v = (s == s) ? (int)s : 0;
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            rgb8[p * 3 + k] = (unsigned char)v;
+        }
+    }
+}
+
+__global__ void k_zminmax(const float *z, int npix, unsigned *mm)
+{
+    // zmin / zmax over hit pixels (scene.h:596-601); positive floats order like their bit patterns
+    unsigned lo = 0x7f800000u, hi = 0u;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        float v = z[p];
+        if (v == RTU_BIG) continue;
+        float vc = v < 0.f ? 0.f : v;
+        unsigned b = __float_as_uint(vc);
+        lo = min(lo, b);
+        hi = max(hi, b);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
+    }
+}
+
+__global__ void k_zimage(const float *z, int npix, const unsigned *mm, unsigned char *z8)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float zmin = __uint_as_float(mm[0]), zmax = __uint_as_float(mm[1]);
+    if (zmin > RTU_BIG) zmin = RTU_BIG; // no hit at all: zmin stays BIGFLOAT (scene.h:596)
+    float v = z[p];
+    unsigned char o = 0;
+    if (v != RTU_BIG) {
+        float f = (zmax - v) / (zmax - zmin); // scene.h:605
+        float s = f * 255;
+        int c = (s == s) ? (int)s : 0;
+        c = c < 0 ? 0 : (c > 255 ? 255 : c);
+        o = (unsigned char)c;
+    }
+    z8[p] = o;
+}
+
+// ------------------------------------------------------------------ launch wrappers
+static inline int wave_grid(const LaunchCfg &cfg) { return cfg.sm_count * cfg.blocks_per_sm; }
+
+static WaveOut make_out(const WaveBuffers &B, int out_q, float4 *accum)
+{
+    WaveOut O;
+    O.next = B.q[out_q];
+    O.aux = B.aux[out_q];
+    O.shadow = B.shadow;
+    O.accum = accum;
+    O.counters = B.counters;
+    return O;
+}
+
+void launch_wave_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
+                         const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter)
+{
+    WaveOut O = make_out(B, out_q, accum);
+    k_wave<true><<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1 - out_q], B.aux[1 - out_q], O, work_counter);
+}
+
+void launch_wave_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
+                       int in_q, float4 *accum, unsigned *work_counter)
+{
+    WaveOut O = make_out(B, 1 - in_q, accum);
+    k_wave<false><<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], O, work_counter);
+}
+
+void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
+                        unsigned *work_counter)
+{
+    k_shadow_wave<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
+}
+
+void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d)
+{
+    k_reset_counts<<<1, 1, 0, st>>>(a, b, c, d);
+}
+
+void launch_primary_ids(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const DCamera &cam, float *z, int *node,
+                        int *face, DCounters *counters)
+{
+    k_primary_ids<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, cam, z, node, face, counters);
+}
+
+void launch_trace_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, long long n,
+                        rtu_hit *hits, DCounters *counters)
+{
+    k_trace_batch<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, rays, n, hits, counters);
+}
+
+void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
+                         long long n, unsigned char *occ, DCounters *counters)
+{
+    k_shadow_batch<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, rays, tmax, n, occ, counters);
+}
+
+void launch_shade_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const rtu_ray *rays,
+                        const rtu_hit *hits, long long n, const WaveBuffers &B, int out_q, float4 *accum)
+{
+    WaveOut O = make_out(B, out_q, accum);
+    k_shade_first<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, F, rays, hits, n, O);
+}
+
+void launch_camera_rays(cudaStream_t st, const DCamera &cam, float ox, float oy, rtu_ray *rays)
+{
+    int n = cam.width * cam.height;
+    k_camera_rays<<<(n + 255) / 256, 256, 0, st>>>(cam, ox, oy, rays);
+}
+
+void launch_resolve(cudaStream_t st, const float4 *accum, int npix, float, int spp, float *rgb, unsigned char *rgb8)
+{
+    k_resolve<<<(npix + 255) / 256, 256, 0, st>>>(accum, npix, spp, rgb, rgb8);
+}
+
+void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8)
+{
+    static const unsigned init[2] = {0x7f800000u, 0u};
+    cudaMemcpyAsync(minmax_bits, init, sizeof init, cudaMemcpyHostToDevice, st);
+    k_zminmax<<<296, 256, 0, st>>>(z, npix, minmax_bits);
+    k_zimage<<<(npix + 255) / 256, 256, 0, st>>>(z, npix, minmax_bits, z8);
+}

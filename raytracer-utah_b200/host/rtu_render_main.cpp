@@ -1,0 +1,71 @@
+// rtu_render: headless replacement for the reference's main() (main.cpp:74-88) for this path.
+//   rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref]
+//              [--bounces B] [--out Result.png] [--zout ZBuffer.png] [--device D]
+// Loads the scene (LoadScene), renders it on the GPU and writes Result.png / ZBuffer.png like
+// SpawnRenderThreads() does (main.cpp:59-61).  There is no window and no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rtu.h"
+
+static int die(const char *what, int rc)
+{
+    fprintf(stderr, "%s failed (%d): %s\n", what, rc, rtu_last_error());
+    return 1;
+}
+
+int main(int argc, char **argv)
+{
+    std::string scene, root = ".", out = "Result.png", zout = "ZBuffer.png", pattern = "center";
+    int width = 0, height = 0, spp = 1, bounces = 5, device = 0;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char * { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
+        if (a == "--root") root = next();
+        else if (a == "--width") width = atoi(next());
+        else if (a == "--height") height = atoi(next());
+        else if (a == "--spp") spp = atoi(next());
+        else if (a == "--pattern") pattern = next();
+        else if (a == "--bounces") bounces = atoi(next());
+        else if (a == "--out") out = next();
+        else if (a == "--zout") zout = next();
+        else if (a == "--device") device = atoi(next());
+        else if (a[0] != '-') scene = a;
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    if (scene.empty()) { fprintf(stderr, "usage: rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref] [--bounces B] [--out Result.png] [--zout ZBuffer.png]\n"); return 2; }
+    rtu_host_scene *hs = nullptr;
+    int rc = rtu_host_load_xml(scene.c_str(), root.c_str(), &hs);
+    if (rc) return die("rtu_host_load_xml", rc);
+    if (rtu_last_error()[0]) fprintf(stderr, "%s\n", rtu_last_error());
+    rtu_context *ctx = nullptr;
+    if ((rc = rtu_context_create(device, nullptr, &ctx))) return die("rtu_context_create", rc);
+    rtu_scene *sc = nullptr;
+    if ((rc = rtu_scene_upload(ctx, rtu_host_scene_desc(hs), &sc))) return die("rtu_scene_upload", rc);
+    rtu_params p;
+    rtu_params_default(&p);
+    p.width = width; p.height = height; p.spp = spp; p.shade_bounces = bounces;
+    p.pattern = (pattern == "ref" || spp > 1) ? RTU_PATTERN_REFERENCE : RTU_PATTERN_CENTER;
+    const rtu_scene_desc *d = rtu_host_scene_desc(hs);
+    int W = width > 0 ? width : d->camera.width, H = height > 0 ? height : d->camera.height;
+    std::vector<uint8_t> rgb8((size_t)W * H * 3), z8((size_t)W * H);
+    rtu_image img;
+    memset(&img, 0, sizeof img);
+    img.rgb8 = rgb8.data();
+    img.z8 = z8.data();
+    if ((rc = rtu_render(sc, &p, &img))) return die("rtu_render", rc);
+    rtu_stats st;
+    rtu_get_stats(sc, &st);
+    if ((rc = rtu_write_png(out.c_str(), rgb8.data(), W, H, 3))) return die("rtu_write_png", rc);
+    if ((rc = rtu_write_png(zout.c_str(), z8.data(), W, H, 1))) return die("rtu_write_png", rc);
+    double rays = (double)(st.trace_rays + st.shadow_rays);
+    printf("{\"width\":%d,\"height\":%d,\"spp\":%d,\"trace_rays\":%llu,\"shadow_rays\":%llu,\"device_ms\":%.3f,\"mrays_per_s\":%.2f}\n", W, H, spp,
+           (unsigned long long)st.trace_rays, (unsigned long long)st.shadow_rays, st.device_ms, st.device_ms > 0 ? rays / st.device_ms * 1e-3 : 0.0);
+    rtu_scene_destroy(sc);
+    rtu_context_destroy(ctx);
+    rtu_host_scene_destroy(hs);
+    return 0;
+}

@@ -284,10 +284,19 @@ class Scene:
         _check(L.rtu_shade(self._h, rays.ctypes.data, hits.ctypes.data, rays.shape[0], bounces, rgb.ctypes.data), "rtu_shade")
         return rgb
 
+    def camera_rays(self, params, sample=0):
+        """The camera ray Render() builds for one sample of every pixel (RenderFunctions.cpp:78-97)."""
+        L = lib()
+        w, h = self._dims(params)
+        rays = np.zeros(w * h, RAY_DTYPE)
+        L.rtu_camera_rays.argtypes = [C.c_void_p, C.POINTER(Params), i32, C.c_void_p]
+        _check(L.rtu_camera_rays(self._h, C.byref(params), sample, rays.ctypes.data), "rtu_camera_rays")
+        return rays
+
     def _dims(self, params):
         w = params.width or self.desc.camera.width
         h = params.height or self.desc.camera.height
-        return w, h
+        return max(w, 1), max(h, 1)  # invalid sizes are rejected by the library, not here
 
     def render(self, params, want=("rgb8", "rgb", "z", "z8", "node_id", "face_id")):
         """rtu_render: whole frame, host buffers out (the e2e path)."""

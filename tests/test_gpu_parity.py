@@ -1,0 +1,233 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+Every expectation comes from tests/golden/*.npz, which the UNMODIFIED reference produced
+(tools/make_golden.py).  All calls go through the C ABI of include/rtu.h.
+
+Bars (BASELINE.json north_star):
+  * hit / miss, winning node, winning face, front flag and z: BIT-EXACT
+  * p, N of hits: bit-exact (only + - * / sqrt are involved); sphere uvw within 2e-6 (atan2f/asinf ULPs)
+  * deterministic Whitted images: |gpu - ref| <= 1e-4 * max(|gpu|,|ref|) + 1e-6 per channel
+  * RGB8: within 1 code value (libm vs CUDA pow), root-level ray counts: equal
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SCENES, bits_equal, load_golden, single_object_scene
+
+pytestmark = pytest.mark.gpu
+
+BIG = np.float32(1.0e30)
+REL_TOL = 1e-4   # north_star: "within 1e-4 relative tolerance"
+ABS_FLOOR = 1e-6
+
+
+def rays_from(g):
+    import rtu_b200 as R
+    r = np.zeros(g["rays"].shape[0], R.RAY_DTYPE)
+    r["p"] = g["rays"][:, :3]
+    r["dir"] = g["rays"][:, 3:]
+    return r
+
+
+def check_kat(rtu, gpu_ctx, prim, kind, mesh_from=None):
+    g, _ = load_golden("kat_" + prim)
+    desc = single_object_scene(rtu, kind, mesh_from)
+    sc = rtu.Scene(gpu_ctx, desc)
+    try:
+        rays = rays_from(g)
+        # the boolean result for every initial z (what ShadowTrace observes)
+        occ = sc.shadow_trace(rays, g["zin"])
+        assert np.array_equal(occ.astype(bool), g["hit"].astype(bool)), "hit/miss differs for %d rays" % np.sum(occ.astype(bool) != g["hit"].astype(bool))
+        # full records for rays that started from a fresh HitInfo
+        fresh = g["zin"] == BIG
+        hits = sc.trace(rays[fresh])
+        ref_hit = g["hit"][fresh].astype(bool)
+        assert np.array_equal(hits["node"] >= 0, ref_hit)
+        m = ref_hit
+        assert bits_equal(hits["z"][m], g["z"][fresh][m]), "z not bit-exact"
+        assert np.array_equal(hits["front"][m], g["front"][fresh][m])
+        assert bits_equal(hits["p"][m], g["p"][fresh][m]), "p not bit-exact"
+        assert bits_equal(hits["N"][m], g["N"][fresh][m]), "N not bit-exact"
+        if prim == "sphere":
+            assert np.max(np.abs(hits["uvw"][m] - g["uvw"][fresh][m])) <= 2e-6
+        else:
+            assert bits_equal(hits["uvw"][m], g["uvw"][fresh][m]), "uvw not bit-exact"
+        if prim == "mesh":
+            assert np.array_equal(hits["face"][m], g["face"][fresh][m]), "winning face differs"
+        assert m.sum() > 1000  # the fixture is not vacuous
+    finally:
+        sc.close()
+
+
+def test_kat_sphere(rtu, gpu_ctx):
+    check_kat(rtu, gpu_ctx, "sphere", rtu.OBJ_SPHERE)
+
+
+def test_kat_plane(rtu, gpu_ctx):
+    check_kat(rtu, gpu_ctx, "plane", rtu.OBJ_PLANE)
+
+
+def test_kat_mesh(rtu, gpu_ctx):
+    hs = rtu.HostScene(os.path.join(SCENES, "Teapot/scene2.xml"))
+    check_kat(rtu, gpu_ctx, "mesh", rtu.OBJ_MESH, hs)
+
+
+PRIMARY_CASES = ["p1example", "p1test", "p4", "p5", "p5low", "p7", "p11", "p13", "teapot1", "teapot2",
+                 "p1example_full", "p4_full", "teapot2_1080p"]
+
+
+@pytest.mark.parametrize("tag", PRIMARY_CASES)
+def test_primary_ids_and_z(rtu, gpu_ctx, tag):
+    g, meta = load_golden("primary_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_PRIMARY)
+        out = sc.render(p, want=("z", "node_id", "face_id"))
+        assert np.array_equal(out["node_id"], g["node"]), "%d pixels with a different node" % np.sum(out["node_id"] != g["node"])
+        assert np.array_equal(out["face_id"], g["face"]), "%d pixels with a different face" % np.sum(out["face_id"] != g["face"])
+        assert bits_equal(out["z"], g["z"]), "%d pixels with a different z" % np.sum(out["z"].view("u4") != g["z"].view("u4"))
+        assert int((g["node"] >= 0).sum()) == meta["hits"]
+        if "p" in g:  # full HitInfo through the batched Trace operator on the same camera rays
+            rays = sc.camera_rays(p)
+            hits = sc.trace(rays).reshape(g["node"].shape)
+            m = g["node"] >= 0
+            assert np.array_equal(hits["node"], g["node"])
+            assert np.array_equal(hits["front"][m], g["front"][m])
+            assert bits_equal(hits["z"], g["z"])
+            assert bits_equal(hits["p"][m], g["p"][m]), "p not bit-exact"
+            assert bits_equal(hits["N"][m], g["N"][m]), "N not bit-exact"
+            assert np.max(np.abs(hits["uvw"][m] - g["uvw"][m])) <= 2e-6
+    finally:
+        sc.close()
+        hs.close()
+
+
+def within_tol(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return np.abs(a - b) <= REL_TOL * np.maximum(np.abs(a), np.abs(b)) + ABS_FLOOR
+
+
+WHITTED_CASES = ["p2", "p3simple", "p3box", "p4", "p5", "p7", "p11", "p13", "teapot2", "p4_spp4", "teapot2_spp4",
+                 "p4_full", "teapot2_1080p"]
+
+
+@pytest.mark.parametrize("tag", WHITTED_CASES)
+def test_whitted_image(rtu, gpu_ctx, tag):
+    g, meta = load_golden("whitted_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        pattern = rtu.PATTERN_CENTER if meta["pattern"] == "center" else rtu.PATTERN_REFERENCE
+        p = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=pattern,
+                               mode=rtu.MODE_WHITTED, shade_bounces=5)
+        out = sc.render(p, want=("rgb", "rgb8"))
+        st = sc.stats()
+        ok = within_tol(out["rgb"], g["rgb"]).all(axis=2)
+        bad = int((~ok).sum())
+        # no pixel may be outside the tolerance
+        assert bad == 0, "%d of %d pixels outside 1e-4 relative tolerance (max abs diff %.3g)" % (
+            bad, ok.size, float(np.max(np.abs(out["rgb"].astype(np.float64) - g["rgb"]))))
+        d8 = np.abs(out["rgb8"].astype(np.int32) - g["rgb8"].astype(np.int32))
+        assert d8.max() <= 1, "RGB8 differs by more than one code value"
+        assert np.mean(d8 > 0) < 1e-3
+        # the same set of root-level rays as the reference's recursion
+        assert st["trace_rays"] == meta["trace_rays"]
+        assert st["shadow_rays"] == meta["shadow_rays"]
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_zbuffer_image_matches_reference_formula(rtu, gpu_ctx):
+    """ZBuffer.png greys = RenderImage::ComputeZBufferImage (scene.h:590-612) of the golden z."""
+    g, meta = load_golden("primary_p1example_full")
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(mode=rtu.MODE_PRIMARY)
+        out = sc.render(p, want=("z", "z8"))
+        z = g["z"]
+        hit = z != BIG
+        zmin = np.float32(z[hit].min())
+        zmax = np.float32(max(np.float32(0), z[hit].max()))
+        f = ((zmax - z) / np.float32(zmax - zmin)).astype(np.float32)
+        ref = np.clip((f * np.float32(255)).astype(np.int32), 0, 255).astype(np.uint8)
+        ref[~hit] = 0
+        assert np.array_equal(out["z8"], ref)
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_culling_flags_do_not_change_the_image(rtu, gpu_ctx):
+    """Skipping zero-contribution rays is result-neutral; only the ray counts drop."""
+    g, meta = load_golden("whitted_p4")
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_WHITTED)
+        a = sc.render(p, want=("rgb",))["rgb"]
+        n0 = sc.stats()
+        p.flags = 3
+        b = sc.render(p, want=("rgb",))["rgb"]
+        n1 = sc.stats()
+        assert within_tol(a, b).all()
+        assert n1["trace_rays"] + n1["shadow_rays"] < n0["trace_rays"] + n0["shadow_rays"]
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_sample_and_row_slices_compose(rtu, gpu_ctx):
+    """spp slices / row ranges rendered separately into one accumulator equal the whole frame
+    (the multi-GPU decompositions of SURVEY section 8e, here on one device)."""
+    hs = rtu.HostScene(os.path.join(SCENES, "Project4.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        kw = dict(width=160, height=120, spp=4, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_WHITTED)
+        full = sc.render(rtu.default_params(**kw), want=("rgb",))["rgb"]
+        sc.render_device(rtu.default_params(sample_begin=0, sample_end=1, **kw), clear=True)
+        sc.render_device(rtu.default_params(sample_begin=1, sample_end=4, **kw), clear=False)
+        parts = sc.resolve(rtu.default_params(**kw), want=("rgb",))["rgb"]
+        assert within_tol(full, parts).all()
+        sc.render_device(rtu.default_params(row_begin=0, row_end=52, **kw), clear=True)
+        sc.render_device(rtu.default_params(row_begin=52, row_end=120, **kw), clear=False)
+        rows = sc.resolve(rtu.default_params(**kw), want=("rgb",))["rgb"]
+        assert within_tol(full, rows).all()
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_shade_operator_matches_render(rtu, gpu_ctx):
+    """rtu_trace + rtu_shade on the camera rays == the fused frame (Material::Shade as an operator)."""
+    g, meta = load_golden("whitted_p4")
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_WHITTED)
+        rays = sc.camera_rays(p)
+        hits = sc.trace(rays)
+        rgb = sc.shade(rays, hits, 5).reshape(meta["height"], meta["width"], 3)
+        m = (hits["node"] >= 0).reshape(meta["height"], meta["width"])
+        assert within_tol(rgb[m], g["rgb"][m]).all()
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_errors_are_reported_not_swallowed(rtu, gpu_ctx):
+    hs = rtu.HostScene(os.path.join(SCENES, "Project1Test.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        with pytest.raises(rtu.RtuError):
+            sc.render(rtu.default_params(spp=4, pattern=rtu.PATTERN_CENTER))  # centre pattern needs spp == 1
+        with pytest.raises(rtu.RtuError):
+            sc.render(rtu.default_params(width=-5))
+    finally:
+        sc.close()
+        hs.close()
