@@ -1,0 +1,178 @@
+"""CPU-only tests of the host side: scene front-end parity with the reference loader, the C ABI
+surface, PNG round trips, and the no-GPU failure mode (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SCENES, bits_equal, load_golden
+
+LOADER_CASES = ["Project1Example", "Project4", "Project5_scene", "Project7_scene", "Project9_scene", "Project10_scene",
+                "Project11_scene_86", "Project13_scene", "Teapot_scene", "Teapot_scene2"]
+
+
+@pytest.mark.parametrize("tag", LOADER_CASES)
+def test_loader_matches_reference_loadscene(rtu, tag):
+    """rtu_host_load_xml leaves bit-identical transforms / camera / materials / lights / meshes / BVH
+    to what LoadScene (xmlload.cpp:64) + TriObj::Load (objects.h:52-60) leave in the reference's globals."""
+    g, meta = load_golden("loader_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    n = hs.nodes()
+    assert bits_equal(n["tm"], g["node_tm"])
+    assert bits_equal(n["itm"], g["node_itm"])
+    assert bits_equal(n["pos"], g["node_pos"])
+    assert np.array_equal(n["meta"], g["node_meta"])
+    assert bits_equal(hs.camera(), g["camera"][:14])
+    assert bits_equal(hs.materials(), g["materials"])
+    assert bits_equal(hs.lights(), g["lights"])
+    assert hs.desc.n_nodes == meta["nodes"] and hs.desc.n_meshes == meta["meshes"]
+    if "mesh0_v" in g:
+        m = hs.mesh(0)
+        for k in ("v", "f", "vn", "fn", "vt", "ft", "bvh_elements", "bound"):
+            assert bits_equal(m[k], g["mesh0_" + k]), k
+        # node 0 of the cyBVH array is unused (cyBVH.h:202)
+        assert bits_equal(m["bvh_boxes"][1:], g["mesh0_bvh_boxes"][1:])
+        assert np.array_equal(m["bvh_data"][1:], g["mesh0_bvh_data"][1:])
+    hs.close()
+
+
+def test_bvh_builder_on_caller_arrays(rtu):
+    g, _ = load_golden("loader_Teapot_scene2")
+    boxes, data, elem = rtu.build_bvh(g["mesh0_v"], g["mesh0_f"], 4)
+    assert np.array_equal(elem, g["mesh0_bvh_elements"])
+    assert np.array_equal(data[1:], g["mesh0_bvh_data"][1:])
+    assert bits_equal(boxes[1:], g["mesh0_bvh_boxes"][1:])
+
+
+def test_bvh_builder_edge_cases(rtu):
+    # a single triangle: the root is a leaf
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], "f4")
+    boxes, data, elem = rtu.build_bvh(v, np.array([[0, 1, 2]], "u4"))
+    assert len(data) == 2 and data[1] == 0x80000000
+    # 9 identical triangles cannot be split by position: forced halving above 8 (cyBVH.h:249-254)
+    f = np.tile(np.array([[0, 1, 2]], "u4"), (9, 1))
+    boxes, data, elem = rtu.build_bvh(v, f)
+    leaves = [d for d in data[1:] if d & 0x80000000]
+    assert sum(((d >> 28) & 7) + 1 for d in leaves) == 9
+    assert sorted(elem.tolist()) == list(range(9))
+    # out-of-range index is an error, not a crash
+    with pytest.raises(rtu.RtuError):
+        rtu.build_bvh(v, np.array([[0, 1, 7]], "u4"))
+
+
+def test_missing_files_and_bad_xml(rtu, tmp_path):
+    with pytest.raises(rtu.RtuError):
+        rtu.HostScene(str(tmp_path / "nope.xml"))
+    bad = tmp_path / "bad.xml"
+    bad.write_text("<xml><scene><object type='sphere'></scene></xml>")
+    with pytest.raises(rtu.RtuError):
+        rtu.HostScene(str(bad))
+    nocam = tmp_path / "nocam.xml"
+    nocam.write_text("<xml><scene></scene></xml>")
+    with pytest.raises(rtu.RtuError):
+        rtu.HostScene(str(nocam))
+    # a mesh that cannot be opened leaves the node without an object, like xmlload.cpp:205
+    ok = tmp_path / "ok.xml"
+    ok.write_text("<xml><scene><object type='obj' name='missing.obj'/><object type='sphere' name='s'/></scene><camera/></xml>")
+    hs = rtu.HostScene(str(ok), asset_root=str(tmp_path))
+    assert hs.desc.n_nodes == 3 and hs.desc.nodes[1].kind == rtu.OBJ_NONE and hs.desc.nodes[2].kind == rtu.OBJ_SPHERE
+    assert "missing.obj" in hs.warnings
+    assert hs.desc.camera.width == 200 and hs.desc.camera.height == 150  # Camera::Init defaults (scene.h:524-534)
+
+
+def test_empty_and_ragged_obj(rtu, tmp_path):
+    (tmp_path / "empty.obj").write_text("# nothing\nv 0 0 0\n")
+    (tmp_path / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 2 0\nf 1 2 3 4 5\nf -5 -4 -3\n")
+    xml = tmp_path / "s.xml"
+    xml.write_text("<xml><scene><object type='obj' name='empty.obj'/><object type='obj' name='quad.obj'/></scene><camera/></xml>")
+    hs = rtu.HostScene(str(xml), asset_root=str(tmp_path))
+    assert hs.desc.n_meshes == 2
+    assert hs.desc.meshes[0].nf == 0                      # cyTriMesh.h:455: no faces, nothing allocated
+    q = hs.mesh(1)
+    # a pentagon is fanned into 3 triangles (cyTriMesh.h:405-418); negative indices are relative
+    assert q["f"].tolist() == [[0, 1, 2], [0, 2, 3], [0, 3, 4], [0, 1, 2]]
+    assert len(q["vn"]) == 5                              # ComputeNormals (objects.h:56)
+    assert np.allclose(np.abs(q["vn"]), [[0, 0, 1]] * 5)  # the fan's last triangle winds the other way
+
+
+def test_png_round_trip(rtu, tmp_path):
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    p = str(tmp_path / "t.png")
+    rtu.write_png(p, img)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(p).convert("RGB")), img)
+    grey = rng.integers(0, 256, (19, 7), dtype=np.uint8)
+    rtu.write_png(p, grey)
+    assert np.array_equal(np.asarray(Image.open(p)), grey)
+
+
+def test_texture_pixels_decode_like_a_png_decoder(rtu):
+    from PIL import Image
+    hs = rtu.HostScene(os.path.join(SCENES, "Project7/scene.xml"))
+    d = hs.desc
+    seen = 0
+    for i in range(d.n_texmaps):
+        t = d.texmaps[i]
+        if t.kind != rtu.TEX_FILE:
+            continue
+        px = np.ctypeslib.as_array(t.rgb8, shape=(t.height, t.width, 3))
+        if (t.width, t.height) == (1024, 1024):
+            seen += 1
+    assert seen >= 2
+    bricks = np.asarray(Image.open(os.path.join(SCENES, "Project7/bricks.png")).convert("RGB"))
+    for i in range(d.n_texmaps):
+        t = d.texmaps[i]
+        if t.kind == rtu.TEX_FILE:
+            px = np.ctypeslib.as_array(t.rgb8, shape=(t.height, t.width, 3))
+            if np.array_equal(px, bricks):
+                return
+    pytest.fail("bricks.png was not decoded identically")
+
+
+def test_abi_exports_every_declared_symbol(rtu):
+    """The shared library exports exactly what include/rtu.h declares (no compute call is made)."""
+    hdr = open(os.path.join(ROOT, "include", "rtu.h")).read()
+    names = sorted(set(re.findall(r"\b(rtu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 18
+    L = rtu.lib()
+    for n in names:
+        assert hasattr(L, n), "missing export " + n
+    assert L.rtu_version() >= 1
+
+
+def test_struct_layouts_match_the_header(rtu):
+    # sizes the C compiler gives the PODs of include/rtu.h (64-bit): guards the ctypes mirrors
+    assert C.sizeof(rtu.Node) == 21 * 4 + 4 * 4
+    assert C.sizeof(rtu.TexColor) == 16
+    assert C.sizeof(rtu.Material) == 5 * 16 + 7 * 4
+    assert C.sizeof(rtu.Light) == 32
+    assert C.sizeof(rtu.Camera) == 14 * 4
+    assert rtu.RAY_DTYPE.itemsize == 24 and rtu.HIT_DTYPE.itemsize == 52
+    assert C.sizeof(rtu.Params) == 56
+
+
+def test_no_gpu_means_an_error_not_a_fallback(rtu):
+    """Without a CUDA device the context cannot be created: the product has no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rtu.RtuError) as e:
+        rtu.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under raytracer-utah_b200/ may import, link or call oracle/."""
+    pkg = os.path.join(ROOT, "raytracer-utah_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower(), os.path.join(dirpath, f)

@@ -1,0 +1,97 @@
+"""Pins the C restatement (oracle/oracle.c) against fixtures the UNMODIFIED reference produced.
+
+CPU only.  If these pass, the oracle is a faithful stand-in for the reference on the GPU box,
+where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SCENES, bits_equal, load_golden, single_object_scene
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+BIG = np.float32(1.0e30)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import oracle_py
+    oracle_py.lib()
+    return oracle_py
+
+
+def rays_from(rtu, g):
+    r = np.zeros(g["rays"].shape[0], rtu.RAY_DTYPE)
+    r["p"] = g["rays"][:, :3]
+    r["dir"] = g["rays"][:, 3:]
+    return r
+
+
+def test_box_functions_bit_exact(oracle):
+    """Box::IntersectRay and BVHBoxIntersection (objFunctions.cpp:143-254, 408-522), incl. zero directions and 0/0."""
+    g, _ = load_golden("kat_box")
+    hit, tb = oracle.box_intersect(g["rays"], g["boxes"], g["tmax"])
+    assert np.array_equal(hit.astype(bool), g["hit"].astype(bool))
+    assert bits_equal(tb, g["tbvh"])
+    assert 0.1 < g["hit"].mean() < 0.95
+
+
+@pytest.mark.parametrize("prim,kind", [("sphere", 1), ("plane", 2), ("mesh", 3)])
+def test_primitive_kats_bit_exact(rtu, oracle, prim, kind):
+    g, _ = load_golden("kat_" + prim)
+    hs = rtu.HostScene(os.path.join(SCENES, "Teapot/scene2.xml")) if kind == 3 else None
+    desc = single_object_scene(rtu, kind, hs)
+    rays = rays_from(rtu, g)
+    occ = oracle.shadow_trace(desc, rays, g["zin"])
+    assert np.array_equal(occ.astype(bool), g["hit"].astype(bool))
+    fresh = g["zin"] == BIG
+    hits = oracle.trace(desc, rays[fresh])
+    m = g["hit"][fresh].astype(bool)
+    assert np.array_equal(hits["node"] >= 0, m)
+    for k in ("z", "p", "N", "uvw"):
+        assert bits_equal(hits[k][m], g[k][fresh][m]), k
+    assert np.array_equal(hits["front"][m], g["front"][fresh][m])
+    if prim == "mesh":
+        assert np.array_equal(hits["face"][m], g["face"][fresh][m])
+
+
+@pytest.mark.parametrize("tag", ["p1example", "p4", "p5", "p7", "p11", "teapot1", "teapot2", "p1example_full"])
+def test_primary_bit_exact(rtu, oracle, tag):
+    g, meta = load_golden("primary_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    o = oracle.render(hs.desc, width=meta["width"], height=meta["height"], mode=rtu.MODE_PRIMARY, want=("z", "node_id", "face_id"))
+    assert np.array_equal(o["node_id"], g["node"])
+    assert np.array_equal(o["face_id"], g["face"])
+    assert bits_equal(o["z"], g["z"])
+    assert o["stats"]["trace_rays"] == meta["rays"]
+
+
+@pytest.mark.parametrize("tag", ["p2", "p3box", "p4", "p5", "p7", "p11", "p13", "teapot2", "p4_spp4", "teapot2_spp4"])
+def test_whitted_matches_reference(rtu, oracle, tag):
+    g, meta = load_golden("whitted_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    pattern = rtu.PATTERN_CENTER if meta["pattern"] == "center" else rtu.PATTERN_REFERENCE
+    o = oracle.render(hs.desc, width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=pattern, mode=rtu.MODE_WHITTED)
+    # same compiler, same libm, same operation order: the restatement reproduces the reference's floats
+    assert bits_equal(o["rgb"], g["rgb"]), "max abs diff %g" % np.max(np.abs(o["rgb"] - g["rgb"]))
+    assert np.array_equal(o["rgb8"], g["rgb8"])
+    assert o["stats"]["trace_rays"] == meta["trace_rays"]
+    assert o["stats"]["shadow_rays"] == meta["shadow_rays"]
+
+
+@pytest.mark.parametrize("tag,scene", [("p7", "Project7/scene.xml"), ("p9", "Project9/scene.xml"), ("p10", "Project10/scene.xml")])
+def test_texture_sampling_bit_exact(rtu, oracle, tag, scene):
+    """TexturedColor::Sample (checker, bilinear PNG, failed loads) and SampleEnvironment."""
+    g, _ = load_golden("tex_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, scene))
+    d = hs.desc
+    assert bits_equal(oracle.sample_texcolor(d, d.background, g["uvw"]), g["background"])
+    assert bits_equal(oracle.sample_environment(d, g["dirs"]), g["environment"])
+    for m in range(d.n_materials):
+        ref = g["mtl%d" % m]
+        mt = d.materials[m]
+        for q, tc in enumerate((mt.diffuse, mt.specular, mt.reflection, mt.refraction)):
+            assert bits_equal(oracle.sample_texcolor(d, tc, g["uvw"]), ref[:, q, :]), (m, q)
