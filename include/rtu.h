@@ -161,7 +161,8 @@ enum {
 };
 enum {
     RTU_FLAG_CULL_NULL_SHADOW_RAYS = 1, /* skip shadow rays whose contribution is exactly 0 (the reference traces them) */
-    RTU_FLAG_CULL_ZERO_WEIGHT_RAYS = 2  /* skip secondary rays whose throughput is exactly 0 (e.g. absorbed TIR; the reference traces them) */
+    RTU_FLAG_CULL_ZERO_WEIGHT_RAYS = 2, /* skip secondary rays whose throughput is exactly 0 (e.g. absorbed TIR; the reference traces them) */
+    RTU_FLAG_TIME_KERNELS = 4           /* bracket every wave kernel with CUDA events (fills rtu_kernel_stats.ms) */
 };
 
 typedef struct rtu_params {
@@ -191,6 +192,15 @@ typedef struct rtu_image {
 /* Counters of the last render/trace call.  A "ray" is one root-level Trace or ShadowTrace
  * (SURVEY section 8d); box/tri/node counts feed the algorithmic-bytes roofline figure
  * 28*box_tests + 52*tri_tests + 48*node_visits. */
+typedef struct rtu_kernel_stats {
+    uint64_t rays;        /* rays this kernel class traced */
+    uint64_t box_tests;   /* slab tests (object bound boxes + BVH child boxes) */
+    uint64_t tri_tests;
+    uint64_t node_visits; /* object nodes visited (one ToNodeCoords each) */
+    uint64_t launches;
+    double ms;            /* summed CUDA-event time of its launches; only with RTU_FLAG_TIME_KERNELS */
+} rtu_kernel_stats;
+
 typedef struct rtu_stats {
     uint64_t trace_rays;
     uint64_t shadow_rays;
@@ -198,9 +208,12 @@ typedef struct rtu_stats {
     uint64_t tri_tests;
     uint64_t node_visits;
     uint64_t kernel_launches;
-    double device_ms;      /* CUDA-event time of the device work of the last call */
-    double trace_kernel_ms;  /* time inside the closest-hit/shade wave kernels */
-    double shadow_kernel_ms; /* time inside the any-hit kernels */
+    double device_ms;               /* CUDA-event time of the device work of the last call */
+    rtu_kernel_stats primary_wave;  /* k_extend<primary>: camera rays, closest hit */
+    rtu_kernel_stats secondary_waves; /* k_extend<queue>: reflection / refraction / Fresnel rays, closest hit */
+    rtu_kernel_stats shadow_waves;  /* k_shadow_wave: any-hit */
+    rtu_kernel_stats shade_kernels; /* k_shade: MtlBlinn::Shade steps on the compacted hits (launches, ms only) */
+    uint64_t scene_device_bytes;    /* bytes rtu_scene_upload copied host -> device */
 } rtu_stats;
 
 typedef struct rtu_context rtu_context; /* one per GPU / host thread */
@@ -245,6 +258,10 @@ int rtu_shade(rtu_scene *scene, const rtu_ray *rays, const rtu_hit *hits, int64_
 /* The camera ray Render() builds for sample `sample` of every pixel (RenderFunctions.cpp:78-97),
  * rays[x + width*y]; lens offsets are 0 (dof is ignored here). */
 int rtu_camera_rays(rtu_scene *scene, const rtu_params *params, int32_t sample, rtu_ray *rays);
+/* Device self-test: the traversal kernels take the six quotients of a slab test through a
+ * reciprocal hoisted out of the BVH loop; this compares that path bit for bit with the IEEE
+ * division on every divisor mantissa x numerators_per_divisor x 9 exponents. */
+int rtu_selftest_division(rtu_context *ctx, uint32_t numerators_per_divisor, uint64_t seed, uint64_t *tested, uint64_t *mismatches);
 
 /* Frame level.  rtu_render: the whole Render() job with HOST output buffers (the e2e path).
  * rtu_render_device: same work, result left in device memory (accum: W*H float4 = sum of

@@ -157,6 +157,7 @@ struct Opts {
     std::string scene, root = ".", mode = "primary", out = "out", pattern = "center";
     int width = 0, height = 0, spp = 1, threads = 1, bounces = 5, n = 100000, seed = 1;
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+    int s0 = 0, s1 = -1;   // --samples a b: only samples [a,b) of the spp-sample pattern (bounded CPU-baseline runs)
     bool quiet = true;
 };
 
@@ -234,7 +235,7 @@ static void ModeWhitted(const Opts &o)
     ParallelRows(y0, y1, o.threads, [&](int y, int tid) {
         for (int x = x0; x < x1; x++) {
             Color sum(0.0, 0.0, 0.0);
-            for (int s = 0; s < spp; s++) {
+            for (int s = o.s0; s < (o.s1 < 0 ? spp : o.s1); s++) {
                 float ox, oy;
                 if (center) { ox = 0.5f; oy = 0.5f; }
                 else {
@@ -547,6 +548,7 @@ int main(int argc, char **argv)
         else if (a == "--bounces") o.bounces = atoi(next());
         else if (a == "--n") o.n = atoi(next());
         else if (a == "--seed") o.seed = atoi(next());
+        else if (a == "--samples") { o.s0 = atoi(next()); o.s1 = atoi(next()); }
         else if (a == "--crop") { o.x0 = atoi(next()); o.y0 = atoi(next()); o.x1 = atoi(next()); o.y1 = atoi(next()); }
         else if (a == "--verbose") o.quiet = false;
         else if (a[0] != '-') o.scene = a;

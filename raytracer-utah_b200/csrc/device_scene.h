@@ -15,7 +15,9 @@
 #include <stdint.h>
 
 #define RTU_MAX_DEPTH 8          // scene-graph nesting handled by the generic (non-flat) path
+#ifndef RTU_STACK
 #define RTU_STACK 64             // BVH traversal stack entries (reference: 100; depth-first needs depth+1)
+#endif
 #define RTU_KIND_BITS 3
 
 struct __align__(16) DNode {
@@ -133,6 +135,12 @@ struct AuxPool {         // extra payload of refracted / Fresnel rays
     uint32_t *count;
     uint32_t cap;
 };
+struct HitQueue {        // compacted closest hits of one wave, consumed by k_shade
+    float4 *a;  // z, node, front, triangle slot (int bits)
+    float4 *b;  // bc1, bc2, bc3, index of the ray in the wave's input (uint bits)
+    uint32_t *count;
+    uint32_t cap;
+};
 struct ShadowQueue {     // any-hit rays
     float4 *o;  // origin.xyz, pixel
     float4 *d;  // dir.xyz, t_max
@@ -150,8 +158,13 @@ enum RayKind {
     RK_GI = 5        // cosine-hemisphere bounce of MonteCarlo() (RenderFunctions.cpp:561-575)
 };
 
-struct DCounters {
+// counters per kernel class: 0 = primary wave (and the batched closest-hit operators),
+// 1 = secondary (queue) waves, 2 = shadow waves (and the batched any-hit operator)
+struct DCounterBlock {
     unsigned long long trace_rays, shadow_rays, box_tests, tri_tests, node_visits;
+};
+struct DCounters {
+    DCounterBlock k[3];
     uint32_t overflow;
     uint32_t pad;
 };

@@ -26,10 +26,13 @@ namespace {
         }                                                                                               \
     } while (0)
 
+thread_local size_t g_upload_bytes = 0; // host->device bytes of the scene upload in progress
+
 template <class T> int dev_upload(const std::vector<T> &h, T **d, cudaStream_t st, std::vector<void *> &owned)
 {
     *d = nullptr;
     if (h.empty()) return RTU_OK;
+    g_upload_bytes += h.size() * sizeof(T);
     CU(cudaMalloc((void **)d, h.size() * sizeof(T)));
     owned.push_back(*d);
     CU(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
@@ -42,7 +45,8 @@ struct rtu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     LaunchCfg cfg;
-    size_t chunk_rays = 1u << 22;
+    size_t chunk_rays = 1u << 25;  // primary rays per wave chunk (~300 B of queue space each)
+    double queue_factor = 1.0;
     // scratch (lazily sized)
     WaveBuffers wb;
     size_t q_cap = 0, shadow_cap = 0;
@@ -51,6 +55,26 @@ struct rtu_context {
     size_t work_n = 0;
     unsigned *zmm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-launch timing (RTU_FLAG_TIME_KERNELS)
+    std::vector<cudaEvent_t> kt_ev;
+    std::vector<int> kt_cls;
+    size_t kt_used = 0;
+    bool kt_on = false;
+    uint64_t cls_launches[4] = {0, 0, 0, 0}; // primary extend, queue extend, shadow, shade
+    // frame buffers: owned by the context so that re-uploading a scene every frame (the e2e
+    // path) does not re-allocate them
+    struct FrameBuffers {
+        float4 *accum = nullptr;
+        size_t accum_n = 0;
+        float *d_rgb = nullptr;
+        unsigned char *d_rgb8 = nullptr;
+        float *d_z = nullptr;
+        unsigned char *d_z8 = nullptr;
+        int *d_node = nullptr, *d_face = nullptr;
+        size_t img_n = 0;
+        float2 *d_offsets = nullptr;
+        size_t offsets_n = 0;
+    } fb;
 };
 
 struct rtu_scene {
@@ -58,23 +82,41 @@ struct rtu_scene {
     DScene S;
     rtu_camera cam;
     std::vector<void *> owned;
+    size_t device_bytes = 0;
     int n_shadow_lights = 0;
-    // frame buffers
-    float4 *accum = nullptr;
-    size_t accum_n = 0;
-    float *d_rgb = nullptr;
-    unsigned char *d_rgb8 = nullptr;
-    float *d_z = nullptr;
-    unsigned char *d_z8 = nullptr;
-    int *d_node = nullptr, *d_face = nullptr;
-    size_t img_n = 0;
-    float2 *d_offsets = nullptr;
-    size_t offsets_n = 0;
     uint64_t launches = 0;
     bool timed = false;
 };
 
 namespace {
+
+void kt_begin(rtu_context *c, int cls)
+{
+    c->cls_launches[cls]++;
+    if (!c->kt_on) return;
+    if (c->kt_used * 2 + 2 > c->kt_ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        c->kt_ev.push_back(a);
+        c->kt_ev.push_back(b);
+        c->kt_cls.push_back(cls);
+    }
+    c->kt_cls[c->kt_used] = cls;
+    cudaEventRecord(c->kt_ev[c->kt_used * 2], c->stream);
+}
+void kt_end(rtu_context *c)
+{
+    if (!c->kt_on) return;
+    cudaEventRecord(c->kt_ev[c->kt_used * 2 + 1], c->stream);
+    c->kt_used++;
+}
+void kt_reset(rtu_context *c, bool on)
+{
+    c->kt_on = on;
+    c->kt_used = 0;
+    c->cls_launches[0] = c->cls_launches[1] = c->cls_launches[2] = c->cls_launches[3] = 0;
+}
 
 int free_list(std::vector<void *> &v)
 {
@@ -114,6 +156,10 @@ int ensure_scratch(rtu_context *c, size_t q_cap, size_t shadow_cap)
     CU(alloc((void **)&c->wb.shadow.c, shadow_cap * sizeof(float4)));
     c->wb.shadow.count = counts + 4;
     c->wb.shadow.cap = (uint32_t)shadow_cap;
+    CU(alloc((void **)&c->wb.hits.a, q_cap * sizeof(float4)));
+    CU(alloc((void **)&c->wb.hits.b, q_cap * sizeof(float4)));
+    c->wb.hits.count = counts + 5;
+    c->wb.hits.cap = (uint32_t)q_cap;
     CU(alloc((void **)&c->wb.counters, sizeof(DCounters)));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     c->q_cap = q_cap;
@@ -332,6 +378,7 @@ int rtu_context_create(int32_t device, void *stream, rtu_context **out)
     c->cfg.blocks_per_sm = 2;
     c->cfg.threads = 256;
     if (const char *s = getenv("RTU_CHUNK_RAYS")) { long long v = atoll(s); if (v >= 1024) c->chunk_rays = (size_t)v; }
+    if (const char *s = getenv("RTU_QUEUE_FACTOR")) { double v = atof(s); if (v >= 1.0 && v <= 8.0) c->queue_factor = v; }
     if (const char *s = getenv("RTU_BLOCKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= 8) c->cfg.blocks_per_sm = v; }
     memset(&c->wb, 0, sizeof c->wb);
     CU(cudaMalloc((void **)&c->zmm, 2 * sizeof(unsigned)));
@@ -351,6 +398,9 @@ void rtu_context_destroy(rtu_context *c)
     if (c->zmm) cudaFree(c->zmm);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->kt_ev) cudaEventDestroy(e);
+    void *fbp[] = {c->fb.accum, c->fb.d_rgb, c->fb.d_rgb8, c->fb.d_z, c->fb.d_z8, c->fb.d_node, c->fb.d_face, c->fb.d_offsets};
+    for (void *p : fbp) if (p) cudaFree(p);
     delete c;
 }
 
@@ -369,6 +419,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     std::unique_ptr<rtu_scene> sc(new rtu_scene);
     sc->ctx = c;
     sc->cam = d->camera;
+    g_upload_bytes = 0;
     memset(&sc->S, 0, sizeof sc->S);
     int rc;
     auto fail = [&](int code) { free_list(sc->owned); return code; };
@@ -426,6 +477,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
                 sc->owned.push_back(dp);
                 CU(cudaMemcpyAsync(dp, t.rgb8, bytes, cudaMemcpyHostToDevice, c->stream));
                 pix.push_back({t.rgb8, dp});
+                g_upload_bytes += bytes;
             }
             o.rgb8 = dp;
         }
@@ -478,6 +530,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.background = pack_tc(d->background, d->n_texmaps);
     S.environment = pack_tc(d->environment, d->n_texmaps);
     memcpy(S.cam_pos, d->camera.pos, sizeof S.cam_pos);
+    sc->device_bytes = g_upload_bytes;
     *out = sc.release();
     return RTU_OK;
 }
@@ -488,14 +541,6 @@ void rtu_scene_destroy(rtu_scene *s)
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     free_list(s->owned);
-    if (s->accum) cudaFree(s->accum);
-    if (s->d_rgb) cudaFree(s->d_rgb);
-    if (s->d_rgb8) cudaFree(s->d_rgb8);
-    if (s->d_z) cudaFree(s->d_z);
-    if (s->d_z8) cudaFree(s->d_z8);
-    if (s->d_node) cudaFree(s->d_node);
-    if (s->d_face) cudaFree(s->d_face);
-    if (s->d_offsets) cudaFree(s->d_offsets);
     delete s;
 }
 
@@ -514,35 +559,35 @@ int frame_dims(const rtu_scene *s, const rtu_params *p, int *W, int *H)
 
 int ensure_image(rtu_scene *s, size_t npix)
 {
-    if (npix <= s->img_n) return RTU_OK;
+    if (npix <= s->ctx->fb.img_n) return RTU_OK;
     CU(cudaStreamSynchronize(s->ctx->stream));
-    if (s->d_rgb) cudaFree(s->d_rgb);
-    if (s->d_rgb8) cudaFree(s->d_rgb8);
-    if (s->d_z) cudaFree(s->d_z);
-    if (s->d_z8) cudaFree(s->d_z8);
-    if (s->d_node) cudaFree(s->d_node);
-    if (s->d_face) cudaFree(s->d_face);
-    s->d_rgb = nullptr; s->d_rgb8 = nullptr; s->d_z = nullptr; s->d_z8 = nullptr; s->d_node = nullptr; s->d_face = nullptr;
-    s->img_n = 0;
-    CU(cudaMalloc((void **)&s->d_rgb, npix * 3 * sizeof(float)));
-    CU(cudaMalloc((void **)&s->d_rgb8, npix * 3));
-    CU(cudaMalloc((void **)&s->d_z, npix * sizeof(float)));
-    CU(cudaMalloc((void **)&s->d_z8, npix));
-    CU(cudaMalloc((void **)&s->d_node, npix * sizeof(int)));
-    CU(cudaMalloc((void **)&s->d_face, npix * sizeof(int)));
-    s->img_n = npix;
+    if (s->ctx->fb.d_rgb) cudaFree(s->ctx->fb.d_rgb);
+    if (s->ctx->fb.d_rgb8) cudaFree(s->ctx->fb.d_rgb8);
+    if (s->ctx->fb.d_z) cudaFree(s->ctx->fb.d_z);
+    if (s->ctx->fb.d_z8) cudaFree(s->ctx->fb.d_z8);
+    if (s->ctx->fb.d_node) cudaFree(s->ctx->fb.d_node);
+    if (s->ctx->fb.d_face) cudaFree(s->ctx->fb.d_face);
+    s->ctx->fb.d_rgb = nullptr; s->ctx->fb.d_rgb8 = nullptr; s->ctx->fb.d_z = nullptr; s->ctx->fb.d_z8 = nullptr; s->ctx->fb.d_node = nullptr; s->ctx->fb.d_face = nullptr;
+    s->ctx->fb.img_n = 0;
+    CU(cudaMalloc((void **)&s->ctx->fb.d_rgb, npix * 3 * sizeof(float)));
+    CU(cudaMalloc((void **)&s->ctx->fb.d_rgb8, npix * 3));
+    CU(cudaMalloc((void **)&s->ctx->fb.d_z, npix * sizeof(float)));
+    CU(cudaMalloc((void **)&s->ctx->fb.d_z8, npix));
+    CU(cudaMalloc((void **)&s->ctx->fb.d_node, npix * sizeof(int)));
+    CU(cudaMalloc((void **)&s->ctx->fb.d_face, npix * sizeof(int)));
+    s->ctx->fb.img_n = npix;
     return RTU_OK;
 }
 
 int ensure_accum(rtu_scene *s, size_t npix)
 {
-    if (npix <= s->accum_n) return RTU_OK;
+    if (npix <= s->ctx->fb.accum_n) return RTU_OK;
     CU(cudaStreamSynchronize(s->ctx->stream));
-    if (s->accum) cudaFree(s->accum);
-    s->accum = nullptr;
-    s->accum_n = 0;
-    CU(cudaMalloc((void **)&s->accum, npix * sizeof(float4)));
-    s->accum_n = npix;
+    if (s->ctx->fb.accum) cudaFree(s->ctx->fb.accum);
+    s->ctx->fb.accum = nullptr;
+    s->ctx->fb.accum_n = 0;
+    CU(cudaMalloc((void **)&s->ctx->fb.accum, npix * sizeof(float4)));
+    s->ctx->fb.accum_n = npix;
     return RTU_OK;
 }
 
@@ -580,16 +625,16 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
             off[i] = make_float2(cur + halton(i, 4), cur + halton(i, 5));
         }
     }
-    if ((size_t)p->spp > s->offsets_n) {
+    if ((size_t)p->spp > s->ctx->fb.offsets_n) {
         CU(cudaStreamSynchronize(s->ctx->stream));
-        if (s->d_offsets) cudaFree(s->d_offsets);
-        s->d_offsets = nullptr;
-        CU(cudaMalloc((void **)&s->d_offsets, (size_t)p->spp * sizeof(float2)));
-        s->offsets_n = p->spp;
+        if (s->ctx->fb.d_offsets) cudaFree(s->ctx->fb.d_offsets);
+        s->ctx->fb.d_offsets = nullptr;
+        CU(cudaMalloc((void **)&s->ctx->fb.d_offsets, (size_t)p->spp * sizeof(float2)));
+        s->ctx->fb.offsets_n = p->spp;
     }
-    CU(cudaMemcpyAsync(s->d_offsets, off.data(), off.size() * sizeof(float2), cudaMemcpyHostToDevice, s->ctx->stream));
+    CU(cudaMemcpyAsync(s->ctx->fb.d_offsets, off.data(), off.size() * sizeof(float2), cudaMemcpyHostToDevice, s->ctx->stream));
     CU(cudaStreamSynchronize(s->ctx->stream)); // `off` is a local
-    F->sample_offsets = s->d_offsets;
+    F->sample_offsets = s->ctx->fb.d_offsets;
     return RTU_OK;
 }
 
@@ -598,14 +643,23 @@ int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_
 {
     rtu_context *c = s->ctx;
     int n_waves = 2 * F.shade_bounces + 1; // a Fresnel ray starts one wave after its sibling at every level
+    kt_begin(c, 2);
     launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
+    kt_end(c);
     s->launches++;
     int in_q = out_q;
     for (int w = 0; w < n_waves; w++) {
-        launch_reset_counts(c->stream, c->wb.q[1 - in_q].count, c->wb.aux[1 - in_q].count, c->wb.shadow.count, nullptr);
-        launch_wave_queue(c->cfg, c->stream, s->S, F, c->wb, in_q, accum, c->work + (*work_i)++);
+        launch_reset_counts(c->stream, c->wb.q[1 - in_q].count, c->wb.aux[1 - in_q].count, c->wb.shadow.count, c->wb.hits.count);
+        kt_begin(c, 1);
+        launch_extend_queue(c->cfg, c->stream, s->S, F, c->wb, in_q, accum, c->work + (*work_i)++);
+        kt_end(c);
+        kt_begin(c, 3);
+        launch_shade_queue(c->cfg, c->stream, s->S, F, c->wb, in_q, accum, c->work + (*work_i)++);
+        kt_end(c);
+        kt_begin(c, 2);
         launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
-        s->launches += 3;
+        kt_end(c);
+        s->launches += 4;
         in_q = 1 - in_q;
     }
     CU(cudaGetLastError());
@@ -641,29 +695,39 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
     float4 *accum = (float4 *)d_accum;
     if (!accum) {
         if ((rc = ensure_accum(s, npix))) return rc;
-        accum = s->accum;
+        accum = s->ctx->fb.accum;
     }
     int rows = F.row_end - F.row_begin;
     size_t per_sample = (size_t)((W + 7) / 8) * ((rows + 3) / 4) * 32;
     size_t chunk_samples = std::max<size_t>(1, c->chunk_rays / per_sample);
     size_t chunk_cap = std::max(per_sample, chunk_samples * per_sample);
     if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
-    size_t q_cap = chunk_cap * 2;
+    // Queue capacities: one entry per primary ray of a chunk.  A hit can spawn up to 3 rays, so no
+    // fixed factor is a bound; overflow is detected on the device (DCounters::overflow) and reported,
+    // and rtu_render retries with smaller chunks.  Scenes whose every pixel is glass need RTU_QUEUE_FACTOR=2.
+    size_t q_cap = (size_t)((double)chunk_cap * c->queue_factor);
+    if (q_cap < chunk_cap) q_cap = chunk_cap;
     size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
     if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
     size_t n_chunks = ((size_t)(s1 - s0) + chunk_samples - 1) / chunk_samples;
-    size_t launches_per_chunk = 2 + 2 * (size_t)(2 * F.shade_bounces + 1);
+    size_t launches_per_chunk = 3 + 3 * (size_t)(2 * F.shade_bounces + 1);
     if ((rc = ensure_work(c, n_chunks * launches_per_chunk + 8))) return rc;
     CU(cudaEventRecord(c->ev0, c->stream));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * sizeof(float4), c->stream));
     s->launches = 0;
+    kt_reset(c, (p->flags & RTU_FLAG_TIME_KERNELS) != 0);
     size_t wi = 0;
     for (int a = s0; a < s1; a += (int)chunk_samples) {
         int b = std::min<int>(s1, a + (int)chunk_samples);
-        launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, nullptr);
-        launch_wave_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, 0, accum, c->work + wi++);
-        s->launches += 2;
+        launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, c->wb.hits.count);
+        kt_begin(c, 0);
+        launch_extend_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, accum, c->work + wi++);
+        kt_end(c);
+        kt_begin(c, 3);
+        launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, accum, c->work + wi++);
+        kt_end(c);
+        s->launches += 3;
         if ((rc = run_waves(s, F, accum, 0, &wi))) return rc;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -681,24 +745,24 @@ int rtu_resolve(rtu_scene *s, const rtu_params *p, const float *d_accum, rtu_ima
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
     size_t npix = (size_t)W * H;
     if ((rc = ensure_image(s, npix))) return rc;
-    const float4 *accum = d_accum ? (const float4 *)d_accum : s->accum;
+    const float4 *accum = d_accum ? (const float4 *)d_accum : s->ctx->fb.accum;
     if (out->rgb || out->rgb8) {
         if (!accum) { rtu::set_error("rtu_resolve: nothing rendered yet"); return RTU_ERR_INVALID; }
-        launch_resolve(c->stream, accum, (int)npix, 0.f, p->spp, out->rgb ? s->d_rgb : nullptr, out->rgb8 ? s->d_rgb8 : nullptr);
-        if (out->rgb) CU(cudaMemcpyAsync(out->rgb, s->d_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, s->d_rgb8, npix * 3, cudaMemcpyDeviceToHost, c->stream));
+        launch_resolve(c->stream, accum, (int)npix, 0.f, p->spp, out->rgb ? s->ctx->fb.d_rgb : nullptr, out->rgb8 ? s->ctx->fb.d_rgb8 : nullptr);
+        if (out->rgb) CU(cudaMemcpyAsync(out->rgb, s->ctx->fb.d_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, s->ctx->fb.d_rgb8, npix * 3, cudaMemcpyDeviceToHost, c->stream));
     }
     if (out->z || out->z8 || out->node_id || out->face_id) {
         DCamera cam;
         make_camera(s->cam, W, H, &cam);
         // visibility at pixel centres: the z the reference meant to store (SURVEY A-3)
         if (!c->wb.counters) { if ((rc = ensure_scratch(c, 1024, 1024))) return rc; }
-        launch_primary_ids(c->cfg, c->stream, s->S, cam, s->d_z, s->d_node, s->d_face, c->wb.counters);
-        if (out->z8) launch_zimage(c->stream, s->d_z, (int)npix, c->zmm, s->d_z8);
-        if (out->z) CU(cudaMemcpyAsync(out->z, s->d_z, npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (out->z8) CU(cudaMemcpyAsync(out->z8, s->d_z8, npix, cudaMemcpyDeviceToHost, c->stream));
-        if (out->node_id) CU(cudaMemcpyAsync(out->node_id, s->d_node, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (out->face_id) CU(cudaMemcpyAsync(out->face_id, s->d_face, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        launch_primary_ids(c->cfg, c->stream, s->S, cam, s->ctx->fb.d_z, s->ctx->fb.d_node, s->ctx->fb.d_face, c->wb.counters);
+        if (out->z8) launch_zimage(c->stream, s->ctx->fb.d_z, (int)npix, c->zmm, s->ctx->fb.d_z8);
+        if (out->z) CU(cudaMemcpyAsync(out->z, s->ctx->fb.d_z, npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->z8) CU(cudaMemcpyAsync(out->z8, s->ctx->fb.d_z8, npix, cudaMemcpyDeviceToHost, c->stream));
+        if (out->node_id) CU(cudaMemcpyAsync(out->node_id, s->ctx->fb.d_node, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (out->face_id) CU(cudaMemcpyAsync(out->face_id, s->ctx->fb.d_face, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -721,9 +785,17 @@ int rtu_render(rtu_scene *s, const rtu_params *p, rtu_image *out)
         s->timed = true;
         return rc;
     }
-    if ((rc = rtu_render_device(s, p, nullptr, 1))) return rc;
-    DCounters hc;
-    if ((rc = check_overflow(s, &hc))) return rc;
+    // a queue overflow (see rtu_render_device) is retried with half the chunk and the same buffers
+    size_t saved_chunk = s->ctx->chunk_rays;
+    for (int attempt = 0;; attempt++) {
+        if ((rc = rtu_render_device(s, p, nullptr, 1))) break;
+        DCounters hc;
+        rc = check_overflow(s, &hc);
+        if (rc != RTU_ERR_UNSUPPORTED || attempt >= 5 || s->ctx->chunk_rays <= 65536) break;
+        s->ctx->chunk_rays /= 2;
+    }
+    s->ctx->chunk_rays = saved_chunk;
+    if (rc) return rc;
     return rtu_resolve(s, p, nullptr, out);
 }
 
@@ -737,11 +809,26 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
     CU(cudaStreamSynchronize(c->stream));
     DCounters hc;
     CU(cudaMemcpy(&hc, c->wb.counters, sizeof hc, cudaMemcpyDeviceToHost));
-    out->trace_rays = hc.trace_rays;
-    out->shadow_rays = hc.shadow_rays;
-    out->box_tests = hc.box_tests;
-    out->tri_tests = hc.tri_tests;
-    out->node_visits = hc.node_visits;
+    rtu_kernel_stats *ks[4] = {&out->primary_wave, &out->secondary_waves, &out->shadow_waves, &out->shade_kernels};
+    out->shade_kernels.launches = c->cls_launches[3];
+    for (int k = 0; k < 3; k++) {
+        const DCounterBlock &b = hc.k[k];
+        out->trace_rays += b.trace_rays;
+        out->shadow_rays += b.shadow_rays;
+        out->box_tests += b.box_tests;
+        out->tri_tests += b.tri_tests;
+        out->node_visits += b.node_visits;
+        ks[k]->rays = b.trace_rays + b.shadow_rays;
+        ks[k]->box_tests = b.box_tests;
+        ks[k]->tri_tests = b.tri_tests;
+        ks[k]->node_visits = b.node_visits;
+        ks[k]->launches = c->cls_launches[k];
+    }
+    for (size_t i = 0; i < c->kt_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->kt_ev[i * 2], c->kt_ev[i * 2 + 1]) == cudaSuccess) ks[c->kt_cls[i]]->ms += ms;
+    }
+    out->scene_device_bytes = s->device_bytes;
     out->kernel_launches = s->launches;
     if (s->timed) {
         float ms = 0;
@@ -816,6 +903,27 @@ int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int6
     return RTU_OK;
 }
 
+int rtu_selftest_division(rtu_context *c, uint32_t numerators_per_divisor, uint64_t seed, uint64_t *tested, uint64_t *mismatches)
+{
+    if (!c || !tested || !mismatches) { rtu::set_error("rtu_selftest_division: null argument"); return RTU_ERR_INVALID; }
+    CU(cudaSetDevice(c->device));
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc((void **)&d, 2 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), c->stream);
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) {
+        launch_selftest_div(c->stream, numerators_per_divisor, seed, d, d + 1);
+        e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d);
+    CU(e);
+    *mismatches = h[0];
+    *tested = h[1];
+    return RTU_OK;
+}
+
 int rtu_camera_rays(rtu_scene *s, const rtu_params *p, int32_t sample, rtu_ray *rays)
 {
     if (!s || !p || !rays) { rtu::set_error("rtu_camera_rays: null argument"); return RTU_ERR_INVALID; }
@@ -856,7 +964,7 @@ int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n,
     size_t q_cap = std::max<size_t>((size_t)n * 2, 1024);
     size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
     if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
-    if ((rc = ensure_work(c, 2 + 2 * (size_t)(2 * bounces + 1) + 8))) return rc;
+    if ((rc = ensure_work(c, 3 + 3 * (size_t)(2 * bounces + 1) + 8))) return rc;
     FrameSetup F;
     memset(&F, 0, sizeof F);
     F.cam.width = (int)n;

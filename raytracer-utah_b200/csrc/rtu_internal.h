@@ -27,16 +27,22 @@ struct WaveBuffers {
     RayQueue q[2];
     AuxPool aux[2];
     ShadowQueue shadow;
+    HitQueue hits;
     unsigned *work;       // device work-fetch counters (one per launch slot)
     DCounters *counters;
 };
 
-// one closest-hit + shade wave over generated primary rays: samples [s0,s1) of rows [row_begin,row_end)
-void launch_wave_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
-                         const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter);
-// one wave over queue q[in_q] -> q[1-in_q]
-void launch_wave_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
-                       int in_q, float4 *accum, unsigned *work_counter);
+// closest hit of generated primary rays: samples [s0,s1) of rows [row_begin,row_end) -> hit queue
+void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
+                           const WaveBuffers &B, float4 *accum, unsigned *work_counter);
+// shade the hit queue of a primary wave -> shadow queue + q[out_q]
+void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0,
+                          const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter);
+// closest hit of queue q[in_q] -> hit queue;  shade -> shadow queue + q[1-in_q]
+void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
+                         int in_q, float4 *accum, unsigned *work_counter);
+void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
+                        int in_q, float4 *accum, unsigned *work_counter);
 // any-hit over the shadow queue, adds unoccluded contributions to accum
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
                         unsigned *work_counter);
@@ -54,6 +60,8 @@ void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
 void launch_shade_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const rtu_ray *rays,
                         const rtu_hit *hits, long long n, const WaveBuffers &B, int out_q, float4 *accum);
 void launch_camera_rays(cudaStream_t st, const DCamera &cam, float ox, float oy, rtu_ray *rays);
+void launch_selftest_div(cudaStream_t st, unsigned per_thread, unsigned long long seed, unsigned long long *mismatch,
+                         unsigned long long *tested);
 // accum -> mean, gamma 1/2.2, Color24 (RenderFunctions.cpp:152-159)
 void launch_resolve(cudaStream_t st, const float4 *accum, int npix, float inv_unused, int spp, float *rgb, unsigned char *rgb8);
 // RenderImage::ComputeZBufferImage (scene.h:590-612)

@@ -1,25 +1,36 @@
-// sm_100a kernels of the render path.
+// sm_100a kernels of the render path: a wavefront of intersect / shade / any-hit kernels.
 //
-//   k_wave<true>    persistent threads; generates camera rays of a chunk of (sample, pixel)
-//                   work items on the fly, closest-hit + shade, appends shadow / secondary rays
-//   k_wave<false>   same, but the rays come from the previous wave's queue
-//   k_shadow_wave   persistent threads; any-hit over the shadow queue, adds unoccluded radiance
-//   k_primary_ids   pixel-centre visibility (ids + z)        k_trace_batch / k_shadow_batch /
-//   k_shade_first   batched operator entry points            k_resolve / k_zminmax / k_zimage
+//   k_extend<true>   persistent threads; generates the camera rays of a chunk of (sample, pixel)
+//                    work items on the fly and finds their closest hit (Trace); misses add the
+//                    background in place, hits are compacted into the hit queue (32 B records)
+//   k_extend<false>  same for the rays of the previous wave's queue (reflection / refraction /
+//                    Fresnel rays); misses add the environment term their parent would have added
+//   k_shade<..>      one MtlBlinn::Shade step per compacted hit: evaluates the hit record, appends
+//                    shadow rays (radiance-if-unoccluded) and the next wave's secondary rays
+//   k_shadow_wave    persistent threads; any-hit (ShadowTrace) over the shadow queue, adds the
+//                    unoccluded contributions to the accumulator
+//   k_primary_ids    pixel-centre visibility (ids + z)        k_trace_batch / k_shadow_batch /
+//   k_shade_first    batched operator entry points            k_resolve / k_zminmax / k_zimage
 //
-// Work distribution replaces PixelIterator's atomic ticket counter (PixelIterator.h:25-38):
-// each warp takes 32 consecutive tickets from a global counter until the wave is drained.
-// Grids are SM-count multiples (148 x blocks/SM), CTAs stay resident for the whole wave.
+// Traversal and shading are separate kernels so that the traversal kernels stay small (4 resident
+// CTAs of 256 threads per SM) and shading runs on dense warps of hits only.
+// Work distribution replaces PixelIterator's atomic ticket counter (PixelIterator.h:25-38): each
+// warp takes 32 consecutive tickets from a global counter until the wave is drained.  Grids are
+// SM-count multiples (148 x resident CTAs per SM, from the occupancy API); CTAs stay resident for
+// the whole wave.
 #include <cstdio>
 
 #include "rtu_internal.h"
 #include "shade.cuh"
 
 #define WAVE_THREADS 256
-#define WAVE_MIN_BLOCKS 2
+#ifndef EXT_BLOCKS
+#define EXT_BLOCKS 4 // resident CTAs per SM the traversal kernels are compiled for (register cap 64)
+#endif
 
-__device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *c)
+__device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *cc, int cls)
 {
+    DCounterBlock *c = &cc->k[cls];
     unsigned t = tl.trace, s = tl.shadow, b = tl.box, r = tl.tri, n = tl.node;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -61,22 +72,53 @@ __device__ __forceinline__ Ray camera_ray(const DCamera &C, int x, int y, float 
     return r;
 }
 
+// Work item -> (sample, pixel) of the primary wave: samples outermost, then 8x4 pixel tiles so
+// that the 32 lanes of a warp trace a compact bundle of camera rays.
+struct PrimaryMap {
+    int W, row_begin, row_end, tilesX;
+    unsigned perSample;
+    __device__ __forceinline__ void init(const FrameSetup &F)
+    {
+        W = F.cam.width;
+        row_begin = F.row_begin;
+        row_end = F.row_end;
+        tilesX = (W + 7) >> 3;
+        int tilesY = (row_end - row_begin + 3) >> 2;
+        perSample = (unsigned)(tilesX * tilesY) * 32u;
+    }
+    __device__ __forceinline__ bool decode(unsigned idx, int s0, int &s, int &x, int &y) const
+    {
+        unsigned sl = idx / perSample, t = idx - sl * perSample;
+        s = s0 + (int)sl;
+        unsigned tile = t >> 5, in5 = t & 31u;
+        int tx = (int)(tile % (unsigned)tilesX), ty = (int)(tile / (unsigned)tilesX);
+        x = tx * 8 + (int)(in5 & 7u);
+        y = row_begin + ty * 4 + (int)(in5 >> 3);
+        return x < W && y < row_end;
+    }
+};
+
+__device__ __forceinline__ Ray primary_ray(const FrameSetup &F, int s, int x, int y, int pixel)
+{
+    float2 off = __ldg(&F.sample_offsets[s]);
+    Rng rng;
+    rng.key = F.seed; rng.pixel = (unsigned)pixel; rng.path = (unsigned)s; rng.dim = 1000u;
+    return camera_ray(F.cam, x, y, off.x, off.y, &rng);
+}
+
+// ------------------------------------------------------------------ closest hit
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
-k_wave(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, WaveOut O, unsigned *work)
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum,
+         DCounters *counters, unsigned *work)
 {
     Tally tl = {0, 0, 0, 0, 0};
     const unsigned lane = threadIdx.x & 31u;
-    const int W = F.cam.width;
-    const int rows = F.row_end - F.row_begin;
-    const int tilesX = (W + 7) >> 3, tilesY = (rows + 3) >> 2;
-    const unsigned perSample = (unsigned)(tilesX * tilesY) * 32u;
+    PrimaryMap pm;
+    pm.init(F);
     unsigned total;
-    if (PRIMARY) total = perSample * (unsigned)(s1 - s0);
+    if (PRIMARY) total = pm.perSample * (unsigned)(s1 - s0);
     else { total = *in.count; if (total > in.cap) total = in.cap; }
-    ShadeParams SP;
-    SP.flags = F.flags;
-    SP.seed = F.seed;
 
     for (;;) {
         unsigned base = 0;
@@ -87,22 +129,89 @@ k_wave(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, WaveO
         if (idx >= total) continue;
 
         Ray ray;
+        int pixel = 0;
+        if (PRIMARY) {
+            int s, x, y;
+            if (!pm.decode(idx, s0, s, x, y)) continue;
+            pixel = y * pm.W + x;
+            ray = primary_ray(F, s, x, y, pixel);
+        } else {
+            float4 o = in.o[idx], d = in.d[idx];
+            ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+            ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+        }
+        Best B;
+        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        tl.trace++;
+        scene_hit<false>(S, ray, B, tl);
+
+        if (B.node >= 0) {
+            unsigned slot = warp_alloc(hq.count, true);
+            if (slot >= hq.cap) { counters->overflow = 1; continue; }
+            hq.a[slot] = make_float4(B.z, __int_as_float(B.node), __int_as_float(B.front), __int_as_float(B.slot));
+            hq.b[slot] = make_float4(B.bc1, B.bc2, B.bc3, __uint_as_float(idx));
+            continue;
+        }
+        // what the recursion adds when Trace() misses
+        Col c = mk(0, 0, 0);
+        if (PRIMARY) {
+            int py = pixel / pm.W, px = pixel - py * pm.W;
+            c = background_sample(S, px, py, pm.W, F.cam.height);                     // RenderFunctions.cpp:145
+        } else {
+            float4 w = in.w[idx];
+            pixel = __float_as_int(in.o[idx].w);
+            int kind = (int)(__float_as_uint(in.d[idx].w) & 7u);
+            int aux = __float_as_int(w.w);
+            Col Wt = mk(w.x, w.y, w.z);
+            if (kind == RK_REFRACT) {
+                c = Wt * environment_sample(S, ray.dx, ray.dy, ray.dz);               // mtlFunctions.cpp:267
+            } else if (kind == RK_REFLECT || kind == RK_FRESNEL) {
+                Col wm = Wt;
+                if (aux >= 0) { float4 a = inaux.a[aux]; wm = mk(a.x, a.y, a.z); }
+                c = wm * environment_sample(S, ray.dx, ray.dy, ray.dz);               // :250, :289
+            }
+        }
+        accum_add(accum, pixel, c);
+    }
+    flush_tally(tl, counters, PRIMARY ? 0 : 1);
+}
+
+// ------------------------------------------------------------------ shade the compacted hits
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WAVE_THREADS, 2)
+k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq, WaveOut O, unsigned *work)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    PrimaryMap pm;
+    pm.init(F);
+    unsigned total = *hq.count;
+    if (total > hq.cap) total = hq.cap;
+    ShadeParams SP;
+    SP.flags = F.flags;
+    SP.seed = F.seed;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        unsigned h = base + lane;
+        if (h >= total) continue;
+        float4 ha = hq.a[h], hb = hq.b[h];
+        Best B;
+        B.z = ha.x; B.node = __float_as_int(ha.y); B.front = __float_as_int(ha.z); B.slot = __float_as_int(ha.w);
+        B.bc1 = hb.x; B.bc2 = hb.y; B.bc3 = hb.z;
+        unsigned idx = __float_as_uint(hb.w);
+
+        Ray ray;
         Col Wt;
         int pixel, kind, bounce, mtl, aux;
         unsigned path;
         if (PRIMARY) {
-            unsigned sl = idx / perSample, t = idx - sl * perSample;
-            int s = s0 + (int)sl;
-            unsigned tile = t >> 5, in5 = t & 31u;
-            int tx = (int)(tile % (unsigned)tilesX), ty = (int)(tile / (unsigned)tilesX);
-            int x = tx * 8 + (int)(in5 & 7u), y = F.row_begin + ty * 4 + (int)(in5 >> 3);
-            if (x >= W || y >= F.row_end) continue;
-            pixel = y * W + x;
-            float2 off = __ldg(&F.sample_offsets[s]);
+            int s, x, y;
+            pm.decode(idx, s0, s, x, y);
+            pixel = y * pm.W + x;
+            ray = primary_ray(F, s, x, y, pixel);
             path = (unsigned)s;
-            Rng rng;
-            rng.key = F.seed; rng.pixel = (unsigned)pixel; rng.path = path; rng.dim = 1000u;
-            ray = camera_ray(F.cam, x, y, off.x, off.y, &rng);
             Wt = mk(1.f, 1.f, 1.f);
             kind = RK_PRIMARY; bounce = F.shade_bounces; mtl = 0; aux = -1;
         } else {
@@ -116,28 +225,6 @@ k_wave(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, WaveO
             Wt = mk(w.x, w.y, w.z);
             aux = __float_as_int(w.w);
         }
-
-        Best B;
-        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
-        tl.trace++;
-        scene_hit<false>(S, ray, B, tl);
-
-        if (B.node < 0) {
-            // what the recursion adds when Trace() misses
-            Col c = mk(0, 0, 0);
-            if (kind == RK_PRIMARY) {
-                int py = pixel / W, px = pixel - py * W;
-                c = Wt * background_sample(S, px, py, W, F.cam.height);            // RenderFunctions.cpp:145
-            } else if (kind == RK_REFRACT) {
-                c = Wt * environment_sample(S, ray.dx, ray.dy, ray.dz);           // mtlFunctions.cpp:267
-            } else if (kind == RK_REFLECT || kind == RK_FRESNEL) {
-                Col wm = Wt;
-                if (aux >= 0) { float4 a = inaux.a[aux]; wm = mk(a.x, a.y, a.z); }
-                c = wm * environment_sample(S, ray.dx, ray.dy, ray.dz);           // :250, :289
-            }
-            accum_add(O.accum, pixel, c);
-            continue;
-        }
         HitRec H;
         finalize_hit(S, ray, B, H);
         if (kind == RK_REFRACT) {
@@ -150,7 +237,7 @@ k_wave(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, WaveO
                 ab = mk(expf((-H.z) * PM.absorption[0]), expf((-H.z) * PM.absorption[1]), expf((-H.z) * PM.absorption[2]));
             }
             Col Wh = (Wt * (ab * Kt)) * (float)(1.0 - (double)Fr);                 // :264
-            // Fresnel mirror ray exists only because the refracted ray hit (:234-251)
+            // the Fresnel mirror ray exists only because the refracted ray hit (:234-251)
             Col Wf = Wt * Fr;
             Col WfKt = Wf * Kt;
             if (!((F.flags & 2u) && !nonblack(Wf))) {
@@ -169,10 +256,10 @@ k_wave(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, WaveO
             shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wt, bounce, pixel, path);
         }
     }
-    flush_tally(tl, O.counters);
 }
 
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+// ------------------------------------------------------------------ any hit
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
 {
     Tally tl = {0, 0, 0, 0, 0};
@@ -186,7 +273,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         if (base >= total) break;
         unsigned idx = base + lane;
         if (idx >= total) continue;
-        float4 o = Q.o[idx], d = Q.d[idx], c = Q.c[idx];
+        float4 o = Q.o[idx], d = Q.d[idx];
         Ray ray;
         ray.px = o.x; ray.py = o.y; ray.pz = o.z;
         ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
@@ -195,9 +282,10 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         tl.shadow++;
         bool occ = scene_hit<true>(S, ray, B, tl);
         if (occ && B.z > 0.0f) continue;                                                // :31-35
+        float4 c = Q.c[idx];
         accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
     }
-    flush_tally(tl, counters);
+    flush_tally(tl, counters, 2);
 }
 
 __global__ void k_reset_counts(unsigned *a, unsigned *b, unsigned *c, unsigned *d)
@@ -208,7 +296,7 @@ __global__ void k_reset_counts(unsigned *a, unsigned *b, unsigned *c, unsigned *
     if (d) *d = 0;
 }
 
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_primary_ids(DScene S, DCamera C, float *z, int *node, int *face, DCounters *counters)
 {
     Tally tl = {0, 0, 0, 0, 0};
@@ -231,10 +319,10 @@ k_primary_ids(DScene S, DCamera C, float *z, int *node, int *face, DCounters *co
             face[p] = f;
         }
     }
-    flush_tally(tl, counters);
+    flush_tally(tl, counters, 0);
 }
 
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WAVE_THREADS, 2)
 k_trace_batch(DScene S, const rtu_ray *rays, long long n, rtu_hit *hits, DCounters *counters)
 {
     Tally tl = {0, 0, 0, 0, 0};
@@ -256,10 +344,10 @@ k_trace_batch(DScene S, const rtu_ray *rays, long long n, rtu_hit *hits, DCounte
         o.node = H.node; o.face = H.face; o.front = H.front;
         hits[i] = o;
     }
-    flush_tally(tl, counters);
+    flush_tally(tl, counters, 0);
 }
 
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_shadow_batch(DScene S, const rtu_ray *rays, const float *tmax, long long n, unsigned char *occ, DCounters *counters)
 {
     Tally tl = {0, 0, 0, 0, 0};
@@ -273,11 +361,11 @@ k_shadow_batch(DScene S, const rtu_ray *rays, const float *tmax, long long n, un
         bool h = scene_hit<true>(S, ray, B, tl);
         occ[i] = (h && B.z > 0.0f) ? 1 : 0;
     }
-    flush_tally(tl, counters);
+    flush_tally(tl, counters, 2);
 }
 
 // First Shade() step on caller-provided hits (rtu_shade); pixel index = ray index.
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WAVE_THREADS, 2)
 k_shade_first(DScene S, FrameSetup F, const rtu_ray *rays, const rtu_hit *hits, long long n, WaveOut O)
 {
     ShadeParams SP;
@@ -371,7 +459,17 @@ __global__ void k_zimage(const float *z, int npix, const unsigned *mm, unsigned 
 }
 
 // ------------------------------------------------------------------ launch wrappers
-static inline int wave_grid(const LaunchCfg &cfg) { return cfg.sm_count * cfg.blocks_per_sm; }
+// grid = SM count x CTAs that are actually resident per SM for that kernel (occupancy API, cached)
+template <class K> static int resident_grid(const LaunchCfg &cfg, K kernel, int *cache)
+{
+    if (*cache == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WAVE_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+        if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
+        *cache = n;
+    }
+    return cfg.sm_count * *cache;
+}
 
 static WaveOut make_out(const WaveBuffers &B, int out_q, float4 *accum)
 {
@@ -384,24 +482,44 @@ static WaveOut make_out(const WaveBuffers &B, int out_q, float4 *accum)
     return O;
 }
 
-void launch_wave_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
-                         const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter)
+void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
+                           const WaveBuffers &B, float4 *accum, unsigned *work_counter)
 {
-    WaveOut O = make_out(B, out_q, accum);
-    k_wave<true><<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1 - out_q], B.aux[1 - out_q], O, work_counter);
+    static int occ = 0;
+    k_extend<true><<<resident_grid(cfg, k_extend<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1], B.aux[1], B.hits, accum,
+                                                                                     B.counters, work_counter);
 }
 
-void launch_wave_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
-                       int in_q, float4 *accum, unsigned *work_counter)
+void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0,
+                          const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter)
 {
+    static int occ = 0;
+    WaveOut O = make_out(B, out_q, accum);
+    k_shade<true><<<resident_grid(cfg, k_shade<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, B.q[1 - out_q], B.aux[1 - out_q], B.hits, O,
+                                                                                   work_counter);
+}
+
+void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
+                         int in_q, float4 *accum, unsigned *work_counter)
+{
+    static int occ = 0;
+    k_extend<false><<<resident_grid(cfg, k_extend<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum,
+                                                                                       B.counters, work_counter);
+}
+
+void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
+                        int in_q, float4 *accum, unsigned *work_counter)
+{
+    static int occ = 0;
     WaveOut O = make_out(B, 1 - in_q, accum);
-    k_wave<false><<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], O, work_counter);
+    k_shade<false><<<resident_grid(cfg, k_shade<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, B.q[in_q], B.aux[in_q], B.hits, O, work_counter);
 }
 
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
                         unsigned *work_counter)
 {
-    k_shadow_wave<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
+    static int occ = 0;
+    k_shadow_wave<<<resident_grid(cfg, k_shadow_wave, &occ), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
 }
 
 void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d)
@@ -412,26 +530,75 @@ void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c,
 void launch_primary_ids(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const DCamera &cam, float *z, int *node,
                         int *face, DCounters *counters)
 {
-    k_primary_ids<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, cam, z, node, face, counters);
+    static int occ = 0;
+    k_primary_ids<<<resident_grid(cfg, k_primary_ids, &occ), WAVE_THREADS, 0, st>>>(S, cam, z, node, face, counters);
 }
 
 void launch_trace_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, long long n,
                         rtu_hit *hits, DCounters *counters)
 {
-    k_trace_batch<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, rays, n, hits, counters);
+    static int occ = 0;
+    k_trace_batch<<<resident_grid(cfg, k_trace_batch, &occ), WAVE_THREADS, 0, st>>>(S, rays, n, hits, counters);
 }
 
 void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
-                         long long n, unsigned char *occ, DCounters *counters)
+                         long long n, unsigned char *occl, DCounters *counters)
 {
-    k_shadow_batch<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, rays, tmax, n, occ, counters);
+    static int occ = 0;
+    k_shadow_batch<<<resident_grid(cfg, k_shadow_batch, &occ), WAVE_THREADS, 0, st>>>(S, rays, tmax, n, occl, counters);
 }
 
 void launch_shade_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const rtu_ray *rays,
                         const rtu_hit *hits, long long n, const WaveBuffers &B, int out_q, float4 *accum)
 {
+    static int occ = 0;
     WaveOut O = make_out(B, out_q, accum);
-    k_shade_first<<<wave_grid(cfg), WAVE_THREADS, 0, st>>>(S, F, rays, hits, n, O);
+    k_shade_first<<<resident_grid(cfg, k_shade_first, &occ), WAVE_THREADS, 0, st>>>(S, F, rays, hits, n, O);
+}
+
+// Self-test of div_hoisted(): thread t owns divisor mantissa t (all 2^23 of them); for a spread of
+// divisor exponents inside the window and `per_thread` hashed numerators (plus the all-zero /
+// all-one mantissas) it compares the hoisted quotient with the compiler's IEEE `a / b`, bit for bit.
+__global__ void k_selftest_div(unsigned per_thread, unsigned long long seed, unsigned long long *mismatch, unsigned long long *tested)
+{
+    unsigned man = blockIdx.x * blockDim.x + threadIdx.x;
+    if (man >= (1u << 23)) return;
+    const int bexp[9] = {-40, -20, -3, -1, 0, 1, 3, 20, 40};
+    unsigned long long bad = 0, n = 0;
+    unsigned long long h = seed ^ (0x9E3779B97F4A7C15ULL * (man + 1));
+    for (int e = 0; e < 9; e++) {
+        float b = __uint_as_float(((unsigned)(127 + bexp[e]) << 23) | man);
+        if (e & 1) b = -b;
+        float y = rcp_refined(b);
+        for (unsigned k = 0; k < per_thread; k++) {
+            h ^= h >> 12; h ^= h << 25; h ^= h >> 27;
+            unsigned long long r = h * 2685821657736338717ULL;
+            unsigned am = (unsigned)(r >> 41);
+            if (k == 0) am = 0;
+            if (k == 1) am = 0x7fffffu;
+            if (k == 2) am = man;
+            int ae = (int)((r >> 8) % 121u) - 60;
+            float a = __uint_as_float(((unsigned)(127 + ae) << 23) | am | ((unsigned)(r & 1u) << 31));
+            float q = div_hoisted(a, b, y);
+            float d = a / b;
+            bad += __float_as_uint(q) != __float_as_uint(d);
+            n++;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(mismatch, bad);
+        atomicAdd(tested, n);
+    }
+}
+
+void launch_selftest_div(cudaStream_t st, unsigned per_thread, unsigned long long seed, unsigned long long *mismatch,
+                         unsigned long long *tested)
+{
+    k_selftest_div<<<(1u << 23) / 256, 256, 0, st>>>(per_thread, seed, mismatch, tested);
 }
 
 void launch_camera_rays(cudaStream_t st, const DCamera &cam, float ox, float oy, rtu_ray *rays)

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))          # raytracer-utah_b200/
 REPO_ROOT = os.path.dirname(PKG_ROOT)
-LIB_PATH = os.path.join(PKG_ROOT, "librtu_b200.so")
+LIB_PATH = os.environ.get("RTU_B200_LIB") or os.path.join(PKG_ROOT, "librtu_b200.so")  # override: tuning variants only
 SCENES = os.path.join(REPO_ROOT, "scenes")
 BIGFLOAT = np.float32(1.0e30)
 
@@ -23,6 +23,8 @@ LIGHT_AMBIENT, LIGHT_DIRECT, LIGHT_POINT = 0, 1, 2
 MODE_PRIMARY, MODE_WHITTED, MODE_PATH = 0, 1, 2
 PATTERN_CENTER, PATTERN_REFERENCE = 0, 1
 FLAG_CULL_NULL_SHADOW_RAYS = 1
+FLAG_CULL_ZERO_WEIGHT_RAYS = 2
+FLAG_TIME_KERNELS = 4
 
 f32, i32, u32, u8 = C.c_float, C.c_int32, C.c_uint32, C.c_uint8
 PF, PU, PB = C.POINTER(f32), C.POINTER(u32), C.POINTER(u8)
@@ -87,13 +89,26 @@ class Image(C.Structure):
                 ("node_id", C.POINTER(i32)), ("face_id", C.POINTER(i32))]
 
 
-class Stats(C.Structure):
-    _fields_ = [("trace_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("box_tests", C.c_uint64),
-                ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("device_ms", C.c_double), ("trace_kernel_ms", C.c_double), ("shadow_kernel_ms", C.c_double)]
+class KernelStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("node_visits", C.c_uint64), ("launches", C.c_uint64), ("ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Stats(C.Structure):
+    _fields_ = [("trace_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("box_tests", C.c_uint64),
+                ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("device_ms", C.c_double), ("primary_wave", KernelStats), ("secondary_waves", KernelStats),
+                ("shadow_waves", KernelStats), ("shade_kernels", KernelStats), ("scene_device_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        out = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            out[k] = v.as_dict() if isinstance(v, KernelStats) else v
+        return out
 
 
 RAY_DTYPE = np.dtype([("p", "<f4", 3), ("dir", "<f4", 3)])
@@ -221,6 +236,14 @@ class Context:
         self._h = C.c_void_p()
         L.rtu_context_create.argtypes = [i32, C.c_void_p, C.POINTER(C.c_void_p)]
         _check(L.rtu_context_create(device, C.c_void_p(stream or 0), C.byref(self._h)), "rtu_context_create")
+
+    def selftest_division(self, numerators_per_divisor=64, seed=1):
+        """rtu_selftest_division: (pairs tested, bitwise mismatches) of the hoisted-reciprocal quotient vs a / b."""
+        L = lib()
+        t, m = C.c_uint64(0), C.c_uint64(0)
+        L.rtu_selftest_division.argtypes = [C.c_void_p, u32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _check(L.rtu_selftest_division(self._h, numerators_per_divisor, seed, C.byref(t), C.byref(m)), "rtu_selftest_division")
+        return t.value, m.value
 
     def synchronize(self):
         L = lib()

@@ -61,6 +61,14 @@ def check_kat(rtu, gpu_ctx, prim, kind, mesh_from=None):
         sc.close()
 
 
+def test_hoisted_division_is_ieee_division(rtu, gpu_ctx):
+    """The BVH loop's quotients (reciprocal hoisted per ray, 3 FFMA each) equal `a / b` bit for bit:
+    every divisor mantissa x 9 divisor exponents x 113 numerators = 2^33 pairs."""
+    tested, bad = gpu_ctx.selftest_division(113, seed=20261018)
+    assert tested == (1 << 23) * 9 * 113
+    assert bad == 0
+
+
 def test_kat_sphere(rtu, gpu_ctx):
     check_kat(rtu, gpu_ctx, "sphere", rtu.OBJ_SPHERE)
 
