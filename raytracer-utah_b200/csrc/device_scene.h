@@ -108,6 +108,8 @@ struct DCamera {
 
 struct DScene {
     const DNode *nodes;
+    const float4 *bounds; // per node: bounding sphere of the object's bound box in root space (xyz, r^2 inflated);
+                          // w = -1: no object, w = -2: object that can never be hit (empty mesh)
     int32_t n_nodes;
     int32_t flat;        // 1: every object node hangs directly off the root
     const DMesh *meshes;

@@ -445,8 +445,48 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
         if (n.kind == RTU_OBJ_MESH && (n.mesh < 0 || n.mesh >= d->n_meshes)) { rtu::set_error("rtu_scene_upload: bad mesh index"); return fail(RTU_ERR_INVALID); }
         if (n.kind < 0 || n.kind > 3) { rtu::set_error("rtu_scene_upload: bad object kind"); return fail(RTU_ERR_INVALID); }
     }
+    if (d->nodes[0].kind != RTU_OBJ_NONE) { rtu::set_error("rtu_scene_upload: the root node cannot hold an object (rootNode never does)"); return fail(RTU_ERR_UNSUPPORTED); }
     DNode *dn = nullptr;
     if ((rc = dev_upload(nodes, &dn, c->stream, sc->owned))) return fail(rc);
+    // bounding spheres for the conservative cull (traverse.cuh), in root space, evaluated in double
+    std::vector<float4> bounds(d->n_nodes);
+    for (int i = 0; i < d->n_nodes; i++) {
+        const rtu_node &n = d->nodes[i];
+        bounds[i] = make_float4(0, 0, 0, -1.f);
+        if (n.kind == RTU_OBJ_NONE) continue;
+        double lo[3] = {-1, -1, -1}, hi[3] = {1, 1, 1};
+        if (n.kind == RTU_OBJ_PLANE) { lo[2] = hi[2] = 0; }
+        if (n.kind == RTU_OBJ_MESH) {
+            const rtu_mesh &m = d->meshes[n.mesh];
+            if (m.nf == 0 || m.bvh_nodes < 2) { bounds[i].w = -2.f; continue; }
+            for (int k = 0; k < 3; k++) { lo[k] = m.bound_min[k]; hi[k] = m.bound_max[k]; }
+        }
+        auto to_root = [&](double p[3]) { // FromNodeCoords chain up to (not including) the root
+            for (int a = i; a > 0; a = d->nodes[a].parent) {
+                const rtu_node &t = d->nodes[a];
+                double q[3];
+                for (int r = 0; r < 3; r++) q[r] = (double)t.tm[r] * p[0] + (double)t.tm[3 + r] * p[1] + (double)t.tm[6 + r] * p[2] + (double)t.pos[r];
+                p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+            }
+        };
+        double ctr[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+        to_root(ctr);
+        double r2 = 0;
+        bool finite = std::isfinite(ctr[0]) && std::isfinite(ctr[1]) && std::isfinite(ctr[2]);
+        for (int corner = 0; corner < 8 && finite; corner++) {
+            double p[3] = {(corner & 1) ? hi[0] : lo[0], (corner & 2) ? hi[1] : lo[1], (corner & 4) ? hi[2] : lo[2]};
+            to_root(p);
+            double dx = p[0] - ctr[0], dy = p[1] - ctr[1], dz = p[2] - ctr[2];
+            double q = dx * dx + dy * dy + dz * dz;
+            if (!std::isfinite(q)) finite = false;
+            r2 = std::max(r2, q);
+        }
+        if (!finite) { bounds[i].w = 3.0e38f; continue; } // never culls
+        double rad = std::sqrt(r2) * 1.002 + 1e-5 * (std::fabs(ctr[0]) + std::fabs(ctr[1]) + std::fabs(ctr[2]) + 1.0);
+        bounds[i] = make_float4((float)ctr[0], (float)ctr[1], (float)ctr[2], (float)std::min(rad * rad, 3.0e38));
+    }
+    float4 *db = nullptr;
+    if ((rc = dev_upload(bounds, &db, c->stream, sc->owned))) return fail(rc);
     // meshes
     std::vector<DMesh> meshes(d->n_meshes);
     for (int i = 0; i < d->n_meshes; i++)
@@ -519,6 +559,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
 
     DScene &S = sc->S;
     S.nodes = dn;
+    S.bounds = db;
     S.n_nodes = d->n_nodes;
     S.flat = flat;
     S.meshes = dm;

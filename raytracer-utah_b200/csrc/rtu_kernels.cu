@@ -25,7 +25,7 @@
 
 #define WAVE_THREADS 256
 #ifndef EXT_BLOCKS
-#define EXT_BLOCKS 4 // resident CTAs per SM the traversal kernels are compiled for (register cap 64)
+#define EXT_BLOCKS 2 // resident CTAs per SM the traversal kernels are compiled for (measured best of 2/3/4 on B200)
 #endif
 
 __device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *cc, int cls)
