@@ -44,6 +44,7 @@ Point3 RefCalculateImageOrigin(float d);
 Point3 RefCalculateCurrentPoint(int i, int j, float ox, float oy, Point3 o);
 void RefRender(PixelIterator &it);
 float BVHBoxIntersection(const Ray &r, Box bvhBox, float t_max);
+int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pattern, double *device_ms, unsigned long long *rays);
 
 // ---------------------------------------------------------------- npy output
 static void WriteNpy(const std::string &path, const void *data, const char *descr,
@@ -154,7 +155,7 @@ static Ray CameraRay(int x, int y, float offX, float offY, float camOffsetX, flo
 
 // ---------------------------------------------------------------- options
 struct Opts {
-    std::string scene, root = ".", mode = "primary", out = "out", pattern = "center";
+    std::string scene, root = ".", mode = "primary", out = "out", pattern = "center", lib = "raytracer-utah_b200/librtu_b200.so";
     int width = 0, height = 0, spp = 1, threads = 1, bounces = 5, n = 100000, seed = 1;
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
     int s0 = 0, s1 = -1;   // --samples a b: only samples [a,b) of the spp-sample pattern (bounded CPU-baseline runs)
@@ -531,6 +532,26 @@ static void ModeTex(const Opts &o)
     fprintf(stderr, "{\"mode\":\"tex\",\"n\":%d}\n", n);
 }
 
+// The reference binary with its render loop replaced by librtu_b200.so (oracle/ref/rtu_binding.cpp):
+// LoadScene() and the PNG writers are the reference's own.
+static void ModeGpu(const Opts &o)
+{
+    double ms = 0;
+    unsigned long long rays = 0;
+    int rc = RtuBeginRender(o.lib.c_str(), o.spp, o.bounces, o.pattern != "center", &ms, &rays);
+    if (rc) exit(rc);
+    int W = camera.imgWidth, H = camera.imgHeight;
+    renderImage.SaveImage((o.out + "_Result.png").c_str());        // main.cpp:59
+    renderImage.ComputeZBufferImage();                             // main.cpp:60
+    renderImage.SaveZImage((o.out + "_ZBuffer.png").c_str());      // main.cpp:61
+    std::vector<unsigned char> rgb8((size_t)W * H * 3), z8((size_t)W * H);
+    memcpy(rgb8.data(), renderImage.GetPixels(), rgb8.size());
+    memcpy(z8.data(), renderImage.GetZBufferImage(), z8.size());
+    NpyU8(o.out + "_rgb8.npy", rgb8, {(size_t)H, (size_t)W, 3});
+    NpyU8(o.out + "_z8.npy", z8, {(size_t)H, (size_t)W});
+    fprintf(stderr, "{\"mode\":\"gpu\",\"width\":%d,\"height\":%d,\"spp\":%d,\"rays\":%llu,\"device_ms\":%.3f}\n", W, H, o.spp, rays, ms);
+}
+
 int main(int argc, char **argv)
 {
     Opts o;
@@ -551,6 +572,7 @@ int main(int argc, char **argv)
         else if (a == "--samples") { o.s0 = atoi(next()); o.s1 = atoi(next()); }
         else if (a == "--crop") { o.x0 = atoi(next()); o.y0 = atoi(next()); o.x1 = atoi(next()); o.y1 = atoi(next()); }
         else if (a == "--verbose") o.quiet = false;
+        else if (a == "--lib") o.lib = next();
         else if (a[0] != '-') o.scene = a;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -565,6 +587,7 @@ int main(int argc, char **argv)
     auto absolutize = [&](const std::string &p) { return (p.empty() || p[0] == '/' || p == "-") ? p : std::string(cwd) + "/" + p; };
     o.scene = absolutize(o.scene);
     o.out = absolutize(o.out);
+    o.lib = absolutize(o.lib);
     if (chdir(o.root.c_str()) != 0) { fprintf(stderr, "cannot chdir to %s\n", o.root.c_str()); return 2; }
     int savedStdout = -1;
     if (o.quiet) { fflush(stdout); savedStdout = dup(1); FILE *nul = fopen("/dev/null", "w"); dup2(fileno(nul), 1); }
@@ -582,6 +605,7 @@ int main(int argc, char **argv)
     else if (o.mode == "kat") ModeKat(o);
     else if (o.mode == "tex") ModeTex(o);
     else if (o.mode == "dump") ModeDump(o);
+    else if (o.mode == "gpu") ModeGpu(o);
     else { fprintf(stderr, "unknown mode %s\n", o.mode.c_str()); return 2; }
     return 0;
 }

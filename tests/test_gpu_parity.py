@@ -228,6 +228,32 @@ def test_shade_operator_matches_render(rtu, gpu_ctx):
         hs.close()
 
 
+def test_reference_binary_with_our_library(rtu, tmp_path):
+    """the reference binary (its LoadScene, its RenderImage, its PNG writer) with the render
+    loop replaced by librtu_b200.so reproduces the pixels it computes itself on the CPU."""
+    import subprocess
+    from conftest import ROOT
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        pytest.skip("oracle/_ref/ref_harness was not shipped to this box")
+    g, meta = load_golden("whitted_p4")
+    gp, _ = load_golden("primary_p4")
+    pre = str(tmp_path / "it")
+    subprocess.run([harness, os.path.join(SCENES, meta["scene"]), "--root", SCENES, "--mode", "gpu", "--width", str(meta["width"]),
+                    "--height", str(meta["height"]), "--lib", rtu.LIB_PATH, "--out", pre], check=True, stdout=subprocess.DEVNULL)
+    rgb8 = np.load(pre + "_rgb8.npy")
+    assert np.abs(rgb8.astype(np.int32) - g["rgb8"].astype(np.int32)).max() <= 1
+    # ZBuffer.png greys computed by the reference's ComputeZBufferImage from the z we wrote into its buffer
+    z = gp["z"]
+    hit = z != BIG
+    zmin, zmax = np.float32(z[hit].min()), np.float32(z[hit].max())
+    ref8 = np.clip((((zmax - z) / np.float32(zmax - zmin)).astype(np.float32) * np.float32(255)).astype(np.int64), 0, 255).astype(np.uint8)
+    ref8[~hit] = 0
+    assert np.array_equal(np.load(pre + "_z8.npy"), ref8)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(pre + "_Result.png")), rgb8)
+
+
 def test_errors_are_reported_not_swallowed(rtu, gpu_ctx):
     hs = rtu.HostScene(os.path.join(SCENES, "Project1Test.xml"))
     sc = rtu.Scene(gpu_ctx, hs.desc)
