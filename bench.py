@@ -28,7 +28,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "raytracer-utah_b200", "python"))
 
-SCENE = "Teapot/scene2.xml"
+SCENE = "Teapot/scene2.xml"   # default workload; --scene / --mode select the GI workload of BASELINE config 4
+MODE = "whitted"
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # dram bytes per launch of the dominant kernel from profiles/ (ncu --set full); None until captured
@@ -88,6 +89,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _mode_id(R):
+    return R.MODE_PATH if MODE == "path" else R.MODE_WHITTED
+
+
 def run_harness(width, height, spp, s0, s1, threads=0):
     cmd = [HARNESS, os.path.join(ROOT, "scenes", SCENE), "--root", os.path.join(ROOT, "scenes"), "--mode", "whitted",
            "--width", str(width), "--height", str(height), "--spp", str(spp), "--pattern", "ref",
@@ -102,7 +107,7 @@ def run_port(width, height, spp, s0, s1):
     import oracle_py
     import rtu_b200 as R
     hs = R.HostScene(os.path.join(R.SCENES, SCENE))
-    p = R.default_params(width=width, height=height, spp=spp, pattern=R.PATTERN_REFERENCE, mode=R.MODE_WHITTED,
+    p = R.default_params(width=width, height=height, spp=spp, pattern=R.PATTERN_REFERENCE, mode=_mode_id(R),
                          sample_begin=s0, sample_end=s1)
     o = oracle_py.render(hs.desc, params=p, want=("rgb",))
     st = o["stats"]
@@ -112,7 +117,9 @@ def run_port(width, height, spp, s0, s1):
 
 def cpu_sample(width, height, spp, target_seconds=12.0):
     """Times the reference's CPU implementation on a bounded sample of the workload."""
-    kind = "reference" if os.path.exists(HARNESS) else "port"
+    # the reference binary's headless modes cover Whitted frames; its GI estimator is only reachable through
+    # Render() at a fixed 1024 spp, so the GI workload is timed with the C port
+    kind = "reference" if (os.path.exists(HARNESS) and MODE == "whitted") else "port"
     fn = run_harness if kind == "reference" else run_port
     probe = fn(width, height, spp, 0, 1)
     k = int(max(1, min(spp, target_seconds / max(probe["seconds"], 1e-3))))
@@ -148,8 +155,9 @@ def reference_arm(args):
 
 
 def workload_config(args, n, note=None):
-    c = {"workload": "%s %dx%d Whitted (Blinn + shadow + reflection/refraction, 5 bounces), %d spp/GPU, reference Halton(4,5) pattern"
-         % (SCENE, args.width, args.height, args.spp),
+    what = "Whitted (Blinn + shadow + reflection/refraction, 5 bounces)" if MODE == "whitted" else \
+        "HEAD estimator (4-bounce MonteCarlo GI + Whitted, RenderFunctions.cpp:129-135)"
+    c = {"workload": "%s %dx%d %s, %d spp/GPU, reference Halton(4,5) pattern" % (SCENE, args.width, args.height, what, args.spp),
          "scene": SCENE, "width": args.width, "height": args.height, "spp_per_gpu": args.spp, "spp_total": args.spp * n,
          "parallelism": "spp-sliced x%d%s" % (n, " + ncclReduce(FP32 accum) to rank 0" if n > 1 else ""),
          "l2": "flushed (256 MiB device write) between timed steps",
@@ -184,7 +192,7 @@ def ours(args):
     accum = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     p = R.default_params(width=W, height=H, spp=spp * world, sample_begin=rank * spp, sample_end=(rank + 1) * spp,
-                         pattern=R.PATTERN_REFERENCE, mode=R.MODE_WHITTED, shade_bounces=5)
+                         pattern=R.PATTERN_REFERENCE, mode=_mode_id(R), shade_bounces=5, gi_bounces=4)
 
     def step():
         sc.render_device(p, accum.data_ptr(), clear=True)
@@ -266,7 +274,7 @@ def ours(args):
 
     # ---- roofline of the dominant kernel: one extra frame with per-launch CUDA events
     pk = R.default_params(width=W, height=H, spp=spp * world, sample_begin=rank * spp, sample_end=(rank + 1) * spp,
-                          pattern=R.PATTERN_REFERENCE, mode=R.MODE_WHITTED, shade_bounces=5, flags=R.FLAG_TIME_KERNELS)
+                          pattern=R.PATTERN_REFERENCE, mode=_mode_id(R), shade_bounces=5, gi_bounces=4, flags=R.FLAG_TIME_KERNELS)
     sc.render_device(pk, accum.data_ptr(), clear=True)
     ks = sc.stats()
     line = None
@@ -315,6 +323,7 @@ def ours(args):
 
 
 def main():
+    global SCENE, MODE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -324,7 +333,10 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scene", default=SCENE, help="scene file under scenes/ (default: the Teapot headline scene)")
+    ap.add_argument("--mode", default="whitted", choices=["whitted", "path"], help="path = HEAD estimator with Monte-Carlo GI")
     args = ap.parse_args()
+    SCENE, MODE = args.scene, args.mode
     if args.impl == "reference":
         return reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -417,20 +417,24 @@ static v3 light_direction(const rtu_light *L, v3 p)
 }
 
 /* ---- MtlBlinn::Shade (mtlFunctions.cpp:120-298) */
-static col shade(ctx_t *c, const ray_t *ray, const hit_t *h, int bounce);
+/* amb != NULL: the light list is one AmbientLight of that intensity (the list MonteCarlo() builds,
+ * RenderFunctions.cpp:587-590); amb == NULL: the scene's lights */
+static col shade(ctx_t *c, const ray_t *ray, const hit_t *h, int bounce, const col *amb);
 
-static col shade_hit_of(ctx_t *c, const ray_t *r, const hit_t *h, int bounce) { return shade(c, r, h, bounce); }
+#define shade_hit_of(c, r, h, bounce) shade(c, r, h, bounce, amb)
 
 static v3 mirror(v3 d, v3 n) { return unit(sub(d, mulf(n, 2 * dot(d, n)))); }
 
-static col shade(ctx_t *c, const ray_t *ray, const hit_t *h, int bounce)
+static col shade(ctx_t *c, const ray_t *ray, const hit_t *h, int bounce, const col *amb)
 {
     const rtu_scene_desc *S = c->S;
     int mi = S->nodes[h->node].material;
     if (mi < 0) return C(1, 1, 1); /* the reference would dereference NULL here */
     const rtu_material *M = &S->materials[mi];
     col out = C(0, 0, 0);
-    if (h->front) {
+    if (h->front && amb) {
+        out = cadd(out, cmul(tc_sample(S, &M->diffuse, h->uvw), *amb)); /* :131-133 with the single ambient light */
+    } else if (h->front) {
         for (int i = 0; i < S->n_lights; i++) {
             const rtu_light *L = &S->lights[i];
             if (L->kind == RTU_LIGHT_AMBIENT) {
@@ -506,6 +510,30 @@ static col shade(ctx_t *c, const ray_t *ray, const hit_t *h, int bounce)
         else out = cadd(out, cmul(env_sample(S, rr.d), C(M->reflection.color[0], M->reflection.color[1], M->reflection.color[2])));
     }
     return out;
+}
+
+/* ---- SampleHemiSphereCosine (RenderFunctions.cpp:320-337), radius 1; the tangent is built from
+ * normal x (s,s,s) with s the first random number (SURVEY A-14) */
+static v3 sample_hemi_cos(ctx_t *c, v3 n)
+{
+    float sx = urand(c);
+    float phi = urand(c) * (float)(2 * M_PI);
+    float theta = 0.5 * acos(1 - 2 * sx);
+    v3 v1 = unit(cross(n, V(sx, sx, sx)));
+    v3 v2 = unit(cross(v1, n));
+    return add(add(mulf(n, cosf(theta)), mulf(v1, sinf(theta) * cosf(phi))), mulf(v2, sinf(theta) * sinf(phi)));
+}
+
+/* ---- MonteCarlo (RenderFunctions.cpp:454-591): intensity of the AmbientLight it appends */
+static col monte_carlo(ctx_t *c, const hit_t *h, int bounces)
+{
+    if (bounces <= 0) return C(0.1f, 0.1f, 0.1f);                                /* :584 */
+    ray_t r = {h->p, unit(sample_hemi_cos(c, h->N))};                             /* :561-562 */
+    hit_t h2;
+    hit_init(&h2);
+    if (!trace(c, &r, &h2)) return env_sample(c->S, r.d);                         /* :575 */
+    col amb2 = monte_carlo(c, &h2, bounces - 1);                                  /* :568 */
+    return cadd(shade(c, &r, &h2, 5, &amb2), shade(c, &r, &h2, 5, NULL));         /* :569-570; /= monteCarloSampleSize (1) */
 }
 
 /* ---- camera (RenderFunctions.cpp:243-269, 88-97) */
@@ -618,7 +646,7 @@ int oracle_shade(const rtu_scene_desc *S, const rtu_ray *rays, const rtu_hit *hi
         h.p = V(hits[i].p[0], hits[i].p[1], hits[i].p[2]);
         h.N = V(hits[i].N[0], hits[i].N[1], hits[i].N[2]);
         h.uvw = V(hits[i].uvw[0], hits[i].uvw[1], hits[i].uvw[2]);
-        col o = shade(&c, &r, &h, bounces);
+        col o = shade(&c, &r, &h, bounces, NULL);
         rgb[3 * i] = o.r; rgb[3 * i + 1] = o.g; rgb[3 * i + 2] = o.b;
     }
     ctx_free(&c);
@@ -669,7 +697,14 @@ static void *render_rows(void *arg)
                 hit_t h;
                 hit_init(&h);
                 col v;
-                if (trace(&c, &r, &h)) v = shade(&c, &r, &h, P->shade_bounces);
+                if (trace(&c, &r, &h)) {
+                    if (P->mode == RTU_MODE_PATH) {                               /* RenderFunctions.cpp:129-135 */
+                        col amb = monte_carlo(&c, &h, P->gi_bounces);
+                        v = cadd(shade(&c, &r, &h, P->shade_bounces, &amb), shade(&c, &r, &h, P->shade_bounces, NULL));
+                    } else {
+                        v = shade(&c, &r, &h, P->shade_bounces, NULL);
+                    }
+                }
                 else v = tc_sample(J->S, &J->S->background, V((float)x / W, (float)y / J->H, 0)); /* :145 */
                 sum = cadd(sum, v);
             }

@@ -54,6 +54,8 @@ struct rtu_context {
     unsigned *work = nullptr;
     size_t work_n = 0;
     unsigned *zmm = nullptr;
+    float4 *gi = nullptr;  // GI records of the current chunk (RTU_MODE_PATH): one per primary hit
+    size_t gi_n = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing (RTU_FLAG_TIME_KERNELS)
     std::vector<cudaEvent_t> kt_ev;
@@ -160,10 +162,23 @@ int ensure_scratch(rtu_context *c, size_t q_cap, size_t shadow_cap)
     CU(alloc((void **)&c->wb.hits.b, q_cap * sizeof(float4)));
     c->wb.hits.count = counts + 5;
     c->wb.hits.cap = (uint32_t)q_cap;
+    c->wb.gi_count = counts + 6;
     CU(alloc((void **)&c->wb.counters, sizeof(DCounters)));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     c->q_cap = q_cap;
     c->shadow_cap = shadow_cap;
+    return RTU_OK;
+}
+
+int ensure_gi(rtu_context *c, size_t n)
+{
+    if (n <= c->gi_n) return RTU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->gi) cudaFree(c->gi);
+    c->gi = nullptr;
+    c->gi_n = 0;
+    CU(cudaMalloc((void **)&c->gi, n * sizeof(float4)));
+    c->gi_n = n;
     return RTU_OK;
 }
 
@@ -396,6 +411,7 @@ void rtu_context_destroy(rtu_context *c)
     free_list(c->scratch);
     if (c->work) cudaFree(c->work);
     if (c->zmm) cudaFree(c->zmm);
+    if (c->gi) cudaFree(c->gi);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->kt_ev) cudaEventDestroy(e);
@@ -638,7 +654,8 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
     if (p->spp < 1 || p->spp > (1 << 20)) { rtu::set_error("bad spp"); return RTU_ERR_INVALID; }
     if (p->pattern == RTU_PATTERN_CENTER && p->spp != 1) { rtu::set_error("RTU_PATTERN_CENTER needs spp == 1"); return RTU_ERR_INVALID; }
-    if (p->mode == RTU_MODE_PATH) { rtu::set_error("RTU_MODE_PATH is not implemented yet"); return RTU_ERR_UNSUPPORTED; }
+    if (p->mode != RTU_MODE_WHITTED && p->mode != RTU_MODE_PATH) { rtu::set_error("bad render mode"); return RTU_ERR_INVALID; }
+    if (p->mode == RTU_MODE_PATH && (p->gi_bounces < 0 || p->gi_bounces > 6)) { rtu::set_error("gi_bounces out of range (0..6)"); return RTU_ERR_INVALID; }
     if (p->shade_bounces < 0 || p->shade_bounces > 15) { rtu::set_error("shade_bounces out of range"); return RTU_ERR_INVALID; }
     make_camera(s->cam, W, H, &F->cam);
     F->spp = p->spp;
@@ -680,10 +697,16 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
 }
 
 // the waves that follow a first wave whose output is in q[out_q]
+int wave_count(const FrameSetup &F)
+{
+    // a Fresnel ray starts one wave after its sibling at every level; every GI vertex restarts a Shade tree
+    return 2 * F.shade_bounces + 1 + (F.mode == RTU_MODE_PATH ? F.gi_bounces : 0);
+}
+
 int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_t *work_i)
 {
     rtu_context *c = s->ctx;
-    int n_waves = 2 * F.shade_bounces + 1; // a Fresnel ray starts one wave after its sibling at every level
+    int n_waves = wave_count(F);
     kt_begin(c, 2);
     launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
     kt_end(c);
@@ -751,8 +774,14 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
     size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
     if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
     size_t n_chunks = ((size_t)(s1 - s0) + chunk_samples - 1) / chunk_samples;
-    size_t launches_per_chunk = 3 + 3 * (size_t)(2 * F.shade_bounces + 1);
+    size_t launches_per_chunk = 3 + 3 * (size_t)wave_count(F);
     if ((rc = ensure_work(c, n_chunks * launches_per_chunk + 8))) return rc;
+    const bool path_mode = F.mode == RTU_MODE_PATH;
+    float4 *target = accum; // the array ray slots index: pixels, or GI records folded into pixels per chunk
+    if (path_mode) {
+        if ((rc = ensure_gi(c, (size_t)c->wb.hits.cap * (size_t)(2 * (F.gi_bounces + 1) + 1)))) return rc;
+        target = c->gi;
+    }
     CU(cudaEventRecord(c->ev0, c->stream));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * sizeof(float4), c->stream));
@@ -763,13 +792,17 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
         int b = std::min<int>(s1, a + (int)chunk_samples);
         launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, c->wb.hits.count);
         kt_begin(c, 0);
-        launch_extend_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, accum, c->work + wi++);
+        launch_extend_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, accum, target, c->work + wi++);
         kt_end(c);
         kt_begin(c, 3);
-        launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, accum, c->work + wi++);
+        launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, target, c->work + wi++);
         kt_end(c);
         s->launches += 3;
-        if ((rc = run_waves(s, F, accum, 0, &wi))) return rc;
+        if ((rc = run_waves(s, F, target, 0, &wi))) return rc;
+        if (path_mode) {
+            launch_gi_combine(c->stream, c->gi, c->wb.gi_count, c->wb.hits.cap, F.gi_bounces, accum);
+            s->launches++;
+        }
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     s->timed = true;

@@ -28,13 +28,14 @@ struct WaveBuffers {
     AuxPool aux[2];
     ShadowQueue shadow;
     HitQueue hits;
+    unsigned *gi_count;   // number of GI records (= primary hits) of the current chunk (RTU_MODE_PATH)
     unsigned *work;       // device work-fetch counters (one per launch slot)
     DCounters *counters;
 };
 
 // closest hit of generated primary rays: samples [s0,s1) of rows [row_begin,row_end) -> hit queue
 void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
-                           const WaveBuffers &B, float4 *accum, unsigned *work_counter);
+                           const WaveBuffers &B, float4 *pixel_accum, float4 *accum, unsigned *work_counter);
 // shade the hit queue of a primary wave -> shadow queue + q[out_q]
 void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0,
                           const WaveBuffers &B, int out_q, float4 *accum, unsigned *work_counter);
@@ -46,6 +47,7 @@ void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 // any-hit over the shadow queue, adds unoccluded contributions to accum
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
                         unsigned *work_counter);
+void launch_gi_combine(cudaStream_t st, const float4 *gi, const unsigned *count, unsigned cap, int gi_bounces, float4 *accum);
 void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d);
 
 // pixel-centre primary visibility: z / node / face per pixel (RTU_MODE_PRIMARY, ZBuffer.png)

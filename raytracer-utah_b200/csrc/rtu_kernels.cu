@@ -98,6 +98,15 @@ struct PrimaryMap {
     }
 };
 
+// RNG path word of a camera sample: a function of (pixel, sample) only, so random streams do not
+// depend on chunking, queue order or the number of GPUs
+__device__ __forceinline__ unsigned primary_path(int pixel, int s)
+{
+    unsigned h = (unsigned)pixel * 0x9E3779B9u ^ ((unsigned)s + 0x7F4A7C15u) * 0x85EBCA6Bu;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+
 __device__ __forceinline__ Ray primary_ray(const FrameSetup &F, int s, int x, int y, int pixel)
 {
     float2 off = __ldg(&F.sample_offsets[s]);
@@ -109,9 +118,11 @@ __device__ __forceinline__ Ray primary_ray(const FrameSetup &F, int s, int x, in
 // ------------------------------------------------------------------ closest hit
 template <bool PRIMARY>
 __global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
-k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum,
+k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
          DCounters *counters, unsigned *work)
 {
+    // accum: the pixel accumulator (primary misses add the background there)
+    // target: the array the rays' slots index: == accum for Whitted frames, the GI records in RTU_MODE_PATH
     Tally tl = {0, 0, 0, 0, 0};
     const unsigned lane = threadIdx.x & 31u;
     PrimaryMap pm;
@@ -157,12 +168,21 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         if (PRIMARY) {
             int py = pixel / pm.W, px = pixel - py * pm.W;
             c = background_sample(S, px, py, pm.W, F.cam.height);                     // RenderFunctions.cpp:145
+            accum_add(accum, pixel, c);
         } else {
             float4 w = in.w[idx];
-            pixel = __float_as_int(in.o[idx].w);
-            int kind = (int)(__float_as_uint(in.d[idx].w) & 7u);
+            int slot = __float_as_int(in.o[idx].w);
+            int kind, bounce, tree, gidepth, mtl;
+            unpack_meta(__float_as_uint(in.d[idx].w), kind, bounce, tree, gidepth, mtl);
             int aux = __float_as_int(w.w);
             Col Wt = mk(w.x, w.y, w.z);
+            if (kind == RK_GI) {
+                // MonteCarlo(): the sample ray left the scene, c = environment (RenderFunctions.cpp:575);
+                // slot = first entry of the GI record, its last entry holds (c, index of the vertex that was missed)
+                Col e = environment_sample(S, ray.dx, ray.dy, ray.dz);
+                target[slot + 2 * (F.gi_bounces + 1)] = make_float4(e.r, e.g, e.b, (float)gidepth);
+                continue;
+            }
             if (kind == RK_REFRACT) {
                 c = Wt * environment_sample(S, ray.dx, ray.dy, ray.dz);               // mtlFunctions.cpp:267
             } else if (kind == RK_REFLECT || kind == RK_FRESNEL) {
@@ -170,8 +190,8 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
                 if (aux >= 0) { float4 a = inaux.a[aux]; wm = mk(a.x, a.y, a.z); }
                 c = wm * environment_sample(S, ray.dx, ray.dy, ray.dz);               // :250, :289
             }
+            accum_add(target, slot + tree, c); // environment terms do not scale with the ambient light: slot+1 in tree 1
         }
-        accum_add(accum, pixel, c);
     }
     flush_tally(tl, counters, PRIMARY ? 0 : 1);
 }
@@ -179,13 +199,16 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
 // ------------------------------------------------------------------ shade the compacted hits
 template <bool PRIMARY>
 __global__ void __launch_bounds__(WAVE_THREADS, 2)
-k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq, WaveOut O, unsigned *work)
+k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq, WaveOut O, unsigned *work, unsigned *gi_count)
 {
     const unsigned lane = threadIdx.x & 31u;
     PrimaryMap pm;
     pm.init(F);
     unsigned total = *hq.count;
     if (total > hq.cap) total = hq.cap;
+    const bool path_mode = F.mode == RTU_MODE_PATH;
+    const int gi_end = 2 * (F.gi_bounces + 1); // GI record: A_0, D_0, ..., A_K-1, D_K-1, End
+    if (PRIMARY && path_mode && blockIdx.x == 0 && threadIdx.x == 0) *gi_count = total; // one GI record per primary hit
     ShadeParams SP;
     SP.flags = F.flags;
     SP.seed = F.seed;
@@ -204,14 +227,14 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
 
         Ray ray;
         Col Wt;
-        int pixel, kind, bounce, mtl, aux;
+        int pixel, kind, bounce, mtl, aux, tree = 0, gidepth = 0;
         unsigned path;
         if (PRIMARY) {
             int s, x, y;
             pm.decode(idx, s0, s, x, y);
             pixel = y * pm.W + x;
             ray = primary_ray(F, s, x, y, pixel);
-            path = (unsigned)s;
+            path = primary_path(pixel, s);
             Wt = mk(1.f, 1.f, 1.f);
             kind = RK_PRIMARY; bounce = F.shade_bounces; mtl = 0; aux = -1;
         } else {
@@ -220,13 +243,44 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             ray.px = o.x; ray.py = o.y; ray.pz = o.z;
             ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
             pixel = __float_as_int(o.w);
-            unsigned meta = __float_as_uint(d.w);
-            kind = (int)(meta & 7u); bounce = (int)((meta >> 3) & 31u); mtl = (int)(meta >> 8);
+            unpack_meta(__float_as_uint(d.w), kind, bounce, tree, gidepth, mtl);
             Wt = mk(w.x, w.y, w.z);
             aux = __float_as_int(w.w);
         }
         HitRec H;
         finalize_hit(S, ray, B, H);
+        if (path_mode && (kind == RK_PRIMARY || kind == RK_GI)) {
+            // A vertex h_k of the GI chain (RenderFunctions.cpp:129-135 for the camera hit, :565-570 for a
+            // MonteCarlo() sample hit).  L(h_k) = Shade(h_k, lights) + Shade(h_k, {Ambient c_k}) where c_k is what
+            // MonteCarlo(h_k) returns.  The second Shade is linear in c_k, so its c_k-factor A_k and everything that
+            // does not depend on c_k (D_k) are accumulated in two slots of the sample's GI record and folded by
+            // k_gi_combine once all waves are done: L_k = D_k + A_k * L_{k+1}.
+            int k = kind == RK_PRIMARY ? 0 : gidepth;
+            int base;
+            if (kind == RK_PRIMARY) {
+                base = (int)h * (gi_end + 1);
+                for (int j = 0; j <= gi_end; j++) O.accum[base + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                O.accum[base].w = __int_as_float(pixel);
+            } else {
+                base = pixel;
+            }
+#pragma unroll 1
+            for (int t = 0; t < 2; t++)
+                shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, mk(1.f, 1.f, 1.f), F.shade_bounces, base + 2 * k + (t ? 0 : 1),
+                          child_path(path, 8u + (unsigned)t), t);
+            if (k < F.gi_bounces) {
+                Rng rng;
+                rng.key = F.seed; rng.pixel = 0x61u; rng.path = path; rng.dim = 0;
+                float ox, oy, oz;
+                sample_hemi_cos(rng, H.nx, H.ny, H.nz, ox, oy, oz);                                   // :561
+                norm3(ox, oy, oz);                                                                    // :562
+                push_ray(O, H.px, H.py, H.pz, ox, oy, oz, mk(1.f, 1.f, 1.f), base, pack_meta(RK_GI, F.shade_bounces, 0, 0, k + 1), -1,
+                         child_path(path, 6u));
+            } else {
+                O.accum[base + gi_end] = make_float4(0.1f, 0.1f, 0.1f, (float)(k + 1));               // :584
+            }
+            continue;
+        }
         if (kind == RK_REFRACT) {
             float4 a = inaux.a[aux], b = inaux.b[aux];
             Col Kt = mk(a.x, a.y, a.z);
@@ -246,14 +300,14 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
                 else {
                     O.aux.a[na] = make_float4(Wf.r, Wf.g, Wf.b, 0.f);
                     O.aux.b[na] = make_float4(0, 0, 0, 0);
-                    push_ray(O, ray.px, ray.py, ray.pz, b.x, b.y, b.z, WfKt, pixel, pack_meta(RK_FRESNEL, bounce, mtl), (int)na,
+                    push_ray(O, ray.px, ray.py, ray.pz, b.x, b.y, b.z, WfKt, pixel, pack_meta(RK_FRESNEL, bounce, mtl, tree), (int)na,
                              child_path(path, 4u));
                 }
             }
             if (!((F.flags & 2u) && !nonblack(Wh)))
-                shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wh, bounce, pixel, path);
+                shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wh, bounce, pixel, path, tree);
         } else {
-            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wt, bounce, pixel, path);
+            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wt, bounce, pixel, path, tree);
         }
     }
 }
@@ -483,11 +537,11 @@ static WaveOut make_out(const WaveBuffers &B, int out_q, float4 *accum)
 }
 
 void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
-                           const WaveBuffers &B, float4 *accum, unsigned *work_counter)
+                           const WaveBuffers &B, float4 *pixel_accum, float4 *accum, unsigned *work_counter)
 {
     static int occ = 0;
-    k_extend<true><<<resident_grid(cfg, k_extend<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1], B.aux[1], B.hits, accum,
-                                                                                     B.counters, work_counter);
+    k_extend<true><<<resident_grid(cfg, k_extend<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum,
+                                                                                     accum, B.counters, work_counter);
 }
 
 void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0,
@@ -496,7 +550,7 @@ void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S
     static int occ = 0;
     WaveOut O = make_out(B, out_q, accum);
     k_shade<true><<<resident_grid(cfg, k_shade<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, B.q[1 - out_q], B.aux[1 - out_q], B.hits, O,
-                                                                                   work_counter);
+                                                                                   work_counter, B.gi_count);
 }
 
 void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
@@ -504,7 +558,7 @@ void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
 {
     static int occ = 0;
     k_extend<false><<<resident_grid(cfg, k_extend<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum,
-                                                                                       B.counters, work_counter);
+                                                                                       accum, B.counters, work_counter);
 }
 
 void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
@@ -512,7 +566,8 @@ void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 {
     static int occ = 0;
     WaveOut O = make_out(B, 1 - in_q, accum);
-    k_shade<false><<<resident_grid(cfg, k_shade<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, B.q[in_q], B.aux[in_q], B.hits, O, work_counter);
+    k_shade<false><<<resident_grid(cfg, k_shade<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, B.q[in_q], B.aux[in_q], B.hits, O, work_counter,
+                                                                                     B.gi_count);
 }
 
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
@@ -520,6 +575,32 @@ void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 {
     static int occ = 0;
     k_shadow_wave<<<resident_grid(cfg, k_shadow_wave, &occ), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
+}
+
+// Folds the GI records of one chunk into the pixel accumulator: L = End; L = D_k + A_k * L for k = end-1 .. 0
+// (the recursion of MonteCarlo(), RenderFunctions.cpp:454-591, unrolled; see k_shade).
+__global__ void k_gi_combine(const float4 *gi, const unsigned *count, unsigned cap, int gi_bounces, float4 *accum)
+{
+    unsigned n = *count;
+    if (n > cap) n = cap;
+    const int end_slot = 2 * (gi_bounces + 1);
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const float4 *rec = gi + (size_t)r * (end_slot + 1);
+        float4 e = rec[end_slot];
+        int end = (int)e.w;
+        if (end > gi_bounces + 1) end = gi_bounces + 1;
+        Col L = mk(e.x, e.y, e.z);
+        for (int k = end - 1; k >= 0; k--) {
+            float4 a = rec[2 * k], d = rec[2 * k + 1];
+            L = mk(d.x, d.y, d.z) + mk(a.x, a.y, a.z) * L;
+        }
+        accum_add(accum, __float_as_int(rec[0].w), L);
+    }
+}
+
+void launch_gi_combine(cudaStream_t st, const float4 *gi, const unsigned *count, unsigned cap, int gi_bounces, float4 *accum)
+{
+    k_gi_combine<<<1184, 256, 0, st>>>(gi, count, cap, gi_bounces, accum);
 }
 
 void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d)

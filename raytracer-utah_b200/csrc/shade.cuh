@@ -61,6 +61,25 @@ __device__ __forceinline__ void sample_ball(Rng &rng, float radius, float &x, fl
     }
 }
 
+// SampleHemiSphereCosine(origin, normal, 1) (RenderFunctions.cpp:320-337): theta = acos(1-2u)/2, phi = 2 pi v,
+// tangent frame built from normal x (u,u,u) (SURVEY A-14).  Returns the (unnormalised) offset.
+__device__ __forceinline__ void sample_hemi_cos(Rng &rng, float nx, float ny, float nz, float &ox, float &oy, float &oz)
+{
+    float4 u = rng.next4();
+    float sx = u.x, phi = u.y * 6.283185307179586f;
+    float theta = 0.5f * acosf(1.f - 2.f * sx);
+    float ax = ny * sx - nz * sx, ay = nz * sx - nx * sx, az = nx * sx - ny * sx; // N x (s,s,s)
+    float l1 = sqrtf(dot3(ax, ay, az, ax, ay, az));
+    ax /= l1; ay /= l1; az /= l1;
+    float bx = ay * nz - az * ny, by = az * nx - ax * nz, bz = ax * ny - ay * nx; // v1 x N
+    float l2 = sqrtf(dot3(bx, by, bz, bx, by, bz));
+    bx /= l2; by /= l2; bz /= l2;
+    float ct = cosf(theta), st = sinf(theta), cp = cosf(phi), sp = sinf(phi);
+    ox = (nx * ct + ax * (st * cp)) + bx * (st * sp);
+    oy = (ny * ct + ay * (st * cp)) + by * (st * sp);
+    oz = (nz * ct + az * (st * cp)) + bz * (st * sp);
+}
+
 // ------------------------------------------------------------------ textures
 // Texture::TileClamp (scene.h:355-365)
 __device__ __forceinline__ float tile_clamp(float v)
@@ -164,9 +183,22 @@ __device__ __forceinline__ void accum_add(float4 *accum, int pixel, Col c)
     if (c.b != 0.f) atomicAdd(a + 2, c.b);
 }
 
-__device__ __forceinline__ unsigned pack_meta(int kind, int bounce, int material)
+// ray meta word: kind (3 bits) | bounceCount left (4) | tree (1) | GI depth (3) | parent material (21)
+//   tree 0: Shade(..., lights, ...)            -> radiance goes to the ray's target slot
+//   tree 1: Shade(..., {AmbientLight c}, ...)  -> the factor of c goes to the target slot, the
+//           c-independent environment terms to target+1 (RTU_MODE_PATH only; see k_shade)
+__device__ __forceinline__ unsigned pack_meta(int kind, int bounce, int material, int tree = 0, int gidepth = 0)
 {
-    return (unsigned)kind | ((unsigned)bounce << 3) | ((unsigned)(material & 0xffffff) << 8);
+    return (unsigned)kind | ((unsigned)bounce << 3) | ((unsigned)tree << 7) | ((unsigned)gidepth << 8) |
+           ((unsigned)(material & 0x1fffff) << 11);
+}
+__device__ __forceinline__ void unpack_meta(unsigned meta, int &kind, int &bounce, int &tree, int &gidepth, int &material)
+{
+    kind = (int)(meta & 7u);
+    bounce = (int)((meta >> 3) & 15u);
+    tree = (int)((meta >> 7) & 1u);
+    gidepth = (int)((meta >> 8) & 7u);
+    material = (int)(meta >> 11);
 }
 
 __device__ __forceinline__ void push_ray(const WaveOut &O, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -211,8 +243,12 @@ struct ShadeParams {
 //   dirx..: ray.dir (world).  H: the hit.  bounce: bounceCount.  path: RNG path word of this ray.
 // Direct light  -> shadow queue (mtlFunctions.cpp:125-155, lightFunctions.cpp:27-84, lights.h:32,48)
 // Refraction    -> RK_REFRACT / RK_TIR rays (:160-270);  Reflection -> RK_REFLECT rays (:273-291)
+//   pixel: the accumulator slot the radiance is added to (a pixel, or a slot of a GI record).
+//   tree 1: the light list is the single AmbientLight MonteCarlo() built (RenderFunctions.cpp:587-590)
+//           with unit intensity; the caller multiplies the accumulated factor by its intensity later.
 __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P, const WaveOut &O, float dirx, float diry,
-                                          float dirz, const HitRec &H, Col Wt, int bounce, int pixel, unsigned path)
+                                          float dirz, const HitRec &H, Col Wt, int bounce, int pixel, unsigned path,
+                                          int tree = 0)
 {
     if (H.material < 0) { // node without material: the reference would dereference NULL
         accum_add(O.accum, pixel, Wt);
@@ -220,9 +256,11 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
     }
     const DMaterial &M = S.materials[H.material];
     Rng rng;
-    rng.key = P.seed; rng.pixel = (unsigned)pixel; rng.path = path; rng.dim = 0;
+    rng.key = P.seed; rng.pixel = tree ? 0x7A11u : 0u; rng.path = path; rng.dim = 0;
     Col local = mk(0, 0, 0);
-    if (H.front) {
+    if (H.front && tree) {
+        local = texcolor_sample(S, M.diffuse, H.u, H.v, H.w); // Kd * Illuminate() of the unit ambient light (:131-133)
+    } else if (H.front) {
         Col Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
         Col Ks = texcolor_sample(S, M.specular, H.u, H.v, H.w);
         // viewDirection uses camera.pos, not the ray origin (mtlFunctions.cpp:137, SURVEY A-6)
@@ -319,7 +357,7 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
             Col ab = mk(expf((-RTU_BIG) * M.absorption[0]), expf((-RTU_BIG) * M.absorption[1]), expf((-RTU_BIG) * M.absorption[2]));
             Col w = Wt * ab;
             if (!((P.flags & 2u) && !nonblack(w)))
-                push_ray(O, H.px, H.py, H.pz, rx, ry, rz, w, pixel, pack_meta(RK_TIR, bounce - 1, H.material), -1, child_path(path, 1u));
+                push_ray(O, H.px, H.py, H.pz, rx, ry, rz, w, pixel, pack_meta(RK_TIR, bounce - 1, H.material, tree), -1, child_path(path, 1u));
         } else {
             // second glossiness sample shadows the first for the refracted / mirror directions (:225-239)
             float o2x, o2y, o2z;
@@ -340,7 +378,7 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
             else {
                 O.aux.a[a] = make_float4(Kt.r, Kt.g, Kt.b, F);
                 O.aux.b[a] = make_float4(mx, my, mz, 0.f);
-                push_ray(O, H.px, H.py, H.pz, rdx, rdy, rdz, Wt, pixel, pack_meta(RK_REFRACT, bounce - 1, H.material), (int)a, child_path(path, 2u));
+                push_ray(O, H.px, H.py, H.pz, rdx, rdy, rdz, Wt, pixel, pack_meta(RK_REFRACT, bounce - 1, H.material, tree), (int)a, child_path(path, 2u));
             }
         }
     }
@@ -362,6 +400,6 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
             O.aux.b[a] = make_float4(0, 0, 0, 0);
             aux = (int)a;
         }
-        push_ray(O, H.px, H.py, H.pz, rx, ry, rz, Wt * Kr, pixel, pack_meta(RK_REFLECT, bounce - 1, H.material), aux, child_path(path, 3u));
+        push_ray(O, H.px, H.py, H.pz, rx, ry, rz, Wt * Kr, pixel, pack_meta(RK_REFLECT, bounce - 1, H.material, tree), aux, child_path(path, 3u));
     }
 }

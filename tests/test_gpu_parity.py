@@ -265,3 +265,62 @@ def test_errors_are_reported_not_swallowed(rtu, gpu_ctx):
     finally:
         sc.close()
         hs.close()
+
+
+@pytest.mark.parametrize("scene", ["Project4.xml", "Project11/scene.xml", "Teapot/scene2.xml"])
+def test_path_mode_without_bounces_is_deterministic(rtu, gpu_ctx, scene):
+    """gi_bounces = 0 makes MonteCarlo() return the constant 0.1 ambient (RenderFunctions.cpp:584): the frame is
+    Shade(h, {Ambient 0.1}) + Shade(h, lights) with no random numbers, so GPU and C oracle agree to 1e-4.  This pins
+    the GI record algebra (A_k / D_k slots, ambient-tree environment terms) of k_shade / k_gi_combine."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    hs = rtu.HostScene(os.path.join(SCENES, scene))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=160, height=120, spp=2, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=0)
+        a = sc.render(p, want=("rgb",))["rgb"]
+        st = sc.stats()
+        o = oracle_py.render(hs.desc, params=p, want=("rgb",))
+        assert within_tol(a, o["rgb"]).all(), "max abs diff %g" % np.abs(a - o["rgb"]).max()
+        assert st["trace_rays"] == o["stats"]["trace_rays"] and st["shadow_rays"] == o["stats"]["shadow_rays"]
+    finally:
+        sc.close()
+        hs.close()
+
+
+@pytest.mark.parametrize("tag", ["Project4", "Project11_scene"])
+def test_path_mode_matches_reference_head_render(rtu, gpu_ctx, tag):
+    """The GPU's RTU_MODE_PATH frame against the reference's own Render() at HEAD (1024 spp + 4-bounce MonteCarlo GI,
+    fixture made by the unmodified reference) and against the C oracle: statistical bars, see tests/test_oracle.py."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    g, meta = load_golden("head_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=rtu.PATTERN_REFERENCE,
+                               mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=4, seed=11)
+        out = sc.render(p, want=("rgb", "rgb8"))
+        a, b = out["rgb8"].astype(np.float64), g["rgb8"].astype(np.float64)
+        assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
+        assert np.abs(a - b).mean() < 2.5
+        o = oracle_py.render(hs.desc, params=p, want=("rgb",))
+        lin, ref = out["rgb"].astype(np.float64), o["rgb"].astype(np.float64)
+        assert abs(lin.mean() - ref.mean()) <= 0.01 * ref.mean()
+        # yardstick for the Monte-Carlo noise: two oracle renders that differ only in their seed
+        p2 = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=rtu.PATTERN_REFERENCE,
+                                mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=4, seed=12345)
+        ref2 = oracle_py.render(hs.desc, params=p2, want=("rgb",))["rgb"].astype(np.float64)
+        noise = np.sqrt(np.mean((ref2 - ref) ** 2))
+        rmse = np.sqrt(np.mean((lin - ref) ** 2))
+        assert rmse <= 1.5 * noise, "RMSE %.3g vs oracle-to-oracle noise %.3g" % (rmse, noise)
+        # same seed, same frame: the counter-based RNG makes the render reproducible (up to float summation order)
+        again = sc.render(p, want=("rgb",))["rgb"]
+        assert np.allclose(again, out["rgb"], rtol=1e-4, atol=1e-6)
+    finally:
+        sc.close()
+        hs.close()

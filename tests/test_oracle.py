@@ -95,3 +95,19 @@ def test_texture_sampling_bit_exact(rtu, oracle, tag, scene):
         mt = d.materials[m]
         for q, tc in enumerate((mt.diffuse, mt.specular, mt.reflection, mt.refraction)):
             assert bits_equal(oracle.sample_texcolor(d, tc, g["uvw"]), ref[:, q, :]), (m, q)
+
+
+@pytest.mark.parametrize("tag", ["Project4", "Project11_scene"])
+def test_path_mode_matches_reference_head_render(rtu, oracle, tag):
+    """RTU_MODE_PATH (MonteCarlo GI + lights, RenderFunctions.cpp:129-135,454-591) against the reference's own
+    Render() at HEAD (1024 spp, 4 GI bounces).  Both are Monte-Carlo estimates with unrelated random streams, so
+    the comparison is statistical: image mean within 1 %, mean |difference| of the 8-bit images below 2.5 codes
+    (the residual noise of two independent 1024-spp renders; measured 0.8-1.2)."""
+    g, meta = load_golden("head_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    p = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=rtu.PATTERN_REFERENCE,
+                           mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=4, seed=3)
+    o = oracle.render(hs.desc, params=p, want=("rgb8",))
+    a, b = o["rgb8"].astype(np.float64), g["rgb8"].astype(np.float64)
+    assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
+    assert np.abs(a - b).mean() < 2.5
