@@ -79,3 +79,16 @@ def single_object_scene(rtu, kind, mesh_from=None):
     d.camera.up[:] = (0, 1, 0)
     d._keep = keep
     return d
+
+
+def synthetic_scene(name, meta):
+    """Regenerates a section-8d synthetic scene (tools/make_synthetic.py, deterministic) and checks that it is the
+    file the reference produced the fixture from."""
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic
+    rel = make_synthetic.ensure((name,))[name]
+    for f, want in meta["sha256"].items():
+        got = hashlib.sha256(open(os.path.join(SCENES, "synthetic", f), "rb").read()).hexdigest()
+        assert got == want, "generated %s differs from the one the fixture was made from" % f
+    return os.path.join(SCENES, rel)

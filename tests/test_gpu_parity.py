@@ -324,3 +324,38 @@ def test_path_mode_matches_reference_head_render(rtu, gpu_ctx, tag):
     finally:
         sc.close()
         hs.close()
+
+
+@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "spheres_1000"])
+def test_synthetic_scenes(rtu, gpu_ctx, name):
+    """SURVEY section 8d shapes: a 1 M-triangle mesh (707 640-node BVH) and flat lists of 100 / 1000 spheres with
+    mirrors and glass; expectations from the unmodified reference on the same generated files."""
+    from conftest import synthetic_scene
+    g, meta = load_golden("synthetic_" + name)
+    hs = rtu.HostScene(synthetic_scene(name, meta))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_PRIMARY)
+        out = sc.render(p, want=("z", "node_id", "face_id"))
+        assert np.array_equal(out["node_id"], g["node"])
+        assert np.array_equal(out["face_id"], g["face"])
+        assert bits_equal(out["z"], g["z"])
+        p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_WHITTED, shade_bounces=5)
+        out = sc.render(p, want=("rgb",))
+        ok = within_tol(out["rgb"], g["rgb"]).all(axis=2)
+        # A pixel whose reference radiance is NEGATIVE is a sum of Fresnel terms of both signs (mtlFunctions.cpp:283-289
+        # with cos > 1 after a back-face hit); the wavefront adds the same terms in a different order, so the
+        # cancellation error is relative to the terms, not to the sum.  Such pixels (1 of 32 400 in spheres_1000) are
+        # held to 1e-3 instead, and there may be at most 3 of them.
+        loose = ~ok & (g["rgb"].min(axis=2) < 0)
+        assert int(loose.sum()) <= 3
+        a, b = out["rgb"].astype(np.float64), g["rgb"].astype(np.float64)
+        assert (np.abs(a - b)[loose] <= 1e-3 * np.maximum(np.abs(a), np.abs(b))[loose] + ABS_FLOOR).all()
+        ok |= loose
+        assert ok.all(), "%d pixels outside tolerance" % int((~ok).sum())
+        st = sc.stats()
+        assert st["trace_rays"] == meta["whitted"]["trace_rays"] and st["shadow_rays"] == meta["whitted"]["shadow_rays"]
+        assert (g["node"] >= 0).mean() > 0.1
+    finally:
+        sc.close()
+        hs.close()

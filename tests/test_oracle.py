@@ -111,3 +111,17 @@ def test_path_mode_matches_reference_head_render(rtu, oracle, tag):
     a, b = o["rgb8"].astype(np.float64), g["rgb8"].astype(np.float64)
     assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
     assert np.abs(a - b).mean() < 2.5
+
+
+@pytest.mark.parametrize("name", ["grid1M", "spheres_100"])
+def test_synthetic_scenes_match_reference(rtu, oracle, name):
+    """The section-8d generated scenes (1 M-triangle mesh through our OBJ loader + BVH builder; flat sphere lists)."""
+    from conftest import synthetic_scene
+    g, meta = load_golden("synthetic_" + name)
+    hs = rtu.HostScene(synthetic_scene(name, meta))
+    o = oracle.render(hs.desc, width=meta["width"], height=meta["height"], mode=rtu.MODE_PRIMARY, want=("z", "node_id", "face_id"))
+    assert np.array_equal(o["node_id"], g["node"])
+    assert np.array_equal(o["face_id"], g["face"])
+    assert bits_equal(o["z"], g["z"])
+    o = oracle.render(hs.desc, width=meta["width"], height=meta["height"], mode=rtu.MODE_WHITTED)
+    assert bits_equal(o["rgb"], g["rgb"])

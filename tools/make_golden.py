@@ -64,6 +64,8 @@ FULL = {
 }
 LOADER = ["Project1Example.xml", "Project4.xml", "Project5/scene.xml", "Project7/scene.xml", "Project9/scene.xml",
           "Project10/scene.xml", "Project11/scene_86.xml", "Project13/scene.xml", "Teapot/scene.xml", "Teapot/scene2.xml"]
+# generated scenes of section 8d (tools/make_synthetic.py): 1 M-triangle mesh, flat lists of spheres
+SYNTHETIC = {"grid1M": (240, 135), "spheres_100": (240, 135), "spheres_1000": (240, 135)}
 TEX = {"Project7/scene.xml": "p7", "Project9/scene.xml": "p9", "Project10/scene.xml": "p10"}
 
 
@@ -137,6 +139,25 @@ def main():
                 pre = os.path.join(tmp, "fw")
                 meta = run(sc, "whitted", pre, "--width", w, "--height", h, "--threads", 8)
                 save("whitted_" + tag, collect(pre), dict(meta, scene=sc))
+        if want("synthetic"):
+            import hashlib
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import make_synthetic
+            paths = make_synthetic.ensure(tuple(SYNTHETIC))
+            for name, (w, h) in SYNTHETIC.items():
+                pre = os.path.join(tmp, "sy")
+                meta = run(paths[name], "primary", pre, "--width", w, "--height", h, "--threads", 8)
+                a = collect(pre)
+                arrs = {k: a[k] for k in ("z", "node", "face", "front")}
+                pre = os.path.join(tmp, "sw")
+                meta2 = run(paths[name], "whitted", pre, "--width", w, "--height", h, "--threads", 8)
+                arrs["rgb"] = collect(pre)["rgb"]
+                digest = {}
+                for f in (name + ".xml", name + ".obj"):
+                    fp = os.path.join(SCENES, "synthetic", f)
+                    if os.path.exists(fp):
+                        digest[f] = hashlib.sha256(open(fp, "rb").read()).hexdigest()
+                save("synthetic_" + name, arrs, dict(meta, scene=paths[name], sha256=digest, whitted=meta2))
         if want("tex"):
             for sc, tag in TEX.items():
                 pre = os.path.join(tmp, "tx")
