@@ -343,8 +343,8 @@ def test_synthetic_scenes(rtu, gpu_ctx, name):
         p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_WHITTED, shade_bounces=5)
         out = sc.render(p, want=("rgb",))
         ok = within_tol(out["rgb"], g["rgb"]).all(axis=2)
-        # A pixel whose reference radiance is NEGATIVE is a sum of Fresnel terms of both signs (mtlFunctions.cpp:283-289
-        # with cos > 1 after a back-face hit); the wavefront adds the same terms in a different order, so the
+        # A pixel whose reference radiance is NEGATIVE is a sum of Fresnel terms of both signs (mtlFunctions.cpp:283-289:
+        # on a back-face hit cos1 < 0, so Fr = R0 + (1-R0)(1-cos1)^5 reaches ~32 and 1-Fr ~ -31); the wavefront adds the same terms in a different order, so the
         # cancellation error is relative to the terms, not to the sum.  Such pixels (1 of 32 400 in spheres_1000) are
         # held to 1e-3 instead, and there may be at most 3 of them.
         loose = ~ok & (g["rgb"].min(axis=2) < 0)
