@@ -33,7 +33,7 @@ template <class T> int dev_upload(const std::vector<T> &h, T **d, cudaStream_t s
     *d = nullptr;
     if (h.empty()) return RTU_OK;
     g_upload_bytes += h.size() * sizeof(T);
-    CU(cudaMalloc((void **)d, h.size() * sizeof(T)));
+    CU(cudaMallocAsync((void **)d, h.size() * sizeof(T), st)); // scene buffers come from the device's stream-ordered pool
     owned.push_back(*d);
     CU(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
     return RTU_OK;
@@ -123,6 +123,14 @@ void kt_reset(rtu_context *c, bool on)
 int free_list(std::vector<void *> &v)
 {
     for (void *p : v) cudaFree(p);
+    v.clear();
+    return 0;
+}
+
+// scene buffers: freed in stream order (no device-wide synchronisation; the pool keeps the memory for the next scene)
+int free_list_async(std::vector<void *> &v, cudaStream_t st)
+{
+    for (void *p : v) cudaFreeAsync(p, st);
     v.clear();
     return 0;
 }
@@ -384,6 +392,13 @@ int rtu_context_create(int32_t device, void *stream, rtu_context **out)
     }
     if (device < 0 || device >= n) { rtu::set_error("rtu_context_create: bad device index"); return RTU_ERR_INVALID; }
     CU(cudaSetDevice(device));
+    {   // scene buffers are stream-ordered allocations: keep freed blocks in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     rtu_context *c = new rtu_context;
     c->device = device;
     c->stream = (cudaStream_t)stream;
@@ -438,7 +453,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     g_upload_bytes = 0;
     memset(&sc->S, 0, sizeof sc->S);
     int rc;
-    auto fail = [&](int code) { free_list(sc->owned); return code; };
+    auto fail = [&](int code) { free_list_async(sc->owned, c->stream); return code; };
 
     // nodes
     std::vector<DNode> nodes(d->n_nodes);
@@ -529,7 +544,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
             for (auto &pr : pix) if (pr.first == t.rgb8) dp = pr.second;
             if (!dp) {
                 size_t bytes = (size_t)t.width * t.height * 3;
-                CU(cudaMalloc((void **)&dp, bytes));
+                CU(cudaMallocAsync((void **)&dp, bytes, c->stream));
                 sc->owned.push_back(dp);
                 CU(cudaMemcpyAsync(dp, t.rgb8, bytes, cudaMemcpyHostToDevice, c->stream));
                 pix.push_back({t.rgb8, dp});
@@ -596,8 +611,7 @@ void rtu_scene_destroy(rtu_scene *s)
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    free_list(s->owned);
+    free_list_async(s->owned, s->ctx->stream); // after everything already queued on the context's stream
     delete s;
 }
 
