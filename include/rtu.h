@@ -153,7 +153,8 @@ typedef struct rtu_hit {
 enum {
     RTU_MODE_PRIMARY = 0, /* one Trace() per pixel centre: node/face ids + z only */
     RTU_MODE_WHITTED = 1, /* Trace + Shade(ray,h,lights,shade_bounces): RenderFunctions.cpp:135 alone */
-    RTU_MODE_PATH = 2     /* HEAD estimator: MonteCarlo GI list + lights (RenderFunctions.cpp:132-135) */
+    RTU_MODE_PATH = 2,    /* HEAD estimator: MonteCarlo GI list + lights (RenderFunctions.cpp:132-135) */
+    RTU_MODE_PHOTON = 3   /* PhotonMapping(ray, hInfo) per sample (RenderFunctions.cpp:141-142, 394-413); needs a photon map */
 };
 enum {
     RTU_PATTERN_CENTER = 0,   /* pixel centre (0.5,0.5); spp must be 1 */
@@ -274,6 +275,51 @@ int rtu_render_device(rtu_scene *scene, const rtu_params *params, float *d_accum
 int rtu_resolve(rtu_scene *scene, const rtu_params *params, const float *d_accum, rtu_image *out);
 int rtu_get_stats(const rtu_scene *scene, rtu_stats *out);
 int rtu_synchronize(rtu_context *ctx);
+
+/* ---- Photon map (dead code at the reference's HEAD, main.cpp:31) -------------------------------
+ * rtu_photon is cyPhotonMap::Photon (cyPhotonMap.h:47-66) byte for byte: a balanced array can be exchanged with the
+ * reference.  plane_dirz: bits 0-1 splitting axis of the kd-tree node, bit 3 = direction z is negative. */
+typedef struct rtu_photon {
+    float position[3];
+    float power;          /* max(r,g,b) of the photon power */
+    uint8_t color[3];     /* Color24(power_rgb / power) */
+    uint8_t plane_dirz;
+    int16_t dir_x, dir_y; /* short(dir * 0x7FFF) */
+} rtu_photon;
+
+typedef struct rtu_photon_params {
+    uint32_t map_size;    /* photonMapSize   = 1000000 (RenderFunctions.cpp:32) */
+    uint32_t max_bounce;  /* photonMaxBounce = 10      (:34) */
+    float est_radius;     /* photonEstRadius = 1       (:35) */
+    float ellipticity;    /* photonEllipticity = 0.5   (:36); at most photonSampleSize = 100 photons per estimate (:33) */
+    uint64_t seed;
+} rtu_photon_params;
+
+typedef struct rtu_photon_stats {
+    uint64_t paths;            /* photon paths emitted (RandomPhoton calls) */
+    uint64_t from_light;       /* photonFromLight: paths whose first segment hit something (:357) */
+    uint64_t stored;           /* photons in the map */
+    uint64_t trace_rays;       /* root-level Trace calls of the emission */
+    float scale_factor;        /* (lights[0] intensity / photonFromLight).Gray()  (:384) */
+    float emit_ms, build_ms;   /* device time of the emission; host time of the kd-tree balancing + upload */
+} rtu_photon_stats;
+
+void rtu_photon_params_default(rtu_photon_params *p);
+/* GeneratePhotonMap(): emits from lights[0] (must be a point light) until map_size photons are stored, scales the
+ * powers, balances the kd-tree (RenderFunctions.cpp:341-392).  Paths are numbered; path i draws from its own
+ * Philox stream and the map holds exactly what the sequential loop over i = 0,1,2,... would have stored. */
+int rtu_photon_map_generate(rtu_scene *scene, const rtu_photon_params *params, rtu_photon_stats *stats);
+/* Installs caller photons (any order, e.g. the reference's own map): PrepareForIrradianceEstimation + upload. */
+int rtu_photon_map_set(rtu_scene *scene, const rtu_photon *photons, uint32_t n, const rtu_photon_params *params);
+/* Copies the balanced map out: out[i] = photons[i+1] of cyPhotonMap, *n = number of photons (cap = room in out). */
+int rtu_photon_map_get(rtu_scene *scene, rtu_photon *out, uint32_t cap, uint32_t *n);
+/* cyPhotonMap::EstimateIrradiance<100>(irrad, direction, radius, pos, &normal, ellipticity, FILTER_TYPE_CONSTANT)
+ * for n query points (cyPhotonMap.h:276-323); found[i] = photons used (may be NULL). */
+int rtu_estimate_irradiance(rtu_scene *scene, const float *pos, const float *normal, int64_t n, float radius, float ellipticity,
+                            float *irrad, float *direction, int32_t *found);
+/* Host only: cyPhotonMap::PrepareForIrradianceEstimation on caller arrays (cyPhotonMap.h:207-274).
+ * in: n photons; out: n+1 records, out[0] unused, out[1..n] the left-balanced kd-tree in heap order. */
+int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_photon *out);
 
 #ifdef __cplusplus
 }

@@ -664,6 +664,8 @@ typedef struct {
     uint64_t seed;
 } job_t;
 
+static col photon_mapping(ctx_t *c, const ray_t *r, const hit_t *h);
+
 static void *render_rows(void *arg)
 {
     job_t *J = (job_t *)arg;
@@ -698,7 +700,9 @@ static void *render_rows(void *arg)
                 hit_init(&h);
                 col v;
                 if (trace(&c, &r, &h)) {
-                    if (P->mode == RTU_MODE_PATH) {                               /* RenderFunctions.cpp:129-135 */
+                    if (P->mode == RTU_MODE_PHOTON) {                             /* RenderFunctions.cpp:141-142 */
+                        v = photon_mapping(&c, &r, &h);
+                    } else if (P->mode == RTU_MODE_PATH) {                        /* RenderFunctions.cpp:129-135 */
                         col amb = monte_carlo(&c, &h, P->gi_bounces);
                         v = cadd(shade(&c, &r, &h, P->shade_bounces, &amb), shade(&c, &r, &h, P->shade_bounces, NULL));
                     } else {
@@ -790,4 +794,277 @@ int oracle_sample_environment(const rtu_scene_desc *S, const float *dir, int64_t
         rgb[3 * i] = c.r; rgb[3 * i + 1] = c.g; rgb[3 * i + 2] = c.b;
     }
     return 0;
+}
+
+/* ================================================================== photon map
+ * cyPhotonMap.h restated on rtu_photon arrays.  Pinned by tests/golden/kat_photonmap.npz, which the reference's own
+ * cyPhotonMap produced: the balanced array is reproduced byte for byte and the estimates bit for bit. */
+
+/* Photon::GetDirection (cyPhotonMap.h:158-181), including the `dirY-dirY` slip at :168 that leaves z = sqrt(1 - x^2) */
+static v3 photon_direction(const rtu_photon *p)
+{
+    v3 d;
+    d.x = (float)p->dir_x / (float)0x7FFF;
+    d.y = (float)p->dir_y / (float)0x7FFF;
+    int xy2 = p->dir_x * p->dir_x + p->dir_y - p->dir_y;
+    if (xy2 > 0x3FFF0001) xy2 = 0x3FFF0001;
+    int z2 = 0x3FFF0001 - xy2;
+    int z = 0, place = 0x40000000, rem = z2;
+    while (place > rem) place >>= 2;
+    while (place) {
+        if (rem >= z + place) {
+            rem = rem - z - place;
+            z = z + (place << 1);
+        }
+        z >>= 1;
+        place >>= 2;
+    }
+    d.z = (float)z / (float)0x7FFF;
+    if (p->plane_dirz & 0x8) d.z = -d.z;
+    return d;
+}
+
+typedef struct {
+    rtu_photon *work; /* 1-based scratch copy that gets partitioned in place */
+    rtu_photon *out;  /* 1-based heap-ordered result */
+} balance_t;
+
+/* PhotonMap::BalanceSegment (cyPhotonMap.h:230-290) */
+static void balance_segment(balance_t *b, v3 lo, v3 hi, int index, int start, int end)
+{
+    int median = 1;
+    while (4 * median <= end - start + 1) median += median;
+    if (3 * median <= end - start + 1) {
+        median += median;
+        median += start - 1;
+    } else {
+        median = end - median + 1;
+    }
+    int axis = 2;
+    v3 ext = sub(hi, lo);
+    if (ext.x > ext.y) {
+        if (ext.x > ext.z) axis = 0;
+    } else if (ext.y > ext.z) {
+        axis = 1;
+    }
+    rtu_photon *ph = b->work;
+    int left = start, right = end;
+    while (right > left) {
+        const float v = ph[right].position[axis];
+        int i = left - 1, j = right;
+        while (ph[++i].position[axis] < v) {}
+        while (ph[--j].position[axis] > v && j > left) {}
+        while (i < j) {
+            rtu_photon t = ph[i]; ph[i] = ph[j]; ph[j] = t;
+            while (ph[++i].position[axis] < v) {}
+            while (ph[--j].position[axis] > v && j > left) {}
+        }
+        rtu_photon t = ph[i]; ph[i] = ph[right]; ph[right] = t;
+        if (i >= median) right = i - 1;
+        if (i <= median) left = i + 1;
+    }
+    b->out[index] = ph[median];
+    b->out[index].plane_dirz = (uint8_t)((b->out[index].plane_dirz & 0x8) | (axis & 0x3)); /* SetPlane (:64) */
+    float split = b->out[index].position[axis];
+    if (median > start) {
+        if (start < median - 1) {
+            v3 h2 = hi;
+            if (axis == 0) h2.x = split; else if (axis == 1) h2.y = split; else h2.z = split;
+            balance_segment(b, lo, h2, 2 * index, start, median - 1);
+        } else {
+            b->out[2 * index] = ph[start];
+        }
+    }
+    if (median < end) {
+        if (median + 1 < end) {
+            v3 l2 = lo;
+            if (axis == 0) l2.x = split; else if (axis == 1) l2.y = split; else l2.z = split;
+            balance_segment(b, l2, hi, 2 * index + 1, median + 1, end);
+        } else {
+            b->out[2 * index + 1] = ph[end];
+        }
+    }
+}
+
+/* PhotonMap::PrepareForIrradianceEstimation (cyPhotonMap.h:207-228).  in: n photons; out: n+1 records (out[0] is
+ * the unused, zeroed slot 0 of the reference's vector).  The bounding box starts from that zero slot (:212-213). */
+int oracle_balance_photons(const rtu_photon *in, uint32_t n, rtu_photon *out)
+{
+    memset(out, 0, sizeof(rtu_photon) * ((size_t)n + 1));
+    if (n == 0) return 0;
+    balance_t b;
+    b.work = (rtu_photon *)malloc(sizeof(rtu_photon) * ((size_t)n + 1));
+    if (!b.work) return 1;
+    memset(&b.work[0], 0, sizeof(rtu_photon));
+    memcpy(&b.work[1], in, sizeof(rtu_photon) * (size_t)n);
+    b.out = out;
+    v3 lo = V(0, 0, 0), hi = V(0, 0, 0);
+    for (uint32_t i = 1; i <= n; i++) {
+        const float *p = b.work[i].position;
+        if (lo.x > p[0]) lo.x = p[0];
+        if (hi.x < p[0]) hi.x = p[0];
+        if (lo.y > p[1]) lo.y = p[1];
+        if (hi.y < p[1]) hi.y = p[1];
+        if (lo.z > p[2]) lo.z = p[2];
+        if (hi.z < p[2]) hi.z = p[2];
+    }
+    balance_segment(&b, lo, hi, 1, 1, (int)n);
+    free(b.work);
+    return 0;
+}
+
+#define ORACLE_MAX_PHOTONS 100 /* photonSampleSize (RenderFunctions.cpp:33) */
+typedef struct {
+    v3 pos, normal;
+    int has_normal;
+    float norm_scale;
+    int found;
+    float dist2[ORACLE_MAX_PHOTONS + 1];
+    rtu_photon photon[ORACLE_MAX_PHOTONS + 1];
+} nearest_t;
+
+/* PhotonMap::LocatePhotons (cyPhotonMap.h:350-424) */
+static void locate_photons(const rtu_photon *map, int half_stored, nearest_t *np, int index)
+{
+    const rtu_photon *p = &map[index];
+    int axis = p->plane_dirz & 0x3;
+    if (index < half_stored) {
+        float qa = axis == 0 ? np->pos.x : (axis == 1 ? np->pos.y : np->pos.z);
+        float dist = qa - p->position[axis];
+        if (dist > 0) {
+            locate_photons(map, half_stored, np, 2 * index + 1);
+            if (dist * dist < np->dist2[0]) locate_photons(map, half_stored, np, 2 * index);
+        } else {
+            locate_photons(map, half_stored, np, 2 * index);
+            if (dist * dist < np->dist2[0]) locate_photons(map, half_stored, np, 2 * index + 1);
+        }
+    }
+    v3 dif = sub(V(p->position[0], p->position[1], p->position[2]), np->pos);
+    float dist2 = dot(dif, dif);
+    if (dist2 < np->dist2[0]) {
+        if (np->has_normal) {
+            v3 dir = photon_direction(p);
+            if (dot(dir, np->normal) >= 0) return;
+            if (np->norm_scale > 0) {
+                float perp = dot(dif, np->normal);
+                dif = add(dif, mulf(np->normal, perp * np->norm_scale));
+                dist2 = dot(dif, dif);
+                if (dist2 >= np->dist2[0]) return;
+            }
+        }
+        if (np->found < ORACLE_MAX_PHOTONS) {
+            np->found++;
+            np->dist2[np->found] = dist2;
+            np->photon[np->found] = *p;
+            if (np->found == ORACLE_MAX_PHOTONS) { /* heapify */
+                int half_found = np->found >> 1;
+                for (int k = half_found; k >= 1; k--) {
+                    int parent = k;
+                    rtu_photon tp = np->photon[k];
+                    float td2 = np->dist2[k];
+                    while (parent <= half_found) {
+                        int j = parent + parent;
+                        if (j < np->found && np->dist2[j] < np->dist2[j + 1]) j++;
+                        if (td2 >= np->dist2[j]) break;
+                        np->dist2[parent] = np->dist2[j];
+                        np->photon[parent] = np->photon[j];
+                        parent = j;
+                    }
+                    np->photon[parent] = tp;
+                    np->dist2[parent] = td2;
+                }
+            }
+        } else {
+            int parent = 1, j = 2;
+            while (j <= np->found) {
+                if (j < np->found && np->dist2[j] < np->dist2[j + 1]) j++;
+                if (dist2 > np->dist2[j]) break;
+                np->dist2[parent] = np->dist2[j];
+                np->photon[parent] = np->photon[j];
+                parent = j;
+                j <<= 1;
+            }
+            np->photon[parent] = *p;
+            np->dist2[parent] = dist2;
+            np->dist2[0] = np->dist2[1];
+        }
+    }
+}
+
+/* PhotonMap::EstimateIrradiance<100>, FILTER_TYPE_CONSTANT (cyPhotonMap.h:276-323).
+ * map: n+1 balanced records (oracle_balance_photons), pos/normal: nq x 3. */
+int oracle_estimate_irradiance(const rtu_photon *map, uint32_t n, const float *pos, const float *normal, int64_t nq, float radius,
+                               float ellipticity, float *irrad, float *direction, int32_t *found)
+{
+    int half_stored = (int)n / 2 - 1;
+    for (int64_t q = 0; q < nq; q++) {
+        col e = C(0, 0, 0);
+        v3 d = V(0, 0, 0);
+        nearest_t np;
+        np.pos = V(pos[q * 3], pos[q * 3 + 1], pos[q * 3 + 2]);
+        np.has_normal = normal != NULL;
+        if (normal) np.normal = V(normal[q * 3], normal[q * 3 + 1], normal[q * 3 + 2]);
+        np.norm_scale = ellipticity == 1 ? 0 : 1 / ellipticity - 1;
+        np.found = 0;
+        np.dist2[0] = radius * radius;
+        if (n > 0) locate_photons(map, half_stored, &np, 1);
+        for (int i = 1; i <= np.found; i++) {
+            const rtu_photon *p = &np.photon[i];
+            col pw = cscale(C(p->color[0] / 255.0f, p->color[1] / 255.0f, p->color[2] / 255.0f), p->power); /* GetPower (:57) */
+            float filter = 1;
+            e = cadd(e, cscale(pw, filter));
+            d = add(d, mulf(photon_direction(p), filter * p->power));
+        }
+        if (np.found > 0) {
+            float area = (float)M_PI * np.dist2[0];
+            if (area > 0) {
+                const float inv = 1.0f / area;
+                e = cscale(e, inv);
+            }
+            d = unit(d); /* Normalize(): *this /= Length() */
+        }
+        irrad[q * 3] = e.r; irrad[q * 3 + 1] = e.g; irrad[q * 3 + 2] = e.b;
+        direction[q * 3] = d.x; direction[q * 3 + 1] = d.y; direction[q * 3 + 2] = d.z;
+        if (found) found[q] = np.found;
+    }
+    return 0;
+}
+
+
+/* The map RTU_MODE_PHOTON renders with: balanced records (n+1) and the estimate's radius / ellipticity. */
+static const rtu_photon *g_map = NULL;
+static uint32_t g_map_n = 0;
+static float g_map_radius = 1.0f, g_map_ellipticity = 0.5f;
+
+int oracle_set_photon_map(const rtu_photon *balanced, uint32_t n, float radius, float ellipticity)
+{
+    g_map = balanced; g_map_n = n; g_map_radius = radius; g_map_ellipticity = ellipticity;
+    return 0;
+}
+
+/* PhotonMapping (RenderFunctions.cpp:394-413): Shade(r, hInfo, {PhotonLight(irradiance, direction)}, 0).
+ * PhotonLight (lights.h:61-74): Illuminate = intensity (no shadow ray), Direction = direction.GetNormalized(). */
+static col photon_mapping(ctx_t *c, const ray_t *r, const hit_t *h)
+{
+    const rtu_scene_desc *S = c->S;
+    float pos[3] = {h->p.x, h->p.y, h->p.z}, nrm[3] = {h->N.x, h->N.y, h->N.z}, e[3], d[3];
+    oracle_estimate_irradiance(g_map, g_map_n, pos, nrm, 1, g_map_radius, g_map_ellipticity, e, d, NULL);
+    v3 dir = unit(V(d[0], d[1], d[2])); /* SetDirection normalises again; 0/0 = NaN when no photon was found */
+    int mi = S->nodes[h->node].material;
+    if (mi < 0) return C(1, 1, 1);
+    const rtu_material *M = &S->materials[mi];
+    col out = C(0, 0, 0);
+    if (h->front) {
+        v3 view = unit(sub(V(S->camera.pos[0], S->camera.pos[1], S->camera.pos[2]), h->p));
+        v3 ld = unit(neg(dir));
+        v3 hv = unit(add(view, ld));
+        float ndl = dot(h->N, ld), ndh = dot(h->N, hv);
+        if (ndl < 0.0) ndl = 0.0;
+        if (ndh < 0.0) ndh = 0.0;
+        col il = C(e[0], e[1], e[2]);
+        col brdf = cadd(tc_sample(S, &M->diffuse, h->uvw), cscale(tc_sample(S, &M->specular, h->uvw), powf(ndh, M->glossiness)));
+        out = cadd(out, cmul(cscale(il, ndl), brdf));
+    }
+    (void)r;
+    return out;
 }

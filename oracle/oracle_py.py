@@ -119,3 +119,43 @@ def sample_environment(desc, dirs):
     out = np.zeros_like(dirs)
     L.oracle_sample_environment(C.byref(desc), C.c_void_p(dirs.ctypes.data), C.c_int64(len(dirs)), C.c_void_p(out.ctypes.data))
     return out
+
+
+PHOTON_DTYPE = np.dtype([("position", "<f4", 3), ("power", "<f4"), ("color", "u1", 3), ("plane_dirz", "u1"), ("dir_x", "<i2"), ("dir_y", "<i2")])
+assert PHOTON_DTYPE.itemsize == 24
+
+
+def balance_photons(photons):
+    """cyPhotonMap::PrepareForIrradianceEstimation; returns n+1 records (index 0 unused)."""
+    L = lib()
+    photons = np.ascontiguousarray(photons, PHOTON_DTYPE)
+    out = np.zeros(photons.shape[0] + 1, PHOTON_DTYPE)
+    rc = L.oracle_balance_photons(C.c_void_p(photons.ctypes.data), C.c_uint32(photons.shape[0]), C.c_void_p(out.ctypes.data))
+    assert rc == 0
+    return out
+
+
+def estimate_irradiance(balanced, pos, normal, radius, ellipticity):
+    """cyPhotonMap::EstimateIrradiance<100> on a balanced map (n+1 records)."""
+    L = lib()
+    balanced = np.ascontiguousarray(balanced, PHOTON_DTYPE)
+    pos = np.ascontiguousarray(pos, "f4")
+    normal = np.ascontiguousarray(normal, "f4")
+    nq = pos.shape[0]
+    irrad = np.zeros((nq, 3), "f4"); direction = np.zeros((nq, 3), "f4"); found = np.zeros(nq, "i4")
+    rc = L.oracle_estimate_irradiance(C.c_void_p(balanced.ctypes.data), C.c_uint32(balanced.shape[0] - 1), C.c_void_p(pos.ctypes.data),
+                                      C.c_void_p(normal.ctypes.data), C.c_int64(nq), C.c_float(radius), C.c_float(ellipticity),
+                                      C.c_void_p(irrad.ctypes.data), C.c_void_p(direction.ctypes.data), C.c_void_p(found.ctypes.data))
+    assert rc == 0
+    return irrad, direction, found
+
+
+_photon_keepalive = None
+
+
+def set_photon_map(balanced, radius=1.0, ellipticity=0.5):
+    """The map RTU_MODE_PHOTON of oracle.render uses (balanced: n+1 records)."""
+    global _photon_keepalive
+    L = lib()
+    _photon_keepalive = np.ascontiguousarray(balanced, PHOTON_DTYPE)
+    L.oracle_set_photon_map(C.c_void_p(_photon_keepalive.ctypes.data), C.c_uint32(_photon_keepalive.shape[0] - 1), C.c_float(radius), C.c_float(ellipticity))

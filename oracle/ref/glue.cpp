@@ -55,3 +55,8 @@ Point3 RefCalculateImageOrigin(float d) { return CalculateImageOrigin(d); }
 Point3 RefCalculateCurrentPoint(int i, int j, float ox, float oy, Point3 o) { return CalculateCurrentPoint(i, j, ox, oy, o); }
 void RefRender(PixelIterator &it) { Render(it); }
 void RefMonteCarlo(LightList &l, const HitInfo &h, int x, int y, int bounces, int n) { MonteCarlo(l, h, x, y, bounces, n); }
+
+// photon path (dead code at the reference's HEAD: main.cpp:31, RenderFunctions.cpp:139-142 are commented out)
+void RefGeneratePhotonMap() { GeneratePhotonMap(); }
+Color RefPhotonMapping(const Ray &r, const HitInfo &h) { return PhotonMapping(r, h); }
+cyPhotonMap *RefPhotonMap() { return &pMap; }

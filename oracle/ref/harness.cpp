@@ -9,6 +9,8 @@
 //             RenderFunctions.cpp:77-97               -> linear RGB mean, RGB8 after gamma
 //   head    : the reference Render() unchanged (threads joined, not busy-waited)
 //   kat     : seeded random rays through Sphere/Plane/Box/BVHBox/TriObj::IntersectRay
+//   photonkat: seeded photons through cyPhotonMap::AddPhoton / PrepareForIrradianceEstimation / EstimateIrradiance<100>
+//   photon  : GeneratePhotonMap() + PhotonMapping() per pixel centre (RenderFunctions.cpp:341-413)
 //   dump    : loader results (node transforms, camera, meshes, BVH, materials, lights)
 // Everything numerical is computed by reference code; this file only drives it and writes
 // .npy files.  Built by oracle/ref/Makefile into oracle/_ref/ref_harness (git-ignored).
@@ -20,6 +22,7 @@
 #include "ExternalLibrary/materials.h"
 #include "ExternalLibrary/lights.h"
 #include "ExternalLibrary/texture.h"
+#include "ExternalLibrary/cyPhotonMap.h"
 #undef private
 #undef protected
 extern RenderImage renderImage;
@@ -44,6 +47,9 @@ Point3 RefCalculateImageOrigin(float d);
 Point3 RefCalculateCurrentPoint(int i, int j, float ox, float oy, Point3 o);
 void RefRender(PixelIterator &it);
 float BVHBoxIntersection(const Ray &r, Box bvhBox, float t_max);
+void RefGeneratePhotonMap();
+Color RefPhotonMapping(const Ray &r, const HitInfo &h);
+cyPhotonMap *RefPhotonMap();
 int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pattern, double *device_ms, unsigned long long *rays);
 
 // ---------------------------------------------------------------- npy output
@@ -552,6 +558,122 @@ static void ModeGpu(const Opts &o)
     fprintf(stderr, "{\"mode\":\"gpu\",\"width\":%d,\"height\":%d,\"spp\":%d,\"rays\":%llu,\"device_ms\":%.3f}\n", W, H, o.spp, rays, ms);
 }
 
+
+// ---------------------------------------------------------------- photon map
+static_assert(sizeof(cyPhotonMap::Photon) == 24, "photon record is 24 bytes");
+static void DumpPhotons(const std::string &path, const cyPhotonMap &m, int first, int count)
+{
+    std::vector<unsigned char> raw((size_t)count * 24);
+    if (count) memcpy(raw.data(), &m.photons[first], raw.size());
+    NpyU8(path, raw, {(size_t)count, 24});
+}
+
+static void ModePhotonKat(const Opts &o)
+{
+    // photons on three surfaces (a floor, a wall, a sphere) so that the normal / ellipticity filters matter
+    g_rng = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)o.seed;
+    const int n = o.n;
+    cyPhotonMap m;
+    m.Resize(n);
+    for (int i = 0; i < n; i++) {
+        Point3 pos, nrm;
+        int s = i % 3;
+        if (s == 0) { pos = Point3(RndS(10), RndS(10), 0.01f * RndS(1)); nrm = Point3(0, 0, 1); }
+        else if (s == 1) { pos = Point3(-10 + 0.01f * RndS(1), RndS(10), 10 * Rnd()); nrm = Point3(1, 0, 0); }
+        else { Point3 d(RndS(1), RndS(1), RndS(1)); d.Normalize(); pos = Point3(2, 1, 3) + d * 2.5f; nrm = d; }
+        Point3 dir(RndS(1), RndS(1), RndS(1));
+        dir.Normalize();
+        if (Rnd() < 0.8f && dir % nrm > 0) dir = -dir;   // most photons arrive from the front side
+        Color pw(Rnd() * 2, Rnd() * 1.5f, Rnd());
+        m.AddPhoton(pos, dir, pw);
+    }
+    m.ScalePhotonPowers(0.37f);
+    DumpPhotons(o.out + "_photons_in.npy", m, 1, m.NumPhotons());
+    m.PrepareForIrradianceEstimation();
+    DumpPhotons(o.out + "_photons_balanced.npy", m, 1, m.NumPhotons());
+    const int q = 4096;
+    std::vector<float> qp(q * 3), qn(q * 3), irr(q * 3 * 4), dir(q * 3 * 4);
+    const float radius[4] = {1.0f, 1.0f, 0.25f, 3.0f}, ell[4] = {0.5f, 1.0f, 0.5f, 0.2f};
+    for (int i = 0; i < q; i++) {
+        Point3 pos, nrm;
+        int s = i % 4;
+        if (s == 0) { pos = Point3(RndS(10), RndS(10), 0); nrm = Point3(0, 0, 1); }
+        else if (s == 1) { pos = Point3(-10, RndS(10), 10 * Rnd()); nrm = Point3(1, 0, 0); }
+        else if (s == 2) { Point3 d(RndS(1), RndS(1), RndS(1)); d.Normalize(); pos = Point3(2, 1, 3) + d * 2.5f; nrm = d; }
+        else { pos = Point3(RndS(12), RndS(12), RndS(12)); nrm = Point3(RndS(1), RndS(1), RndS(1)); nrm.Normalize(); }
+        for (int k = 0; k < 3; k++) { qp[i * 3 + k] = pos[k]; qn[i * 3 + k] = nrm[k]; }
+        for (int v = 0; v < 4; v++) {
+            Color c;
+            Point3 d;
+            m.EstimateIrradiance<100>(c, d, radius[v], pos, &nrm, ell[v]);
+            irr[(v * q + i) * 3 + 0] = c.r; irr[(v * q + i) * 3 + 1] = c.g; irr[(v * q + i) * 3 + 2] = c.b;
+            for (int k = 0; k < 3; k++) dir[(v * q + i) * 3 + k] = d[k];
+        }
+    }
+    NpyF(o.out + "_qpos.npy", qp, {(size_t)q, 3});
+    NpyF(o.out + "_qnormal.npy", qn, {(size_t)q, 3});
+    NpyF(o.out + "_irrad.npy", irr, {4, (size_t)q, 3});
+    NpyF(o.out + "_dir.npy", dir, {4, (size_t)q, 3});
+    fprintf(stderr, "{\"mode\":\"photonkat\",\"photons\":%d,\"queries\":%d,\"radius\":[1.0,1.0,0.25,3.0],\"ellipticity\":[0.5,1.0,0.5,0.2],\"max_photons\":100}\n", n, q);
+}
+
+static void ModePhoton(const Opts &o)
+{
+    int W = camera.imgWidth, H = camera.imgHeight;
+    srand((unsigned)o.seed);
+    g_traceCalls = 0;
+    double t0 = Now();
+    fflush(stdout);
+    int saved = dup(1);
+    FILE *cap = tmpfile();
+    dup2(fileno(cap), 1);
+    RefGeneratePhotonMap();       // prints "Photon From Light: %i" / "Photon Scale Factor: %f" (RenderFunctions.cpp:386-387)
+    fflush(stdout);
+    dup2(saved, 1);
+    double tGen = Now() - t0;
+    unsigned long long emitTraces = g_traceCalls;
+    rewind(cap);
+    int fromLight = 0;
+    float scale = 0;
+    char line[256];
+    while (fgets(line, sizeof line, cap)) {
+        sscanf(line, "Photon From Light: %i", &fromLight);
+        sscanf(line, "Photon Scale Factor: %f", &scale);
+    }
+    fclose(cap);
+    cyPhotonMap *m = RefPhotonMap();
+    DumpPhotons(o.out + "_photons_balanced.npy", *m, 1, m->NumPhotons());
+    std::vector<float> rgb((size_t)W * H * 3), irr((size_t)W * H * 3), dir((size_t)W * H * 3);
+    std::vector<int> node((size_t)W * H);
+    t0 = Now();
+    ParallelRows(0, H, o.threads, [&](int y, int) {
+        for (int x = 0; x < W; x++) {
+            Ray r = CameraRay(x, y, 0.5f, 0.5f, 0, 0);
+            HitInfo h;
+            size_t i = x + (size_t)W * y;
+            Color c = background.Sample(Point3((float)x / camera.imgWidth, (float)y / camera.imgHeight, 0));
+            Color e(0, 0, 0);
+            Point3 d(0, 0, 0);
+            node[i] = -1;
+            if (Trace(r, &rootNode, h)) {
+                node[i] = g_nodeIndex[h.node];
+                m->EstimateIrradiance<100>(e, d, 1.0f, h.p, &h.N, 0.5f);   // what PhotonMapping computes first (RenderFunctions.cpp:401)
+                c = RefPhotonMapping(r, h);
+            }
+            rgb[i * 3] = c.r; rgb[i * 3 + 1] = c.g; rgb[i * 3 + 2] = c.b;
+            irr[i * 3] = e.r; irr[i * 3 + 1] = e.g; irr[i * 3 + 2] = e.b;
+            for (int k = 0; k < 3; k++) dir[i * 3 + k] = d[k];
+        }
+    });
+    double tGather = Now() - t0;
+    NpyF(o.out + "_rgb.npy", rgb, {(size_t)H, (size_t)W, 3});
+    NpyF(o.out + "_irrad.npy", irr, {(size_t)H, (size_t)W, 3});
+    NpyF(o.out + "_dir.npy", dir, {(size_t)H, (size_t)W, 3});
+    NpyI(o.out + "_node.npy", node, {(size_t)H, (size_t)W});
+    fprintf(stderr, "{\"mode\":\"photon\",\"width\":%d,\"height\":%d,\"photons\":%d,\"from_light\":%d,\"scale\":%.9g,\"emit_traces\":%llu,\"emit_seconds\":%.3f,\"gather_seconds\":%.3f,\"threads\":%d}\n",
+            W, H, m->NumPhotons(), fromLight, scale, emitTraces, tGen, tGather, o.threads);
+}
+
 int main(int argc, char **argv)
 {
     Opts o;
@@ -606,6 +728,8 @@ int main(int argc, char **argv)
     else if (o.mode == "tex") ModeTex(o);
     else if (o.mode == "dump") ModeDump(o);
     else if (o.mode == "gpu") ModeGpu(o);
+    else if (o.mode == "photonkat") ModePhotonKat(o);
+    else if (o.mode == "photon") ModePhoton(o);
     else { fprintf(stderr, "unknown mode %s\n", o.mode.c_str()); return 2; }
     return 0;
 }

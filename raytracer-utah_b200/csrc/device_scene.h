@@ -160,6 +160,14 @@ enum RayKind {
     RK_GI = 5        // cosine-hemisphere bounce of MonteCarlo() (RenderFunctions.cpp:561-575)
 };
 
+// The photon map (cyPhotonMap): n+1 records in heap order, record 0 unused; nodes below `half` are internal
+// (halfStoredPhotons = n/2 - 1, cyPhotonMap.h:227,356)
+struct DPhotonMap {
+    const rtu_photon *map;
+    int n, half;
+    float radius, norm_scale; // photonEstRadius; 1/ellipticity - 1 (0 when ellipticity == 1)
+};
+
 // counters per kernel class: 0 = primary wave (and the batched closest-hit operators),
 // 1 = secondary (queue) waves, 2 = shadow waves (and the batched any-hit operator)
 struct DCounterBlock {

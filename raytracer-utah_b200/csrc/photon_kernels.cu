@@ -1,0 +1,472 @@
+// sm_100a kernels of the photon path (reference: RenderFunctions.cpp:341-413,
+// mtlFunctions.cpp:19-118, lightFunctions.cpp:19-25, cyPhotonMap.h:104-424).
+//
+//   k_photon_emit     one thread per photon PATH (numbered; path i owns Philox stream i): RandomPhoton, Trace, up to
+//                     max_bounce x RandomPhotonBounce; the photons the path would store go to a per-path staging slot
+//   k_photon_compact  staging -> map, at offsets from the scan of the per-path counts (path order = the order of the
+//                     reference's sequential loop, so the map holds exactly the photons that loop would have stored)
+//   k_photon_scale    ScalePhotonPowers
+//   k_estimate        EstimateIrradiance<100> per query point (batched operator)
+//   k_photon_shade    PhotonMapping(ray, hInfo) per primary hit of the hit queue (RTU_MODE_PHOTON)
+//
+// The gather walks the kd-tree in the reference's order (near child, far child if still in range, then the node
+// itself) with the reference's 100-entry max-heap, so the photons it returns and the order they are summed in are
+// the reference's: irradiance and direction are bit-identical to cyPhotonMap's on the same map.
+#include "rtu_internal.h"
+#include "shade.cuh"
+#include "camera.cuh"
+
+#define WAVE_THREADS_PHOTON 256
+
+#define PHOTON_K 100 // photonSampleSize (RenderFunctions.cpp:33)
+
+struct PhotonRec {
+    float x, y, z, power;
+    unsigned packed0; // color r,g,b, plane_dirz
+    unsigned packed1; // dir_x | dir_y << 16
+};
+
+__device__ __forceinline__ PhotonRec load_photon(const rtu_photon *map, int index)
+{
+    const uint2 *q = reinterpret_cast<const uint2 *>(map + index);
+    uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    PhotonRec p;
+    p.x = __uint_as_float(a.x); p.y = __uint_as_float(a.y);
+    p.z = __uint_as_float(b.x); p.power = __uint_as_float(b.y);
+    p.packed0 = c.x; p.packed1 = c.y;
+    return p;
+}
+
+// Photon::GetDirection (cyPhotonMap.h:158-181) with its `dirY-dirY` slip: z = isqrt(0x3FFF0001 - dirX^2)
+__device__ __forceinline__ void photon_direction(const PhotonRec &p, float &dx, float &dy, float &dz)
+{
+    int ix = (int)(short)(p.packed1 & 0xffffu), iy = (int)(short)(p.packed1 >> 16);
+    dx = (float)ix / 32767.0f;
+    dy = (float)iy / 32767.0f;
+    int xy2 = ix * ix + iy - iy;
+    if (xy2 > 0x3FFF0001) xy2 = 0x3FFF0001;
+    int rem = 0x3FFF0001 - xy2, z = 0, place = 0x40000000;
+    while (place > rem) place >>= 2;
+    while (place) {
+        if (rem >= z + place) {
+            rem = rem - z - place;
+            z = z + (place << 1);
+        }
+        z >>= 1;
+        place >>= 2;
+    }
+    dz = (float)z / 32767.0f;
+    if ((p.packed0 >> 24) & 0x8u) dz = -dz;
+}
+
+struct Gather {
+    float d2[PHOTON_K + 1];
+    int idx[PHOTON_K + 1];
+    int found;
+};
+
+// LocatePhotons's per-node part (cyPhotonMap.h:368-423)
+__device__ __forceinline__ void gather_visit(const rtu_photon *map, int index, float qx, float qy, float qz, bool has_n, float nx,
+                                             float ny, float nz, float norm_scale, Gather &G)
+{
+    const PhotonRec p = load_photon(map, index);
+    float fx = p.x - qx, fy = p.y - qy, fz = p.z - qz;
+    float dist2 = dot3(fx, fy, fz, fx, fy, fz);
+    if (!(dist2 < G.d2[0])) return;
+    if (has_n) {
+        float dx, dy, dz;
+        photon_direction(p, dx, dy, dz);
+        if (dot3(dx, dy, dz, nx, ny, nz) >= 0.f) return;
+        if (norm_scale > 0.f) {
+            float perp = dot3(fx, fy, fz, nx, ny, nz);
+            float s = perp * norm_scale;
+            fx = fx + nx * s; fy = fy + ny * s; fz = fz + nz * s;
+            dist2 = dot3(fx, fy, fz, fx, fy, fz);
+            if (dist2 >= G.d2[0]) return;
+        }
+    }
+    if (G.found < PHOTON_K) {
+        G.found++;
+        G.d2[G.found] = dist2;
+        G.idx[G.found] = index;
+        if (G.found == PHOTON_K) { // build the max-heap (:385-401)
+            const int half = G.found >> 1;
+            for (int k = half; k >= 1; k--) {
+                int parent = k;
+                int ti = G.idx[k];
+                float td = G.d2[k];
+                while (parent <= half) {
+                    int j = parent + parent;
+                    if (j < G.found && G.d2[j] < G.d2[j + 1]) j++;
+                    if (td >= G.d2[j]) break;
+                    G.d2[parent] = G.d2[j];
+                    G.idx[parent] = G.idx[j];
+                    parent = j;
+                }
+                G.idx[parent] = ti;
+                G.d2[parent] = td;
+            }
+        }
+    } else { // replace the farthest (:403-418)
+        int parent = 1, j = 2;
+        while (j <= G.found) {
+            if (j < G.found && G.d2[j] < G.d2[j + 1]) j++;
+            if (dist2 > G.d2[j]) break;
+            G.d2[parent] = G.d2[j];
+            G.idx[parent] = G.idx[j];
+            parent = j;
+            j <<= 1;
+        }
+        G.idx[parent] = index;
+        G.d2[parent] = dist2;
+        G.d2[0] = G.d2[1];
+    }
+}
+
+// EstimateIrradiance<100>(irrad, direction, radius, pos, normal, ellipticity, FILTER_TYPE_CONSTANT) (:276-323)
+__device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx, float qy, float qz, bool has_n, float nx, float ny,
+                                                 float nz, float radius, float norm_scale, Col &irrad, float &ox, float &oy,
+                                                 float &oz, int &found)
+{
+    Gather G;
+    G.found = 0;
+    G.d2[0] = radius * radius;
+    if (PM.n > 0) {
+        // explicit form of the recursion: frame = node | state << 28; state 0 = entered, 1 = near child done, 2 = both done
+        unsigned frame[32];
+        float fdist[32];
+        int top = 0;
+        frame[0] = 1u;
+        fdist[0] = 0.f;
+        while (top >= 0) {
+            unsigned f = frame[top];
+            int index = (int)(f & 0x0fffffffu);
+            unsigned state = f >> 28;
+            if (state == 0) {
+                if (index < PM.half) {
+                    const PhotonRec p = load_photon(PM.map, index);
+                    unsigned axis = (p.packed0 >> 24) & 0x3u;
+                    float dist = (axis == 0 ? qx : (axis == 1 ? qy : qz)) - (axis == 0 ? p.x : (axis == 1 ? p.y : p.z));
+                    fdist[top] = dist;
+                    frame[top] = (unsigned)index | (1u << 28);
+                    int near_child = dist > 0 ? 2 * index + 1 : 2 * index;
+                    top++;
+                    frame[top] = (unsigned)near_child;
+                    continue;
+                }
+                state = 2;
+            }
+            if (state == 1) {
+                float dist = fdist[top];
+                frame[top] = (unsigned)index | (2u << 28);
+                if (dist * dist < G.d2[0]) {
+                    int far_child = dist > 0 ? 2 * index : 2 * index + 1;
+                    top++;
+                    frame[top] = (unsigned)far_child;
+                    continue;
+                }
+            }
+            gather_visit(PM.map, index, qx, qy, qz, has_n, nx, ny, nz, norm_scale, G);
+            top--;
+        }
+    }
+    irrad = mk(0, 0, 0);
+    ox = oy = oz = 0.f;
+    for (int i = 1; i <= G.found; i++) {
+        const PhotonRec p = load_photon(PM.map, G.idx[i]);
+        Col pw = mk((float)(p.packed0 & 0xffu) / 255.0f, (float)((p.packed0 >> 8) & 0xffu) / 255.0f, (float)((p.packed0 >> 16) & 0xffu) / 255.0f) * p.power;
+        const float filter = 1.f;
+        irrad = irrad + pw * filter;
+        float dx, dy, dz;
+        photon_direction(p, dx, dy, dz);
+        float w = filter * p.power;
+        ox = ox + dx * w; oy = oy + dy * w; oz = oz + dz * w;
+    }
+    if (G.found > 0) {
+        float area = 3.14159274101257324f * G.d2[0]; // (float)M_PI
+        if (area > 0.f) {
+            const float inv = 1.0f / area;
+            irrad = irrad * inv;
+        }
+        norm3(ox, oy, oz);
+    }
+    found = G.found;
+}
+
+__global__ void __launch_bounds__(128)
+k_estimate(DPhotonMap PM, const float *pos, const float *normal, long long n, float radius, float norm_scale, float *irrad,
+           float *direction, int *found)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Col e;
+    float dx, dy, dz;
+    int f;
+    bool has_n = normal != nullptr;
+    float nx = has_n ? normal[i * 3] : 0.f, ny = has_n ? normal[i * 3 + 1] : 0.f, nz = has_n ? normal[i * 3 + 2] : 0.f;
+    estimate_irradiance(PM, pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2], has_n, nx, ny, nz, radius, norm_scale, e, dx, dy, dz, f);
+    irrad[i * 3] = e.r; irrad[i * 3 + 1] = e.g; irrad[i * 3 + 2] = e.b;
+    direction[i * 3] = dx; direction[i * 3 + 1] = dy; direction[i * 3 + 2] = dz;
+    if (found) found[i] = f;
+}
+
+// PhotonMapping (RenderFunctions.cpp:394-413): the estimate becomes a PhotonLight (lights.h:61-74: Illuminate =
+// intensity, Direction = direction, not ambient, no shadow ray) and the hit is shaded with it alone, bounceCount 0.
+// A hit without photons in range has direction 0/0 = NaN and shades to NaN, as in the reference.
+__global__ void __launch_bounds__(128)
+k_photon_shade(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float4 *accum)
+{
+    unsigned total = *hq.count;
+    if (total > hq.cap) total = hq.cap;
+    unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= total) return;
+    float4 a = hq.a[h], b = hq.b[h];
+    Best B;
+    B.z = a.x; B.node = __float_as_int(a.y); B.front = __float_as_int(a.z); B.slot = __float_as_int(a.w);
+    B.bc1 = b.x; B.bc2 = b.y; B.bc3 = b.z;
+    unsigned idx = __float_as_uint(b.w);
+    // the primary ray of work item idx (same mapping as k_extend<primary>)
+    PrimaryMap pm;
+    pm.init(F);
+    int s, x, y;
+    pm.decode(idx, s0, s, x, y);
+    int pixel = y * pm.W + x;
+    Ray ray = primary_ray(F, s, x, y, pixel);
+    HitRec H;
+    finalize_hit(S, ray, B, H);
+    Col e;
+    float dx, dy, dz;
+    int found;
+    estimate_irradiance(PM, H.px, H.py, H.pz, true, H.nx, H.ny, H.nz, PM.radius, PM.norm_scale, e, dx, dy, dz, found);
+    norm3(dx, dy, dz); // PhotonLight::SetDirection normalises once more (lights.h:70)
+    Col out = mk(0, 0, 0);
+    if (H.material < 0) {
+        out = mk(1, 1, 1);
+    } else if (H.front) {
+        const DMaterial &M = S.materials[H.material];
+        Col Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
+        Col Ks = texcolor_sample(S, M.specular, H.u, H.v, H.w);
+        float vx = S.cam_pos[0] - H.px, vy = S.cam_pos[1] - H.py, vz = S.cam_pos[2] - H.pz; // mtlFunctions.cpp:137
+        norm3(vx, vy, vz);
+        float lx = -dx, ly = -dy, lz = -dz;
+        norm3(lx, ly, lz);
+        float hx = vx + lx, hy = vy + ly, hz = vz + lz;
+        norm3(hx, hy, hz);
+        float ndl = dot3(H.nx, H.ny, H.nz, lx, ly, lz);
+        float ndh = dot3(H.nx, H.ny, H.nz, hx, hy, hz);
+        if (ndl < 0.f) ndl = 0.f;
+        if (ndh < 0.f) ndh = 0.f;
+        out = (e * ndl) * (Kd + Ks * powf(ndh, M.glossiness));
+    }
+    float *acc = reinterpret_cast<float *>(accum + pixel);
+    atomicAdd(acc, out.r);
+    atomicAdd(acc + 1, out.g);
+    atomicAdd(acc + 2, out.b);
+}
+
+// ------------------------------------------------------------------ emission
+// Photon::SetDirection / SetPower (cyPhotonMap.h:142-156)
+__device__ __forceinline__ void encode_photon(rtu_photon *dst, float px, float py, float pz, float dx, float dy, float dz, Col c)
+{
+    float power = c.r;
+    if (power < c.g) power = c.g;
+    if (power < c.b) power = c.b;
+    Col q = mk(c.r / power, c.g / power, c.b / power);
+    int r = (int)(q.r * 255), g = (int)(q.g * 255), b = (int)(q.b * 255); // Color24::FloatToByte (cyColor.h:245-246)
+    r = r < 0 ? 0 : (r > 255 ? 255 : r);
+    g = g < 0 ? 0 : (g > 255 ? 255 : g);
+    b = b < 0 ? 0 : (b > 255 ? 255 : b);
+    int ix = (int)(dx * 32767.0f), iy = (int)(dy * 32767.0f); // short(dir * 0x7FFF)
+    unsigned plane = dz > 0 ? 0u : 0x8u;
+    uint2 *o = reinterpret_cast<uint2 *>(dst);
+    o[0] = make_uint2(__float_as_uint(px), __float_as_uint(py));
+    o[1] = make_uint2(__float_as_uint(pz), __float_as_uint(power));
+    o[2] = make_uint2((unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16) | (plane << 24),
+                      ((unsigned)ix & 0xffffu) | (((unsigned)iy & 0xffffu) << 16));
+}
+
+__device__ __forceinline__ float gray(Col c) { return ((c.r + c.g) + c.b) / 3.0f; } // Color::Gray (cyColor.h:83)
+
+__global__ void __launch_bounds__(WAVE_THREADS_PHOTON, 2)
+k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_bounce, uint2 seed, int light, rtu_photon *staging,
+              unsigned char *counts, DCounters *counters, unsigned *work)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u;
+    const DLight L = S.lights[light];
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_paths) break;
+        unsigned k = base + lane;
+        if (k >= n_paths) continue;
+        unsigned long long path = path0 + k;
+        Rng rng;
+        rng.key = seed; rng.pixel = 0x9407u ^ (unsigned)(path >> 32); rng.path = (unsigned)path; rng.dim = 0;
+        // PointLight::RandomPhoton (lightFunctions.cpp:19-25)
+        Ray ray;
+        ray.px = L.v[0]; ray.py = L.v[1]; ray.pz = L.v[2];
+        sample_ball(rng, 1.0f, ray.dx, ray.dy, ray.dz);
+        norm3(ray.dx, ray.dy, ray.dz);
+        Best B;
+        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        tl.trace++;
+        unsigned stored = 0, flag = 0;
+        if (scene_hit<false>(S, ray, B, tl)) {
+            flag = 0x80u; // photonFromLight++ (RenderFunctions.cpp:357)
+            Col outgoing = mk(L.I[0], L.I[1], L.I[2]);
+            for (int i = 0; i < max_bounce; i++) {
+                Col incoming = outgoing;
+                HitRec H;
+                finalize_hit(S, ray, B, H);
+                if (H.material < 0) break; // the reference would dereference a NULL material
+                const DMaterial &M = S.materials[H.material];
+                // MtlBlinn::RandomPhotonBounce (mtlFunctions.cpp:19-118)
+                Col Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
+                Col Ks = texcolor_sample(S, M.specular, H.u, H.v, H.w);
+                Col Kt = texcolor_sample(S, M.refraction, H.u, H.v, H.w);
+                float dG = gray(Kd), sG = gray(Ks), rG = gray(Kt);
+                float sum = (dG + sG) + rG;
+                dG = dG / sum; sG = sG / sum; rG = rG / sum;
+                float4 u = rng.next4();
+                float pick = u.x;
+                Ray nr;
+                nr.px = H.px; nr.py = H.py; nr.pz = H.pz;
+                if (pick > dG) {
+                    if (pick > dG + sG) {
+                        if (pick > (dG + sG) + rG) break; // absorbed
+                        float ox, oy, oz;
+                        sample_ball(rng, M.refr_gloss, ox, oy, oz);
+                        float snx = ((H.px + H.nx) + ox) - H.px, sny = ((H.py + H.ny) + oy) - H.py, snz = ((H.pz + H.nz) + oz) - H.pz;
+                        norm3(snx, sny, snz);
+                        float cos1 = dot3(snx, sny, snz, -ray.dx, -ray.dy, -ray.dz);
+                        float sin1 = (float)sqrt(1.0 - (double)cos1 * (double)cos1);
+                        if (sin1 > 1) sin1 = 1.0f;
+                        if (sin1 < -1) sin1 = -1.0f;
+                        if (cos1 > 1) cos1 = 1.0f;
+                        if (cos1 < -1) cos1 = -1.0f;
+                        float n1 = M.ior, n2 = 1.0f;
+                        if (H.front) { n1 = 1.0f; n2 = M.ior; }
+                        float sin2 = (n1 / n2) * sin1;
+                        float cos2 = sqrtf(1 - sin2 * sin2);
+                        if (cos2 > 1) cos2 = 1.0f;
+                        float cx = sny * (-ray.dz) - snz * (-ray.dy), cy = snz * (-ray.dx) - snx * (-ray.dz), cz = snx * (-ray.dy) - sny * (-ray.dx);
+                        norm3(cx, cy, cz);
+                        float svx = sny * cz - snz * cy, svy = snz * cx - snx * cz, svz = snx * cy - sny * cx;
+                        norm3(svx, svy, svz);
+                        nr.dx = (-snx) * cos2 + svx * sin2; nr.dy = (-sny) * cos2 + svy * sin2; nr.dz = (-snz) * cos2 + svz * sin2;
+                        norm3(nr.dx, nr.dy, nr.dz);
+                        float w = rG / 1.0f;
+                        outgoing = outgoing * mk(Kt.r / w, Kt.g / w, Kt.b / w);
+                    } else {
+                        sample_ball(rng, 1.0f, nr.dx, nr.dy, nr.dz); // unnormalised point of the unit ball (SURVEY A-16)
+                        float w = sG / 1.0f;
+                        outgoing = outgoing * mk(Ks.r / w, Ks.g / w, Ks.b / w);
+                    }
+                } else {
+                    sample_ball(rng, 1.0f, nr.dx, nr.dy, nr.dz);
+                    float w = dG / 1.0f;
+                    outgoing = outgoing * mk(Kd.r / w, Kd.g / w, Kd.b / w);
+                }
+                ray = nr;
+                // Trace(r, &rootNode, hInfo) into the SAME HitInfo: its z still holds the previous segment's length, so
+                // only nearer hits are found (SURVEY A-16)
+                tl.trace++;
+                if (!scene_hit<false>(S, ray, B, tl)) break;
+                int mtl = __ldg(&S.nodes[B.node].material);
+                if (mtl < 0) break;
+                const DMaterial &M2 = S.materials[mtl];
+                if (gray(mk(M2.diffuse.c[0], M2.diffuse.c[1], M2.diffuse.c[2])) > 0.f) { // IsPhotonSurface (materials.h:48)
+                    HitRec H2;
+                    finalize_hit(S, ray, B, H2);
+                    float dx = ray.dx, dy = ray.dy, dz = ray.dz;
+                    norm3(dx, dy, dz);
+                    encode_photon(staging + (size_t)k * (size_t)max_bounce + stored, H2.px, H2.py, H2.pz, dx, dy, dz, incoming);
+                    stored++;
+                }
+            }
+        }
+        counts[k] = (unsigned char)(stored | flag);
+    }
+    // emission rays are booked with the primary class
+    DCounterBlock *c = &counters->k[0];
+    unsigned t = tl.trace, b = tl.box, r = tl.tri, nn = tl.node;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&c->trace_rays, (unsigned long long)t);
+        atomicAdd(&c->box_tests, (unsigned long long)b);
+        atomicAdd(&c->tri_tests, (unsigned long long)r);
+        atomicAdd(&c->node_visits, (unsigned long long)nn);
+    }
+}
+
+// staging -> map: path k's photons go to offsets[k] .. ; photons past the map's capacity are dropped (AddPhoton
+// returns false, cyPhotonMap.h:192) and paths at or after `cut` never ran in the sequential loop.
+__global__ void k_photon_compact(const rtu_photon *staging, const unsigned char *counts, const unsigned *offsets, unsigned n_paths,
+                                 unsigned cut, int max_bounce, rtu_photon *map1, unsigned cap)
+{
+    unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_paths || k >= cut) return;
+    unsigned cnt = counts[k] & 0x7fu, off = offsets[k];
+    for (unsigned j = 0; j < cnt; j++) {
+        if (off + j >= cap) break;
+        const uint2 *s = reinterpret_cast<const uint2 *>(staging + (size_t)k * (size_t)max_bounce + j);
+        uint2 *d = reinterpret_cast<uint2 *>(map1 + off + j);
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    }
+}
+
+__global__ void k_photon_scale(rtu_photon *map1, unsigned n, float scale)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) map1[i].power *= scale;
+}
+
+// ------------------------------------------------------------------ launch wrappers
+void launch_estimate(cudaStream_t st, const DPhotonMap &PM, const float *pos, const float *normal, long long n, float radius,
+                     float norm_scale, float *irrad, float *direction, int *found)
+{
+    if (n <= 0) return;
+    k_estimate<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(PM, pos, normal, n, radius, norm_scale, irrad, direction, found);
+}
+
+void launch_photon_shade(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
+                         const DPhotonMap &PM, float4 *accum)
+{
+    if (max_hits == 0) return;
+    k_photon_shade<<<(max_hits + 127) / 128, 128, 0, st>>>(S, F, s0, B.hits, PM, accum);
+}
+
+void launch_photon_emit(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, unsigned long long path0, unsigned n_paths,
+                        int max_bounce, uint2 seed, int light, rtu_photon *staging, unsigned char *counts, DCounters *counters,
+                        unsigned *work_counter)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_photon_emit, WAVE_THREADS_PHOTON, 0) != cudaSuccess || n < 1) n = 1;
+        occ = n;
+    }
+    k_photon_emit<<<cfg.sm_count * occ, WAVE_THREADS_PHOTON, 0, st>>>(S, path0, n_paths, max_bounce, seed, light, staging, counts,
+                                                                     counters, work_counter);
+}
+
+void launch_photon_compact(cudaStream_t st, const rtu_photon *staging, const unsigned char *counts, const unsigned *offsets,
+                           unsigned n_paths, unsigned cut, int max_bounce, rtu_photon *map1, unsigned cap)
+{
+    if (n_paths == 0) return;
+    k_photon_compact<<<(n_paths + 255) / 256, 256, 0, st>>>(staging, counts, offsets, n_paths, cut, max_bounce, map1, cap);
+}
+
+void launch_photon_scale(cudaStream_t st, rtu_photon *map1, unsigned n, float scale)
+{
+    if (n == 0) return;
+    k_photon_scale<<<(n + 255) / 256, 256, 0, st>>>(map1, n, scale);
+}

@@ -2,6 +2,7 @@
 // There is no CPU fallback: every entry point that renders or traces needs a CUDA device and
 // returns RTU_ERR_NO_DEVICE / RTU_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -88,6 +89,12 @@ struct rtu_scene {
     int n_shadow_lights = 0;
     uint64_t launches = 0;
     bool timed = false;
+    // photon map (balanced, n+1 records, record 0 unused) and the parameters it was made with
+    int h_light0_kind = -1;       // lights[0]: the only light GeneratePhotonMap emits from
+    float h_light0_I[3] = {0, 0, 0};
+    rtu_photon *d_photons = nullptr;
+    uint32_t n_photons = 0;
+    rtu_photon_params photon_params;
 };
 
 namespace {
@@ -583,6 +590,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
         memcpy(o.v, l.v, sizeof o.v);
         o.size = l.size;
         if (l.kind != RTU_LIGHT_AMBIENT) sc->n_shadow_lights++;
+        if (i == 0) { sc->h_light0_kind = l.kind; memcpy(sc->h_light0_I, l.intensity, sizeof sc->h_light0_I); }
     }
     DLight *dl = nullptr;
     if ((rc = dev_upload(lts, &dl, c->stream, sc->owned))) return fail(rc);
@@ -612,6 +620,7 @@ void rtu_scene_destroy(rtu_scene *s)
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     free_list_async(s->owned, s->ctx->stream); // after everything already queued on the context's stream
+    if (s->d_photons) cudaFreeAsync(s->d_photons, s->ctx->stream);
     delete s;
 }
 
@@ -668,7 +677,8 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
     if (p->spp < 1 || p->spp > (1 << 20)) { rtu::set_error("bad spp"); return RTU_ERR_INVALID; }
     if (p->pattern == RTU_PATTERN_CENTER && p->spp != 1) { rtu::set_error("RTU_PATTERN_CENTER needs spp == 1"); return RTU_ERR_INVALID; }
-    if (p->mode != RTU_MODE_WHITTED && p->mode != RTU_MODE_PATH) { rtu::set_error("bad render mode"); return RTU_ERR_INVALID; }
+    if (p->mode != RTU_MODE_WHITTED && p->mode != RTU_MODE_PATH && p->mode != RTU_MODE_PHOTON) { rtu::set_error("bad render mode"); return RTU_ERR_INVALID; }
+    if (p->mode == RTU_MODE_PHOTON && !s->d_photons) { rtu::set_error("RTU_MODE_PHOTON needs a photon map: call rtu_photon_map_generate or rtu_photon_map_set first"); return RTU_ERR_INVALID; }
     if (p->mode == RTU_MODE_PATH && (p->gi_bounces < 0 || p->gi_bounces > 6)) { rtu::set_error("gi_bounces out of range (0..6)"); return RTU_ERR_INVALID; }
     if (p->shade_bounces < 0 || p->shade_bounces > 15) { rtu::set_error("shade_bounces out of range"); return RTU_ERR_INVALID; }
     make_camera(s->cam, W, H, &F->cam);
@@ -744,6 +754,17 @@ int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_
     return RTU_OK;
 }
 
+DPhotonMap photon_map_of(const rtu_scene *s)
+{
+    DPhotonMap PM;
+    PM.map = s->d_photons;
+    PM.n = (int)s->n_photons;
+    PM.half = (int)s->n_photons / 2 - 1; // halfStoredPhotons (cyPhotonMap.h:227)
+    PM.radius = s->photon_params.est_radius;
+    PM.norm_scale = s->photon_params.ellipticity == 1.f ? 0.f : 1.f / s->photon_params.ellipticity - 1.f;
+    return PM;
+}
+
 int check_overflow(rtu_scene *s, DCounters *host)
 {
     rtu_context *c = s->ctx;
@@ -808,6 +829,13 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
         kt_begin(c, 0);
         launch_extend_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, accum, target, c->work + wi++);
         kt_end(c);
+        if (F.mode == RTU_MODE_PHOTON) { // PhotonMapping(ray, hInfo) per hit; no secondary or shadow rays (bounceCount 0)
+            kt_begin(c, 3);
+            launch_photon_shade(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum);
+            kt_end(c);
+            s->launches += 3;
+            continue;
+        }
         kt_begin(c, 3);
         launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, target, c->work + wi++);
         kt_end(c);
@@ -1091,6 +1119,180 @@ int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n,
     for (int64_t i = 0; i < n; i++) { rgb[i * 3] = host_acc[i].x; rgb[i * 3 + 1] = host_acc[i].y; rgb[i * 3 + 2] = host_acc[i].z; }
     DCounters hc;
     return check_overflow(s, &hc);
+}
+
+} // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------- photon map
+namespace {
+
+int install_photon_map(rtu_scene *s, const std::vector<rtu_photon> &balanced, uint32_t n, const rtu_photon_params &pp)
+{
+    rtu_context *c = s->ctx;
+    if (s->d_photons) { cudaFreeAsync(s->d_photons, c->stream); s->d_photons = nullptr; s->n_photons = 0; }
+    CU(cudaMallocAsync((void **)&s->d_photons, sizeof(rtu_photon) * ((size_t)n + 1), c->stream));
+    CU(cudaMemcpyAsync(s->d_photons, balanced.data(), sizeof(rtu_photon) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream)); // `balanced` is pageable and goes out of scope
+    s->n_photons = n;
+    s->photon_params = pp;
+    return RTU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rtu_photon_map_set(rtu_scene *s, const rtu_photon *photons, uint32_t n, const rtu_photon_params *params)
+{
+    if (!s || (n && !photons)) { rtu::set_error("rtu_photon_map_set: null argument"); return RTU_ERR_INVALID; }
+    CU(cudaSetDevice(s->ctx->device));
+    rtu_photon_params pp;
+    rtu_photon_params_default(&pp);
+    if (params) pp = *params;
+    std::vector<rtu_photon> balanced((size_t)n + 1);
+    int rc = rtu_host_balance_photons(photons, n, balanced.data());
+    if (rc) return rc;
+    return install_photon_map(s, balanced, n, pp);
+}
+
+int rtu_photon_map_get(rtu_scene *s, rtu_photon *out, uint32_t cap, uint32_t *n)
+{
+    if (!s || !n) { rtu::set_error("rtu_photon_map_get: null argument"); return RTU_ERR_INVALID; }
+    *n = s->n_photons;
+    if (!out || !s->d_photons) return RTU_OK;
+    CU(cudaSetDevice(s->ctx->device));
+    uint32_t m = std::min(cap, s->n_photons);
+    CU(cudaMemcpyAsync(out, s->d_photons + 1, sizeof(rtu_photon) * (size_t)m, cudaMemcpyDeviceToHost, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    return RTU_OK;
+}
+
+int rtu_estimate_irradiance(rtu_scene *s, const float *pos, const float *normal, int64_t n, float radius, float ellipticity,
+                            float *irrad, float *direction, int32_t *found)
+{
+    if (!s || !pos || !irrad || !direction || n < 0) { rtu::set_error("rtu_estimate_irradiance: bad argument"); return RTU_ERR_INVALID; }
+    if (!s->d_photons) { rtu::set_error("rtu_estimate_irradiance: the scene has no photon map"); return RTU_ERR_INVALID; }
+    if (n == 0) return RTU_OK;
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    float *dpos = nullptr, *dn = nullptr, *dirr = nullptr, *ddir = nullptr;
+    int *dfound = nullptr;
+    size_t b3 = (size_t)n * 3 * sizeof(float);
+    cudaError_t e = cudaMallocAsync((void **)&dpos, b3, c->stream);
+    if (e == cudaSuccess && normal) e = cudaMallocAsync((void **)&dn, b3, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dirr, b3, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&ddir, b3, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dfound, (size_t)n * sizeof(int), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpos, pos, b3, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && normal) e = cudaMemcpyAsync(dn, normal, b3, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        DPhotonMap PM = photon_map_of(s);
+        float norm_scale = ellipticity == 1.f ? 0.f : 1.f / ellipticity - 1.f;
+        launch_estimate(c->stream, PM, dpos, dn, n, radius, norm_scale, dirr, ddir, dfound);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(irrad, dirr, b3, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(direction, ddir, b3, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && found) e = cudaMemcpyAsync(found, dfound, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    for (void *q : {(void *)dpos, (void *)dn, (void *)dirr, (void *)ddir, (void *)dfound}) if (q) cudaFreeAsync(q, c->stream);
+    CU(e);
+    return RTU_OK;
+}
+
+int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_photon_stats *stats)
+{
+    if (!s) { rtu::set_error("rtu_photon_map_generate: null scene"); return RTU_ERR_INVALID; }
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    rtu_photon_params pp;
+    rtu_photon_params_default(&pp);
+    if (params) pp = *params;
+    if (pp.map_size == 0 || pp.map_size >= (1u << 28) || pp.max_bounce == 0 || pp.max_bounce > 100) { rtu::set_error("bad photon parameters"); return RTU_ERR_INVALID; }
+    // "TODO: Randomly decide on light source" (RenderFunctions.cpp:348): the reference always emits from lights[0]
+    // and casts it to PointLight
+    if (s->S.n_lights < 1 || s->h_light0_kind != RTU_LIGHT_POINT) { rtu::set_error("photon emission needs lights[0] to be a point light (RenderFunctions.cpp:349)"); return RTU_ERR_UNSUPPORTED; }
+    int rc;
+    if (!c->wb.counters) { if ((rc = ensure_scratch(c, 1024, 1024))) return rc; }
+    if ((rc = ensure_work(c, 4096))) return rc;
+    const unsigned batch = 1u << 19;
+    const unsigned cap = pp.map_size;
+    rtu_photon *staging = nullptr, *d_map = nullptr;
+    unsigned char *d_counts = nullptr;
+    unsigned *d_offsets = nullptr;
+    std::vector<unsigned char> counts(batch);
+    std::vector<unsigned> offsets(batch);
+    cudaError_t e = cudaMallocAsync((void **)&staging, sizeof(rtu_photon) * (size_t)batch * pp.max_bounce, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_map, sizeof(rtu_photon) * (size_t)cap, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_counts, batch, c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_offsets, sizeof(unsigned) * batch, c->stream);
+    auto cleanup = [&]() {
+        for (void *q : {(void *)staging, (void *)d_map, (void *)d_counts, (void *)d_offsets}) if (q) cudaFreeAsync(q, c->stream);
+    };
+    if (e != cudaSuccess) { cleanup(); CU(e); }
+    CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, c->stream);
+    uint64_t paths = 0, from_light = 0, stored = 0;
+    uint2 seed = make_uint2((unsigned)pp.seed, (unsigned)(pp.seed >> 32));
+    size_t wi = 0;
+    while (stored < cap) {
+        if (wi >= 4096 || paths > (1ull << 40)) { cleanup(); rtu::set_error("photon emission does not converge (no photon surface reachable?)"); return RTU_ERR_UNSUPPORTED; }
+        cudaMemsetAsync(c->work + wi, 0, sizeof(unsigned), c->stream);
+        launch_photon_emit(c->cfg, c->stream, s->S, paths, batch, (int)pp.max_bounce, seed, 0, staging, d_counts, c->wb.counters, c->work + wi);
+        wi++;
+        e = cudaMemcpyAsync(counts.data(), d_counts, batch, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cleanup(); CU(e); }
+        // the sequential loop of GeneratePhotonMap: path k runs while the map is not yet full (RenderFunctions.cpp:346)
+        unsigned cut = batch;
+        for (unsigned k = 0; k < batch; k++) {
+            if (stored >= cap) { cut = k; break; }
+            offsets[k] = (unsigned)stored;
+            if (counts[k] & 0x80u) from_light++;
+            stored += counts[k] & 0x7fu; // photons past the capacity are dropped by AddPhoton
+        }
+        if (stored > cap) stored = cap;
+        paths += cut;
+        e = cudaMemcpyAsync(d_offsets, offsets.data(), sizeof(unsigned) * cut, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { cleanup(); CU(e); }
+        launch_photon_compact(c->stream, staging, d_counts, d_offsets, batch, cut, (int)pp.max_bounce, d_map, cap);
+        if (from_light == 0 && paths >= (8ull << 20)) { cleanup(); rtu::set_error("photon emission: no photon hits the scene"); return RTU_ERR_UNSUPPORTED; }
+    }
+    // scaleFactor = (lights[0] intensity / photonFromLight).Gray() (RenderFunctions.cpp:384)
+    float fl = (float)(int)from_light;
+    float scale = ((s->h_light0_I[0] / fl + s->h_light0_I[1] / fl) + s->h_light0_I[2] / fl) / 3.0f;
+    launch_photon_scale(c->stream, d_map, cap, scale);
+    cudaEventRecord(ev1, c->stream);
+    std::vector<rtu_photon> raw(cap);
+    e = cudaMemcpyAsync(raw.data(), d_map, sizeof(rtu_photon) * (size_t)cap, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    DCounters hc;
+    if (e == cudaSuccess) e = cudaMemcpy(&hc, c->wb.counters, sizeof hc, cudaMemcpyDeviceToHost);
+    float emit_ms = 0.f;
+    cudaEventElapsedTime(&emit_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cleanup();
+    CU(e);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<rtu_photon> balanced((size_t)cap + 1);
+    if ((rc = rtu_host_balance_photons(raw.data(), cap, balanced.data()))) return rc;
+    if ((rc = install_photon_map(s, balanced, cap, pp))) return rc;
+    float build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) {
+        stats->paths = paths;
+        stats->from_light = from_light;
+        stats->stored = cap;
+        stats->trace_rays = hc.k[0].trace_rays;
+        stats->scale_factor = scale;
+        stats->emit_ms = emit_ms;
+        stats->build_ms = build_ms;
+    }
+    return RTU_OK;
 }
 
 } // extern "C"

@@ -68,3 +68,15 @@ void launch_selftest_div(cudaStream_t st, unsigned per_thread, unsigned long lon
 void launch_resolve(cudaStream_t st, const float4 *accum, int npix, float inv_unused, int spp, float *rgb, unsigned char *rgb8);
 // RenderImage::ComputeZBufferImage (scene.h:590-612)
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8);
+
+// photon path (photon_kernels.cu)
+void launch_estimate(cudaStream_t st, const DPhotonMap &PM, const float *pos, const float *normal, long long n, float radius,
+                     float norm_scale, float *irrad, float *direction, int *found);
+void launch_photon_shade(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
+                         const DPhotonMap &PM, float4 *accum);
+void launch_photon_emit(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, unsigned long long path0, unsigned n_paths,
+                        int max_bounce, uint2 seed, int light, rtu_photon *staging, unsigned char *counts, DCounters *counters,
+                        unsigned *work_counter);
+void launch_photon_compact(cudaStream_t st, const rtu_photon *staging, const unsigned char *counts, const unsigned *offsets,
+                           unsigned n_paths, unsigned cut, int max_bounce, rtu_photon *map1, unsigned cap);
+void launch_photon_scale(cudaStream_t st, rtu_photon *map1, unsigned n, float scale);

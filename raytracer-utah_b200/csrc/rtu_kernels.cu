@@ -22,6 +22,7 @@
 
 #include "rtu_internal.h"
 #include "shade.cuh"
+#include "camera.cuh"
 
 #define WAVE_THREADS 256
 #ifndef EXT_BLOCKS
@@ -47,72 +48,6 @@ __device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *cc, int 
         if (r) atomicAdd(&c->tri_tests, (unsigned long long)r);
         if (n) atomicAdd(&c->node_visits, (unsigned long long)n);
     }
-}
-
-// Camera ray of pixel (x,y) with sub-pixel offset (ox,oy): RenderFunctions.cpp:88-97, 258-269
-__device__ __forceinline__ Ray camera_ray(const DCamera &C, int x, int y, float ox, float oy, Rng *rng)
-{
-    float fi = (float)x + ox, fj = (float)y + oy;
-    float cx = (C.origin[0] + fi * C.u[0]) + fj * C.v[0];
-    float cy = (C.origin[1] + fi * C.u[1]) + fj * C.v[1];
-    float cz = (C.origin[2] + fi * C.u[2]) + fj * C.v[2];
-    Ray r;
-    r.px = C.pos[0]; r.py = C.pos[1]; r.pz = C.pos[2];
-    if (C.dof > 0.f && rng) {
-        float4 u = rng->next4();
-        float th = u.y * 6.283185307179586f;
-        float rad = sqrtf(u.x * C.dof * C.dof);
-        float lx = rad * cosf(th), ly = rad * sinf(th);
-        r.px = (C.pos[0] + C.lens_y[0] * ly) + C.lens_x[0] * lx;
-        r.py = (C.pos[1] + C.lens_y[1] * ly) + C.lens_x[1] * lx;
-        r.pz = (C.pos[2] + C.lens_y[2] * ly) + C.lens_x[2] * lx;
-    }
-    r.dx = cx - r.px; r.dy = cy - r.py; r.dz = cz - r.pz;
-    norm3(r.dx, r.dy, r.dz);
-    return r;
-}
-
-// Work item -> (sample, pixel) of the primary wave: samples outermost, then 8x4 pixel tiles so
-// that the 32 lanes of a warp trace a compact bundle of camera rays.
-struct PrimaryMap {
-    int W, row_begin, row_end, tilesX;
-    unsigned perSample;
-    __device__ __forceinline__ void init(const FrameSetup &F)
-    {
-        W = F.cam.width;
-        row_begin = F.row_begin;
-        row_end = F.row_end;
-        tilesX = (W + 7) >> 3;
-        int tilesY = (row_end - row_begin + 3) >> 2;
-        perSample = (unsigned)(tilesX * tilesY) * 32u;
-    }
-    __device__ __forceinline__ bool decode(unsigned idx, int s0, int &s, int &x, int &y) const
-    {
-        unsigned sl = idx / perSample, t = idx - sl * perSample;
-        s = s0 + (int)sl;
-        unsigned tile = t >> 5, in5 = t & 31u;
-        int tx = (int)(tile % (unsigned)tilesX), ty = (int)(tile / (unsigned)tilesX);
-        x = tx * 8 + (int)(in5 & 7u);
-        y = row_begin + ty * 4 + (int)(in5 >> 3);
-        return x < W && y < row_end;
-    }
-};
-
-// RNG path word of a camera sample: a function of (pixel, sample) only, so random streams do not
-// depend on chunking, queue order or the number of GPUs
-__device__ __forceinline__ unsigned primary_path(int pixel, int s)
-{
-    unsigned h = (unsigned)pixel * 0x9E3779B9u ^ ((unsigned)s + 0x7F4A7C15u) * 0x85EBCA6Bu;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
-    return h;
-}
-
-__device__ __forceinline__ Ray primary_ray(const FrameSetup &F, int s, int x, int y, int pixel)
-{
-    float2 off = __ldg(&F.sample_offsets[s]);
-    Rng rng;
-    rng.key = F.seed; rng.pixel = (unsigned)pixel; rng.path = (unsigned)s; rng.dim = 1000u;
-    return camera_ray(F.cam, x, y, off.x, off.y, &rng);
 }
 
 // ------------------------------------------------------------------ closest hit

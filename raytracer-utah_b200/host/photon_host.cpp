@@ -1,0 +1,119 @@
+// Host side of the photon map: the left-balanced kd-tree of cyPhotonMap (cyPhotonMap.h:207-290) built over caller
+// photons.  The tree is stored the way the reference stores it (heap order, slot 0 unused, splitting axis in the low
+// two bits of plane_dirz), so a map balanced here can be handed to the reference and vice versa, and the device
+// gather walks the same nodes the reference's LocatePhotons walks.
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "rtu.h"
+
+namespace rtu {
+void set_error(const std::string &msg);
+}
+
+namespace {
+
+struct Balancer {
+    std::vector<rtu_photon> work; // 1-based; partitioned in place
+    rtu_photon *out;              // 1-based heap order
+
+    // Position of the median that leaves a complete left subtree (cyPhotonMap.h:233-241)
+    static int median_of(int start, int end)
+    {
+        const int count = end - start + 1;
+        int m = 1;
+        while (4 * m <= count) m += m;
+        if (3 * m <= count) return 2 * m + start - 1;
+        return end - m + 1;
+    }
+
+    // Hoare-style selection around the value of the right-most element until `median` is in place (:252-267)
+    void select(int axis, int start, int end, int median)
+    {
+        int left = start, right = end;
+        while (right > left) {
+            const float pivot = work[right].position[axis];
+            int i = left - 1, j = right;
+            for (;;) {
+                while (work[++i].position[axis] < pivot) {}
+                while (work[--j].position[axis] > pivot && j > left) {}
+                if (i >= j) break;
+                std::swap(work[i], work[j]);
+            }
+            std::swap(work[i], work[right]);
+            if (i >= median) right = i - 1;
+            if (i <= median) left = i + 1;
+        }
+    }
+
+    void segment(const float lo[3], const float hi[3], int index, int start, int end)
+    {
+        const int median = median_of(start, end);
+        const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        int axis = 2; // widest extent; ties fall through exactly like :244-248
+        if (ex > ey) {
+            if (ex > ez) axis = 0;
+        } else if (ey > ez) {
+            axis = 1;
+        }
+        select(axis, start, end, median);
+        out[index] = work[median];
+        out[index].plane_dirz = (uint8_t)((out[index].plane_dirz & 0x8) | axis);
+        const float split = out[index].position[axis];
+        if (median > start) {
+            if (start < median - 1) {
+                float h2[3] = {hi[0], hi[1], hi[2]};
+                h2[axis] = split;
+                segment(lo, h2, 2 * index, start, median - 1);
+            } else {
+                out[2 * index] = work[start];
+            }
+        }
+        if (median < end) {
+            if (median + 1 < end) {
+                float l2[3] = {lo[0], lo[1], lo[2]};
+                l2[axis] = split;
+                segment(l2, hi, 2 * index + 1, median + 1, end);
+            } else {
+                out[2 * index + 1] = work[end];
+            }
+        }
+    }
+};
+
+} // namespace
+
+extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_photon *out)
+{
+    if (!out || (n && !in)) { rtu::set_error("rtu_host_balance_photons: null argument"); return RTU_ERR_INVALID; }
+    if (n >= (1u << 30)) { rtu::set_error("rtu_host_balance_photons: too many photons"); return RTU_ERR_INVALID; }
+    std::memset(out, 0, sizeof(rtu_photon) * ((size_t)n + 1));
+    if (n == 0) return RTU_OK;
+    Balancer b;
+    b.work.resize((size_t)n + 1);
+    std::memset(&b.work[0], 0, sizeof(rtu_photon));
+    std::memcpy(&b.work[1], in, sizeof(rtu_photon) * (size_t)n);
+    b.out = out;
+    // the reference seeds the bounding box with the zeroed slot 0 of its vector (:212-213): the origin is always inside
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (uint32_t i = 1; i <= n; i++)
+        for (int k = 0; k < 3; k++) {
+            const float v = b.work[i].position[k];
+            if (lo[k] > v) lo[k] = v;
+            if (hi[k] < v) hi[k] = v;
+        }
+    b.segment(lo, hi, 1, 1, (int)n);
+    return RTU_OK;
+}
+
+extern "C" void rtu_photon_params_default(rtu_photon_params *p)
+{
+    if (!p) return;
+    p->map_size = 1000000; // RenderFunctions.cpp:32-36
+    p->max_bounce = 10;
+    p->est_radius = 1.0f;
+    p->ellipticity = 0.5f;
+    p->seed = 0;
+}

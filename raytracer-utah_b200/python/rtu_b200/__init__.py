@@ -20,7 +20,7 @@ BIGFLOAT = np.float32(1.0e30)
 OBJ_NONE, OBJ_SPHERE, OBJ_PLANE, OBJ_MESH = 0, 1, 2, 3
 TEX_NULL, TEX_CHECKER, TEX_FILE = 0, 1, 2
 LIGHT_AMBIENT, LIGHT_DIRECT, LIGHT_POINT = 0, 1, 2
-MODE_PRIMARY, MODE_WHITTED, MODE_PATH = 0, 1, 2
+MODE_PRIMARY, MODE_WHITTED, MODE_PATH, MODE_PHOTON = 0, 1, 2, 3
 PATTERN_CENTER, PATTERN_REFERENCE = 0, 1
 FLAG_CULL_NULL_SHADOW_RAYS = 1
 FLAG_CULL_ZERO_WEIGHT_RAYS = 2
@@ -116,6 +116,22 @@ HIT_DTYPE = np.dtype([("z", "<f4"), ("p", "<f4", 3), ("N", "<f4", 3), ("uvw", "<
                       ("node", "<i4"), ("face", "<i4"), ("front", "<i4")])
 
 _lib = None
+
+
+# cyPhotonMap::Photon, 24 bytes (include/rtu.h rtu_photon)
+PHOTON_DTYPE = np.dtype([("position", "<f4", 3), ("power", "<f4"), ("color", "u1", 3), ("plane_dirz", "u1"), ("dir_x", "<i2"), ("dir_y", "<i2")])
+
+
+class PhotonParams(C.Structure):
+    _fields_ = [("map_size", u32), ("max_bounce", u32), ("est_radius", f32), ("ellipticity", f32), ("seed", C.c_uint64)]
+
+
+class PhotonStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("from_light", C.c_uint64), ("stored", C.c_uint64), ("trace_rays", C.c_uint64),
+                ("scale_factor", f32), ("emit_ms", f32), ("build_ms", f32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class RtuError(RuntimeError):
@@ -357,12 +373,74 @@ class Scene:
         _check(L.rtu_resolve(self._h, C.byref(params), C.c_void_p(d_accum), C.byref(img)), "rtu_resolve")
         return bufs
 
+    # ---- photon map
+    def photon_map_generate(self, **kw):
+        """GeneratePhotonMap() (RenderFunctions.cpp:341-392) on the device; returns the emission statistics."""
+        L = lib()
+        pp = photon_params(**kw)
+        st = PhotonStats()
+        L.rtu_photon_map_generate.argtypes = [C.c_void_p, C.POINTER(PhotonParams), C.POINTER(PhotonStats)]
+        _check(L.rtu_photon_map_generate(self._h, C.byref(pp), C.byref(st)), "rtu_photon_map_generate")
+        return st.as_dict()
+
+    def photon_map_set(self, photons, **kw):
+        """Installs caller photons (any order): PrepareForIrradianceEstimation + upload."""
+        L = lib()
+        photons = np.ascontiguousarray(photons, PHOTON_DTYPE)
+        pp = photon_params(**kw)
+        L.rtu_photon_map_set.argtypes = [C.c_void_p, C.c_void_p, u32, C.POINTER(PhotonParams)]
+        _check(L.rtu_photon_map_set(self._h, photons.ctypes.data, photons.shape[0], C.byref(pp)), "rtu_photon_map_set")
+
+    def photon_map_get(self):
+        """The balanced map as cyPhotonMap stores it (photons[1..n])."""
+        L = lib()
+        n = u32(0)
+        L.rtu_photon_map_get.argtypes = [C.c_void_p, C.c_void_p, u32, C.POINTER(u32)]
+        _check(L.rtu_photon_map_get(self._h, None, 0, C.byref(n)), "rtu_photon_map_get")
+        out = np.zeros(n.value, PHOTON_DTYPE)
+        if n.value:
+            _check(L.rtu_photon_map_get(self._h, out.ctypes.data, n.value, C.byref(n)), "rtu_photon_map_get")
+        return out
+
+    def estimate_irradiance(self, pos, normal, radius=1.0, ellipticity=0.5):
+        """cyPhotonMap::EstimateIrradiance<100> for a batch of points (cyPhotonMap.h:276-323)."""
+        L = lib()
+        pos = np.ascontiguousarray(pos, "f4")
+        nq = pos.shape[0]
+        nrm = None if normal is None else np.ascontiguousarray(normal, "f4")
+        irrad = np.zeros((nq, 3), "f4"); direction = np.zeros((nq, 3), "f4"); found = np.zeros(nq, "i4")
+        L.rtu_estimate_irradiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, f32, f32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.rtu_estimate_irradiance(self._h, pos.ctypes.data, None if nrm is None else nrm.ctypes.data, nq, radius, ellipticity,
+                                         irrad.ctypes.data, direction.ctypes.data, found.ctypes.data), "rtu_estimate_irradiance")
+        return irrad, direction, found
+
     def stats(self):
         L = lib()
         s = Stats()
         L.rtu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         _check(L.rtu_get_stats(self._h, C.byref(s)), "rtu_get_stats")
         return s.as_dict()
+
+
+def photon_params(**kw):
+    L = lib()
+    pp = PhotonParams()
+    L.rtu_photon_params_default.argtypes = [C.POINTER(PhotonParams)]
+    L.rtu_photon_params_default.restype = None
+    L.rtu_photon_params_default(C.byref(pp))
+    for k, v in kw.items():
+        setattr(pp, k, v)
+    return pp
+
+
+def balance_photons(photons):
+    """rtu_host_balance_photons: cyPhotonMap::PrepareForIrradianceEstimation on the host; n+1 records, [0] unused."""
+    L = lib()
+    photons = np.ascontiguousarray(photons, PHOTON_DTYPE)
+    out = np.zeros(photons.shape[0] + 1, PHOTON_DTYPE)
+    L.rtu_host_balance_photons.argtypes = [C.c_void_p, u32, C.c_void_p]
+    _check(L.rtu_host_balance_photons(photons.ctypes.data, photons.shape[0], out.ctypes.data), "rtu_host_balance_photons")
+    return out
 
 
 def build_bvh(v, f, max_per_leaf=4):

@@ -359,3 +359,104 @@ def test_synthetic_scenes(rtu, gpu_ctx, name):
     finally:
         sc.close()
         hs.close()
+
+
+# ---------------------------------------------------------------------------------------------- photon map (a20)
+def test_photon_map_kat(rtu, gpu_ctx):
+    """cyPhotonMap on the device: the kd-tree our host code balances is the reference's byte for byte, and
+    EstimateIrradiance<100> (kd walk + 100-entry heap in the reference's order) is bit-exact for irradiance and direction."""
+    g, meta = load_golden("kat_photonmap")
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        pin = g["photons_in"].view(rtu.PHOTON_DTYPE).reshape(-1)
+        sc.photon_map_set(pin)
+        assert sc.photon_map_get().tobytes() == g["photons_balanced"].tobytes()
+        for v, (r, e) in enumerate(zip(meta["radius"], meta["ellipticity"])):
+            irr, d, found = sc.estimate_irradiance(g["qpos"], g["qnormal"], r, e)
+            assert bits_equal(irr, g["irrad"][v]), "irradiance differs for %d queries" % int((irr.view("u4") != g["irrad"][v].view("u4")).any(axis=1).sum())
+            assert np.array_equal(d.view("u4"), g["dir"][v].view("u4")), "direction differs"
+            assert found.max() <= 100 and found.mean() > 3
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_photon_mapping_image_matches_oracle(rtu, gpu_ctx):
+    """RTU_MODE_PHOTON = PhotonMapping(ray, hInfo) per sample, on a map emitted by the device; the oracle (bit-exact
+    with the reference's PhotonMapping on the reference's map, tests/test_oracle.py) renders with the same map."""
+    from oracle import oracle_py as O
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        st = sc.photon_map_generate(map_size=200000, seed=11)
+        assert st["stored"] == 200000 and st["from_light"] > 0
+        ph = sc.photon_map_get()
+        bal = np.zeros(len(ph) + 1, rtu.PHOTON_DTYPE)
+        bal[1:] = ph
+        O.set_photon_map(bal, 1.0, 0.5)
+        p = rtu.default_params(width=160, height=120, mode=rtu.MODE_PHOTON)
+        out = sc.render(p, want=("rgb",))
+        ref = O.render(hs.desc, width=160, height=120, mode=rtu.MODE_PHOTON, want=("rgb",))["rgb"]
+        assert np.array_equal(np.isnan(out["rgb"]), np.isnan(ref)), "pixels without photons (NaN in the reference) differ"
+        m = ~np.isnan(ref)
+        assert m.mean() > 0.5
+        assert within_tol(out["rgb"][m], ref[m]).all()
+        # a second generation with the same seed gives the same map, a different seed a different one
+        sc.photon_map_generate(map_size=200000, seed=11)
+        assert sc.photon_map_get().tobytes() == ph.tobytes()
+        sc.photon_map_generate(map_size=200000, seed=12)
+        assert sc.photon_map_get().tobytes() != ph.tobytes()
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_photon_emission_statistics(rtu, gpu_ctx):
+    """GeneratePhotonMap() is rand()-driven in the reference, so the device emission is compared in distribution:
+    photons per path, positions (8x8x8 histogram), power per cell and the mean photon colour, each against the
+    reference's own run-to-run differences (two seeds in the fixture)."""
+    import json
+    g, meta = load_golden("photon_Project13")
+    m0 = json.loads(bytes(g["meta0"]).decode())
+    m1 = json.loads(bytes(g["meta1"]).decode())
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        st = sc.photon_map_generate(seed=3)
+        assert st["stored"] == 1000000 == m0["photons"]
+        ref_fl = 0.5 * (m0["from_light"] + m1["from_light"])
+        noise_fl = abs(m0["from_light"] - m1["from_light"])
+        assert abs(st["from_light"] - ref_fl) <= 4 * noise_fl + 0.002 * ref_fl, (st["from_light"], m0["from_light"], m1["from_light"])
+        assert abs(st["trace_rays"] - m0["emit_traces"]) <= 0.01 * m0["emit_traces"]
+        ph = sc.photon_map_get()
+        rng = [tuple(r) for r in meta["range"]]
+        H, _ = np.histogramdd(ph["position"], bins=meta["bins"], range=rng)
+        P, _ = np.histogramdd(ph["position"], bins=meta["bins"], range=rng, weights=ph["power"])
+        h0, h1, p0, p1 = g["hist0"], g["hist1"], g["power0"], g["power1"]
+        big = (h0 + h1) > 2000
+        assert big.sum() > 50
+        # Poisson noise of a cell with n photons is sqrt(n); allow 6 sigma plus the reference's own spread
+        tol = 6 * np.sqrt(np.maximum(h0, 1)) + np.abs(h0 - h1)
+        assert (np.abs(H - 0.5 * (h0 + h1))[big] <= tol[big]).all(), "photon density differs from the reference's"
+        rel = np.abs(P - 0.5 * (p0 + p1))[big] / (0.5 * (p0 + p1))[big]
+        ref_rel = (np.abs(p0 - p1)[big] / (0.5 * (p0 + p1))[big])
+        assert rel.max() <= max(0.15, 2.5 * ref_rel.max()), rel.max()
+        col = ph["color"].astype("f4") / 255.0
+        mean_col = (col * ph["power"][:, None]).sum(0) / ph["power"].sum()
+        assert np.abs(mean_col - g["mean_color0"]).max() <= 0.01
+        # the scale factor follows from the path count (RenderFunctions.cpp:384)
+        assert abs(st["scale_factor"] - 100.5 / st["from_light"]) <= 1e-4 * st["scale_factor"]
+        # and the PhotonMapping image agrees with the reference's to within its own seed-to-seed noise
+        p = rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_PHOTON)
+        out = sc.render(p, want=("rgb",))["rgb"]
+        r0, r1 = g["rgb0"], g["rgb1"]
+        ok = ~(np.isnan(out) | np.isnan(r0) | np.isnan(r1))
+        assert ok.mean() > 0.6
+        noise = np.sqrt(((r0 - r1)[ok] ** 2).mean())
+        err = np.sqrt(((out - r0)[ok] ** 2).mean())
+        assert err <= 1.5 * noise, (err, noise)
+        assert abs(out[ok].mean() - r0[ok].mean()) <= 0.03 * r0[ok].mean()
+    finally:
+        sc.close()
+        hs.close()

@@ -176,3 +176,13 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+def test_photon_map_balancing_matches_reference(rtu):
+    """rtu_host_balance_photons == cyPhotonMap::PrepareForIrradianceEstimation, byte for byte (kat_photonmap.npz)."""
+    g, _ = load_golden("kat_photonmap")
+    pin = g["photons_in"].view(rtu.PHOTON_DTYPE).reshape(-1)
+    bal = rtu.balance_photons(pin)
+    assert bal[1:].tobytes() == g["photons_balanced"].tobytes()
+    assert bal[:1].tobytes() == bytes(24)
+    assert rtu.balance_photons(pin[:0]).shape == (1,)

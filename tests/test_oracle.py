@@ -125,3 +125,41 @@ def test_synthetic_scenes_match_reference(rtu, oracle, name):
     assert bits_equal(o["z"], g["z"])
     o = oracle.render(hs.desc, width=meta["width"], height=meta["height"], mode=rtu.MODE_WHITTED)
     assert bits_equal(o["rgb"], g["rgb"])
+
+
+def test_photon_map_balance_and_estimate_bit_exact(oracle):
+    """cyPhotonMap::PrepareForIrradianceEstimation reproduces the reference's kd-tree byte for byte and
+    EstimateIrradiance<100> its irradiance / mean direction bit for bit (4 radius x ellipticity variants)."""
+    g, meta = load_golden("kat_photonmap")
+    pin = g["photons_in"].view(oracle.PHOTON_DTYPE).reshape(-1)
+    bal = oracle.balance_photons(pin)
+    assert bal[1:].tobytes() == g["photons_balanced"].tobytes()
+    for v, (r, e) in enumerate(zip(meta["radius"], meta["ellipticity"])):
+        irr, d, found = oracle.estimate_irradiance(bal, g["qpos"], g["qnormal"], r, e)
+        assert bits_equal(irr, g["irrad"][v])
+        assert np.array_equal(d.view("u4"), g["dir"][v].view("u4"))
+        assert found.max() == 100 or r < 0.5
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_harness")),
+                    reason="needs the compiled reference (oracle/_ref), present in the build container only")
+def test_photon_mapping_bit_exact_with_reference(rtu, oracle, tmp_path):
+    """PhotonMapping(): the reference emits its own 10^6-photon map (too large for a fixture), dumps it and renders
+    pixel centres; the oracle renders with the same map.  Bit-exact incl. the NaN pixels that found no photon."""
+    import json, subprocess
+    pre = str(tmp_path / "ph")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_harness"), os.path.join(SCENES, "Project13/scene.xml"), "--root", SCENES,
+                        "--mode", "photon", "--width", "96", "--height", "72", "--threads", "8", "--seed", "9", "--out", pre],
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, check=True)
+    meta = json.loads([l for l in r.stderr.splitlines() if l.startswith("{")][-1])
+    assert meta["photons"] == 1000000
+    ph = np.load(pre + "_photons_balanced.npy").view(oracle.PHOTON_DTYPE).reshape(-1)
+    bal = np.zeros(len(ph) + 1, oracle.PHOTON_DTYPE)
+    bal[1:] = ph
+    oracle.set_photon_map(bal, 1.0, 0.5)
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    o = oracle.render(hs.desc, width=96, height=72, mode=rtu.MODE_PHOTON, want=("rgb",))["rgb"]
+    ref = np.load(pre + "_rgb.npy")
+    assert np.array_equal(np.isnan(o), np.isnan(ref))
+    m = ~np.isnan(ref)
+    assert np.array_equal(o.view("u4")[m], ref.view("u4")[m])

@@ -158,6 +158,33 @@ def main():
                     if os.path.exists(fp):
                         digest[f] = hashlib.sha256(open(fp, "rb").read()).hexdigest()
                 save("synthetic_" + name, arrs, dict(meta, scene=paths[name], sha256=digest, whitted=meta2))
+        if want("photonkat"):
+            pre = os.path.join(tmp, "pk")
+            meta = run("Project13/scene.xml", "photonkat", pre, "--n", 20000, "--seed", 3)
+            save("kat_photonmap", collect(pre), meta)
+        if want("photon"):
+            # GeneratePhotonMap() is rand()-driven: the fixture keeps distributional summaries of two runs (the second
+            # one is the noise yardstick) plus a low-resolution PhotonMapping() image
+            stats = {}
+            for run_i, seed in enumerate((5, 6)):
+                pre = os.path.join(tmp, "ph%d" % run_i)
+                meta = run("Project13/scene.xml", "photon", pre, "--width", 160, "--height", 120, "--threads", 8, "--seed", seed)
+                a = collect(pre)
+                ph = a["photons_balanced"].reshape(-1, 24)
+                pos = ph[:, :12].copy().view("<f4")
+                pw = ph[:, 12:16].copy().view("<f4")[:, 0]
+                col = ph[:, 16:19].astype("f4") / 255.0
+                H, edges = np.histogramdd(pos, bins=(8, 8, 8), range=((-32, 32), (-32, 32), (-20, 44)))
+                Pw, _ = np.histogramdd(pos, bins=(8, 8, 8), range=((-32, 32), (-32, 32), (-20, 44)), weights=pw)
+                stats["hist%d" % run_i] = H.astype("f8")
+                stats["power%d" % run_i] = Pw
+                stats["mean_color%d" % run_i] = (col * pw[:, None]).sum(0) / pw.sum()
+                stats["rgb%d" % run_i] = a["rgb"]
+                stats["irrad%d" % run_i] = a["irrad"]
+                stats["node%d" % run_i] = a["node"]
+                stats["meta%d" % run_i] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+            save("photon_Project13", stats, dict(scene="Project13/scene.xml", width=160, height=120, bins=[8, 8, 8],
+                                                 range=[[-32, 32], [-32, 32], [-20, 44]]))
         if want("tex"):
             for sc, tag in TEX.items():
                 pre = os.path.join(tmp, "tx")
