@@ -1241,15 +1241,21 @@ int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_p
     size_t wi = 0;
     while (stored < cap) {
         if (wi >= 4096 || paths > (1ull << 40)) { cleanup(); rtu::set_error("photon emission does not converge (no photon surface reachable?)"); return RTU_ERR_UNSUPPORTED; }
+        // size the batch from the yield so far, so that little is traced past the point where the map is full
+        unsigned n_batch = batch;
+        if (paths > 0 && stored > 0) {
+            double need = (double)(cap - stored) * (double)paths / (double)stored * 1.02 + 1024.0;
+            if (need < (double)batch) n_batch = (unsigned)need;
+        }
         cudaMemsetAsync(c->work + wi, 0, sizeof(unsigned), c->stream);
-        launch_photon_emit(c->cfg, c->stream, s->S, paths, batch, (int)pp.max_bounce, seed, 0, staging, d_counts, c->wb.counters, c->work + wi);
+        launch_photon_emit(c->cfg, c->stream, s->S, paths, n_batch, (int)pp.max_bounce, seed, 0, staging, d_counts, c->wb.counters, c->work + wi);
         wi++;
-        e = cudaMemcpyAsync(counts.data(), d_counts, batch, cudaMemcpyDeviceToHost, c->stream);
+        e = cudaMemcpyAsync(counts.data(), d_counts, n_batch, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { cleanup(); CU(e); }
         // the sequential loop of GeneratePhotonMap: path k runs while the map is not yet full (RenderFunctions.cpp:346)
-        unsigned cut = batch;
-        for (unsigned k = 0; k < batch; k++) {
+        unsigned cut = n_batch;
+        for (unsigned k = 0; k < n_batch; k++) {
             if (stored >= cap) { cut = k; break; }
             offsets[k] = (unsigned)stored;
             if (counts[k] & 0x80u) from_light++;
@@ -1259,7 +1265,7 @@ int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_p
         paths += cut;
         e = cudaMemcpyAsync(d_offsets, offsets.data(), sizeof(unsigned) * cut, cudaMemcpyHostToDevice, c->stream);
         if (e != cudaSuccess) { cleanup(); CU(e); }
-        launch_photon_compact(c->stream, staging, d_counts, d_offsets, batch, cut, (int)pp.max_bounce, d_map, cap);
+        launch_photon_compact(c->stream, staging, d_counts, d_offsets, n_batch, cut, (int)pp.max_bounce, d_map, cap);
         if (from_light == 0 && paths >= (8ull << 20)) { cleanup(); rtu::set_error("photon emission: no photon hits the scene"); return RTU_ERR_UNSUPPORTED; }
     }
     // scaleFactor = (lights[0] intensity / photonFromLight).Gray() (RenderFunctions.cpp:384)
