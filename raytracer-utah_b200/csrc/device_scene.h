@@ -112,6 +112,7 @@ struct DScene {
                           // w = -1: no object, w = -2: object that can never be hit (empty mesh)
     int32_t n_nodes;
     int32_t flat;        // 1: every object node hangs directly off the root
+    int32_t pool_ok;     // 1: every mesh fits the item encoding of the pooled shadow kernel (<= 2^24 triangles, < 2^27 pairs)
     const DMesh *meshes;
     const DMaterial *materials;
     int32_t n_materials;

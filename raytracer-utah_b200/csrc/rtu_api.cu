@@ -601,6 +601,9 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.bounds = db;
     S.n_nodes = d->n_nodes;
     S.flat = flat;
+    S.pool_ok = 1;
+    for (int m = 0; m < d->n_meshes; m++)
+        if (d->meshes[m].nf > (1u << 24) || d->meshes[m].bvh_nodes >= (1u << 27)) S.pool_ok = 0;
     S.meshes = dm;
     S.materials = dmt;
     S.n_materials = d->n_materials;

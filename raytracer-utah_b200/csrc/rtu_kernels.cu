@@ -19,6 +19,7 @@
 // SM-count multiples (148 x resident CTAs per SM, from the occupancy API); CTAs stay resident for
 // the whole wave.
 #include <cstdio>
+#include <cstdlib>
 
 #include "rtu_internal.h"
 #include "shade.cuh"
@@ -249,7 +250,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
 
 // ------------------------------------------------------------------ any hit
 __global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
-k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
 {
     Tally tl = {0, 0, 0, 0, 0};
     const unsigned lane = threadIdx.x & 31u;
@@ -273,6 +274,249 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         if (occ && B.z > 0.0f) continue;                                                // :31-35
         float4 c = Q.c[idx];
         accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
+    }
+    flush_tally(tl, counters, 2);
+}
+
+
+// Flat scenes (every object a child of the root): any-hit with the mesh walks pooled per warp.
+//
+// Inside a BVH walk the lanes of a warp drift apart: rays that skim the teapot walk ten times longer than rays that
+// are stopped by its first triangle, and in the plain kernel above 8 of 32 lanes are active per instruction of the
+// walk (profiles/).  Only the boolean of a shadow ray is observable and it does not depend on the order in which
+// the boxes of a mesh are opened, so here a warp walks the meshes of 32 rays as ONE pool of (ray, node) items in
+// shared memory: every iteration 32 items are popped, each lane tests the two child boxes of its item and pushes the
+// children that were hit; leaves go to a second pool whose triangles are tested 32 leaves at a time.  A ray is
+// occluded as soon as one of its triangles accepts (its remaining items are dropped when popped); rays whose items
+// run out resume their node loop after the mesh, so every ray still visits its nodes in the reference's order
+// (RenderFunctions.cpp:224-240) and the first object that reports a hit still decides.  If the pool is about to
+// overflow, the popped items are walked to the end by their lanes (bvh_walk) instead of being expanded.
+#define SP_JOBS 64   // parked (ray, mesh node) entries waiting for a batch
+#define SP_RES 96    // rays that missed their mesh and resume the node loop behind it
+#define SP_POOL 512  // internal-node items: slot << 27 | pair index
+#define SP_LEAF 128  // leaf items: slot << 27 | (count - 1) << 24 | first triangle
+
+struct SpWarp {
+    float4 o[32];                // mesh-local origin, t_max
+    float4 d[32];                // mesh-local direction, InvDir::ok
+    float4 y[32];                // hoisted reciprocals
+    const BvhPair *pairs[32];
+    const TriRec *tris[32];
+    unsigned idx[32], node[32];  // shadow-queue entry and mesh node of the slot
+    unsigned pool[SP_POOL];
+    unsigned leaf[SP_LEAF];
+    uint2 jobs[SP_JOBS];
+    uint2 res[SP_RES];
+    unsigned occl;               // bit s: the ray in slot s is occluded
+};
+
+template <bool FLAT>
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+{
+    extern __shared__ __align__(16) unsigned char sp_raw[];
+    SpWarp &W = reinterpret_cast<SpWarp *>(sp_raw)[threadIdx.x >> 5];
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u, FULL = 0xffffffffu, NONE = 0x7fffffffu;
+    unsigned total = *Q.count;
+    if (total > Q.cap) total = Q.cap;
+    unsigned njobs = 0, nres = 0; // warp-uniform
+    bool drained = false;         // warp-uniform: no tickets left
+    DNode root;
+    load_node(S.nodes, root);
+    for (;;) {
+        if (njobs >= 32u || (njobs > 0u && nres == 0u && drained)) {
+            // ------------------------------------------------------------ one batch of mesh walks
+            const unsigned take = njobs < 32u ? njobs : 32u;
+            njobs -= take;
+            unsigned rootw = NONE;
+            if (lane < take) {
+                uint2 j = W.jobs[njobs + lane];
+                float4 o = Q.o[j.x], d = Q.d[j.x];
+                Ray ray;
+                ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+                ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+                DNode nd;
+                load_node(S.nodes + j.y, nd);
+                const Ray lr = FLAT ? to_node(nd.itm, nd.pos, to_node(root.itm, root.pos, ray)) : local_ray_of(S, (int)j.y, ray, nullptr);
+                const DMesh &M = S.meshes[nd.mesh];
+                InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
+                I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                W.o[lane] = make_float4(lr.px, lr.py, lr.pz, d.w);
+                W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
+                W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
+                W.pairs[lane] = M.pairs;
+                W.tris[lane] = M.tris;
+                W.idx[lane] = j.x;
+                W.node[lane] = j.y;
+                rootw = M.root;
+            }
+            unsigned bi = __ballot_sync(FULL, rootw < NONE), bl = __ballot_sync(FULL, rootw > NONE);
+            if (rootw < NONE) W.pool[__popc(bi & lt)] = (lane << 27) | rootw;
+            if (rootw > NONE) W.leaf[__popc(bl & lt)] = (lane << 27) | (((rootw >> 28) & 7u) << 24) | (rootw & 0x00ffffffu);
+            unsigned pool_n = __popc(bi), leaf_n = __popc(bl);
+            if (lane == 0) W.occl = 0u;
+            __syncwarp();
+            for (;;) {
+                const bool do_leaf = leaf_n >= 32u || (pool_n == 0u && leaf_n > 0u);
+                if (!do_leaf && pool_n == 0u) break;
+                const unsigned occl = *(volatile unsigned *)&W.occl;
+                if (do_leaf) {
+                    const unsigned n = leaf_n < 32u ? leaf_n : 32u;
+                    leaf_n -= n;
+                    if (lane < n) {
+                        const unsigned it = W.leaf[leaf_n + lane], sl = it >> 27;
+                        if (!((occl >> sl) & 1u)) {
+                            const float4 o = W.o[sl], d = W.d[sl];
+                            Ray r;
+                            r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                            const TriRec *tris = W.tris[sl];
+                            const unsigned first = it & 0x00ffffffu, cnt = ((it >> 24) & 7u) + 1u;
+                            for (unsigned i = 0; i < cnt; i++) {
+                                const float4 *q = reinterpret_cast<const float4 *>(tris + first + i);
+                                float4 x = __ldg(q), yv = __ldg(q + 1), w4 = __ldg(q + 2);
+                                TriRec T;
+                                T.nx = x.x; T.ny = x.y; T.nz = x.z; T.ax = x.w;
+                                T.ay = yv.x; T.az = yv.y; T.area = yv.z; T.fbits = yv.w;
+                                T.cau = w4.x; T.cav = w4.y; T.bau = w4.z; T.bav = w4.w;
+                                tl.tri++;
+                                float z = o.w, b1, b2, b3;
+                                int fr;
+                                if (tri_hit(T, r, z, fr, b1, b2, b3)) { atomicOr(&W.occl, 1u << sl); break; }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                const bool finish = pool_n > SP_POOL - 64u; // no room to expand 32 items: walk them to the end instead
+                const unsigned n = pool_n < 32u ? pool_n : 32u;
+                pool_n -= n;
+                unsigned c1 = NONE, c2 = NONE, sl = 0;
+                if (lane < n) {
+                    const unsigned it = W.pool[pool_n + lane];
+                    sl = it >> 27;
+                    if (!((occl >> sl) & 1u)) {
+                        const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
+                        Ray r;
+                        r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                        InvDir I;
+                        I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                        const BvhPair *pairs = W.pairs[sl];
+                        if (finish) {
+                            float z = o.w, b1, b2, b3;
+                            int fr, tslot;
+                            if (bvh_walk<true>(pairs, W.tris[sl], it & 0x07ffffffu, r, I, z, fr, tslot, b1, b2, b3, tl)) atomicOr(&W.occl, 1u << sl);
+                        } else {
+                            float4 a, b, c, dd;
+                            load_pair(pairs + (it & 0x07ffffffu), a, b, c, dd);
+                            float e1, e2;
+                            bool h1 = slab_fast(r, I, a.x, a.y, a.z, a.w, b.x, b.y, RTU_BIG, e1);
+                            bool h2 = slab_fast(r, I, b.z, b.w, c.x, c.y, c.z, c.w, RTU_BIG, e2);
+                            tl.box += 2;
+                            if (h1) c1 = __float_as_uint(dd.x);
+                            if (h2) c2 = __float_as_uint(dd.y);
+                        }
+                    }
+                }
+                // push the children that were hit: child 2 below child 1, so that child 1 is popped first
+                const unsigned n2 = __ballot_sync(FULL, c2 < NONE), n1 = __ballot_sync(FULL, c1 < NONE);
+                const unsigned l2 = __ballot_sync(FULL, c2 > NONE), l1 = __ballot_sync(FULL, c1 > NONE);
+                if (c2 < NONE) W.pool[pool_n + __popc(n2 & lt)] = (sl << 27) | c2;
+                if (c1 < NONE) W.pool[pool_n + __popc(n2) + __popc(n1 & lt)] = (sl << 27) | c1;
+                if (c2 > NONE) W.leaf[leaf_n + __popc(l2 & lt)] = (sl << 27) | (((c2 >> 28) & 7u) << 24) | (c2 & 0x00ffffffu);
+                if (c1 > NONE) W.leaf[leaf_n + __popc(l2) + __popc(l1 & lt)] = (sl << 27) | (((c1 >> 28) & 7u) << 24) | (c1 & 0x00ffffffu);
+                pool_n += __popc(n2) + __popc(n1);
+                leaf_n += __popc(l2) + __popc(l1);
+                __syncwarp();
+            }
+            // rays that were not stopped by their mesh go on with the node behind it
+            const unsigned occl = *(volatile unsigned *)&W.occl;
+            const bool go_on = lane < take && !((occl >> lane) & 1u);
+            const unsigned m = __ballot_sync(FULL, go_on);
+            if (go_on) W.res[nres + __popc(m & lt)] = make_uint2(W.idx[lane], W.node[lane] + 1u);
+            nres += __popc(m);
+            __syncwarp();
+            continue;
+        }
+        // -------------------------------------------------------------------- node loop of 32 rays
+        if (nres == 0u && drained) break; // (njobs == 0 here)
+        const unsigned k = nres < 32u ? nres : 32u;
+        unsigned fresh = drained ? 0u : 32u - k;
+        unsigned base = 0;
+        if (fresh) {
+            if (lane == 0) base = atomicAdd(work, fresh);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= total) { drained = true; fresh = 0; }
+        }
+        unsigned idx = 0;
+        int i0 = 1;
+        bool have = false;
+        if (lane < k) {
+            uint2 e = W.res[nres - k + lane];
+            idx = e.x; i0 = (int)e.y;
+            have = true;
+        } else if (lane - k < fresh) {
+            idx = base + (lane - k);
+            have = idx < total;
+            if (have) tl.shadow++;
+        }
+        nres -= k;
+        int park = 0; // mesh node whose walk this lane's ray has to wait for
+        if (have) {
+            float4 o = Q.o[idx], d = Q.d[idx];
+            Ray ray;
+            ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+            ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+            Best B;
+            B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
+            const Ray r0 = to_node(root.itm, root.pos, ray);
+            const float dd = dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz);
+            bool occ = false;
+            Ray lvl[FLAT ? 1 : RTU_MAX_DEPTH]; // hierarchies: the ray at every depth of the current branch
+            if (!FLAT) {
+                lvl[0] = r0;
+                if (i0 > 1 && i0 < S.n_nodes) local_ray_of(S, __ldg(&S.nodes[i0].parent), ray, lvl); // resumed behind a mesh
+            }
+            for (int i = i0; i < S.n_nodes; i++) {
+                DNode nd;
+                Ray lr;
+                if (FLAT) {
+                    const float4 bs = __ldg(&S.bounds[i]);
+                    if (bs.w < 0.f && bs.w > -1.5f) continue; // no object
+                    if (bound_culled(bs, r0, dd)) { tl.node++; tl.box++; continue; }
+                    load_node(S.nodes + i, nd);
+                    lr = to_node(nd.itm, nd.pos, r0);
+                } else {
+                    load_node(S.nodes + i, nd);
+                    lr = to_node(nd.itm, nd.pos, lvl[nd.depth - 1]);
+                    lvl[nd.depth] = lr; // children need it even when this node's own object is culled
+                    if (nd.kind == 0) continue;
+                    if (bound_culled(__ldg(&S.bounds[i]), r0, dd)) { tl.node++; tl.box++; continue; }
+                }
+                if (nd.kind == 3) { // TriObj::IntersectRay up to its bound-box gate (objFunctions.cpp:337)
+                    const DMesh &M = S.meshes[nd.mesh];
+                    tl.node++;
+                    if (M.empty) continue;
+                    tl.box++;
+                    InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
+                    I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                    float te;
+                    if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
+                    park = i;
+                    break;
+                }
+                if (sphere_or_plane_hit(nd, i, lr, B, tl)) { occ = true; break; }
+            }
+            if (!park && !(occ && B.z > 0.0f)) {                                          // :31-35
+                float4 c = Q.c[idx];
+                accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, park != 0);
+        if (park) W.jobs[njobs + __popc(m & lt)] = make_uint2(idx, (unsigned)park);
+        njobs += __popc(m);
+        __syncwarp();
     }
     flush_tally(tl, counters, 2);
 }
@@ -508,8 +752,28 @@ void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
                         unsigned *work_counter)
 {
-    static int occ = 0;
-    k_shadow_wave<<<resident_grid(cfg, k_shadow_wave, &occ), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
+    static int occ = 0, occ_simple = 0, mode = -1;
+    if (mode < 0) { // RTU_SHADOW_KERNEL=simple selects the plain kernel (A/B measurements)
+        const char *e = getenv("RTU_SHADOW_KERNEL");
+        mode = (e && e[0] == 's') ? 0 : 1;
+    }
+    if (mode == 1 && S.pool_ok) {
+        const size_t smem = sizeof(SpWarp) * (WAVE_THREADS / 32);
+        if (occ == 0) {
+            cudaFuncSetAttribute(k_shadow_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_shadow_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int n = 0, n2 = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow_wave<true>, WAVE_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, k_shadow_wave<false>, WAVE_THREADS, smem) != cudaSuccess || n2 < 1) n2 = 1;
+            if (n2 < n) n = n2;
+            if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
+            occ = n;
+        }
+        if (S.flat) k_shadow_wave<true><<<cfg.sm_count * occ, WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        else k_shadow_wave<false><<<cfg.sm_count * occ, WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+    } else {
+        k_shadow_wave_simple<<<resident_grid(cfg, k_shadow_wave_simple, &occ_simple), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
+    }
 }
 
 // Folds the GI records of one chunk into the pixel accumulator: L = End; L = D_k + A_k * L for k = end-1 .. 0
