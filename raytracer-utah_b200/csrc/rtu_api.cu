@@ -178,6 +178,7 @@ int ensure_scratch(rtu_context *c, size_t q_cap, size_t shadow_cap)
     c->wb.hits.count = counts + 5;
     c->wb.hits.cap = (uint32_t)q_cap;
     c->wb.gi_count = counts + 6;
+    CU(alloc((void **)&c->wb.park, (size_t)XP_MAX_WARPS * (XP_JOBS + XP_RES) * 3 * sizeof(float4)));
     CU(alloc((void **)&c->wb.counters, sizeof(DCounters)));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     c->q_cap = q_cap;
@@ -601,7 +602,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.bounds = db;
     S.n_nodes = d->n_nodes;
     S.flat = flat;
-    S.pool_ok = 1;
+    S.pool_ok = d->n_meshes > 0 ? 1 : 0; // without meshes nothing would ever be pooled
     for (int m = 0; m < d->n_meshes; m++)
         if (d->meshes[m].nf > (1u << 24) || d->meshes[m].bvh_nodes >= (1u << 27)) S.pool_ok = 0;
     S.meshes = dm;

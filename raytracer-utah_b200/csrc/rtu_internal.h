@@ -23,11 +23,17 @@ struct LaunchCfg {
     int threads;
 };
 
+// rays a warp of the pooled closest-hit kernel can have parked (jobs) and resuming (res); 3 float4 per entry
+#define XP_JOBS 64
+#define XP_RES 96
+#define XP_MAX_WARPS (148 * 4 * 8 * 2)
+
 struct WaveBuffers {
     RayQueue q[2];
     AuxPool aux[2];
     ShadowQueue shadow;
     HitQueue hits;
+    float4 *park;         // per-warp lists of rays parked at a mesh / resuming behind it (pooled closest-hit kernel)
     unsigned *gi_count;   // number of GI records (= primary hits) of the current chunk (RTU_MODE_PATH)
     unsigned *work;       // device work-fetch counters (one per launch slot)
     DCounters *counters;

@@ -51,7 +51,52 @@ __device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *cc, int 
     }
 }
 
+// What happens to a ray once Trace() is over: hits are compacted into the hit queue, misses add what the recursion adds.
+template <bool PRIMARY>
+__device__ __forceinline__ void extend_finish(const DScene &S, const FrameSetup &F, const PrimaryMap &pm, const RayQueue &in,
+                                              const AuxPool &inaux, const HitQueue &hq, float4 *accum, float4 *target,
+                                              DCounters *counters, unsigned idx, const Ray &ray, int pixel, const Best &B)
+{
+    if (B.node >= 0) {
+        unsigned slot = warp_alloc(hq.count, true);
+        if (slot >= hq.cap) { counters->overflow = 1; return; }
+        hq.a[slot] = make_float4(B.z, __int_as_float(B.node), __int_as_float(B.front), __int_as_float(B.slot));
+        hq.b[slot] = make_float4(B.bc1, B.bc2, B.bc3, __uint_as_float(idx));
+        return;
+    }
+    // what the recursion adds when Trace() misses
+    Col c = mk(0, 0, 0);
+    if (PRIMARY) {
+        int py = pixel / pm.W, px = pixel - py * pm.W;
+        c = background_sample(S, px, py, pm.W, F.cam.height);                     // RenderFunctions.cpp:145
+        accum_add(accum, pixel, c);
+    } else {
+        float4 w = in.w[idx];
+        int slot = __float_as_int(in.o[idx].w);
+        int kind, bounce, tree, gidepth, mtl;
+        unpack_meta(__float_as_uint(in.d[idx].w), kind, bounce, tree, gidepth, mtl);
+        int aux = __float_as_int(w.w);
+        Col Wt = mk(w.x, w.y, w.z);
+        if (kind == RK_GI) {
+            // MonteCarlo(): the sample ray left the scene, c = environment (RenderFunctions.cpp:575);
+            // slot = first entry of the GI record, its last entry holds (c, index of the vertex that was missed)
+            Col e = environment_sample(S, ray.dx, ray.dy, ray.dz);
+            target[slot + 2 * (F.gi_bounces + 1)] = make_float4(e.r, e.g, e.b, (float)gidepth);
+            return;
+        }
+        if (kind == RK_REFRACT) {
+            c = Wt * environment_sample(S, ray.dx, ray.dy, ray.dz);               // mtlFunctions.cpp:267
+        } else if (kind == RK_REFLECT || kind == RK_FRESNEL) {
+            Col wm = Wt;
+            if (aux >= 0) { float4 a = inaux.a[aux]; wm = mk(a.x, a.y, a.z); }
+            c = wm * environment_sample(S, ray.dx, ray.dy, ray.dz);               // :250, :289
+        }
+        accum_add(target, slot + tree, c); // environment terms do not scale with the ambient light: slot+1 in tree 1
+    }
+}
+
 // ------------------------------------------------------------------ closest hit
+// Plain version: every lane walks its own meshes (used when a mesh does not fit the pooled kernel's item encoding).
 template <bool PRIMARY>
 __global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
@@ -92,42 +137,308 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         tl.trace++;
         scene_hit<false>(S, ray, B, tl);
 
-        if (B.node >= 0) {
-            unsigned slot = warp_alloc(hq.count, true);
-            if (slot >= hq.cap) { counters->overflow = 1; continue; }
-            hq.a[slot] = make_float4(B.z, __int_as_float(B.node), __int_as_float(B.front), __int_as_float(B.slot));
-            hq.b[slot] = make_float4(B.bc1, B.bc2, B.bc3, __uint_as_float(idx));
+        extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, B);
+    }
+    flush_tally(tl, counters, PRIMARY ? 0 : 1);
+}
+
+// Pooled version (see k_shadow_wave below for the idea): a ray that reaches a mesh whose bound box it enters is
+// parked; 32 parked rays are walked as ONE pool of (ray, node) items per warp, 32 items per iteration, leaves in a
+// second pool.  Closest hit does not depend on the order in which boxes are opened - the reference never prunes by the
+// current z (objFunctions.cpp:358-359), so the boxes and triangles tested are the same set, and so are the counters -
+// EXCEPT when two triangles report exactly the same distance: the reference keeps the one it visits first.  Distances
+// are merged with a 64-bit atomicMin on (z bits, triangle); an equal z from another triangle flags the ray, and a
+// flagged ray is re-walked in the reference's order (bvh_walk) at the end of the batch.  After its mesh a ray resumes
+// its node loop with the updated HitInfo, so the order of nodes (stale-z sphere returns, ties between objects) is the
+// reference's too.
+#ifndef XP_POOL
+#define XP_POOL 512
+#endif
+#define XP_LEAF 128
+
+struct XpWarp {
+    float4 o[32];                  // mesh-local origin, z of the HitInfo when the mesh was entered
+    float4 d[32];                  // mesh-local direction, InvDir::ok
+    float4 y[32];                  // hoisted reciprocals
+    const BvhPair *pairs[32];
+    const TriRec *tris[32];
+    unsigned long long zkey[32];   // (closest z so far) << 32 | triangle, merged with atomicMin
+    unsigned pool[XP_POOL];
+    unsigned leaf[XP_LEAF];
+    unsigned tie;                  // bit s: slot s saw two triangles at the same z
+};
+
+__device__ __forceinline__ void tri_load(const TriRec *p, TriRec &T)
+{
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    float4 x = __ldg(q), y = __ldg(q + 1), w4 = __ldg(q + 2);
+    T.nx = x.x; T.ny = x.y; T.nz = x.z; T.ax = x.w;
+    T.ay = y.x; T.az = y.y; T.area = y.z; T.fbits = y.w;
+    T.cau = w4.x; T.cav = w4.y; T.bau = w4.z; T.bav = w4.w;
+}
+
+template <bool PRIMARY, bool FLAT>
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
+              DCounters *counters, unsigned *work, float4 *park)
+{
+    extern __shared__ __align__(16) unsigned char xp_raw[];
+    XpWarp &W = reinterpret_cast<XpWarp *>(xp_raw)[threadIdx.x >> 5];
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u, FULL = 0xffffffffu, NONE = 0x7fffffffu;
+    // this warp's lists of parked / resuming rays: 3 float4 per entry = (idx, node, z, hit node | front, tri, bc1, bc2 | bc3)
+    float4 *jobs = park + (size_t)(blockIdx.x * (WAVE_THREADS / 32) + (threadIdx.x >> 5)) * (size_t)((XP_JOBS + XP_RES) * 3);
+    float4 *res = jobs + XP_JOBS * 3;
+    PrimaryMap pm;
+    pm.init(F);
+    unsigned total;
+    if (PRIMARY) total = pm.perSample * (unsigned)(s1 - s0);
+    else { total = *in.count; if (total > in.cap) total = in.cap; }
+    unsigned njobs = 0, nres = 0; // warp-uniform
+    bool drained = false;
+    DNode root;
+    load_node(S.nodes, root);
+
+    for (;;) {
+        if (njobs >= 32u || (njobs > 0u && nres == 0u && drained)) {
+            // ------------------------------------------------------------ one batch of mesh walks
+            const unsigned take = njobs < 32u ? njobs : 32u;
+            njobs -= take;
+            unsigned rootw = NONE, idx = 0, node = 0;
+            Best B;
+            B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+            if (lane < take) {
+                const float4 e0 = jobs[(njobs + lane) * 3], e1 = jobs[(njobs + lane) * 3 + 1], e2 = jobs[(njobs + lane) * 3 + 2];
+                idx = __float_as_uint(e0.x); node = __float_as_uint(e0.y);
+                B.z = e0.z; B.node = __float_as_int(e0.w);
+                B.front = __float_as_int(e1.x); B.slot = __float_as_int(e1.y); B.bc1 = e1.z; B.bc2 = e1.w; B.bc3 = e2.x;
+                Ray ray;
+                if (PRIMARY) {
+                    int s, x, y;
+                    pm.decode(idx, s0, s, x, y);
+                    ray = primary_ray(F, s, x, y, y * pm.W + x);
+                } else {
+                    float4 o = in.o[idx], d = in.d[idx];
+                    ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+                    ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+                }
+                DNode nd;
+                load_node(S.nodes + node, nd);
+                const Ray lr = FLAT ? to_node(nd.itm, nd.pos, to_node(root.itm, root.pos, ray)) : local_ray_of(S, (int)node, ray, nullptr);
+                const DMesh &M = S.meshes[nd.mesh];
+                InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
+                I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                W.o[lane] = make_float4(lr.px, lr.py, lr.pz, B.z);
+                W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
+                W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
+                W.pairs[lane] = M.pairs;
+                W.tris[lane] = M.tris;
+                W.zkey[lane] = ((unsigned long long)__float_as_uint(B.z) << 32) | 0xffffffffull;
+                rootw = M.root;
+            }
+            unsigned bi = __ballot_sync(FULL, rootw < NONE), bl = __ballot_sync(FULL, rootw > NONE);
+            if (rootw < NONE) W.pool[__popc(bi & lt)] = (lane << 27) | rootw;
+            if (rootw > NONE) W.leaf[__popc(bl & lt)] = (lane << 27) | (((rootw >> 28) & 7u) << 24) | (rootw & 0x00ffffffu);
+            unsigned pool_n = __popc(bi), leaf_n = __popc(bl);
+            if (lane == 0) W.tie = 0u;
+            __syncwarp();
+            for (;;) {
+                const bool do_leaf = leaf_n >= 32u || (pool_n == 0u && leaf_n > 0u);
+                if (!do_leaf && pool_n == 0u) break;
+                if (do_leaf) {
+                    const unsigned n = leaf_n < 32u ? leaf_n : 32u;
+                    leaf_n -= n;
+                    if (lane < n) {
+                        const unsigned it = W.leaf[leaf_n + lane], sl = it >> 27;
+                        const float4 o = W.o[sl], d = W.d[sl];
+                        Ray r;
+                        r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                        const TriRec *tris = W.tris[sl];
+                        const unsigned first = it & 0x00ffffffu, cnt = ((it >> 24) & 7u) + 1u;
+                        for (unsigned i = 0; i < cnt; i++) {
+                            TriRec T;
+                            tri_load(tris + first + i, T);
+                            tl.tri++;
+                            // gate with the closest distance any lane has found so far (<=: equal distances are looked at below)
+                            float z = __uint_as_float((unsigned)(*(volatile unsigned long long *)&W.zkey[sl] >> 32)), b1, b2, b3;
+                            int fr;
+                            if (tri_hit<true>(T, r, z, fr, b1, b2, b3) && z < o.w) {
+                                const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned long long)(first + i);
+                                const unsigned long long old = atomicMin(&W.zkey[sl], key);
+                                if ((unsigned)(old >> 32) == __float_as_uint(z) && (unsigned)old != 0xffffffffu && (unsigned)old != first + i)
+                                    atomicOr(&W.tie, 1u << sl);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                const bool finish = pool_n > XP_POOL - 64u; // no room to expand 32 items: walk them to the end instead
+                const unsigned n = pool_n < 32u ? pool_n : 32u;
+                pool_n -= n;
+                unsigned c1 = NONE, c2 = NONE, sl = 0;
+                if (lane < n) {
+                    const unsigned it = W.pool[pool_n + lane];
+                    sl = it >> 27;
+                    const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
+                    Ray r;
+                    r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                    InvDir I;
+                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                    const BvhPair *pairs = W.pairs[sl];
+                    if (finish) {
+                        float z = o.w, b1, b2, b3;
+                        int fr, tslot = -1;
+                        if (bvh_walk<false>(pairs, W.tris[sl], it & 0x07ffffffu, r, I, z, fr, tslot, b1, b2, b3, tl)) {
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned long long)(unsigned)tslot;
+                            const unsigned long long old = atomicMin(&W.zkey[sl], key);
+                            if ((unsigned)(old >> 32) == __float_as_uint(z) && (unsigned)old != 0xffffffffu && (unsigned)old != (unsigned)tslot)
+                                atomicOr(&W.tie, 1u << sl);
+                        }
+                    } else {
+                        float4 a, b, c, dd;
+                        load_pair(pairs + (it & 0x07ffffffu), a, b, c, dd);
+                        float e1, e2;
+                        bool h1 = slab_fast(r, I, a.x, a.y, a.z, a.w, b.x, b.y, RTU_BIG, e1);
+                        bool h2 = slab_fast(r, I, b.z, b.w, c.x, c.y, c.z, c.w, RTU_BIG, e2);
+                        tl.box += 2;
+                        if (h1) c1 = __float_as_uint(dd.x);
+                        if (h2) c2 = __float_as_uint(dd.y);
+                    }
+                }
+                const unsigned n2 = __ballot_sync(FULL, c2 < NONE), n1 = __ballot_sync(FULL, c1 < NONE);
+                const unsigned l2 = __ballot_sync(FULL, c2 > NONE), l1 = __ballot_sync(FULL, c1 > NONE);
+                if (c2 < NONE) W.pool[pool_n + __popc(n2 & lt)] = (sl << 27) | c2;
+                if (c1 < NONE) W.pool[pool_n + __popc(n2) + __popc(n1 & lt)] = (sl << 27) | c1;
+                if (c2 > NONE) W.leaf[leaf_n + __popc(l2 & lt)] = (sl << 27) | (((c2 >> 28) & 7u) << 24) | (c2 & 0x00ffffffu);
+                if (c1 > NONE) W.leaf[leaf_n + __popc(l2) + __popc(l1 & lt)] = (sl << 27) | (((c1 >> 28) & 7u) << 24) | (c1 & 0x00ffffffu);
+                pool_n += __popc(n2) + __popc(n1);
+                leaf_n += __popc(l2) + __popc(l1);
+                __syncwarp();
+            }
+            // every slot's ray takes the closest triangle into its HitInfo and goes on with the node behind the mesh
+            if (lane < take) {
+                const unsigned long long key = *(volatile unsigned long long *)&W.zkey[lane];
+                const float4 o = W.o[lane], d = W.d[lane];
+                Ray r;
+                r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                if ((*(volatile unsigned *)&W.tie >> lane) & 1u) {
+                    // two triangles at the same distance: the first one in the reference's visiting order wins
+                    const float4 yv = W.y[lane];
+                    InvDir I;
+                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                    Tally scratch = {0, 0, 0, 0, 0}; // this walk repeats tests that are already booked
+                    if (bvh_walk<false>(W.pairs[lane], W.tris[lane], rootw, r, I, B.z, B.front, B.slot, B.bc1, B.bc2, B.bc3, scratch)) B.node = (int)node;
+                } else if ((unsigned)key != 0xffffffffu) {
+                    TriRec T;
+                    tri_load(W.tris[lane] + (unsigned)key, T);
+                    float z = RTU_BIG;
+                    tri_hit(T, r, z, B.front, B.bc1, B.bc2, B.bc3); // front / barycentrics of the winner; z is the merged one
+                    B.z = __uint_as_float((unsigned)(key >> 32));
+                    B.slot = (int)(unsigned)key;
+                    B.node = (int)node;
+                }
+                float4 *e = res + (nres + lane) * 3;
+                e[0] = make_float4(__uint_as_float(idx), __uint_as_float(node + 1u), B.z, __int_as_float(B.node));
+                e[1] = make_float4(__int_as_float(B.front), __int_as_float(B.slot), B.bc1, B.bc2);
+                e[2] = make_float4(B.bc3, 0.f, 0.f, 0.f);
+            }
+            nres += take;
+            __syncwarp();
             continue;
         }
-        // what the recursion adds when Trace() misses
-        Col c = mk(0, 0, 0);
-        if (PRIMARY) {
-            int py = pixel / pm.W, px = pixel - py * pm.W;
-            c = background_sample(S, px, py, pm.W, F.cam.height);                     // RenderFunctions.cpp:145
-            accum_add(accum, pixel, c);
-        } else {
-            float4 w = in.w[idx];
-            int slot = __float_as_int(in.o[idx].w);
-            int kind, bounce, tree, gidepth, mtl;
-            unpack_meta(__float_as_uint(in.d[idx].w), kind, bounce, tree, gidepth, mtl);
-            int aux = __float_as_int(w.w);
-            Col Wt = mk(w.x, w.y, w.z);
-            if (kind == RK_GI) {
-                // MonteCarlo(): the sample ray left the scene, c = environment (RenderFunctions.cpp:575);
-                // slot = first entry of the GI record, its last entry holds (c, index of the vertex that was missed)
-                Col e = environment_sample(S, ray.dx, ray.dy, ray.dz);
-                target[slot + 2 * (F.gi_bounces + 1)] = make_float4(e.r, e.g, e.b, (float)gidepth);
-                continue;
-            }
-            if (kind == RK_REFRACT) {
-                c = Wt * environment_sample(S, ray.dx, ray.dy, ray.dz);               // mtlFunctions.cpp:267
-            } else if (kind == RK_REFLECT || kind == RK_FRESNEL) {
-                Col wm = Wt;
-                if (aux >= 0) { float4 a = inaux.a[aux]; wm = mk(a.x, a.y, a.z); }
-                c = wm * environment_sample(S, ray.dx, ray.dy, ray.dz);               // :250, :289
-            }
-            accum_add(target, slot + tree, c); // environment terms do not scale with the ambient light: slot+1 in tree 1
+        // -------------------------------------------------------------------- node loop of 32 rays
+        if (nres == 0u && drained) break; // (njobs == 0 here)
+        const unsigned k = nres < 32u ? nres : 32u;
+        unsigned fresh = drained ? 0u : 32u - k;
+        unsigned base = 0;
+        if (fresh) {
+            if (lane == 0) base = atomicAdd(work, fresh);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= total) { drained = true; fresh = 0; }
         }
+        unsigned idx = 0;
+        int i0 = 1;
+        bool have = false;
+        Best B;
+        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+        if (lane < k) {
+            const float4 *e = res + (nres - k + lane) * 3;
+            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+            idx = __float_as_uint(e0.x); i0 = (int)__float_as_uint(e0.y);
+            B.z = e0.z; B.node = __float_as_int(e0.w);
+            B.front = __float_as_int(e1.x); B.slot = __float_as_int(e1.y); B.bc1 = e1.z; B.bc2 = e1.w; B.bc3 = e2.x;
+            have = true;
+        } else if (lane - k < fresh) {
+            idx = base + (lane - k);
+            have = idx < total;
+        }
+        nres -= k;
+        Ray ray;
+        int pixel = 0;
+        if (have) {
+            if (PRIMARY) {
+                int s, x, y;
+                have = pm.decode(idx, s0, s, x, y);
+                pixel = y * pm.W + x;
+                if (have) ray = primary_ray(F, s, x, y, pixel);
+            } else {
+                float4 o = in.o[idx], d = in.d[idx];
+                ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+                ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+            }
+        }
+        int parked = 0;
+        if (have) {
+            if (i0 == 1) tl.trace++;
+            const Ray r0 = to_node(root.itm, root.pos, ray);
+            const float dd = dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz);
+            Ray lvl[FLAT ? 1 : RTU_MAX_DEPTH];
+            if (!FLAT) {
+                lvl[0] = r0;
+                if (i0 > 1 && i0 < S.n_nodes) local_ray_of(S, __ldg(&S.nodes[i0].parent), ray, lvl);
+            }
+            for (int i = i0; i < S.n_nodes; i++) {
+                DNode nd;
+                Ray lr;
+                if (FLAT) {
+                    const float4 bs = __ldg(&S.bounds[i]);
+                    if (bs.w < 0.f && bs.w > -1.5f) continue; // no object
+                    if (bound_culled(bs, r0, dd)) { tl.node++; tl.box++; continue; }
+                    load_node(S.nodes + i, nd);
+                    lr = to_node(nd.itm, nd.pos, r0);
+                } else {
+                    load_node(S.nodes + i, nd);
+                    lr = to_node(nd.itm, nd.pos, lvl[nd.depth - 1]);
+                    lvl[nd.depth] = lr;
+                    if (nd.kind == 0) continue;
+                    if (bound_culled(__ldg(&S.bounds[i]), r0, dd)) { tl.node++; tl.box++; continue; }
+                }
+                if (nd.kind == 3) { // TriObj::IntersectRay up to its bound-box gate (objFunctions.cpp:337)
+                    const DMesh &M = S.meshes[nd.mesh];
+                    tl.node++;
+                    if (M.empty) continue;
+                    tl.box++;
+                    InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
+                    I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                    float te;
+                    if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
+                    parked = i;
+                    break;
+                }
+                sphere_or_plane_hit(nd, i, lr, B, tl);
+            }
+            if (!parked) extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, B);
+        }
+        const unsigned m = __ballot_sync(FULL, parked != 0);
+        if (parked) {
+            float4 *e = jobs + (njobs + __popc(m & lt)) * 3;
+            e[0] = make_float4(__uint_as_float(idx), __uint_as_float((unsigned)parked), B.z, __int_as_float(B.node));
+            e[1] = make_float4(__int_as_float(B.front), __int_as_float(B.slot), B.bc1, B.bc2);
+            e[2] = make_float4(B.bc3, 0.f, 0.f, 0.f);
+        }
+        njobs += __popc(m);
+        __syncwarp();
     }
     flush_tally(tl, counters, PRIMARY ? 0 : 1);
 }
@@ -293,8 +604,13 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
 // overflow, the popped items are walked to the end by their lanes (bvh_walk) instead of being expanded.
 #define SP_JOBS 64   // parked (ray, mesh node) entries waiting for a batch
 #define SP_RES 96    // rays that missed their mesh and resume the node loop behind it
+#ifndef SP_POOL
 #define SP_POOL 512  // internal-node items: slot << 27 | pair index
+#endif
 #define SP_LEAF 128  // leaf items: slot << 27 | (count - 1) << 24 | first triangle
+#ifndef SHADOW_BLOCKS
+#define SHADOW_BLOCKS EXT_BLOCKS
+#endif
 
 struct SpWarp {
     float4 o[32];                // mesh-local origin, t_max
@@ -311,7 +627,7 @@ struct SpWarp {
 };
 
 template <bool FLAT>
-__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+__global__ void __launch_bounds__(WAVE_THREADS, SHADOW_BLOCKS)
 k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
 {
     extern __shared__ __align__(16) unsigned char sp_raw[];
@@ -715,10 +1031,43 @@ static WaveOut make_out(const WaveBuffers &B, int out_q, float4 *accum)
     return O;
 }
 
+static int extend_mode()
+{
+    static int mode = -1;
+    if (mode < 0) { // RTU_EXTEND_KERNEL=simple selects the plain kernel (A/B measurements)
+        const char *e = getenv("RTU_EXTEND_KERNEL");
+        mode = (e && e[0] == 's') ? 0 : 1;
+    }
+    return mode;
+}
+
+template <class K> static int pooled_grid(const LaunchCfg &cfg, K kernel, size_t smem, int *cache)
+{
+    if (*cache == 0) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WAVE_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+        if (n > 4) n = 4; // XP_MAX_WARPS
+        if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
+        *cache = n;
+    }
+    return cfg.sm_count * *cache;
+}
+
 void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
                            const WaveBuffers &B, float4 *pixel_accum, float4 *accum, unsigned *work_counter)
 {
-    static int occ = 0;
+    static int occ = 0, occ_f = 0, occ_n = 0;
+    const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
+    if (extend_mode() == 1 && S.pool_ok) {
+        if (S.flat)
+            k_extend_pool<true, true><<<pooled_grid(cfg, k_extend_pool<true, true>, smem, &occ_f), WAVE_THREADS, smem, st>>>(
+                S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter, B.park);
+        else
+            k_extend_pool<true, false><<<pooled_grid(cfg, k_extend_pool<true, false>, smem, &occ_n), WAVE_THREADS, smem, st>>>(
+                S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter, B.park);
+        return;
+    }
     k_extend<true><<<resident_grid(cfg, k_extend<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum,
                                                                                      accum, B.counters, work_counter);
 }
@@ -735,7 +1084,17 @@ void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S
 void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
                          int in_q, float4 *accum, unsigned *work_counter)
 {
-    static int occ = 0;
+    static int occ = 0, occ_f = 0, occ_n = 0;
+    const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
+    if (extend_mode() == 1 && S.pool_ok) {
+        if (S.flat)
+            k_extend_pool<false, true><<<pooled_grid(cfg, k_extend_pool<false, true>, smem, &occ_f), WAVE_THREADS, smem, st>>>(
+                S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter, B.park);
+        else
+            k_extend_pool<false, false><<<pooled_grid(cfg, k_extend_pool<false, false>, smem, &occ_n), WAVE_THREADS, smem, st>>>(
+                S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter, B.park);
+        return;
+    }
     k_extend<false><<<resident_grid(cfg, k_extend<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum,
                                                                                        accum, B.counters, work_counter);
 }
