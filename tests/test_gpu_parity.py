@@ -326,7 +326,7 @@ def test_path_mode_matches_reference_head_render(rtu, gpu_ctx, tag):
         hs.close()
 
 
-@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "spheres_1000"])
+@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "spheres_1000", "dupmesh"])
 def test_synthetic_scenes(rtu, gpu_ctx, name):
     """SURVEY section 8d shapes: a 1 M-triangle mesh (707 640-node BVH) and flat lists of 100 / 1000 spheres with
     mirrors and glass; expectations from the unmodified reference on the same generated files."""
@@ -356,6 +356,15 @@ def test_synthetic_scenes(rtu, gpu_ctx, name):
         st = sc.stats()
         assert st["trace_rays"] == meta["whitted"]["trace_rays"] and st["shadow_rays"] == meta["whitted"]["shadow_rays"]
         assert (g["node"] >= 0).mean() > 0.1
+        if name == "dupmesh":
+            # every triangle of this mesh exists twice, so every mesh hit is an exact tie in z and the winning face is
+            # whichever copy the reference's BVH walk reaches first (both copies win about half of the pixels)
+            f = g["face"][g["face"] >= 0]
+            nf = hs.desc.meshes[0].nf
+            assert min((f < nf // 2).mean(), (f >= nf // 2).mean()) > 0.3
+            rays = sc.camera_rays(rtu.default_params(width=meta["width"], height=meta["height"], mode=rtu.MODE_PRIMARY))
+            hits = sc.trace(rays).reshape(g["node"].shape)
+            assert np.array_equal(hits["face"], g["face"])
     finally:
         sc.close()
         hs.close()

@@ -94,6 +94,32 @@ def write_soup(path, n=1000000):
         f.write("".join(lines))
 
 
+def write_dupmesh(path, n=24):
+    """A bumpy n x n quad patch whose every triangle exists twice (same three vertices): every hit is an exact tie in z,
+    so the winner is decided by the reference's visiting order alone."""
+    rng = np.random.default_rng(SEED + 7)
+    xs = np.linspace(-6, 6, n + 1)
+    X, Y = np.meshgrid(xs, xs)
+    Z = 0.8 * np.sin(X * 0.9) * np.cos(Y * 0.7) + 0.05 * rng.standard_normal(X.shape)
+    with open(path, "w") as f:
+        f.write("# dupmesh: %d x %d quads, every triangle twice\n" % (n, n))
+        for x, y, z in zip(X.ravel(), Y.ravel(), Z.ravel()):
+            f.write("v %.4f %.4f %.4f\n" % (x, y, z))
+        for x, y in zip(X.ravel(), Y.ravel()):
+            f.write("vt %.4f %.4f 0.0000\n" % ((x + 6) / 12, (y + 6) / 12))
+        w = n + 1
+        tris = []
+        for j in range(n):
+            for i in range(n):
+                a = j * w + i + 1
+                tris.append((a, a + 1, a + 1 + w))
+                tris.append((a, a + 1 + w, a + w))
+        order = list(range(len(tris))) + list(rng.permutation(len(tris)))   # the copies come in a shuffled order
+        for t in order:
+            a, b, c = tris[t]
+            f.write("f %d/%d %d/%d %d/%d\n" % (a, a, b, b, c, c))
+
+
 def write_mesh_scene(path, obj, w, h, dist, height):
     with open(path, "w") as f:
         f.write("<xml>\n  <scene>\n    <background r=\"0.05\" g=\"0.06\" b=\"0.09\"/>\n    <environment value=\"0.2\"/>\n")
@@ -126,12 +152,12 @@ def ensure(names=("grid1M", "spheres_100", "spheres_1000", "spheres_10000")):
     out = {}
     for n in names:
         xml = os.path.join(OUT, n + ".xml")
-        if n in ("grid1M", "soup1M"):
+        if n in ("grid1M", "soup1M", "dupmesh"):
             obj = os.path.join(OUT, n + ".obj")
             if not os.path.exists(obj):
-                (write_grid if n == "grid1M" else write_soup)(obj)
+                {"grid1M": write_grid, "soup1M": write_soup, "dupmesh": write_dupmesh}[n](obj)
             if not os.path.exists(xml):
-                write_mesh_scene(xml, n + ".obj", 3840, 2160, 22 if n == "grid1M" else 40, 12)
+                write_mesh_scene(xml, n + ".obj", 3840, 2160, 22 if n != "soup1M" else 40, 12)
         elif n.startswith("spheres_"):
             if not os.path.exists(xml):
                 write_spheres(xml, int(n.split("_")[1]))
