@@ -32,6 +32,7 @@ __device__ __forceinline__ Ray camera_ray(const DCamera &C, int x, int y, float 
 struct PrimaryMap {
     int W, row_begin, row_end, tilesX;
     unsigned perSample;
+    unsigned m_ps, m_tx; // floor(2^32 / divisor) - 1: quotient estimates for the two divisions of decode()
     __device__ __forceinline__ void init(const FrameSetup &F)
     {
         W = F.cam.width;
@@ -40,15 +41,29 @@ struct PrimaryMap {
         tilesX = (W + 7) >> 3;
         int tilesY = (row_end - row_begin + 3) >> 2;
         perSample = (unsigned)(tilesX * tilesY) * 32u;
+        // 2^32 / d in double is off by less than 1/d from the true quotient, so its floor is exact; one less keeps the
+        // estimate q' = umulhi(n, m) at or below the true quotient for every n
+        m_ps = (unsigned)(4294967296.0 / (double)perSample) - 1u;
+        m_tx = tilesX > 1 ? (unsigned)(4294967296.0 / (double)tilesX) - 1u : 0xfffffffeu;
+    }
+    // n / d and n % d from the precomputed estimate (a 32-bit division costs ~20 instructions, this one 5)
+    static __device__ __forceinline__ unsigned divmod(unsigned n, unsigned d, unsigned m, unsigned &rem)
+    {
+        unsigned q = __umulhi(n, m);
+        unsigned r = n - q * d;
+        while (r >= d) { q++; r -= d; }
+        rem = r;
+        return q;
     }
     __device__ __forceinline__ bool decode(unsigned idx, int s0, int &s, int &x, int &y) const
     {
-        unsigned sl = idx / perSample, t = idx - sl * perSample;
+        unsigned t;
+        unsigned sl = divmod(idx, perSample, m_ps, t);
         s = s0 + (int)sl;
-        unsigned tile = t >> 5, in5 = t & 31u;
-        int tx = (int)(tile % (unsigned)tilesX), ty = (int)(tile / (unsigned)tilesX);
-        x = tx * 8 + (int)(in5 & 7u);
-        y = row_begin + ty * 4 + (int)(in5 >> 3);
+        unsigned tile = t >> 5, in5 = t & 31u, utx;
+        unsigned uty = divmod(tile, (unsigned)tilesX, m_tx, utx);
+        x = (int)utx * 8 + (int)(in5 & 7u);
+        y = row_begin + (int)uty * 4 + (int)(in5 >> 3);
         return x < W && y < row_end;
     }
 };

@@ -55,7 +55,8 @@ __device__ __forceinline__ void flush_tally(const Tally &tl, DCounters *cc, int 
 template <bool PRIMARY>
 __device__ __forceinline__ void extend_finish(const DScene &S, const FrameSetup &F, const PrimaryMap &pm, const RayQueue &in,
                                               const AuxPool &inaux, const HitQueue &hq, float4 *accum, float4 *target,
-                                              DCounters *counters, unsigned idx, const Ray &ray, int pixel, const Best &B)
+                                              DCounters *counters, unsigned idx, const Ray &ray, int pixel, int px, int py,
+                                              const Best &B)
 {
     if (B.node >= 0) {
         unsigned slot = warp_alloc(hq.count, true);
@@ -67,7 +68,6 @@ __device__ __forceinline__ void extend_finish(const DScene &S, const FrameSetup 
     // what the recursion adds when Trace() misses
     Col c = mk(0, 0, 0);
     if (PRIMARY) {
-        int py = pixel / pm.W, px = pixel - py * pm.W;
         c = background_sample(S, px, py, pm.W, F.cam.height);                     // RenderFunctions.cpp:145
         accum_add(accum, pixel, c);
     } else {
@@ -121,9 +121,9 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         if (idx >= total) continue;
 
         Ray ray;
-        int pixel = 0;
+        int pixel = 0, x = 0, y = 0;
         if (PRIMARY) {
-            int s, x, y;
+            int s;
             if (!pm.decode(idx, s0, s, x, y)) continue;
             pixel = y * pm.W + x;
             ray = primary_ray(F, s, x, y, pixel);
@@ -137,7 +137,7 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         tl.trace++;
         scene_hit<false>(S, ray, B, tl);
 
-        extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, B);
+        extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, x, y, B);
     }
     flush_tally(tl, counters, PRIMARY ? 0 : 1);
 }
@@ -375,10 +375,10 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
         }
         nres -= k;
         Ray ray;
-        int pixel = 0;
+        int pixel = 0, x = 0, y = 0;
         if (have) {
             if (PRIMARY) {
-                int s, x, y;
+                int s;
                 have = pm.decode(idx, s0, s, x, y);
                 pixel = y * pm.W + x;
                 if (have) ray = primary_ray(F, s, x, y, pixel);
@@ -428,7 +428,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 }
                 sphere_or_plane_hit(nd, i, lr, B, tl);
             }
-            if (!parked) extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, B);
+            if (!parked) extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, x, y, B);
         }
         const unsigned m = __ballot_sync(FULL, parked != 0);
         if (parked) {
