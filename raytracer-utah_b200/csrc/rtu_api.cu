@@ -46,7 +46,7 @@ struct rtu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     LaunchCfg cfg;
-    size_t chunk_rays = 1u << 25;  // primary rays per wave chunk (~300 B of queue space each)
+    size_t chunk_rays = 1u << 27;  // primary rays per wave chunk (~300 B of queue space each): a 64-spp 1080p frame is one chunk
     double queue_factor = 1.0;
     // scratch (lazily sized)
     WaveBuffers wb;
@@ -803,6 +803,7 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
     int rows = F.row_end - F.row_begin;
     size_t per_sample = (size_t)((W + 7) / 8) * ((rows + 3) / 4) * 32;
     size_t chunk_samples = std::max<size_t>(1, c->chunk_rays / per_sample);
+    chunk_samples = std::min<size_t>(chunk_samples, (size_t)(s1 - s0)); // queues are sized for what this call renders
     size_t chunk_cap = std::max(per_sample, chunk_samples * per_sample);
     if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
     // Queue capacities: one entry per primary ray of a chunk.  A hit can spawn up to 3 rays, so no
