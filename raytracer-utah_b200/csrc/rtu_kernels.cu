@@ -349,8 +349,9 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
         }
         // -------------------------------------------------------------------- node loop of 32 rays
         if (nres == 0u && drained) break; // (njobs == 0 here)
-        const unsigned k = nres < 32u ? nres : 32u;
-        unsigned fresh = drained ? 0u : 32u - k;
+        // resuming rays have short node loops left, fresh rays long ones: a pass takes 32 of one kind, not a mix
+        const unsigned k = (nres >= 32u || drained) ? (nres < 32u ? nres : 32u) : 0u;
+        unsigned fresh = (k == 0u && !drained) ? 32u : 0u;
         unsigned base = 0;
         if (fresh) {
             if (lane == 0) base = atomicAdd(work, fresh);
@@ -757,8 +758,9 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         }
         // -------------------------------------------------------------------- node loop of 32 rays
         if (nres == 0u && drained) break; // (njobs == 0 here)
-        const unsigned k = nres < 32u ? nres : 32u;
-        unsigned fresh = drained ? 0u : 32u - k;
+        // resuming rays have short node loops left, fresh rays long ones: a pass takes 32 of one kind, not a mix
+        const unsigned k = (nres >= 32u || drained) ? (nres < 32u ? nres : 32u) : 0u;
+        unsigned fresh = (k == 0u && !drained) ? 32u : 0u;
         unsigned base = 0;
         if (fresh) {
             if (lane == 0) base = atomicAdd(work, fresh);
