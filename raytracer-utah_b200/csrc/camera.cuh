@@ -55,6 +55,13 @@ struct PrimaryMap {
         rem = r;
         return q;
     }
+    // the tile (index into FrameSetup::tile_empty) of a work item
+    __device__ __forceinline__ unsigned tile_of(unsigned idx) const
+    {
+        unsigned t;
+        divmod(idx, perSample, m_ps, t);
+        return t >> 5;
+    }
     __device__ __forceinline__ bool decode(unsigned idx, int s0, int &s, int &x, int &y) const
     {
         unsigned t;

@@ -63,6 +63,7 @@ struct DMesh {
     uint32_t n_tris;
     float bmin[3], bmax[3];
     uint32_t empty;      // no faces: cyTriMesh's "not ready" box never intersects
+    uint32_t coords_ok;  // every box coordinate of the mesh is 0 or at least 2^-36 in magnitude (see mesh_invdir)
 };
 
 struct DTexMap {

@@ -77,6 +77,8 @@ struct rtu_context {
         size_t img_n = 0;
         float2 *d_offsets = nullptr;
         size_t offsets_n = 0;
+        unsigned char *d_tile = nullptr; // FrameSetup::tile_empty
+        size_t tile_n = 0;
     } fb;
 };
 
@@ -90,6 +92,10 @@ struct rtu_scene {
     uint64_t launches = 0;
     bool timed = false;
     // photon map (balanced, n+1 records, record 0 unused) and the parameters it was made with
+    struct Footprint { double c[8][3]; bool finite; }; // world-space corners of an object's bound box
+    std::vector<Footprint> footprints;
+    bool root_identity = true;
+    int n_obj = 0;                // nodes whose object Trace() tests (what a ray that misses everything books)
     int h_light0_kind = -1;       // lights[0]: the only light GeneratePhotonMap emits from
     float h_light0_I[3] = {0, 0, 0};
     rtu_photon *d_photons = nullptr;
@@ -363,6 +369,16 @@ int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *
     out->shade = ds;
     out->n_pairs = (uint32_t)pairs.size();
     out->n_tris = m.nf;
+    {   // box coordinates that are 0 or >= 2^-36 in magnitude: then "bound - origin" is 0 or >= 2^-60 for every such
+        // origin, which is what the hoisted division needs (intersect.cuh, mesh_invdir)
+        auto fine = [](float v) { return v == 0.f || (std::fabs(v) >= 1.4551915228366852e-11f && std::isfinite(v)); };
+        bool ok = true;
+        const float *pf = reinterpret_cast<const float *>(pairs.data());
+        for (size_t i = 0; i < pairs.size() && ok; i++)
+            for (int k = 0; k < 12; k++) ok = ok && fine(pf[i * (sizeof(BvhPair) / 4) + k]);
+        for (int k = 0; k < 3; k++) ok = ok && fine(out->bmin[k]) && fine(out->bmax[k]);
+        out->coords_ok = ok ? 1u : 0u;
+    }
     return RTU_OK;
 }
 
@@ -440,6 +456,7 @@ void rtu_context_destroy(rtu_context *c)
     for (cudaEvent_t e : c->kt_ev) cudaEventDestroy(e);
     void *fbp[] = {c->fb.accum, c->fb.d_rgb, c->fb.d_rgb8, c->fb.d_z, c->fb.d_z8, c->fb.d_node, c->fb.d_face, c->fb.d_offsets};
     for (void *p : fbp) if (p) cudaFree(p);
+    if (c->fb.d_tile) cudaFree(c->fb.d_tile);
     delete c;
 }
 
@@ -520,9 +537,26 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
             if (!std::isfinite(q)) finite = false;
             r2 = std::max(r2, q);
         }
+        {   // the same 8 corners, kept for the per-frame image-space footprint of the object (setup_frame)
+            rtu_scene::Footprint fp;
+            fp.finite = finite;
+            for (int corner = 0; corner < 8; corner++) {
+                double p[3] = {(corner & 1) ? hi[0] : lo[0], (corner & 2) ? hi[1] : lo[1], (corner & 4) ? hi[2] : lo[2]};
+                to_root(p);
+                for (int k = 0; k < 3; k++) fp.c[corner][k] = p[k];
+            }
+            sc->footprints.push_back(fp);
+        }
         if (!finite) { bounds[i].w = 3.0e38f; continue; } // never culls
         double rad = std::sqrt(r2) * 1.002 + 1e-5 * (std::fabs(ctr[0]) + std::fabs(ctr[1]) + std::fabs(ctr[2]) + 1.0);
         bounds[i] = make_float4((float)ctr[0], (float)ctr[1], (float)ctr[2], (float)std::min(rad * rad, 3.0e38));
+    }
+    sc->n_obj = 0;
+    for (int i = 0; i < d->n_nodes; i++) if (d->nodes[i].kind != RTU_OBJ_NONE) sc->n_obj++;
+    {   // the bounding spheres are in root space; camera rays are in world space: the same thing for the identity root of every XML scene
+        const rtu_node &r = d->nodes[0];
+        const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        sc->root_identity = memcmp(r.itm, ident, sizeof ident) == 0 && r.pos[0] == 0.f && r.pos[1] == 0.f && r.pos[2] == 0.f;
     }
     float4 *db = nullptr;
     if ((rc = dev_upload(bounds, &db, c->stream, sc->owned))) return fail(rc);
@@ -675,6 +709,86 @@ int ensure_accum(rtu_scene *s, size_t npix)
     return RTU_OK;
 }
 
+// Image-space footprint of every object for one camera: the convex hull of the projected corners of its bound box
+// (clipped against the eye plane), as a pixel-space bounding box plus outward half-planes.  A camera ray can only pass an
+// object's bound-box gate (objFunctions.cpp:17,109,337) where its image-plane point lies inside that hull.
+// Returns false when the camera is degenerate (then no tile is ever called empty).
+bool image_footprints(const rtu_scene *s, const DCamera &C, std::vector<TileObject> *objs, std::vector<float4> *edges)
+{
+    // image-plane point of pixel coordinates (fi,fj): origin + fi u + fj v; ray direction D = w0 + fi u + fj v with
+    // w0 = origin - eye.  A world point X lies on that ray iff X - eye = t (w0 + fi u + fj v), t > 0: solve the 3x3 system
+    double M[3][3], inv[3][3];
+    for (int r = 0; r < 3; r++) { M[r][0] = (double)C.origin[r] - (double)C.pos[r]; M[r][1] = C.u[r]; M[r][2] = C.v[r]; }
+    double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                 M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+    if (!std::isfinite(det) || std::fabs(det) < 1e-300) return false;
+    inv[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) / det; inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) / det; inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) / det;
+    inv[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) / det; inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) / det; inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) / det;
+    inv[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) / det; inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) / det; inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) / det;
+    const double len0 = std::sqrt(M[0][0] * M[0][0] + M[1][0] * M[1][0] + M[2][0] * M[2][0]);
+    // nothing nearer than 1e-6 along a ray can be hit (the primitives' own epsilons are 1e-5 and 1e-3): clip there
+    const double t_near = 1e-6 / std::max(len0, 1e-30) * 0.5;
+    static const int E[12][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    for (const rtu_scene::Footprint &fp : s->footprints) {
+        TileObject o;
+        o.first_edge = (int)edges->size();
+        o.n_edges = 0;
+        o.lo[0] = o.lo[1] = -3.0e38f; o.hi[0] = o.hi[1] = 3.0e38f; // everywhere
+        if (!fp.finite) { objs->push_back(o); continue; }
+        double q[8][3];
+        bool ok = true;
+        for (int c = 0; c < 8; c++) {
+            double d[3] = {fp.c[c][0] - (double)C.pos[0], fp.c[c][1] - (double)C.pos[1], fp.c[c][2] - (double)C.pos[2]};
+            for (int r = 0; r < 3; r++) q[c][r] = inv[r][0] * d[0] + inv[r][1] * d[1] + inv[r][2] * d[2];
+            if (!std::isfinite(q[c][0]) || !std::isfinite(q[c][1]) || !std::isfinite(q[c][2])) ok = false;
+        }
+        if (!ok) { objs->push_back(o); continue; }
+        std::vector<std::pair<double, double>> pts;
+        for (int c = 0; c < 8; c++) if (q[c][0] >= t_near) pts.push_back({q[c][1] / q[c][0], q[c][2] / q[c][0]});
+        for (auto &e : E) {
+            const double *a = q[e[0]], *b = q[e[1]];
+            if ((a[0] - t_near) * (b[0] - t_near) < 0) {
+                double l = (t_near - a[0]) / (b[0] - a[0]);
+                pts.push_back({(a[1] + l * (b[1] - a[1])) / t_near, (a[2] + l * (b[2] - a[2])) / t_near});
+            }
+        }
+        if (pts.empty()) { o.lo[0] = o.lo[1] = 1.f; o.hi[0] = o.hi[1] = -1.f; objs->push_back(o); continue; } // entirely behind the eye
+        double lo[2] = {pts[0].first, pts[0].second}, hi[2] = {lo[0], lo[1]}, big = 0;
+        for (auto &p : pts) {
+            lo[0] = std::min(lo[0], p.first); hi[0] = std::max(hi[0], p.first);
+            lo[1] = std::min(lo[1], p.second); hi[1] = std::max(hi[1], p.second);
+            big = std::max(big, std::max(std::fabs(p.first), std::fabs(p.second)));
+        }
+        if (!std::isfinite(big) || big > 1e7) { objs->push_back(o); continue; } // touches the eye plane: treat as everywhere
+        const double margin = 0.05 + 1e-5 * big; // pixels: far above the float error of ray construction and slab tests
+        o.lo[0] = (float)(lo[0] - margin); o.lo[1] = (float)(lo[1] - margin);
+        o.hi[0] = (float)(hi[0] + margin); o.hi[1] = (float)(hi[1] + margin);
+        // convex hull (monotone chain), counter-clockwise
+        std::sort(pts.begin(), pts.end());
+        pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+        std::vector<std::pair<double, double>> h(2 * pts.size() + 2);
+        int k = 0;
+        auto cross = [](const std::pair<double, double> &O, const std::pair<double, double> &A, const std::pair<double, double> &B) {
+            return (A.first - O.first) * (B.second - O.second) - (A.second - O.second) * (B.first - O.first);
+        };
+        for (size_t i = 0; i < pts.size(); i++) { while (k >= 2 && cross(h[k - 2], h[k - 1], pts[i]) <= 0) k--; h[k++] = pts[i]; }
+        for (size_t i = pts.size() - 1, t = k + 1; i > 0; i--) { while ((size_t)k >= t && cross(h[k - 2], h[k - 1], pts[i - 1]) <= 0) k--; h[k++] = pts[i - 1]; }
+        int n = k - 1;
+        if (n >= 3) {
+            for (int i = 0; i < n; i++) {
+                const auto &A = h[i], &B = h[(i + 1) % n];
+                double ex = B.first - A.first, ey = B.second - A.second, l = std::sqrt(ex * ex + ey * ey);
+                if (!(l > 0)) continue;
+                double nx = ey / l, ny = -ex / l; // outward normal of a counter-clockwise polygon
+                edges->push_back(make_float4((float)nx, (float)ny, (float)(nx * A.first + ny * A.second + margin + 1e-4 * big * 1e-3), 0.f));
+                o.n_edges++;
+            }
+        }
+        objs->push_back(o);
+    }
+    return true;
+}
+
 int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, int *s_end)
 {
     int W, H, rc;
@@ -721,6 +835,48 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     CU(cudaMemcpyAsync(s->ctx->fb.d_offsets, off.data(), off.size() * sizeof(float2), cudaMemcpyHostToDevice, s->ctx->stream));
     CU(cudaStreamSynchronize(s->ctx->stream)); // `off` is a local
     F->sample_offsets = s->ctx->fb.d_offsets;
+    // tiles of the primary wave that no camera ray of the rendered samples can leave with a hit
+    F->tile_empty = nullptr;
+    F->n_obj = s->n_obj;
+    if (!getenv("RTU_NO_TILE_MASK") && s->cam.dof <= 0.f && s->root_identity) {
+        float ox0 = off[*s_begin].x, ox1 = ox0, oy0 = off[*s_begin].y, oy1 = oy0;
+        for (int i = *s_begin; i < *s_end; i++) {
+            ox0 = std::min(ox0, off[i].x); ox1 = std::max(ox1, off[i].x);
+            oy0 = std::min(oy0, off[i].y); oy1 = std::max(oy1, off[i].y);
+        }
+        std::vector<TileObject> objs;
+        std::vector<float4> edges;
+        if (image_footprints(s, F->cam, &objs, &edges)) {
+            size_t tiles = (size_t)((W + 7) / 8) * (size_t)((F->row_end - F->row_begin + 3) / 4);
+            size_t need = tiles + objs.size() * sizeof(TileObject) + edges.size() * sizeof(float4) + 64;
+            if (need > s->ctx->fb.tile_n) {
+                CU(cudaStreamSynchronize(s->ctx->stream));
+                if (s->ctx->fb.d_tile) cudaFree(s->ctx->fb.d_tile);
+                s->ctx->fb.d_tile = nullptr;
+                s->ctx->fb.tile_n = 0;
+                CU(cudaMalloc((void **)&s->ctx->fb.d_tile, need));
+                s->ctx->fb.tile_n = need;
+            }
+            // layout: [objects][edges][mask]
+            unsigned char *base = s->ctx->fb.d_tile;
+            TileObject *d_objs = (TileObject *)base;
+            float4 *d_edges = (float4 *)(base + ((objs.size() * sizeof(TileObject) + 15) / 16) * 16);
+            unsigned char *d_mask = (unsigned char *)(d_edges + edges.size());
+            if (!objs.empty()) CU(cudaMemcpyAsync(d_objs, objs.data(), objs.size() * sizeof(TileObject), cudaMemcpyHostToDevice, s->ctx->stream));
+            if (!edges.empty()) CU(cudaMemcpyAsync(d_edges, edges.data(), edges.size() * sizeof(float4), cudaMemcpyHostToDevice, s->ctx->stream));
+            launch_tile_mask(s->ctx->stream, *F, d_objs, (int)objs.size(), d_edges, ox0, ox1, oy0, oy1, d_mask);
+            CU(cudaStreamSynchronize(s->ctx->stream)); // objs / edges are locals
+            F->tile_empty = d_mask;
+            if (getenv("RTU_TILE_DEBUG")) {
+                std::vector<unsigned char> hm(tiles);
+                cudaMemcpy(hm.data(), d_mask, tiles, cudaMemcpyDeviceToHost);
+                size_t e = 0;
+                for (unsigned char v : hm) e += v;
+                fprintf(stderr, "tile mask: %zu of %zu tiles empty, %zu objects, %zu hull edges, offsets [%g,%g]x[%g,%g]\n", e, tiles, objs.size(), edges.size(), ox0, ox1, oy0, oy1);
+                for (auto &o : objs) fprintf(stderr, "  object bbox [%g,%g]x[%g,%g] edges %d\n", o.lo[0], o.hi[0], o.lo[1], o.hi[1], o.n_edges);
+            }
+        }
+    }
     return RTU_OK;
 }
 

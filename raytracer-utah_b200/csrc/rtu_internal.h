@@ -15,6 +15,10 @@ struct FrameSetup {
     int gi_bounces;
     unsigned flags;
     uint2 seed;
+    // primary wave: tile_empty[tile] != 0 when no camera ray of that 8x4-pixel tile (any rendered sample) can reach the
+    // bounding sphere of any object; such rays book n_obj culled nodes each and add the background (may be NULL)
+    const unsigned char *tile_empty;
+    int n_obj;
 };
 
 struct LaunchCfg {
@@ -86,3 +90,13 @@ void launch_photon_emit(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 void launch_photon_compact(cudaStream_t st, const rtu_photon *staging, const unsigned char *counts, const unsigned *offsets,
                            unsigned n_paths, unsigned cut, int max_bounce, rtu_photon *map1, unsigned cap);
 void launch_photon_scale(cudaStream_t st, rtu_photon *map1, unsigned n, float scale);
+
+// image-space footprint of one object: pixel-space bounding box and n_edges outward half-planes (nx, ny, c):
+// a point p is outside when nx p.x + ny p.y > c
+struct TileObject {
+    float lo[2], hi[2];
+    int first_edge, n_edges;
+};
+// tiles of the primary wave that no object's footprint touches (see FrameSetup::tile_empty)
+void launch_tile_mask(cudaStream_t st, const FrameSetup &F, const TileObject *objs, int n_objs, const float4 *edges, float ox0,
+                      float ox1, float oy0, float oy1, unsigned char *mask);

@@ -95,6 +95,17 @@ __device__ __forceinline__ void extend_finish(const DScene &S, const FrameSetup 
     }
 }
 
+// A tile none of whose camera rays can reach any object (FrameSetup::tile_empty): the ray is not built at all; it books
+// what Trace() books for a ray whose every node fails its bound-box gate, and adds the background (RenderFunctions.cpp:145).
+__device__ __forceinline__ void primary_miss_fast(const DScene &S, const FrameSetup &F, const PrimaryMap &pm, float4 *accum, int x,
+                                                  int y, Tally &tl)
+{
+    tl.trace++;
+    tl.node += F.n_obj;
+    tl.box += F.n_obj;
+    accum_add(accum, y * pm.W + x, background_sample(S, x, y, pm.W, F.cam.height));
+}
+
 // ------------------------------------------------------------------ closest hit
 // Plain version: every lane walks its own meshes (used when a mesh does not fit the pooled kernel's item encoding).
 template <bool PRIMARY>
@@ -125,6 +136,7 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         if (PRIMARY) {
             int s;
             if (!pm.decode(idx, s0, s, x, y)) continue;
+            if (F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, tl); continue; }
             pixel = y * pm.W + x;
             ray = primary_ray(F, s, x, y, pixel);
         } else {
@@ -226,8 +238,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 load_node(S.nodes + node, nd);
                 const Ray lr = FLAT ? to_node(nd.itm, nd.pos, to_node(root.itm, root.pos, ray)) : local_ray_of(S, (int)node, ray, nullptr);
                 const DMesh &M = S.meshes[nd.mesh];
-                InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
-                I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                const InvDir I = mesh_invdir(M, lr);
                 W.o[lane] = make_float4(lr.px, lr.py, lr.pz, B.z);
                 W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
                 W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
@@ -382,6 +393,10 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 int s;
                 have = pm.decode(idx, s0, s, x, y);
                 pixel = y * pm.W + x;
+                if (have && i0 == 1 && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { // warp-uniform: a ticket is one tile
+                    primary_miss_fast(S, F, pm, accum, x, y, tl);
+                    have = false;
+                }
                 if (have) ray = primary_ray(F, s, x, y, pixel);
             } else {
                 float4 o = in.o[idx], d = in.d[idx];
@@ -420,8 +435,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                     tl.node++;
                     if (M.empty) continue;
                     tl.box++;
-                    InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
-                    I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                    const InvDir I = mesh_invdir(M, lr);
                     float te;
                     if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
                     parked = i;
@@ -657,8 +671,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 load_node(S.nodes + j.y, nd);
                 const Ray lr = FLAT ? to_node(nd.itm, nd.pos, to_node(root.itm, root.pos, ray)) : local_ray_of(S, (int)j.y, ray, nullptr);
                 const DMesh &M = S.meshes[nd.mesh];
-                InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
-                I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                const InvDir I = mesh_invdir(M, lr);
                 W.o[lane] = make_float4(lr.px, lr.py, lr.pz, d.w);
                 W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
                 W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
@@ -817,8 +830,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                     tl.node++;
                     if (M.empty) continue;
                     tl.box++;
-                    InvDir I = make_invdir(lr.dx, lr.dy, lr.dz);
-                    I.ok = I.ok && numerators_bounded(lr, M.bmin, M.bmax);
+                    const InvDir I = mesh_invdir(M, lr);
                     float te;
                     if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
                     park = i;
@@ -1007,6 +1019,40 @@ __global__ void k_zimage(const float *z, int npix, const unsigned *mm, unsigned 
         o = (unsigned char)c;
     }
     z8[p] = o;
+}
+
+// ------------------------------------------------------------------ empty tiles of the primary wave
+// One thread per 8x4-pixel tile.  The image-plane points of the tile's camera rays (all rendered samples: sub-pixel
+// offsets in [ox0,ox1] x [oy0,oy1]) fill a rectangle in pixel coordinates; the tile is empty when that rectangle is
+// separated from the footprint of every object (bounding boxes disjoint, or all four corners outside one hull edge).
+__global__ void k_tile_mask(FrameSetup F, const TileObject *objs, int n_objs, const float4 *edges, float ox0, float ox1, float oy0,
+                            float oy1, unsigned char *mask)
+{
+    const int tilesX = (F.cam.width + 7) >> 3, tilesY = (F.row_end - F.row_begin + 3) >> 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tilesX * tilesY) return;
+    const int tx = t % tilesX, ty = t / tilesX;
+    const float i0 = tx * 8 + ox0, i1 = tx * 8 + 7 + ox1;
+    const float j0 = F.row_begin + ty * 4 + oy0, j1 = F.row_begin + ty * 4 + 3 + oy1;
+    bool empty = true;
+    for (int k = 0; k < n_objs && empty; k++) {
+        const TileObject o = objs[k];
+        if (i1 < o.lo[0] || i0 > o.hi[0] || j1 < o.lo[1] || j0 > o.hi[1]) continue;
+        bool separated = false;
+        for (int e = 0; e < o.n_edges && !separated; e++) {
+            const float4 h = edges[o.first_edge + e];
+            separated = h.x * i0 + h.y * j0 > h.z && h.x * i1 + h.y * j0 > h.z && h.x * i0 + h.y * j1 > h.z && h.x * i1 + h.y * j1 > h.z;
+        }
+        if (!separated) empty = false;
+    }
+    mask[t] = empty ? 1 : 0;
+}
+
+void launch_tile_mask(cudaStream_t st, const FrameSetup &F, const TileObject *objs, int n_objs, const float4 *edges, float ox0,
+                      float ox1, float oy0, float oy1, unsigned char *mask)
+{
+    const int tiles = ((F.cam.width + 7) >> 3) * ((F.row_end - F.row_begin + 3) >> 2);
+    k_tile_mask<<<(tiles + 127) / 128, 128, 0, st>>>(F, objs, n_objs, edges, ox0, ox1, oy0, oy1, mask);
 }
 
 // ------------------------------------------------------------------ launch wrappers
