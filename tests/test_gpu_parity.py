@@ -473,3 +473,26 @@ def test_photon_emission_statistics(rtu, gpu_ctx):
     finally:
         sc.close()
         hs.close()
+
+
+@pytest.mark.parametrize("scene,size", [("Teapot/scene2.xml", (480, 270)), ("Project5/scene.xml", (240, 180)), ("Project4.xml", (240, 180))])
+def test_primary_wave_books_the_reference_work(rtu, gpu_ctx, scene, size):
+    """The closest-hit wave walks meshes as pools of (ray, node) items, skips empty tiles and culls by bounding spheres,
+    yet it books exactly the node visits, box tests and triangle tests the reference's Trace() performs for the same
+    camera rays (the oracle counts them; SURVEY 8d builds the roofline figure from these counters)."""
+    from oracle import oracle_py as O
+    hs = rtu.HostScene(os.path.join(SCENES, scene))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        w, h = size
+        ref = O.render(hs.desc, width=w, height=h, mode=rtu.MODE_PRIMARY, want=("node_id",))["stats"]
+        p = rtu.default_params(width=w, height=h, mode=rtu.MODE_WHITTED, shade_bounces=0)
+        sc.render_device(p)
+        st = sc.stats()["primary_wave"]
+        assert st["rays"] == w * h == ref["trace_rays"]
+        assert st["node_visits"] == ref["node_visits"]
+        assert st["box_tests"] == ref["box_tests"]
+        assert st["tri_tests"] == ref["tri_tests"]
+    finally:
+        sc.close()
+        hs.close()
