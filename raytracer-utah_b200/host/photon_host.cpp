@@ -4,6 +4,7 @@
 // gather walks the same nodes the reference's LocatePhotons walks.
 #include <cstring>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -48,7 +49,9 @@ struct Balancer {
         }
     }
 
-    void segment(const float lo[3], const float hi[3], int index, int start, int end)
+    // The two sides of a median are disjoint ranges of `work` and disjoint heap slots of `out`, so below the top few
+    // levels the recursion runs on separate threads; the result is the sequential one.
+    void segment(const float lo[3], const float hi[3], int index, int start, int end, int fork_levels)
     {
         const int median = median_of(start, end);
         const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
@@ -62,24 +65,20 @@ struct Balancer {
         out[index] = work[median];
         out[index].plane_dirz = (uint8_t)((out[index].plane_dirz & 0x8) | axis);
         const float split = out[index].position[axis];
-        if (median > start) {
-            if (start < median - 1) {
-                float h2[3] = {hi[0], hi[1], hi[2]};
-                h2[axis] = split;
-                segment(lo, h2, 2 * index, start, median - 1);
-            } else {
-                out[2 * index] = work[start];
-            }
+        float h2[3] = {hi[0], hi[1], hi[2]}, l2[3] = {lo[0], lo[1], lo[2]};
+        h2[axis] = split;
+        l2[axis] = split;
+        const bool left_rec = median > start && start < median - 1, right_rec = median < end && median + 1 < end;
+        if (median > start && !left_rec) out[2 * index] = work[start];
+        if (median < end && !right_rec) out[2 * index + 1] = work[end];
+        if (left_rec && right_rec && fork_levels > 0 && end - start > 4096) {
+            std::thread t([&]() { segment(lo, h2, 2 * index, start, median - 1, fork_levels - 1); });
+            segment(l2, hi, 2 * index + 1, median + 1, end, fork_levels - 1);
+            t.join();
+            return;
         }
-        if (median < end) {
-            if (median + 1 < end) {
-                float l2[3] = {lo[0], lo[1], lo[2]};
-                l2[axis] = split;
-                segment(l2, hi, 2 * index + 1, median + 1, end);
-            } else {
-                out[2 * index + 1] = work[end];
-            }
-        }
+        if (left_rec) segment(lo, h2, 2 * index, start, median - 1, fork_levels);
+        if (right_rec) segment(l2, hi, 2 * index + 1, median + 1, end, fork_levels);
     }
 };
 
@@ -104,7 +103,10 @@ extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_ph
             if (lo[k] > v) lo[k] = v;
             if (hi[k] < v) hi[k] = v;
         }
-    b.segment(lo, hi, 1, 1, (int)n);
+    unsigned hw = std::thread::hardware_concurrency();
+    int fork_levels = 0;
+    while ((1u << (fork_levels + 1)) <= (hw ? hw : 1u) && fork_levels < 6) fork_levels++;
+    b.segment(lo, hi, 1, 1, (int)n, fork_levels);
     return RTU_OK;
 }
 
