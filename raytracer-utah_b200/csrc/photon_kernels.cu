@@ -45,16 +45,12 @@ __device__ __forceinline__ void photon_direction(const PhotonRec &p, float &dx, 
     dy = (float)iy / 32767.0f;
     int xy2 = ix * ix + iy - iy;
     if (xy2 > 0x3FFF0001) xy2 = 0x3FFF0001;
-    int rem = 0x3FFF0001 - xy2, z = 0, place = 0x40000000;
-    while (place > rem) place >>= 2;
-    while (place) {
-        if (rem >= z + place) {
-            rem = rem - z - place;
-            z = z + (place << 1);
-        }
-        z >>= 1;
-        place >>= 2;
-    }
+    // the reference extracts floor(sqrt(0x3FFF0001 - xy2)) bit by bit (16 rounds); the same integer from one sqrtf
+    // and a correction step (equal for all 32 768 reachable arguments, tests/test_host.py)
+    const int v = 0x3FFF0001 - xy2;
+    int z = (int)sqrtf((float)v);
+    while (z * z > v) z--;
+    while ((z + 1) * (z + 1) <= v) z++;
     dz = (float)z / 32767.0f;
     if ((p.packed0 >> 24) & 0x8u) dz = -dz;
 }

@@ -186,3 +186,26 @@ def test_photon_map_balancing_matches_reference(rtu):
     assert bal[1:].tobytes() == g["photons_balanced"].tobytes()
     assert bal[:1].tobytes() == bytes(24)
     assert rtu.balance_photons(pin[:0]).shape == (1,)
+
+
+def test_photon_direction_integer_sqrt_shortcut():
+    """Photon::GetDirection (cyPhotonMap.h:166-178) takes floor(sqrt(0x3FFF0001 - dirX^2)) with a 16-round bitwise
+    routine; the device code uses sqrtf plus a correction step.  Equal for every reachable argument."""
+    def bitwise(v):
+        place, rem, z = 0x40000000, v, 0
+        while place > rem:
+            place >>= 2
+        while place:
+            if rem >= z + place:
+                rem, z = rem - z - place, z + (place << 1)
+            z >>= 1
+            place >>= 2
+        return z
+    for x in range(0, 32769):
+        v = 0x3FFF0001 - min(x * x, 0x3FFF0001)
+        z = int(np.float32(np.sqrt(np.float32(v))))
+        while z * z > v:
+            z -= 1
+        while (z + 1) * (z + 1) <= v:
+            z += 1
+        assert z == bitwise(v), x
