@@ -154,7 +154,9 @@ enum {
     RTU_MODE_PRIMARY = 0, /* one Trace() per pixel centre: node/face ids + z only */
     RTU_MODE_WHITTED = 1, /* Trace + Shade(ray,h,lights,shade_bounces): RenderFunctions.cpp:135 alone */
     RTU_MODE_PATH = 2,    /* HEAD estimator: MonteCarlo GI list + lights (RenderFunctions.cpp:132-135) */
-    RTU_MODE_PHOTON = 3   /* PhotonMapping(ray, hInfo) per sample (RenderFunctions.cpp:141-142, 394-413); needs a photon map */
+    RTU_MODE_PHOTON = 3,  /* PhotonMapping(ray, hInfo) per sample (RenderFunctions.cpp:141-142, 394-413); needs a photon map */
+    RTU_MODE_PHOTON_GATHER = 4 /* Shade(ray,h,lights,bounces) + MonteCarloPhoton(h,x,y,1): direct light plus a final gather of
+                                  gi_bounces cosine samples into the photon map (RenderFunctions.cpp:137-139, 416-451) */
 };
 enum {
     RTU_PATTERN_CENTER = 0,   /* pixel centre (0.5,0.5); spp must be 1 */

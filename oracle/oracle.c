@@ -665,6 +665,7 @@ typedef struct {
 } job_t;
 
 static col photon_mapping(ctx_t *c, const ray_t *r, const hit_t *h);
+static col monte_carlo_photon(ctx_t *c, const hit_t *h, int x, int y, int W, int H, int bounces);
 
 static void *render_rows(void *arg)
 {
@@ -702,6 +703,8 @@ static void *render_rows(void *arg)
                 if (trace(&c, &r, &h)) {
                     if (P->mode == RTU_MODE_PHOTON) {                             /* RenderFunctions.cpp:141-142 */
                         v = photon_mapping(&c, &r, &h);
+                    } else if (P->mode == RTU_MODE_PHOTON_GATHER) {               /* RenderFunctions.cpp:137-139 */
+                        v = cadd(shade(&c, &r, &h, P->shade_bounces, NULL), monte_carlo_photon(&c, &h, x, y, W, J->H, P->gi_bounces));
                     } else if (P->mode == RTU_MODE_PATH) {                        /* RenderFunctions.cpp:129-135 */
                         col amb = monte_carlo(&c, &h, P->gi_bounces);
                         v = cadd(shade(&c, &r, &h, P->shade_bounces, &amb), shade(&c, &r, &h, P->shade_bounces, NULL));
@@ -1067,4 +1070,28 @@ static col photon_mapping(ctx_t *c, const ray_t *r, const hit_t *h)
     }
     (void)r;
     return out;
+}
+
+
+/* MonteCarloPhoton(hInfo, x, y, 1) (RenderFunctions.cpp:416-451).  Every bounce samples the hemisphere of the SAME
+ * first hit, and the HitInfo of the sample rays is initialised once and never reset, so a later sample only "hits"
+ * what is nearer than the previous sample's hit (SURVEY A-16 for the same pattern in the photon bounces). */
+static col monte_carlo_photon(ctx_t *c, const hit_t *h, int x, int y, int W, int H, int bounces)
+{
+    col sum = C(0, 0, 0);
+    hit_t hs;
+    hit_init(&hs);
+    int actual = 0;
+    for (int b = 0; b < bounces; b++) {
+        ray_t r = {h->p, unit(sample_hemi_cos(c, h->N))};                          /* :428-429 */
+        actual++;
+        if (trace(c, &r, &hs)) {
+            sum = cadd(sum, photon_mapping(c, &r, &hs));                           /* :436-437 */
+        } else {
+            sum = cadd(sum, tc_sample(c->S, &c->S->background, V((float)x / W, (float)y / H, 0))); /* :440 */
+            break;
+        }
+    }
+    float n = (float)actual;
+    return C(sum.r / n, sum.g / n, sum.b / n);                                     /* :445; /= monteCarloSampleSize (1) */
 }

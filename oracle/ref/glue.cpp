@@ -60,3 +60,4 @@ void RefMonteCarlo(LightList &l, const HitInfo &h, int x, int y, int bounces, in
 void RefGeneratePhotonMap() { GeneratePhotonMap(); }
 Color RefPhotonMapping(const Ray &r, const HitInfo &h) { return PhotonMapping(r, h); }
 cyPhotonMap *RefPhotonMap() { return &pMap; }
+Color RefMonteCarloPhoton(const HitInfo &h, int x, int y, int n) { return MonteCarloPhoton(h, x, y, n); }

@@ -50,6 +50,7 @@ float BVHBoxIntersection(const Ray &r, Box bvhBox, float t_max);
 void RefGeneratePhotonMap();
 Color RefPhotonMapping(const Ray &r, const HitInfo &h);
 cyPhotonMap *RefPhotonMap();
+Color RefMonteCarloPhoton(const HitInfo &h, int x, int y, int n);
 int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pattern, double *device_ms, unsigned long long *rays);
 
 // ---------------------------------------------------------------- npy output
@@ -666,6 +667,30 @@ static void ModePhoton(const Opts &o)
         }
     });
     double tGather = Now() - t0;
+    if (o.spp > 1) {
+        // the commented-out "Photon Map + MonteCarlo" estimator of Render() (RenderFunctions.cpp:137-139):
+        // Shade(ray, h, lights, 5) + MonteCarloPhoton(h, x, y, 1), averaged over --spp evaluations at the pixel centre
+        std::vector<float> gi((size_t)W * H * 3);
+        ParallelRows(0, H, 1, [&](int y, int) {   // one thread: MonteCarloPhoton draws from rand()
+            for (int x = 0; x < W; x++) {
+                Ray r = CameraRay(x, y, 0.5f, 0.5f, 0, 0);
+                size_t i = x + (size_t)W * y;
+                Color sum(0, 0, 0);
+                for (int s = 0; s < o.spp; s++) {
+                    HitInfo h;
+                    if (Trace(r, &rootNode, h)) {
+                        sum += h.node->GetMaterial()->Shade(r, h, lights, 5);
+                        sum += RefMonteCarloPhoton(h, x, y, 1);
+                    } else {
+                        sum += background.Sample(Point3((float)x / camera.imgWidth, (float)y / camera.imgHeight, 0));
+                    }
+                }
+                sum /= (float)o.spp;
+                gi[i * 3] = sum.r; gi[i * 3 + 1] = sum.g; gi[i * 3 + 2] = sum.b;
+            }
+        });
+        NpyF(o.out + "_gi.npy", gi, {(size_t)H, (size_t)W, 3});
+    }
     NpyF(o.out + "_rgb.npy", rgb, {(size_t)H, (size_t)W, 3});
     NpyF(o.out + "_irrad.npy", irr, {(size_t)H, (size_t)W, 3});
     NpyF(o.out + "_dir.npy", dir, {(size_t)H, (size_t)W, 3});

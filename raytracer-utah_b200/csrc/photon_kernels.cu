@@ -206,30 +206,11 @@ k_estimate(DPhotonMap PM, const float *pos, const float *normal, long long n, fl
     if (found) found[i] = f;
 }
 
-// PhotonMapping (RenderFunctions.cpp:394-413): the estimate becomes a PhotonLight (lights.h:61-74: Illuminate =
+// PhotonMapping(ray, hInfo) (RenderFunctions.cpp:394-413): the estimate becomes a PhotonLight (lights.h:61-74: Illuminate =
 // intensity, Direction = direction, not ambient, no shadow ray) and the hit is shaded with it alone, bounceCount 0.
 // A hit without photons in range has direction 0/0 = NaN and shades to NaN, as in the reference.
-__global__ void __launch_bounds__(128)
-k_photon_shade(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float4 *accum)
+__device__ __forceinline__ Col photon_mapping(const DScene &S, const DPhotonMap &PM, const HitRec &H)
 {
-    unsigned total = *hq.count;
-    if (total > hq.cap) total = hq.cap;
-    unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= total) return;
-    float4 a = hq.a[h], b = hq.b[h];
-    Best B;
-    B.z = a.x; B.node = __float_as_int(a.y); B.front = __float_as_int(a.z); B.slot = __float_as_int(a.w);
-    B.bc1 = b.x; B.bc2 = b.y; B.bc3 = b.z;
-    unsigned idx = __float_as_uint(b.w);
-    // the primary ray of work item idx (same mapping as k_extend<primary>)
-    PrimaryMap pm;
-    pm.init(F);
-    int s, x, y;
-    pm.decode(idx, s0, s, x, y);
-    int pixel = y * pm.W + x;
-    Ray ray = primary_ray(F, s, x, y, pixel);
-    HitRec H;
-    finalize_hit(S, ray, B, H);
     Col e;
     float dx, dy, dz;
     int found;
@@ -254,10 +235,109 @@ k_photon_shade(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float
         if (ndh < 0.f) ndh = 0.f;
         out = (e * ndl) * (Kd + Ks * powf(ndh, M.glossiness));
     }
+    return out;
+}
+
+// RTU_MODE_PHOTON: PhotonMapping per primary hit of the hit queue.
+__global__ void __launch_bounds__(128)
+k_photon_shade(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float4 *accum)
+{
+    unsigned total = *hq.count;
+    if (total > hq.cap) total = hq.cap;
+    unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= total) return;
+    float4 a = hq.a[h], b = hq.b[h];
+    Best B;
+    B.z = a.x; B.node = __float_as_int(a.y); B.front = __float_as_int(a.z); B.slot = __float_as_int(a.w);
+    B.bc1 = b.x; B.bc2 = b.y; B.bc3 = b.z;
+    unsigned idx = __float_as_uint(b.w);
+    // the primary ray of work item idx (same mapping as k_extend<primary>)
+    PrimaryMap pm;
+    pm.init(F);
+    int s, x, y;
+    pm.decode(idx, s0, s, x, y);
+    int pixel = y * pm.W + x;
+    Ray ray = primary_ray(F, s, x, y, pixel);
+    HitRec H;
+    finalize_hit(S, ray, B, H);
+    Col out = photon_mapping(S, PM, H);
     float *acc = reinterpret_cast<float *>(accum + pixel);
     atomicAdd(acc, out.r);
     atomicAdd(acc + 1, out.g);
     atomicAdd(acc + 2, out.b);
+}
+
+// RTU_MODE_PHOTON_GATHER: MonteCarloPhoton(hInfo, x, y, 1) per primary hit (RenderFunctions.cpp:416-451), added to the
+// Whitted radiance the other kernels produce.  Up to gi_bounces cosine samples of the hemisphere of the SAME first hit; the
+// HitInfo of the sample rays is never reset, so a later sample only finds what is nearer than the previous sample's hit;
+// a sample that finds nothing adds the background and ends the loop; the sum is divided by the samples taken.
+__global__ void __launch_bounds__(128)
+k_photon_gather(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float4 *accum, DCounters *counters)
+{
+    Tally tl = {0, 0, 0, 0, 0};
+    unsigned total = *hq.count;
+    if (total > hq.cap) total = hq.cap;
+    unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < total) {
+        float4 a = hq.a[h], b = hq.b[h];
+        Best B;
+        B.z = a.x; B.node = __float_as_int(a.y); B.front = __float_as_int(a.z); B.slot = __float_as_int(a.w);
+        B.bc1 = b.x; B.bc2 = b.y; B.bc3 = b.z;
+        unsigned idx = __float_as_uint(b.w);
+        PrimaryMap pm;
+        pm.init(F);
+        int s, x, y;
+        pm.decode(idx, s0, s, x, y);
+        int pixel = y * pm.W + x;
+        Ray ray = primary_ray(F, s, x, y, pixel);
+        HitRec H;
+        finalize_hit(S, ray, B, H);
+        Rng rng;
+        rng.key = F.seed; rng.pixel = 0x50474154u; rng.path = primary_path(pixel, s); rng.dim = 0;
+        Best Bs;
+        Bs.z = RTU_BIG; Bs.node = -1; Bs.front = 1; Bs.slot = 0; Bs.bc1 = Bs.bc2 = Bs.bc3 = 0.f;
+        Col sum = mk(0, 0, 0);
+        int actual = 0;
+        for (int bnc = 0; bnc < F.gi_bounces; bnc++) {
+            Ray sr;
+            sr.px = H.px; sr.py = H.py; sr.pz = H.pz;
+            sample_hemi_cos(rng, H.nx, H.ny, H.nz, sr.dx, sr.dy, sr.dz);
+            norm3(sr.dx, sr.dy, sr.dz);
+            actual++;
+            tl.trace++;
+            if (scene_hit<false>(S, sr, Bs, tl)) {
+                HitRec Hs;
+                finalize_hit(S, sr, Bs, Hs);
+                sum = sum + photon_mapping(S, PM, Hs);
+            } else {
+                sum = sum + background_sample(S, x, y, pm.W, F.cam.height);
+                break;
+            }
+        }
+        if (actual > 0) {
+            float n = (float)actual;
+            float *acc = reinterpret_cast<float *>(accum + pixel);
+            atomicAdd(acc, sum.r / n);
+            atomicAdd(acc + 1, sum.g / n);
+            atomicAdd(acc + 2, sum.b / n);
+        }
+    }
+    // the sample rays are booked with the secondary class
+    DCounterBlock *c = &counters->k[1];
+    unsigned t = tl.trace, bx = tl.box, r = tl.tri, nn = tl.node;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+        bx += __shfl_xor_sync(0xffffffffu, bx, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if ((threadIdx.x & 31) == 0 && t) {
+        atomicAdd(&c->trace_rays, (unsigned long long)t);
+        atomicAdd(&c->box_tests, (unsigned long long)bx);
+        atomicAdd(&c->tri_tests, (unsigned long long)r);
+        atomicAdd(&c->node_visits, (unsigned long long)nn);
+    }
 }
 
 // ------------------------------------------------------------------ emission
@@ -438,6 +518,13 @@ void launch_photon_shade(cudaStream_t st, const DScene &S, const FrameSetup &F, 
 {
     if (max_hits == 0) return;
     k_photon_shade<<<(max_hits + 127) / 128, 128, 0, st>>>(S, F, s0, B.hits, PM, accum);
+}
+
+void launch_photon_gather(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
+                          const DPhotonMap &PM, float4 *accum)
+{
+    if (max_hits == 0) return;
+    k_photon_gather<<<(max_hits + 127) / 128, 128, 0, st>>>(S, F, s0, B.hits, PM, accum, B.counters);
 }
 
 void launch_photon_emit(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, unsigned long long path0, unsigned n_paths,

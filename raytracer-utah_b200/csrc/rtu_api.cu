@@ -795,8 +795,9 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
     if (p->spp < 1 || p->spp > (1 << 20)) { rtu::set_error("bad spp"); return RTU_ERR_INVALID; }
     if (p->pattern == RTU_PATTERN_CENTER && p->spp != 1) { rtu::set_error("RTU_PATTERN_CENTER needs spp == 1"); return RTU_ERR_INVALID; }
-    if (p->mode != RTU_MODE_WHITTED && p->mode != RTU_MODE_PATH && p->mode != RTU_MODE_PHOTON) { rtu::set_error("bad render mode"); return RTU_ERR_INVALID; }
-    if (p->mode == RTU_MODE_PHOTON && !s->d_photons) { rtu::set_error("RTU_MODE_PHOTON needs a photon map: call rtu_photon_map_generate or rtu_photon_map_set first"); return RTU_ERR_INVALID; }
+    if (p->mode != RTU_MODE_WHITTED && p->mode != RTU_MODE_PATH && p->mode != RTU_MODE_PHOTON && p->mode != RTU_MODE_PHOTON_GATHER) { rtu::set_error("bad render mode"); return RTU_ERR_INVALID; }
+    if (p->mode == RTU_MODE_PHOTON_GATHER && (p->gi_bounces < 1 || p->gi_bounces > 16)) { rtu::set_error("gi_bounces out of range (1..16)"); return RTU_ERR_INVALID; }
+    if ((p->mode == RTU_MODE_PHOTON || p->mode == RTU_MODE_PHOTON_GATHER) && !s->d_photons) { rtu::set_error("RTU_MODE_PHOTON needs a photon map: call rtu_photon_map_generate or rtu_photon_map_set first"); return RTU_ERR_INVALID; }
     if (p->mode == RTU_MODE_PATH && (p->gi_bounces < 0 || p->gi_bounces > 6)) { rtu::set_error("gi_bounces out of range (0..6)"); return RTU_ERR_INVALID; }
     if (p->shade_bounces < 0 || p->shade_bounces > 15) { rtu::set_error("shade_bounces out of range"); return RTU_ERR_INVALID; }
     make_camera(s->cam, W, H, &F->cam);
@@ -999,6 +1000,10 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
         }
         kt_begin(c, 3);
         launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, target, c->work + wi++);
+        if (F.mode == RTU_MODE_PHOTON_GATHER) { // + MonteCarloPhoton per primary hit (the hit queue is still intact)
+            launch_photon_gather(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum);
+            s->launches++;
+        }
         kt_end(c);
         s->launches += 3;
         if ((rc = run_waves(s, F, target, 0, &wi))) return rc;

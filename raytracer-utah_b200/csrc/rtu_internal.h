@@ -84,6 +84,8 @@ void launch_estimate(cudaStream_t st, const DPhotonMap &PM, const float *pos, co
                      float norm_scale, float *irrad, float *direction, int *found);
 void launch_photon_shade(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
                          const DPhotonMap &PM, float4 *accum);
+void launch_photon_gather(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
+                          const DPhotonMap &PM, float4 *accum);
 void launch_photon_emit(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, unsigned long long path0, unsigned n_paths,
                         int max_bounce, uint2 seed, int light, rtu_photon *staging, unsigned char *counts, DCounters *counters,
                         unsigned *work_counter);

@@ -20,7 +20,7 @@ BIGFLOAT = np.float32(1.0e30)
 OBJ_NONE, OBJ_SPHERE, OBJ_PLANE, OBJ_MESH = 0, 1, 2, 3
 TEX_NULL, TEX_CHECKER, TEX_FILE = 0, 1, 2
 LIGHT_AMBIENT, LIGHT_DIRECT, LIGHT_POINT = 0, 1, 2
-MODE_PRIMARY, MODE_WHITTED, MODE_PATH, MODE_PHOTON = 0, 1, 2, 3
+MODE_PRIMARY, MODE_WHITTED, MODE_PATH, MODE_PHOTON, MODE_PHOTON_GATHER = 0, 1, 2, 3, 4
 PATTERN_CENTER, PATTERN_REFERENCE = 0, 1
 FLAG_CULL_NULL_SHADOW_RAYS = 1
 FLAG_CULL_ZERO_WEIGHT_RAYS = 2

@@ -496,3 +496,41 @@ def test_primary_wave_books_the_reference_work(rtu, gpu_ctx, scene, size):
     finally:
         sc.close()
         hs.close()
+
+
+def test_photon_gather_mode_matches_oracle_in_distribution(rtu, gpu_ctx):
+    """RTU_MODE_PHOTON_GATHER = Shade(ray,h,lights,5) + MonteCarloPhoton(h,x,y,1) (RenderFunctions.cpp:137-139, 416-451).
+    The oracle's estimator agrees with the reference's in distribution on the reference's own map (checked in the build
+    container: NaN fraction 59.8 % vs 60.1 %, mean 0.2835 vs 0.2857); here device and oracle share a device-made map
+    and are compared against the oracle's own seed-to-seed noise."""
+    from oracle import oracle_py as O
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        sc.photon_map_generate(map_size=300000, seed=21)
+        ph = sc.photon_map_get()
+        bal = np.zeros(len(ph) + 1, rtu.PHOTON_DTYPE)
+        bal[1:] = ph
+        O.set_photon_map(bal, 1.0, 0.5)
+        w, h, spp = 96, 72, 8
+        def params(seed):
+            return rtu.default_params(width=w, height=h, spp=spp, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_PHOTON_GATHER,
+                                      shade_bounces=5, gi_bounces=4, seed=seed)
+        gpu = sc.render(params(1), want=("rgb",))["rgb"]
+        o1 = O.render(hs.desc, params=params(2), want=("rgb",))["rgb"]
+        o2 = O.render(hs.desc, params=params(3), want=("rgb",))["rgb"]
+        nan = lambda a: np.isnan(a).any(axis=2)
+        # a sample whose estimate finds no photon is NaN in the reference and poisons its pixel: same rate everywhere
+        assert abs(nan(gpu).mean() - nan(o1).mean()) <= abs(nan(o1).mean() - nan(o2).mean()) + 0.04
+        ok = ~(nan(gpu) | nan(o1) | nan(o2))
+        assert ok.mean() > 0.1
+        noise = np.sqrt(((o1 - o2)[ok] ** 2).mean())
+        err = np.sqrt(((gpu - o1)[ok] ** 2).mean())
+        assert err <= 1.5 * noise, (err, noise)
+        assert abs(gpu[ok].mean() - o1[ok].mean()) <= 2.0 * abs(o1[ok].mean() - o2[ok].mean()) + 0.03 * o1[ok].mean()
+        # with gi_bounces = 1 the chain is one sample: still stochastic, but the direct part must be present
+        direct = sc.render(rtu.default_params(width=w, height=h, spp=1, mode=rtu.MODE_WHITTED, shade_bounces=5), want=("rgb",))["rgb"]
+        assert np.nanmean(gpu) > np.nanmean(direct) * 0.9
+    finally:
+        sc.close()
+        hs.close()
