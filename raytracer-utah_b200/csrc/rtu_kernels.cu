@@ -1095,7 +1095,7 @@ template <class K> static int pooled_grid(const LaunchCfg &cfg, K kernel, size_t
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WAVE_THREADS, smem) != cudaSuccess || n < 1) n = 1;
-        if (n > 4) n = 4; // XP_MAX_WARPS
+        while (n > 1 && cfg.sm_count * n * (WAVE_THREADS / 32) > XP_MAX_WARPS) n--; // one parking region per resident warp
         if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
         *cache = n;
     }
