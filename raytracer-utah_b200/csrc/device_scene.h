@@ -107,12 +107,28 @@ struct DCamera {
     float inv_w, inv_h; // not used for parity-critical math
 };
 
+// Top-level hierarchy over the objects' bounding spheres (root space), used when a scene has many nodes: it only
+// NOMINATES nodes for a ray (a superset of those the per-node sphere cull lets through); the nominees are then visited in
+// node order by the usual code, so results and counters are those of the linear visit of every node.
+struct TopNode {
+    float lo[3];
+    int32_t a;  // internal: left child; leaf: -(first item + 1)
+    float hi[3];
+    int32_t b;  // internal: right child; leaf: item count
+};
+#define RTU_TOP_CAND 64 // nominees per ray before the linear visit takes over
+
 struct DScene {
     const DNode *nodes;
     const float4 *bounds; // per node: bounding sphere of the object's bound box in root space (xyz, r^2 inflated);
                           // w = -1: no object, w = -2: object that can never be hit (empty mesh)
     int32_t n_nodes;
     int32_t flat;        // 1: every object node hangs directly off the root
+    int32_t n_obj;       // nodes that hold an object
+    int32_t n_top;       // nodes of the top-level hierarchy (0: not built, every node is visited linearly)
+    const TopNode *top;
+    const int32_t *top_items;
+    const int32_t *obj_rank; // per node: number of object nodes with index <= that node
     int32_t pool_ok;     // 1: every mesh fits the item encoding of the pooled shadow kernel (<= 2^24 triangles, < 2^27 pairs)
     const DMesh *meshes;
     const DMaterial *materials;

@@ -305,7 +305,7 @@ k_photon_gather(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, floa
             norm3(sr.dx, sr.dy, sr.dz);
             actual++;
             tl.trace++;
-            if (scene_hit<false>(S, sr, Bs, tl)) {
+            if (scene_hit<false>(S, sr, Bs, tl, false)) {
                 HitRec Hs;
                 finalize_hit(S, sr, Bs, Hs);
                 sum = sum + photon_mapping(S, PM, Hs);
@@ -389,7 +389,7 @@ k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_boun
         B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
         tl.trace++;
         unsigned stored = 0, flag = 0;
-        if (scene_hit<false>(S, ray, B, tl)) {
+        if (scene_hit<false>(S, ray, B, tl, false)) {
             flag = 0x80u; // photonFromLight++ (RenderFunctions.cpp:357)
             Col outgoing = mk(L.I[0], L.I[1], L.I[2]);
             for (int i = 0; i < max_bounce; i++) {
@@ -449,7 +449,7 @@ k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_boun
                 // Trace(r, &rootNode, hInfo) into the SAME HitInfo: its z still holds the previous segment's length, so
                 // only nearer hits are found (SURVEY A-16)
                 tl.trace++;
-                if (!scene_hit<false>(S, ray, B, tl)) break;
+                if (!scene_hit<false>(S, ray, B, tl, false)) break;
                 int mtl = __ldg(&S.nodes[B.node].material);
                 if (mtl < 0) break;
                 const DMaterial &M2 = S.materials[mtl];

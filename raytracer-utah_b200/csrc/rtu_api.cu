@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -560,6 +561,81 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     }
     float4 *db = nullptr;
     if ((rc = dev_upload(bounds, &db, c->stream, sc->owned))) return fail(rc);
+    // top-level hierarchy over the bounding spheres for scenes with many nodes (device_scene.h TopNode)
+    std::vector<TopNode> top_nodes;
+    std::vector<int32_t> top_items, obj_rank(d->n_nodes, 0);
+    {
+        int rank = 0;
+        for (int i = 0; i < d->n_nodes; i++) { if (d->nodes[i].kind != RTU_OBJ_NONE) rank++; obj_rank[i] = rank; }
+        int top_min = 256; // below that, stepping through every node in lock-step is cheaper
+        if (const char *e = getenv("RTU_TOP_MIN")) top_min = atoi(e);
+        std::vector<int> objs;
+        bool usable = top_min > 0 && rank >= top_min;
+        for (int i = 0; i < d->n_nodes && usable; i++) {
+            if (bounds[i].w < 0.f) continue;            // no object / never hit: nothing to nominate
+            if (!(bounds[i].w < 1.0e37f)) usable = false; // a node that must never be culled: keep the linear visit
+            objs.push_back(i);
+        }
+        if (usable && !objs.empty()) {
+            struct Box { float lo[3], hi[3]; };
+            auto box_of = [&](int i) {
+                Box b;
+                double r = std::sqrt((double)bounds[i].w) * 1.0001;
+                const float cc[3] = {bounds[i].x, bounds[i].y, bounds[i].z};
+                for (int k = 0; k < 3; k++) {
+                    double m = r + 1e-5 * (std::fabs((double)cc[k]) + 1.0);
+                    b.lo[k] = (float)((double)cc[k] - m);
+                    b.hi[k] = (float)((double)cc[k] + m);
+                }
+                return b;
+            };
+            std::function<int(int, int)> build = [&](int first, int last) -> int { // objs[first, last)
+                int me = (int)top_nodes.size();
+                top_nodes.push_back(TopNode());
+                Box bb = box_of(objs[first]);
+                float cmin[3], cmax[3];
+                {
+                    const float c0[3] = {bounds[objs[first]].x, bounds[objs[first]].y, bounds[objs[first]].z};
+                    for (int k = 0; k < 3; k++) cmin[k] = cmax[k] = c0[k];
+                }
+                for (int j = first; j < last; j++) {
+                    Box b = box_of(objs[j]);
+                    const float cc[3] = {bounds[objs[j]].x, bounds[objs[j]].y, bounds[objs[j]].z};
+                    for (int k = 0; k < 3; k++) {
+                        bb.lo[k] = std::min(bb.lo[k], b.lo[k]); bb.hi[k] = std::max(bb.hi[k], b.hi[k]);
+                        cmin[k] = std::min(cmin[k], cc[k]); cmax[k] = std::max(cmax[k], cc[k]);
+                    }
+                }
+                TopNode n;
+                for (int k = 0; k < 3; k++) { n.lo[k] = bb.lo[k]; n.hi[k] = bb.hi[k]; }
+                if (last - first <= 4) {
+                    n.a = -((int)top_items.size() + 1);
+                    n.b = last - first;
+                    for (int j = first; j < last; j++) top_items.push_back(objs[j]);
+                    top_nodes[me] = n;
+                    return me;
+                }
+                int axis = 0;
+                if (cmax[1] - cmin[1] > cmax[axis] - cmin[axis]) axis = 1;
+                if (cmax[2] - cmin[2] > cmax[axis] - cmin[axis]) axis = 2;
+                int mid = (first + last) / 2;
+                std::nth_element(objs.begin() + first, objs.begin() + mid, objs.begin() + last, [&](int a, int b) {
+                    const float ca[3] = {bounds[a].x, bounds[a].y, bounds[a].z}, cb[3] = {bounds[b].x, bounds[b].y, bounds[b].z};
+                    return ca[axis] < cb[axis];
+                });
+                n.a = build(first, mid);
+                n.b = build(mid, last);
+                top_nodes[me] = n;
+                return me;
+            };
+            build(0, (int)objs.size());
+        }
+    }
+    TopNode *dtop = nullptr;
+    int32_t *dtop_items = nullptr, *drank = nullptr;
+    if ((rc = dev_upload(top_nodes, &dtop, c->stream, sc->owned))) return fail(rc);
+    if ((rc = dev_upload(top_items, &dtop_items, c->stream, sc->owned))) return fail(rc);
+    if ((rc = dev_upload(obj_rank, &drank, c->stream, sc->owned))) return fail(rc);
     // meshes
     std::vector<DMesh> meshes(d->n_meshes);
     for (int i = 0; i < d->n_meshes; i++)
@@ -636,6 +712,11 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.bounds = db;
     S.n_nodes = d->n_nodes;
     S.flat = flat;
+    S.n_obj = sc->n_obj;
+    S.n_top = (int)top_nodes.size();
+    S.top = dtop;
+    S.top_items = dtop_items;
+    S.obj_rank = drank;
     S.pool_ok = d->n_meshes > 0 ? 1 : 0; // without meshes nothing would ever be pooled
     for (int m = 0; m < d->n_meshes; m++)
         if (d->meshes[m].nf > (1u << 24) || d->meshes[m].bvh_nodes >= (1u << 27)) S.pool_ok = 0;

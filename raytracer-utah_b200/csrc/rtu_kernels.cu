@@ -147,7 +147,7 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         Best B;
         B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
         tl.trace++;
-        scene_hit<false>(S, ray, B, tl);
+        scene_hit<false>(S, ray, B, tl, PRIMARY);
 
         extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, x, y, B);
     }
@@ -596,7 +596,7 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
         Best B;
         B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
         tl.shadow++;
-        bool occ = scene_hit<true>(S, ray, B, tl);
+        bool occ = scene_hit<true>(S, ray, B, tl, false);
         if (occ && B.z > 0.0f) continue;                                                // :31-35
         float4 c = Q.c[idx];
         accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
@@ -1107,7 +1107,7 @@ void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &
 {
     static int occ = 0, occ_f = 0, occ_n = 0;
     const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
-    if (extend_mode() == 1 && S.pool_ok) {
+    if (extend_mode() == 1 && S.pool_ok && S.n_top == 0) { // many-node scenes: plain kernels with top-level nomination
         if (S.flat)
             k_extend_pool<true, true><<<pooled_grid(cfg, k_extend_pool<true, true>, smem, &occ_f), WAVE_THREADS, smem, st>>>(
                 S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter, B.park);
@@ -1134,7 +1134,7 @@ void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
 {
     static int occ = 0, occ_f = 0, occ_n = 0;
     const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
-    if (extend_mode() == 1 && S.pool_ok) {
+    if (extend_mode() == 1 && S.pool_ok && S.n_top == 0) { // many-node scenes: plain kernels with top-level nomination
         if (S.flat)
             k_extend_pool<false, true><<<pooled_grid(cfg, k_extend_pool<false, true>, smem, &occ_f), WAVE_THREADS, smem, st>>>(
                 S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter, B.park);
@@ -1164,7 +1164,7 @@ void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
         const char *e = getenv("RTU_SHADOW_KERNEL");
         mode = (e && e[0] == 's') ? 0 : 1;
     }
-    if (mode == 1 && S.pool_ok) {
+    if (mode == 1 && S.pool_ok && S.n_top == 0) {
         const size_t smem = sizeof(SpWarp) * (WAVE_THREADS / 32);
         if (occ == 0) {
             cudaFuncSetAttribute(k_shadow_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
