@@ -93,7 +93,7 @@ struct rtu_scene {
     uint64_t launches = 0;
     bool timed = false;
     // photon map (balanced, n+1 records, record 0 unused) and the parameters it was made with
-    struct Footprint { double c[8][3]; bool finite; }; // world-space corners of an object's bound box
+    struct Footprint { double c[8][3]; bool finite; int node; }; // world-space corners of an object's bound box
     std::vector<Footprint> footprints;
     bool root_identity = true;
     int n_obj = 0;                // nodes whose object Trace() tests (what a ray that misses everything books)
@@ -546,6 +546,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
                 to_root(p);
                 for (int k = 0; k < 3; k++) fp.c[corner][k] = p[k];
             }
+            fp.node = i;
             sc->footprints.push_back(fp);
         }
         if (!finite) { bounds[i].w = 3.0e38f; continue; } // never culls
@@ -578,14 +579,19 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
         }
         if (usable && !objs.empty()) {
             struct Box { float lo[3], hi[3]; };
+            // the box a ray has to cross to pass the object's own bound-box gate: the world-space extent of that bound
+            // box (tighter than the bounding sphere, which is what the per-node cull uses), inflated by 1e-4
+            std::vector<int> fp_of(d->n_nodes, -1);
+            for (size_t f = 0; f < sc->footprints.size(); f++) fp_of[sc->footprints[f].node] = (int)f;
             auto box_of = [&](int i) {
                 Box b;
-                double r = std::sqrt((double)bounds[i].w) * 1.0001;
-                const float cc[3] = {bounds[i].x, bounds[i].y, bounds[i].z};
+                const rtu_scene::Footprint &fp = sc->footprints[fp_of[i]];
                 for (int k = 0; k < 3; k++) {
-                    double m = r + 1e-5 * (std::fabs((double)cc[k]) + 1.0);
-                    b.lo[k] = (float)((double)cc[k] - m);
-                    b.hi[k] = (float)((double)cc[k] + m);
+                    double lo = fp.c[0][k], hi = fp.c[0][k];
+                    for (int c8 = 1; c8 < 8; c8++) { lo = std::min(lo, fp.c[c8][k]); hi = std::max(hi, fp.c[c8][k]); }
+                    double m = 1e-4 * (hi - lo) + 1e-5 * (std::fabs(lo) + std::fabs(hi) + 1.0);
+                    b.lo[k] = (float)(lo - m);
+                    b.hi[k] = (float)(hi + m);
                 }
                 return b;
             };

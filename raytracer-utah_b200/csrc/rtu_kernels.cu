@@ -1021,6 +1021,183 @@ __global__ void k_zimage(const float *z, int npix, const unsigned *mm, unsigned 
     z8[p] = o;
 }
 
+// ------------------------------------------------------------------ scenes with very many nodes
+// Thousands of objects: stepping through every node per ray (what Trace() does) is the whole cost, and letting every
+// lane walk the top-level hierarchy on its own serialises 32 different walks.  Here the warp nominates the nodes of
+// its 32 rays together: a pool of (ray, hierarchy node) items in shared memory, 32 box tests per iteration, leaves
+// append their object nodes to the ray's list.  Each lane then sorts its own list by node index and runs the usual
+// per-node code over it (scene_hit_list), so results and counters are those of the linear visit.
+#define TW_POOL 512
+struct TopWarp {
+    float4 p[32], d[32], inv[32];
+    unsigned pool[TW_POOL];
+    int count[32];
+    int list[32][RTU_TOP_CAND];
+};
+
+// returns the number of nominees of this lane's ray (in W.list[lane], ascending), or -1 if they did not fit
+__device__ __forceinline__ int warp_nominate(const DScene &S, TopWarp &W, const Ray &r0, bool have, unsigned lane)
+{
+    const unsigned lt = (1u << lane) - 1u, FULL = 0xffffffffu, NONE = 0x7fffffffu;
+    W.p[lane] = make_float4(r0.px, r0.py, r0.pz, 0.f);
+    W.d[lane] = make_float4(r0.dx, r0.dy, r0.dz, 0.f);
+    W.inv[lane] = make_float4(1.f / r0.dx, 1.f / r0.dy, 1.f / r0.dz, 0.f);
+    W.count[lane] = 0;
+    const unsigned hv = __ballot_sync(FULL, have);
+    if (have) W.pool[__popc(hv & lt)] = lane << 27; // hierarchy node 0 = root
+    unsigned pool_n = __popc(hv);
+    __syncwarp();
+    while (pool_n > 0u) {
+        const bool finish = pool_n > TW_POOL - 64u; // no room to expand: the popped items are finished by their lanes
+        const unsigned n = pool_n < 32u ? pool_n : 32u;
+        pool_n -= n;
+        unsigned c1 = NONE, c2 = NONE, sl = 0;
+        if (lane < n) {
+            const unsigned it = W.pool[pool_n + lane];
+            sl = it >> 27;
+            const float4 p = W.p[sl], d = W.d[sl], iv = W.inv[sl];
+            int stack[32];
+            int top = 0;
+            stack[0] = (int)(it & 0x07ffffffu);
+            if (*(volatile int *)&W.count[sl] > RTU_TOP_CAND) top = -1; // the ray's list is already full: it will be visited linearly
+            while (top >= 0) {
+                const int ni = stack[top--];
+                const float4 *q = reinterpret_cast<const float4 *>(S.top + ni);
+                const float4 lo = __ldg(q), hi = __ldg(q + 1);
+                if (!top_box_crossed(lo, hi, p.x, p.y, p.z, d.x, d.y, d.z, iv.x, iv.y, iv.z)) continue;
+                const int a = __float_as_int(lo.w), b = __float_as_int(hi.w);
+                if (a >= 0) {
+                    if (!finish) { c1 = (unsigned)a; c2 = (unsigned)b; break; } // children go back to the pool
+                    if (top + 2 >= 32) { atomicAdd(&W.count[sl], RTU_TOP_CAND + 1); break; }
+                    stack[++top] = a;
+                    stack[++top] = b;
+                } else {
+                    const int first = -a - 1;
+                    for (int k = 0; k < b; k++) {
+                        const int pos = atomicAdd(&W.count[sl], 1);
+                        if (pos < RTU_TOP_CAND) W.list[sl][pos] = __ldg(&S.top_items[first + k]);
+                    }
+                }
+            }
+        }
+        const unsigned b2 = __ballot_sync(FULL, c2 != NONE), b1 = __ballot_sync(FULL, c1 != NONE);
+        if (c2 != NONE) W.pool[pool_n + __popc(b2 & lt)] = (sl << 27) | c2;
+        if (c1 != NONE) W.pool[pool_n + __popc(b2) + __popc(b1 & lt)] = (sl << 27) | c1;
+        pool_n += __popc(b2) + __popc(b1);
+        __syncwarp();
+    }
+    int nc = W.count[lane];
+    if (!have) return 0;
+    if (nc > RTU_TOP_CAND) return -1;
+    int *L = W.list[lane];
+    for (int i = 1; i < nc; i++) { // ascending node order
+        const int v = L[i];
+        int j = i;
+        while (j > 0 && L[j - 1] > v) { L[j] = L[j - 1]; j--; }
+        L[j] = v;
+    }
+    return nc;
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_extend_top(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
+             DCounters *counters, unsigned *work)
+{
+    extern __shared__ __align__(16) unsigned char tw_raw[];
+    TopWarp &W = reinterpret_cast<TopWarp *>(tw_raw)[threadIdx.x >> 5];
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u;
+    PrimaryMap pm;
+    pm.init(F);
+    unsigned total;
+    if (PRIMARY) total = pm.perSample * (unsigned)(s1 - s0);
+    else { total = *in.count; if (total > in.cap) total = in.cap; }
+    DNode root;
+    load_node(S.nodes, root);
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const unsigned idx = base + lane;
+        bool have = idx < total;
+        Ray ray;
+        ray.px = ray.py = ray.pz = 0.f; ray.dx = ray.dy = 0.f; ray.dz = 1.f;
+        int pixel = 0, x = 0, y = 0;
+        if (have) {
+            if (PRIMARY) {
+                int s;
+                have = pm.decode(idx, s0, s, x, y);
+                if (have && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, tl); have = false; }
+                pixel = y * pm.W + x;
+                if (have) ray = primary_ray(F, s, x, y, pixel);
+            } else {
+                float4 o = in.o[idx], d = in.d[idx];
+                ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+                ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+            }
+        }
+        const Ray r0 = to_node(root.itm, root.pos, ray);
+        const int nc = warp_nominate(S, W, r0, have, lane);
+        if (have) {
+            Best B;
+            B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+            tl.trace++;
+            if (nc >= 0) scene_hit_list<false>(S, ray, r0, dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz), W.list[lane], nc, B, tl);
+            else scene_hit<false>(S, ray, B, tl, false);
+            extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, x, y, B);
+        }
+        __syncwarp();
+    }
+    flush_tally(tl, counters, PRIMARY ? 0 : 1);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_shadow_wave_top(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+{
+    extern __shared__ __align__(16) unsigned char tw_raw[];
+    TopWarp &W = reinterpret_cast<TopWarp *>(tw_raw)[threadIdx.x >> 5];
+    Tally tl = {0, 0, 0, 0, 0};
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned total = *Q.count;
+    if (total > Q.cap) total = Q.cap;
+    DNode root;
+    load_node(S.nodes, root);
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const unsigned idx = base + lane;
+        const bool have = idx < total;
+        Ray ray;
+        ray.px = ray.py = ray.pz = 0.f; ray.dx = ray.dy = 0.f; ray.dz = 1.f;
+        float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
+        if (have) {
+            o = Q.o[idx]; d = Q.d[idx];
+            ray.px = o.x; ray.py = o.y; ray.pz = o.z;
+            ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+        }
+        const Ray r0 = to_node(root.itm, root.pos, ray);
+        const int nc = warp_nominate(S, W, r0, have, lane);
+        if (have) {
+            Best B;
+            B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
+            tl.shadow++;
+            bool occ;
+            if (nc >= 0) occ = scene_hit_list<true>(S, ray, r0, dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz), W.list[lane], nc, B, tl);
+            else occ = scene_hit<true>(S, ray, B, tl, false);
+            if (!(occ && B.z > 0.0f)) {                                                 // :31-35
+                float4 c = Q.c[idx];
+                accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
+            }
+        }
+        __syncwarp();
+    }
+    flush_tally(tl, counters, 2);
+}
+
 // ------------------------------------------------------------------ empty tiles of the primary wave
 // One thread per 8x4-pixel tile.  The image-plane points of the tile's camera rays (all rendered samples: sub-pixel
 // offsets in [ox0,ox1] x [oy0,oy1]) fill a rectangle in pixel coordinates; the tile is empty when that rectangle is
@@ -1116,6 +1293,13 @@ void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &
                 S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter, B.park);
         return;
     }
+    if (S.n_top > 0 && extend_mode() == 1) {
+        static int occ_t = 0;
+        const size_t tsmem = sizeof(TopWarp) * (WAVE_THREADS / 32);
+        k_extend_top<true><<<pooled_grid(cfg, k_extend_top<true>, tsmem, &occ_t), WAVE_THREADS, tsmem, st>>>(
+            S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter);
+        return;
+    }
     k_extend<true><<<resident_grid(cfg, k_extend<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum,
                                                                                      accum, B.counters, work_counter);
 }
@@ -1141,6 +1325,13 @@ void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
         else
             k_extend_pool<false, false><<<pooled_grid(cfg, k_extend_pool<false, false>, smem, &occ_n), WAVE_THREADS, smem, st>>>(
                 S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter, B.park);
+        return;
+    }
+    if (S.n_top > 0 && extend_mode() == 1) {
+        static int occ_t = 0;
+        const size_t tsmem = sizeof(TopWarp) * (WAVE_THREADS / 32);
+        k_extend_top<false><<<pooled_grid(cfg, k_extend_top<false>, tsmem, &occ_t), WAVE_THREADS, tsmem, st>>>(
+            S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter);
         return;
     }
     k_extend<false><<<resident_grid(cfg, k_extend<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum,
@@ -1178,6 +1369,17 @@ void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
         }
         if (S.flat) k_shadow_wave<true><<<cfg.sm_count * occ, WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
         else k_shadow_wave<false><<<cfg.sm_count * occ, WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+    } else if (S.n_top > 0 && mode == 1) {
+        static int occ_t = 0;
+        const size_t tsmem = sizeof(TopWarp) * (WAVE_THREADS / 32);
+        if (occ_t == 0) {
+            cudaFuncSetAttribute(k_shadow_wave_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow_wave_top, WAVE_THREADS, tsmem) != cudaSuccess || n < 1) n = 1;
+            if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
+            occ_t = n;
+        }
+        k_shadow_wave_top<<<cfg.sm_count * occ_t, WAVE_THREADS, tsmem, st>>>(S, B.shadow, accum, B.counters, work_counter);
     } else {
         k_shadow_wave_simple<<<resident_grid(cfg, k_shadow_wave_simple, &occ_simple), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
     }
