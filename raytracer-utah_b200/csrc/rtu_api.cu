@@ -95,6 +95,7 @@ struct rtu_scene {
     // photon map (balanced, n+1 records, record 0 unused) and the parameters it was made with
     struct Footprint { double c[8][3]; bool finite; int node; }; // world-space corners of an object's bound box
     std::vector<Footprint> footprints;
+    size_t chunk_limit = 0;       // set after a queue overflow: later frames of this scene start with smaller chunks
     bool root_identity = true;
     int n_obj = 0;                // nodes whose object Trace() tests (what a ray that misses everything books)
     int h_light0_kind = -1;       // lights[0]: the only light GeneratePhotonMap emits from
@@ -1029,7 +1030,7 @@ int check_overflow(rtu_scene *s, DCounters *host)
 
 extern "C" {
 
-int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
+static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
 {
     if (!s || !p) { rtu::set_error("rtu_render_device: null argument"); return RTU_ERR_INVALID; }
     rtu_context *c = s->ctx;
@@ -1046,7 +1047,9 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
     }
     int rows = F.row_end - F.row_begin;
     size_t per_sample = (size_t)((W + 7) / 8) * ((rows + 3) / 4) * 32;
-    size_t chunk_samples = std::max<size_t>(1, c->chunk_rays / per_sample);
+    size_t chunk_rays = c->chunk_rays;
+    if (s->chunk_limit && s->chunk_limit < chunk_rays) chunk_rays = s->chunk_limit;
+    size_t chunk_samples = std::max<size_t>(1, chunk_rays / per_sample);
     chunk_samples = std::min<size_t>(chunk_samples, (size_t)(s1 - s0)); // queues are sized for what this call renders
     size_t chunk_cap = std::max(per_sample, chunk_samples * per_sample);
     if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
@@ -1105,6 +1108,25 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
     return RTU_OK;
 }
 
+// The queues hold one entry per primary ray of a chunk; a scene whose hits spawn more rays than that (glossy rooms in
+// RTU_MODE_PATH) overflows them.  The device flags it; a frame that started from a cleared accumulator is then rendered
+// again with half the chunk, and the scene remembers the smaller chunk for its next frames.
+int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
+{
+    for (int attempt = 0;; attempt++) {
+        int rc = render_device_once(s, p, d_accum, clear_accum);
+        if (rc || !clear_accum) return rc;
+        rtu_context *c = s->ctx;
+        uint32_t overflow = 0;
+        CU(cudaMemcpyAsync(&overflow, &c->wb.counters->overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (!overflow) return RTU_OK;
+        size_t cur = s->chunk_limit ? std::min(s->chunk_limit, c->chunk_rays) : c->chunk_rays;
+        if (attempt >= 8 || cur <= 65536) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS or raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
+        s->chunk_limit = cur / 2;
+    }
+}
+
 int rtu_resolve(rtu_scene *s, const rtu_params *p, const float *d_accum, rtu_image *out)
 {
     if (!s || !p || !out) { rtu::set_error("rtu_resolve: null argument"); return RTU_ERR_INVALID; }
@@ -1154,16 +1176,7 @@ int rtu_render(rtu_scene *s, const rtu_params *p, rtu_image *out)
         s->timed = true;
         return rc;
     }
-    // a queue overflow (see rtu_render_device) is retried with half the chunk and the same buffers
-    size_t saved_chunk = s->ctx->chunk_rays;
-    for (int attempt = 0;; attempt++) {
-        if ((rc = rtu_render_device(s, p, nullptr, 1))) break;
-        DCounters hc;
-        rc = check_overflow(s, &hc);
-        if (rc != RTU_ERR_UNSUPPORTED || attempt >= 5 || s->ctx->chunk_rays <= 65536) break;
-        s->ctx->chunk_rays /= 2;
-    }
-    s->ctx->chunk_rays = saved_chunk;
+    rc = rtu_render_device(s, p, nullptr, 1); // retries with smaller chunks if a queue overflows
     if (rc) return rc;
     return rtu_resolve(s, p, nullptr, out);
 }
