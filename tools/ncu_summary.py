@@ -10,11 +10,13 @@ keys = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
         ("sm__inst_executed.avg.per_cycle_elapsed", "ipc/SM"), ("smsp__inst_executed.sum", "warp_inst"),
         ("l1tex__t_sector_hit_rate.pct", "L1hit%"), ("lts__t_sector_hit_rate.pct", "L2hit%"),
         ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
-        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%")]
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"), ("lts__t_bytes.sum", "L2_bytes"), ("lts__t_bytes.sum.per_second", "L2_B/s"),
+        ("dram__bytes_read.sum.per_second", "dram_rd/s"), ("l1tex__t_bytes.sum", "L1_bytes"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pipe%"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pipe%"), ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue%")]
 units = rows[1]
 for n, r in enumerate(rows[2:]):
     print("[%d] %s" % (n, r[hdr.index("Kernel Name")][:70]))
-    print("    " + "  ".join("%s=%s%s" % (lab, r[hdr.index(k)][:10], units[hdr.index(k)] if lab in ("time", "dram_rd", "dram_wr") else "") for k, lab in keys if k in hdr))
+    print("    " + "  ".join("%s=%s%s" % (lab, r[hdr.index(k)][:10], units[hdr.index(k)] if lab in ("time", "dram_rd", "dram_wr", "L2_bytes", "L2_B/s", "dram_rd/s", "L1_bytes") else "") for k, lab in keys if k in hdr))
     st = [(float(r[i] or 0), h.replace("smsp__pcsamp_warps_issue_stalled_", "")) for i, h in enumerate(hdr) if h.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in h]
     tot = sum(v for v, _ in st) or 1
     print("    stalls: " + "  ".join("%s %.0f%%" % (h, 100 * v / tot) for v, h in sorted(st, reverse=True)[:7]))
