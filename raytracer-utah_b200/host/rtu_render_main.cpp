@@ -1,6 +1,9 @@
 // rtu_render: headless replacement for the reference's main() (main.cpp:74-88) for this path.
 //   rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref]
-//              [--bounces B] [--out Result.png] [--zout ZBuffer.png] [--device D]
+//              [--mode whitted|head|photon|gather] [--bounces B] [--gi-bounces G] [--photons N] [--seed S]
+//              [--out Result.png] [--zout ZBuffer.png] [--device D]
+// --mode head is what Render() does at the reference's HEAD (4-bounce GI + direct light; the reference uses 1024 spp);
+// photon / gather are its two commented-out photon-map estimators (RenderFunctions.cpp:137-142).
 // Loads the scene (LoadScene), renders it on the GPU and writes Result.png / ZBuffer.png like
 // SpawnRenderThreads() does (main.cpp:59-61).  There is no window and no CPU path.
 #include <cstdio>
@@ -19,8 +22,9 @@ static int die(const char *what, int rc)
 
 int main(int argc, char **argv)
 {
-    std::string scene, root = ".", out = "Result.png", zout = "ZBuffer.png", pattern = "center";
-    int width = 0, height = 0, spp = 1, bounces = 5, device = 0;
+    std::string scene, root = ".", out = "Result.png", zout = "ZBuffer.png", pattern = "center", mode = "whitted";
+    int width = 0, height = 0, spp = 1, bounces = 5, device = 0, gi_bounces = 4;
+    long long photons = 1000000, seed = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -30,13 +34,17 @@ int main(int argc, char **argv)
         else if (a == "--spp") spp = atoi(next());
         else if (a == "--pattern") pattern = next();
         else if (a == "--bounces") bounces = atoi(next());
+        else if (a == "--mode") mode = next();
+        else if (a == "--gi-bounces") gi_bounces = atoi(next());
+        else if (a == "--photons") photons = atoll(next());
+        else if (a == "--seed") seed = atoll(next());
         else if (a == "--out") out = next();
         else if (a == "--zout") zout = next();
         else if (a == "--device") device = atoi(next());
         else if (a[0] != '-') scene = a;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
-    if (scene.empty()) { fprintf(stderr, "usage: rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref] [--bounces B] [--out Result.png] [--zout ZBuffer.png]\n"); return 2; }
+    if (scene.empty()) { fprintf(stderr, "usage: rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref] [--mode whitted|head|photon|gather] [--bounces B] [--gi-bounces G] [--photons N] [--seed S] [--out Result.png] [--zout ZBuffer.png]\n"); return 2; }
     rtu_host_scene *hs = nullptr;
     int rc = rtu_host_load_xml(scene.c_str(), root.c_str(), &hs);
     if (rc) return die("rtu_host_load_xml", rc);
@@ -47,7 +55,21 @@ int main(int argc, char **argv)
     if ((rc = rtu_scene_upload(ctx, rtu_host_scene_desc(hs), &sc))) return die("rtu_scene_upload", rc);
     rtu_params p;
     rtu_params_default(&p);
-    p.width = width; p.height = height; p.spp = spp; p.shade_bounces = bounces;
+    p.width = width; p.height = height; p.spp = spp; p.shade_bounces = bounces; p.gi_bounces = gi_bounces; p.seed = (uint64_t)seed;
+    if (mode == "whitted") p.mode = RTU_MODE_WHITTED;
+    else if (mode == "head") p.mode = RTU_MODE_PATH;
+    else if (mode == "photon") p.mode = RTU_MODE_PHOTON;
+    else if (mode == "gather") p.mode = RTU_MODE_PHOTON_GATHER;
+    else { fprintf(stderr, "unknown mode %s\n", mode.c_str()); return 2; }
+    if (p.mode == RTU_MODE_PHOTON || p.mode == RTU_MODE_PHOTON_GATHER) { // GeneratePhotonMap() (main.cpp:31)
+        rtu_photon_params pp;
+        rtu_photon_params_default(&pp);
+        pp.map_size = (uint32_t)photons;
+        pp.seed = (uint64_t)seed;
+        rtu_photon_stats ps;
+        if ((rc = rtu_photon_map_generate(sc, &pp, &ps))) return die("rtu_photon_map_generate", rc);
+        fprintf(stderr, "Photon From Light: %llu \nPhoton Scale Factor: %f \nPhoton Map Generated\n", (unsigned long long)ps.from_light, ps.scale_factor);
+    }
     p.pattern = (pattern == "ref" || spp > 1) ? RTU_PATTERN_REFERENCE : RTU_PATTERN_CENTER;
     const rtu_scene_desc *d = rtu_host_scene_desc(hs);
     int W = width > 0 ? width : d->camera.width, H = height > 0 ? height : d->camera.height;
