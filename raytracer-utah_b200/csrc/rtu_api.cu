@@ -95,7 +95,9 @@ struct rtu_scene {
     // photon map (balanced, n+1 records, record 0 unused) and the parameters it was made with
     struct Footprint { double c[8][3]; bool finite; int node; }; // world-space corners of an object's bound box
     std::vector<Footprint> footprints;
-    size_t chunk_limit = 0;       // set after a queue overflow: later frames of this scene start with smaller chunks
+    size_t chunk_limit = 0;       // set after a queue overflow: later frames of this scene start with smaller chunks ...
+    double queue_boost = 1.0;     // ... or with more queue entries per primary ray
+    size_t last_chunk_cap = 0;    // primary rays per chunk of the last frame
     bool root_identity = true;
     int n_obj = 0;                // nodes whose object Trace() tests (what a ray that misses everything books)
     int h_light0_kind = -1;       // lights[0]: the only light GeneratePhotonMap emits from
@@ -1056,7 +1058,8 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
     // Queue capacities: one entry per primary ray of a chunk.  A hit can spawn up to 3 rays, so no
     // fixed factor is a bound; overflow is detected on the device (DCounters::overflow) and reported,
     // and rtu_render retries with smaller chunks.  Scenes whose every pixel is glass need RTU_QUEUE_FACTOR=2.
-    size_t q_cap = (size_t)((double)chunk_cap * c->queue_factor);
+    s->last_chunk_cap = chunk_cap;
+    size_t q_cap = (size_t)((double)chunk_cap * c->queue_factor * s->queue_boost);
     if (q_cap < chunk_cap) q_cap = chunk_cap;
     size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
     if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
@@ -1121,9 +1124,14 @@ int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t
         CU(cudaMemcpyAsync(&overflow, &c->wb.counters->overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         if (!overflow) return RTU_OK;
-        size_t cur = s->chunk_limit ? std::min(s->chunk_limit, c->chunk_rays) : c->chunk_rays;
-        if (attempt >= 8 || cur <= 65536) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS or raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
-        s->chunk_limit = cur / 2;
+        // the queues hold queue_factor x queue_boost entries per primary ray of a chunk: a scene whose hits spawn more
+        // rays than that needs more entries per ray (up to ~64 GB of queues), after that smaller chunks
+        const double bytes_per_entry = 300.0 * std::max(1, s->n_shadow_lights);
+        const double doubled = (double)s->last_chunk_cap * c->queue_factor * s->queue_boost * 2.0 * bytes_per_entry;
+        if (attempt >= 10) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS or raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
+        if (doubled <= 64e9 && s->queue_boost < 16.0) s->queue_boost *= 2.0;
+        else if (s->last_chunk_cap > 65536) s->chunk_limit = s->last_chunk_cap / 2;
+        else { rtu::set_error("ray queue overflow: raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
     }
 }
 

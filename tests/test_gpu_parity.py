@@ -534,3 +534,25 @@ def test_photon_gather_mode_matches_oracle_in_distribution(rtu, gpu_ctx):
     finally:
         sc.close()
         hs.close()
+
+
+def test_queue_overflow_is_absorbed(rtu):
+    """A closed, glossy room in RTU_MODE_PATH spawns several rays per hit, more than the one queue entry per primary ray
+    a fresh context starts with: the device flags the overflow and rtu_render_device re-renders with larger queues.
+    The frame that comes out has the same ray counts as one rendered with queues that were large from the start."""
+    ctx = rtu.Context(0)
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=160, height=120, spp=4, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=4, seed=5)
+        a = sc.render(p, want=("rgb",))["rgb"]
+        st1 = sc.stats()
+        b = sc.render(p, want=("rgb",))["rgb"]     # the scene now knows its queue size: no retry
+        st2 = sc.stats()
+        assert st1["trace_rays"] == st2["trace_rays"] and st1["shadow_rays"] == st2["shadow_rays"]
+        assert st1["trace_rays"] > 6 * 160 * 120 * 4
+        assert np.isfinite(a).all() and np.allclose(a, b, rtol=1e-3, atol=1e-4)
+    finally:
+        sc.close()
+        hs.close()
+        ctx.close()
