@@ -1,23 +1,26 @@
 // sm_100a kernels of the render path: a wavefront of intersect / shade / any-hit kernels.
 //
-//   k_extend<true>   persistent threads; generates the camera rays of a chunk of (sample, pixel)
-//                    work items on the fly and finds their closest hit (Trace); misses add the
-//                    background in place, hits are compacted into the hit queue (32 B records)
-//   k_extend<false>  same for the rays of the previous wave's queue (reflection / refraction /
-//                    Fresnel rays); misses add the environment term their parent would have added
-//   k_shade<..>      one MtlBlinn::Shade step per compacted hit: evaluates the hit record, appends
-//                    shadow rays (radiance-if-unoccluded) and the next wave's secondary rays
-//   k_shadow_wave    persistent threads; any-hit (ShadowTrace) over the shadow queue, adds the
-//                    unoccluded contributions to the accumulator
-//   k_primary_ids    pixel-centre visibility (ids + z)        k_trace_batch / k_shadow_batch /
-//   k_shade_first    batched operator entry points            k_resolve / k_zminmax / k_zimage
+//   k_extend_pool<primary>   persistent threads; builds the camera rays of a chunk of (sample, pixel) work items on the
+//                            fly and finds their closest hit (Trace).  32 rays step through the node list; rays that
+//                            enter a mesh are parked and walked as one pool of (ray, node) items per warp.  Misses add
+//                            the background in place, hits are compacted into the hit queue (32 B records).  Tiles
+//                            that k_tile_mask found empty are not traced at all.
+//   k_extend_pool<queue>     same for the rays of the previous wave's queue (reflection / refraction / Fresnel / GI
+//                            rays); misses add the environment term their parent would have added
+//   k_shade<..>              one MtlBlinn::Shade step per compacted hit: evaluates the hit record, appends shadow rays
+//                            (radiance-if-unoccluded) and the next wave's secondary rays; GI records in RTU_MODE_PATH
+//   k_shadow_wave            any-hit (ShadowTrace) over the shadow queue with pooled mesh walks; adds the unoccluded
+//                            contributions to the accumulator
+//   k_extend / k_shadow_wave_simple      the same waves with one walk per lane (meshes beyond the pool's item encoding)
+//   k_extend_top / k_shadow_wave_top     scenes with hundreds of objects: nodes nominated through a top-level hierarchy
+//   k_primary_ids    pixel-centre visibility (ids + z)        k_trace_batch / k_shadow_batch / k_shade_first: the
+//   k_gi_combine     folds the GI records into the pixels     batched operators; k_resolve / k_zminmax / k_zimage
 //
-// Traversal and shading are separate kernels so that the traversal kernels stay small (4 resident
-// CTAs of 256 threads per SM) and shading runs on dense warps of hits only.
-// Work distribution replaces PixelIterator's atomic ticket counter (PixelIterator.h:25-38): each
-// warp takes 32 consecutive tickets from a global counter until the wave is drained.  Grids are
-// SM-count multiples (148 x resident CTAs per SM, from the occupancy API); CTAs stay resident for
-// the whole wave.
+// Traversal and shading are separate kernels so that the traversal kernels stay small (2 resident CTAs of 256 threads
+// per SM, measured best) and shading runs on dense warps of hits only.
+// Work distribution replaces PixelIterator's atomic ticket counter (PixelIterator.h:25-38): each warp takes 32
+// consecutive tickets from a global counter until the wave is drained.  Grids are SM-count multiples (148 x resident
+// CTAs per SM, from the occupancy API); CTAs stay resident for the whole wave.
 #include <cstdio>
 #include <cstdlib>
 
