@@ -1148,7 +1148,11 @@ k_extend_top(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux,
             B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
             tl.trace++;
             if (nc >= 0) scene_hit_list<false>(S, ray, r0, dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz), W.list[lane], nc, B, tl);
-            else scene_hit<false>(S, ray, B, tl, false);
+            else {
+                bool done;
+                scene_hit_long_list<false>(S, ray, B, tl, done);
+                if (!done) scene_hit<false>(S, ray, B, tl, false);
+            }
             extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, x, y, B);
         }
         __syncwarp();
@@ -1190,7 +1194,11 @@ k_shadow_wave_top(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, u
             tl.shadow++;
             bool occ;
             if (nc >= 0) occ = scene_hit_list<true>(S, ray, r0, dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz), W.list[lane], nc, B, tl);
-            else occ = scene_hit<true>(S, ray, B, tl, false);
+            else {
+                bool done;
+                occ = scene_hit_long_list<true>(S, ray, B, tl, done);
+                if (!done) occ = scene_hit<true>(S, ray, B, tl, false);
+            }
             if (!(occ && B.z > 0.0f)) {                                                 // :31-35
                 float4 c = Q.c[idx];
                 accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));

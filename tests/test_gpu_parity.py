@@ -556,3 +556,24 @@ def test_queue_overflow_is_absorbed(rtu):
         sc.close()
         hs.close()
         ctx.close()
+
+
+def test_nominated_nodes_book_the_reference_work(rtu, gpu_ctx):
+    """1000 spheres: the top-level hierarchy nominates a few dozen nodes per ray, the rest are never touched, and the
+    counters are still those of Trace() visiting all 1001 objects for every camera ray."""
+    from conftest import synthetic_scene
+    from oracle import oracle_py as O
+    g, meta = load_golden("synthetic_spheres_1000")
+    hs = rtu.HostScene(synthetic_scene("spheres_1000", meta))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        w, h = 240, 135
+        ref = O.render(hs.desc, width=w, height=h, mode=rtu.MODE_PRIMARY, want=("node_id",))["stats"]
+        sc.render_device(rtu.default_params(width=w, height=h, mode=rtu.MODE_WHITTED, shade_bounces=0))
+        st = sc.stats()["primary_wave"]
+        assert st["rays"] == w * h
+        assert st["node_visits"] == ref["node_visits"] == w * h * 1001
+        assert st["box_tests"] == ref["box_tests"]
+    finally:
+        sc.close()
+        hs.close()
