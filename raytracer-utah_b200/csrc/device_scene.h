@@ -135,6 +135,7 @@ struct DScene {
     int32_t n_materials;
     const DLight *lights;
     int32_t n_lights;
+    int32_t n_shadow_lights; // lights that send a shadow ray (everything but ambient)
     const DTexMap *texmaps;
     DTexColor background, environment;
     float cam_pos[3];    // Shade uses camera.pos for the view vector (mtlFunctions.cpp:137)

@@ -734,6 +734,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.n_materials = d->n_materials;
     S.lights = dl;
     S.n_lights = d->n_lights;
+    S.n_shadow_lights = sc->n_shadow_lights;
     S.texmaps = dt;
     S.background = pack_tc(d->background, d->n_texmaps);
     S.environment = pack_tc(d->environment, d->n_texmaps);

@@ -534,13 +534,21 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
                 shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, mk(1.f, 1.f, 1.f), F.shade_bounces, base + 2 * k + (t ? 0 : 1),
                           child_path(path, 8u + (unsigned)t), t);
             if (k < F.gi_bounces) {
+                SlotTicket tk; // the slot of the sample ray is reserved before its direction is drawn
+                tk.issue(O.next.count, 1u);
                 Rng rng;
                 rng.key = F.seed; rng.pixel = 0x61u; rng.path = path; rng.dim = 0;
                 float ox, oy, oz;
                 sample_hemi_cos(rng, H.nx, H.ny, H.nz, ox, oy, oz);                                   // :561
                 norm3(ox, oy, oz);                                                                    // :562
-                push_ray(O, H.px, H.py, H.pz, ox, oy, oz, mk(1.f, 1.f, 1.f), base, pack_meta(RK_GI, F.shade_bounces, 0, 0, k + 1), -1,
-                         child_path(path, 6u));
+                const unsigned slot = tk.slot();
+                if (slot >= O.next.cap) O.counters->overflow = 1;
+                else {
+                    O.next.o[slot] = make_float4(H.px, H.py, H.pz, __int_as_float(base));
+                    O.next.d[slot] = make_float4(ox, oy, oz, __uint_as_float(pack_meta(RK_GI, F.shade_bounces, 0, 0, k + 1)));
+                    O.next.w[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(-1));
+                    O.next.path[slot] = child_path(path, 6u);
+                }
             } else {
                 O.accum[base + gi_end] = make_float4(0.1f, 0.1f, 0.1f, (float)(k + 1));               // :584
             }

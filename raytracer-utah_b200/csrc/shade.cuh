@@ -167,6 +167,25 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned *counter, bool want)
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// Split-phase, warp-aggregated queue allocation.  issue(): one atomic per warp reserves n slots for every participating
+// lane; its result stays in the leader's register.  slot(): fetched (one shuffle) only where the first slot is written,
+// so the atomic's round trip to L2 overlaps whatever is computed in between.  Lane's k-th slot = slot() + k * stride.
+struct SlotTicket {
+    unsigned mask, leader, base_in_leader, rank, stride;
+    __device__ __forceinline__ void issue(unsigned *counter, unsigned n)
+    {
+        mask = __activemask();
+        const unsigned lane = threadIdx.x & 31u;
+        leader = __ffs(mask) - 1;
+        stride = __popc(mask);
+        rank = __popc(mask & ((1u << lane) - 1u));
+        base_in_leader = 0;
+        if (lane == leader) base_in_leader = atomicAdd(counter, stride * n);
+    }
+    // must be called by exactly the lanes that called issue() (still converged or reconverged)
+    __device__ __forceinline__ unsigned slot() const { return __shfl_sync(mask, base_in_leader, leader) + rank; }
+};
+
 struct WaveOut {
     RayQueue next;
     AuxPool aux;
@@ -264,6 +283,12 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
         Col Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
         Col Ks = texcolor_sample(S, M.specular, H.u, H.v, H.w);
         // viewDirection uses camera.pos, not the ray origin (mtlFunctions.cpp:137, SURVEY A-6)
+        // every non-ambient light sends one shadow ray (unless null rays are culled): their queue slots are reserved
+        // up front with one atomic per warp, whose latency then hides behind the Blinn terms
+        const bool reserve = !(P.flags & 1u) && S.n_shadow_lights > 0;
+        SlotTicket st;
+        unsigned sslot = 0, sk = 0;
+        if (reserve) st.issue(O.shadow.count, (unsigned)S.n_shadow_lights);
         float vx = S.cam_pos[0] - H.px, vy = S.cam_pos[1] - H.py, vz = S.cam_pos[2] - H.pz;
         norm3(vx, vy, vz);
         for (int i = 0; i < S.n_lights; i++) {
@@ -320,7 +345,17 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
             c = c * Wt;
             bool null = !nonblack(c) || !(c.r == c.r) || !(c.g == c.g) || !(c.b == c.b);
             if ((P.flags & 1u) && null) continue; // RTU_FLAG_CULL_NULL_SHADOW_RAYS
-            push_shadow(O, H.px, H.py, H.pz, sx, sy, sz, tmax, c, pixel);
+            if (reserve) {
+                if (sk == 0) sslot = st.slot(); // first use of the reservation: all reserving lanes arrive here together
+                const unsigned slot = sslot + sk * st.stride;
+                sk++;
+                if (slot >= O.shadow.cap) { O.counters->overflow = 1; continue; }
+                O.shadow.o[slot] = make_float4(H.px, H.py, H.pz, __int_as_float(pixel));
+                O.shadow.d[slot] = make_float4(sx, sy, sz, tmax);
+                O.shadow.c[slot] = make_float4(c.r, c.g, c.b, 0.f);
+            } else {
+                push_shadow(O, H.px, H.py, H.pz, sx, sy, sz, tmax, c, pixel);
+            }
         }
     }
     accum_add(O.accum, pixel, local * Wt);
