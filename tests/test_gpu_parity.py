@@ -577,3 +577,28 @@ def test_nominated_nodes_book_the_reference_work(rtu, gpu_ctx):
     finally:
         sc.close()
         hs.close()
+
+
+def test_photon_mode_slices_compose(rtu, gpu_ctx):
+    """The photon-map modes shard like every other mode: spp slices and row ranges rendered into one accumulator equal
+    the whole frame (every rank regenerates the same map from the seed)."""
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        sc.photon_map_generate(map_size=100000, seed=4)
+        kw = dict(width=96, height=72, spp=4, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_PHOTON)
+        full = sc.render(rtu.default_params(**kw), want=("rgb",))["rgb"]
+        sc.render_device(rtu.default_params(sample_begin=0, sample_end=2, **kw), clear=True)
+        sc.render_device(rtu.default_params(sample_begin=2, sample_end=4, **kw), clear=False)
+        parts = sc.resolve(rtu.default_params(**kw), want=("rgb",))["rgb"]
+        assert np.array_equal(np.isnan(full), np.isnan(parts))
+        m = ~np.isnan(full)
+        assert within_tol(full[m], parts[m]).all()
+        sc.render_device(rtu.default_params(row_begin=0, row_end=40, **kw), clear=True)
+        sc.render_device(rtu.default_params(row_begin=40, row_end=72, **kw), clear=False)
+        rows = sc.resolve(rtu.default_params(**kw), want=("rgb",))["rgb"]
+        assert np.array_equal(np.isnan(full), np.isnan(rows))
+        assert within_tol(full[m], rows[m]).all()
+    finally:
+        sc.close()
+        hs.close()
