@@ -240,6 +240,10 @@ def ours(args):
     # ---- e2e: pack + H2D + render + (reduce) + resolve + D2H to host buffers, every step
     brk = {"upload": 0.0, "render_and_readback": 0.0, "destroy": 0.0}
 
+    # page-locked host buffers for the frame's outputs (Result.png and ZBuffer.png pixels)
+    pinned = {"rgb8": torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True).numpy(),
+              "z8": torch.empty((H, W), dtype=torch.uint8, pin_memory=True).numpy()}
+
     def e2e_step():
         t_a = time.perf_counter()
         s2 = R.Scene(ctx, hs.desc)
@@ -249,7 +253,7 @@ def ours(args):
             dist.reduce(accum, dst=0)
             out = s2.resolve(p, accum.data_ptr(), want=("rgb8", "z8")) if rank == 0 else None
         else:
-            out = s2.render(p, want=("rgb8", "z8"))
+            out = s2.render(p, want=("rgb8", "z8"), out=pinned)
         t_c = time.perf_counter()
         nbytes = s2.stats()["scene_device_bytes"]
         s2.close()

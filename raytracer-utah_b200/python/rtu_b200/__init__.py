@@ -337,8 +337,9 @@ class Scene:
         h = params.height or self.desc.camera.height
         return max(w, 1), max(h, 1)  # invalid sizes are rejected by the library, not here
 
-    def render(self, params, want=("rgb8", "rgb", "z", "z8", "node_id", "face_id")):
-        """rtu_render: whole frame, host buffers out (the e2e path)."""
+    def render(self, params, want=("rgb8", "rgb", "z", "z8", "node_id", "face_id"), out=None):
+        """rtu_render: whole frame, host buffers out (the e2e path).  out: optional dict of caller-owned arrays (e.g.
+        page-locked ones) to write into instead of fresh numpy arrays."""
         L = lib()
         w, h = self._dims(params)
         bufs = {}
@@ -347,7 +348,13 @@ class Scene:
                 "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
         for k in want:
             shp, dt, ct = spec[k]
-            bufs[k] = np.zeros(shp, dt)
+            if out is not None and k in out:
+                a = out[k]
+                if a.shape != shp or a.dtype != np.dtype(dt) or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (k, dt, shp))
+                bufs[k] = a
+            else:
+                bufs[k] = np.zeros(shp, dt)
             setattr(img, k, _ptr(bufs[k], ct))
         L.rtu_render.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Image)]
         _check(L.rtu_render(self._h, C.byref(params), C.byref(img)), "rtu_render")
