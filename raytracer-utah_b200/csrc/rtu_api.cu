@@ -1076,7 +1076,7 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
     CU(cudaEventRecord(c->ev0, c->stream));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * sizeof(float4), c->stream));
-    s->launches = 0;
+    s->launches = F.tile_empty ? 1 : 0; // k_tile_mask ran in setup_frame
     kt_reset(c, (p->flags & RTU_FLAG_TIME_KERNELS) != 0);
     size_t wi = 0;
     for (int a = s0; a < s1; a += (int)chunk_samples) {
