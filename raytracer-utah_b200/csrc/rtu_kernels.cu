@@ -328,6 +328,9 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 if (c1 > NONE) W.leaf[leaf_n + __popc(l2) + __popc(l1 & lt)] = (sl << 27) | (((c1 >> 28) & 7u) << 24) | (c1 & 0x00ffffffu);
                 pool_n += __popc(n2) + __popc(n1);
                 leaf_n += __popc(l2) + __popc(l1);
+#ifdef RTU_DEBUG_BOUNDS
+                if (pool_n > XP_POOL || leaf_n > XP_LEAF) counters->overflow = 0xBAD1;
+#endif
                 __syncwarp();
             }
             // every slot's ray takes the closest triangle into its HitInfo and goes on with the node behind the mesh
@@ -358,6 +361,9 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 e[2] = make_float4(B.bc3, 0.f, 0.f, 0.f);
             }
             nres += take;
+#ifdef RTU_DEBUG_BOUNDS
+            if (nres > XP_RES) counters->overflow = 0xBAD2;
+#endif
             __syncwarp();
             continue;
         }
@@ -456,6 +462,9 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
             e[2] = make_float4(B.bc3, 0.f, 0.f, 0.f);
         }
         njobs += __popc(m);
+#ifdef RTU_DEBUG_BOUNDS
+        if (njobs > XP_JOBS) counters->overflow = 0xBAD3;
+#endif
         __syncwarp();
     }
     flush_tally(tl, counters, PRIMARY ? 0 : 1);
@@ -769,6 +778,9 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 if (c1 > NONE) W.leaf[leaf_n + __popc(l2) + __popc(l1 & lt)] = (sl << 27) | (((c1 >> 28) & 7u) << 24) | (c1 & 0x00ffffffu);
                 pool_n += __popc(n2) + __popc(n1);
                 leaf_n += __popc(l2) + __popc(l1);
+#ifdef RTU_DEBUG_BOUNDS
+                if (pool_n > SP_POOL || leaf_n > SP_LEAF) counters->overflow = 0xBAD4;
+#endif
                 __syncwarp();
             }
             // rays that were not stopped by their mesh go on with the node behind it
@@ -777,6 +789,9 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
             const unsigned m = __ballot_sync(FULL, go_on);
             if (go_on) W.res[nres + __popc(m & lt)] = make_uint2(W.idx[lane], W.node[lane] + 1u);
             nres += __popc(m);
+#ifdef RTU_DEBUG_BOUNDS
+            if (nres > SP_RES) counters->overflow = 0xBAD5;
+#endif
             __syncwarp();
             continue;
         }
@@ -857,6 +872,9 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         const unsigned m = __ballot_sync(FULL, park != 0);
         if (park) W.jobs[njobs + __popc(m & lt)] = make_uint2(idx, (unsigned)park);
         njobs += __popc(m);
+#ifdef RTU_DEBUG_BOUNDS
+        if (njobs > SP_JOBS) counters->overflow = 0xBAD6;
+#endif
         __syncwarp();
     }
     flush_tally(tl, counters, 2);
@@ -1095,6 +1113,9 @@ __device__ __forceinline__ int warp_nominate(const DScene &S, TopWarp &W, const 
         if (c2 != NONE) W.pool[pool_n + __popc(b2 & lt)] = (sl << 27) | c2;
         if (c1 != NONE) W.pool[pool_n + __popc(b2) + __popc(b1 & lt)] = (sl << 27) | c1;
         pool_n += __popc(b2) + __popc(b1);
+#ifdef RTU_DEBUG_BOUNDS
+        if (pool_n > TW_POOL) asm volatile("trap;");
+#endif
         __syncwarp();
     }
     int nc = W.count[lane];
