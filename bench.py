@@ -304,7 +304,8 @@ def ours(args):
                 "kernel_share_of_step": dom["ms"] / max(1e-9, sum(c["ms"] for c in classes.values())),
                 "rays_per_step": dom["rays"], "kernel_mrays_per_s": dom["rays"] / (dom["ms"] * 1e-3) * 1e-6 if dom["ms"] > 0 else 0.0,
                 "fp32": {"achieved_tflops": flops / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0,
-                         "peak_tflops_no_fma": fp32_peak / 1e12, "note": "the Teapot BVH (0.6 MB) is L1/L2 resident: latency/issue bound, not HBM bound"},
+                         "peak_tflops_no_fma": fp32_peak / 1e12,
+                         "frac": (flops / (dom["ms"] * 1e-3)) / fp32_peak if dom["ms"] > 0 else 0.0, "note": "the Teapot BVH (0.6 MB) is L1/L2 resident: latency/issue bound, not HBM bound"},
                 "all_kernels_ms": {k: v["ms"] for k, v in classes.items()}}
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
