@@ -930,6 +930,7 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     // tiles of the primary wave that no camera ray of the rendered samples can leave with a hit
     F->tile_empty = nullptr;
     F->n_obj = s->n_obj;
+    F->ticket_block = 32;
     if (!getenv("RTU_NO_TILE_MASK") && s->cam.dof <= 0.f && s->root_identity) {
         float ox0 = off[*s_begin].x, ox1 = ox0, oy0 = off[*s_begin].y, oy1 = oy0;
         for (int i = *s_begin; i < *s_end; i++) {
@@ -940,7 +941,7 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
         std::vector<float4> edges;
         if (image_footprints(s, F->cam, &objs, &edges)) {
             size_t tiles = (size_t)((W + 7) / 8) * (size_t)((F->row_end - F->row_begin + 3) / 4);
-            size_t need = tiles + objs.size() * sizeof(TileObject) + edges.size() * sizeof(float4) + 64;
+            size_t need = tiles + objs.size() * sizeof(TileObject) + edges.size() * sizeof(float4) + 128;
             if (need > s->ctx->fb.tile_n) {
                 CU(cudaStreamSynchronize(s->ctx->stream));
                 if (s->ctx->fb.d_tile) cudaFree(s->ctx->fb.d_tile);
@@ -956,9 +957,13 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
             unsigned char *d_mask = (unsigned char *)(d_edges + edges.size());
             if (!objs.empty()) CU(cudaMemcpyAsync(d_objs, objs.data(), objs.size() * sizeof(TileObject), cudaMemcpyHostToDevice, s->ctx->stream));
             if (!edges.empty()) CU(cudaMemcpyAsync(d_edges, edges.data(), edges.size() * sizeof(float4), cudaMemcpyHostToDevice, s->ctx->stream));
-            launch_tile_mask(s->ctx->stream, *F, d_objs, (int)objs.size(), d_edges, ox0, ox1, oy0, oy1, d_mask);
+            unsigned *d_count = (unsigned *)(base + ((size_t)(d_mask - base) + tiles + 15) / 16 * 16);
+            launch_tile_mask(s->ctx->stream, *F, d_objs, (int)objs.size(), d_edges, ox0, ox1, oy0, oy1, d_mask, d_count);
+            unsigned n_empty = 0;
+            CU(cudaMemcpyAsync(&n_empty, d_count, sizeof n_empty, cudaMemcpyDeviceToHost, s->ctx->stream));
             CU(cudaStreamSynchronize(s->ctx->stream)); // objs / edges are locals
             F->tile_empty = d_mask;
+            if ((size_t)n_empty * 2 > tiles) F->ticket_block = 256; // mostly empty tiles: hand them out in blocks
             if (getenv("RTU_TILE_DEBUG")) {
                 std::vector<unsigned char> hm(tiles);
                 cudaMemcpy(hm.data(), d_mask, tiles, cudaMemcpyDeviceToHost);

@@ -19,6 +19,7 @@ struct FrameSetup {
     // bounding sphere of any object; such rays book n_obj culled nodes each and add the background (may be NULL)
     const unsigned char *tile_empty;
     int n_obj;
+    int ticket_block;    // work items a warp of the primary wave takes per atomic: 256 when most tiles are empty, else 32
 };
 
 struct LaunchCfg {
@@ -101,4 +102,4 @@ struct TileObject {
 };
 // tiles of the primary wave that no object's footprint touches (see FrameSetup::tile_empty)
 void launch_tile_mask(cudaStream_t st, const FrameSetup &F, const TileObject *objs, int n_objs, const float4 *edges, float ox0,
-                      float ox1, float oy0, float oy1, unsigned char *mask);
+                      float ox1, float oy0, float oy1, unsigned char *mask, unsigned *n_empty);

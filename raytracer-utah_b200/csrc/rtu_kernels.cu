@@ -29,6 +29,7 @@
 #include "camera.cuh"
 
 #define WAVE_THREADS 256
+#define TICKET_BLOCK 256u // work items a warp takes from the global counter at a time (pooled kernels)
 #ifndef EXT_BLOCKS
 #define EXT_BLOCKS 2 // resident CTAs per SM the traversal kernels are compiled for (measured best of 2/3/4 on B200)
 #endif
@@ -210,6 +211,15 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
     if (PRIMARY) total = pm.perSample * (unsigned)(s1 - s0);
     else { total = *in.count; if (total > in.cap) total = in.cap; }
     unsigned njobs = 0, nres = 0; // warp-uniform
+    unsigned t_next = 0, t_end = 0; // this warp's block of work items: large waves take TICKET_BLOCK items per atomic,
+    unsigned t_block;               // small ones fewer, so that every resident warp still gets several blocks
+    {
+        // blocks only pay where most work items are nearly free (frames whose tiles are mostly empty, FrameSetup::ticket_block);
+        // heavy items are better handed out 32 at a time
+        const unsigned want = PRIMARY ? (unsigned)F.ticket_block : 32u;
+        const unsigned per_warp = total / (gridDim.x * (WAVE_THREADS / 32) * 8u);
+        t_block = per_warp >= want ? want : (per_warp < 32u ? 32u : (per_warp & ~31u));
+    }
     bool drained = false;
     DNode root;
     load_node(S.nodes, root);
@@ -374,8 +384,15 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
         unsigned fresh = (k == 0u && !drained) ? 32u : 0u;
         unsigned base = 0;
         if (fresh) {
-            if (lane == 0) base = atomicAdd(work, fresh);
-            base = __shfl_sync(FULL, base, 0);
+            // work items come in blocks of TICKET_BLOCK (8 tiles / 8 x 32 queue entries) per atomic: a wave of mostly empty
+            // tiles would otherwise spend its time waiting for the single work counter
+            if (t_next >= t_end) {
+                if (lane == 0) t_next = atomicAdd(work, t_block);
+                t_next = __shfl_sync(FULL, t_next, 0);
+                t_end = t_next + t_block;
+            }
+            base = t_next;
+            t_next += 32u;
             if (base >= total) { drained = true; fresh = 0; }
         }
         unsigned idx = 0;
@@ -672,6 +689,9 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
     unsigned total = *Q.count;
     if (total > Q.cap) total = Q.cap;
     unsigned njobs = 0, nres = 0; // warp-uniform
+    unsigned t_next = 0, t_end = 0; // this warp's block of work items: large waves take TICKET_BLOCK items per atomic,
+    unsigned t_block;               // small ones fewer, so that every resident warp still gets several blocks
+    t_block = 32u;
     bool drained = false;         // warp-uniform: no tickets left
     DNode root;
     load_node(S.nodes, root);
@@ -802,8 +822,15 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         unsigned fresh = (k == 0u && !drained) ? 32u : 0u;
         unsigned base = 0;
         if (fresh) {
-            if (lane == 0) base = atomicAdd(work, fresh);
-            base = __shfl_sync(FULL, base, 0);
+            // work items come in blocks of TICKET_BLOCK (8 tiles / 8 x 32 queue entries) per atomic: a wave of mostly empty
+            // tiles would otherwise spend its time waiting for the single work counter
+            if (t_next >= t_end) {
+                if (lane == 0) t_next = atomicAdd(work, t_block);
+                t_next = __shfl_sync(FULL, t_next, 0);
+                t_end = t_next + t_block;
+            }
+            base = t_next;
+            t_next += 32u;
             if (base >= total) { drained = true; fresh = 0; }
         }
         unsigned idx = 0;
@@ -1243,7 +1270,7 @@ k_shadow_wave_top(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, u
 // offsets in [ox0,ox1] x [oy0,oy1]) fill a rectangle in pixel coordinates; the tile is empty when that rectangle is
 // separated from the footprint of every object (bounding boxes disjoint, or all four corners outside one hull edge).
 __global__ void k_tile_mask(FrameSetup F, const TileObject *objs, int n_objs, const float4 *edges, float ox0, float ox1, float oy0,
-                            float oy1, unsigned char *mask)
+                            float oy1, unsigned char *mask, unsigned *n_empty)
 {
     const int tilesX = (F.cam.width + 7) >> 3, tilesY = (F.row_end - F.row_begin + 3) >> 2;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1263,13 +1290,16 @@ __global__ void k_tile_mask(FrameSetup F, const TileObject *objs, int n_objs, co
         if (!separated) empty = false;
     }
     mask[t] = empty ? 1 : 0;
+    const unsigned votes = __ballot_sync(__activemask(), empty);
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(n_empty, (unsigned)__popc(votes));
 }
 
 void launch_tile_mask(cudaStream_t st, const FrameSetup &F, const TileObject *objs, int n_objs, const float4 *edges, float ox0,
-                      float ox1, float oy0, float oy1, unsigned char *mask)
+                      float ox1, float oy0, float oy1, unsigned char *mask, unsigned *n_empty)
 {
     const int tiles = ((F.cam.width + 7) >> 3) * ((F.row_end - F.row_begin + 3) >> 2);
-    k_tile_mask<<<(tiles + 127) / 128, 128, 0, st>>>(F, objs, n_objs, edges, ox0, ox1, oy0, oy1, mask);
+    cudaMemsetAsync(n_empty, 0, sizeof(unsigned), st);
+    k_tile_mask<<<(tiles + 127) / 128, 128, 0, st>>>(F, objs, n_objs, edges, ox0, ox1, oy0, oy1, mask, n_empty);
 }
 
 // ------------------------------------------------------------------ launch wrappers
