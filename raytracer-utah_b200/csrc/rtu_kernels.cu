@@ -540,47 +540,27 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
         }
         HitRec H;
         finalize_hit(S, ray, B, H);
-        if (path_mode && (kind == RK_PRIMARY || kind == RK_GI)) {
+        // shade_hit() is inlined exactly once: a GI vertex runs it twice (t = 0, 1), every other ray kind once, all lanes of
+        // the warp together.  (Three inlined copies made the kernel ~300 KB of SASS and bound by instruction fetch.)
+        const bool gi = path_mode && (kind == RK_PRIMARY || kind == RK_GI);
+        int n_shade = 1, k = 0, rec = 0;
+        Col Ws = Wt;
+        if (gi) {
             // A vertex h_k of the GI chain (RenderFunctions.cpp:129-135 for the camera hit, :565-570 for a
             // MonteCarlo() sample hit).  L(h_k) = Shade(h_k, lights) + Shade(h_k, {Ambient c_k}) where c_k is what
             // MonteCarlo(h_k) returns.  The second Shade is linear in c_k, so its c_k-factor A_k and everything that
             // does not depend on c_k (D_k) are accumulated in two slots of the sample's GI record and folded by
             // k_gi_combine once all waves are done: L_k = D_k + A_k * L_{k+1}.
-            int k = kind == RK_PRIMARY ? 0 : gidepth;
-            int base;
+            k = kind == RK_PRIMARY ? 0 : gidepth;
             if (kind == RK_PRIMARY) {
-                base = (int)h * (gi_end + 1);
-                for (int j = 0; j <= gi_end; j++) O.accum[base + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                O.accum[base].w = __int_as_float(pixel);
+                rec = (int)h * (gi_end + 1);
+                for (int j = 0; j <= gi_end; j++) O.accum[rec + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                O.accum[rec].w = __int_as_float(pixel);
             } else {
-                base = pixel;
+                rec = pixel;
             }
-#pragma unroll 1
-            for (int t = 0; t < 2; t++)
-                shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, mk(1.f, 1.f, 1.f), F.shade_bounces, base + 2 * k + (t ? 0 : 1),
-                          child_path(path, 8u + (unsigned)t), t);
-            if (k < F.gi_bounces) {
-                SlotTicket tk; // the slot of the sample ray is reserved before its direction is drawn
-                tk.issue(O.next.count, 1u);
-                Rng rng;
-                rng.key = F.seed; rng.pixel = 0x61u; rng.path = path; rng.dim = 0;
-                float ox, oy, oz;
-                sample_hemi_cos(rng, H.nx, H.ny, H.nz, ox, oy, oz);                                   // :561
-                norm3(ox, oy, oz);                                                                    // :562
-                const unsigned slot = tk.slot();
-                if (slot >= O.next.cap) O.counters->overflow = 1;
-                else {
-                    O.next.o[slot] = make_float4(H.px, H.py, H.pz, __int_as_float(base));
-                    O.next.d[slot] = make_float4(ox, oy, oz, __uint_as_float(pack_meta(RK_GI, F.shade_bounces, 0, 0, k + 1)));
-                    O.next.w[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(-1));
-                    O.next.path[slot] = child_path(path, 6u);
-                }
-            } else {
-                O.accum[base + gi_end] = make_float4(0.1f, 0.1f, 0.1f, (float)(k + 1));               // :584
-            }
-            continue;
-        }
-        if (kind == RK_REFRACT) {
+            n_shade = 2;
+        } else if (kind == RK_REFRACT) {
             float4 a = inaux.a[aux], b = inaux.b[aux];
             Col Kt = mk(a.x, a.y, a.z);
             float Fr = a.w;
@@ -589,7 +569,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
                 const DMaterial &PM = S.materials[mtl];
                 ab = mk(expf((-H.z) * PM.absorption[0]), expf((-H.z) * PM.absorption[1]), expf((-H.z) * PM.absorption[2]));
             }
-            Col Wh = (Wt * (ab * Kt)) * (float)(1.0 - (double)Fr);                 // :264
+            Ws = (Wt * (ab * Kt)) * (float)(1.0 - (double)Fr);                     // :264
             // the Fresnel mirror ray exists only because the refracted ray hit (:234-251)
             Col Wf = Wt * Fr;
             Col WfKt = Wf * Kt;
@@ -603,10 +583,36 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
                              child_path(path, 4u));
                 }
             }
-            if (!((F.flags & 2u) && !nonblack(Wh)))
-                shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wh, bounce, pixel, path, tree);
-        } else {
-            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, Wt, bounce, pixel, path, tree);
+            if ((F.flags & 2u) && !nonblack(Ws)) n_shade = 0;
+        }
+#pragma unroll 1
+        for (int t = 0; t < n_shade; t++) {
+            const Col w = gi ? mk(1.f, 1.f, 1.f) : Ws;
+            const int sb = gi ? F.shade_bounces : bounce;
+            const int target = gi ? rec + 2 * k + (t ? 0 : 1) : pixel;
+            const unsigned sp = gi ? child_path(path, 8u + (unsigned)t) : path;
+            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, w, sb, target, sp, gi ? t : tree);
+        }
+        if (gi) {
+            if (k < F.gi_bounces) {
+                SlotTicket tk; // the slot of the sample ray is reserved before its direction is drawn
+                tk.issue(O.next.count, 1u);
+                Rng rng;
+                rng.key = F.seed; rng.pixel = 0x61u; rng.path = path; rng.dim = 0;
+                float ox, oy, oz;
+                sample_hemi_cos(rng, H.nx, H.ny, H.nz, ox, oy, oz);                                   // :561
+                norm3(ox, oy, oz);                                                                    // :562
+                const unsigned slot = tk.slot();
+                if (slot >= O.next.cap) O.counters->overflow = 1;
+                else {
+                    O.next.o[slot] = make_float4(H.px, H.py, H.pz, __int_as_float(rec));
+                    O.next.d[slot] = make_float4(ox, oy, oz, __uint_as_float(pack_meta(RK_GI, F.shade_bounces, 0, 0, k + 1)));
+                    O.next.w[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(-1));
+                    O.next.path[slot] = child_path(path, 6u);
+                }
+            } else {
+                O.accum[rec + gi_end] = make_float4(0.1f, 0.1f, 0.1f, (float)(k + 1));               // :584
+            }
         }
     }
 }

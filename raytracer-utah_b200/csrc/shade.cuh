@@ -90,7 +90,9 @@ __device__ __forceinline__ float tile_clamp(float v)
 }
 
 // TextureMap::Sample -> TextureFile::Sample / TextureChecker::Sample (scene.h:382, texture.cpp:95-133)
-__device__ __forceinline__ Col texmap_sample(const DTexMap &T, float u, float v, float w)
+// One copy per kernel (not inlined): the bilinear fetch with its twelve IEEE divisions is ~350 instructions, and the shading
+// kernels are bound by instruction fetch once warps spread over many such copies.
+static __device__ __noinline__ Col texmap_sample(const DTexMap &T, float u, float v, float w)
 {
     if (T.kind == 0) return mk(0, 0, 0); // texture == NULL (failed load)
     // Transformation::TransformTo (scene.h:235)
@@ -277,10 +279,11 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
     Rng rng;
     rng.key = P.seed; rng.pixel = tree ? 0x7A11u : 0u; rng.path = path; rng.dim = 0;
     Col local = mk(0, 0, 0);
+    Col Kd = mk(0, 0, 0);
+    if (H.front) Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
     if (H.front && tree) {
-        local = texcolor_sample(S, M.diffuse, H.u, H.v, H.w); // Kd * Illuminate() of the unit ambient light (:131-133)
+        local = Kd; // Kd * Illuminate() of the unit ambient light (:131-133)
     } else if (H.front) {
-        Col Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
         Col Ks = texcolor_sample(S, M.specular, H.u, H.v, H.w);
         // viewDirection uses camera.pos, not the ray origin (mtlFunctions.cpp:137, SURVEY A-6)
         // every non-ambient light sends one shadow ray (unless null rays are culled): their queue slots are reserved
