@@ -503,12 +503,16 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
     ShadeParams SP;
     SP.flags = F.flags;
     SP.seed = F.seed;
+    // The shading code is long and nearly loop-free, so the kernel is bound by instruction fetch: the warps of a CTA
+    // therefore take their hits together and start every round at a barrier, which keeps them within an instruction-cache
+    // window of each other (one warp's misses are the others' hits).
+    __shared__ unsigned cta_base;
     for (;;) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= total) break;
-        unsigned h = base + lane;
+        __syncthreads();
+        if (threadIdx.x == 0) cta_base = atomicAdd(work, (unsigned)WAVE_THREADS);
+        __syncthreads();
+        if (cta_base >= total) break;
+        const unsigned h = cta_base + threadIdx.x;
         if (h >= total) continue;
         float4 ha = hq.a[h], hb = hq.b[h];
         Best B;
