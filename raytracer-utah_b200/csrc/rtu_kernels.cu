@@ -488,8 +488,13 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
 }
 
 // ------------------------------------------------------------------ shade the compacted hits
+#ifndef SHADE_BLOCKS
+#define SHADE_BLOCKS 3 // resident CTAs per SM of the shading kernel (80 registers; measured best of 2/3/4 over Teapot, Project10, Project11)
+#endif
+#define SHADE_SMEM_LIGHTS 16     // scenes with no more lights / materials than this shade out of shared-memory copies
+#define SHADE_SMEM_MATERIALS 32
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WAVE_THREADS, 2)
+__global__ void __launch_bounds__(WAVE_THREADS, SHADE_BLOCKS)
 k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq, WaveOut O, unsigned *work, unsigned *gi_count)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -503,6 +508,19 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
     ShadeParams SP;
     SP.flags = F.flags;
     SP.seed = F.seed;
+    // lights and materials are read all through the shading code: out of shared memory they never wait on L2
+    __shared__ DLight s_lights[SHADE_SMEM_LIGHTS];
+    __shared__ DMaterial s_materials[SHADE_SMEM_MATERIALS];
+    if (S.n_lights <= SHADE_SMEM_LIGHTS) {
+        const int words = S.n_lights * (int)(sizeof(DLight) / 4);
+        for (int i = threadIdx.x; i < words; i += WAVE_THREADS) ((unsigned *)s_lights)[i] = ((const unsigned *)S.lights)[i];
+        S.lights = s_lights;
+    }
+    if (S.n_materials <= SHADE_SMEM_MATERIALS) {
+        const int words = S.n_materials * (int)(sizeof(DMaterial) / 4);
+        for (int i = threadIdx.x; i < words; i += WAVE_THREADS) ((unsigned *)s_materials)[i] = ((const unsigned *)S.materials)[i];
+        S.materials = s_materials;
+    }
     // The shading code is long and nearly loop-free, so the kernel is bound by instruction fetch: the warps of a CTA
     // therefore take their hits together and start every round at a barrier, which keeps them within an instruction-cache
     // window of each other (one warp's misses are the others' hits).
@@ -589,6 +607,11 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             }
             if ((F.flags & 2u) && !nonblack(Ws)) n_shade = 0;
         }
+        // the queue slot of a GI vertex's sample ray is reserved before the vertex is shaded: the atomic's round trip hides
+        // behind shade_hit()
+        const bool gi_ray = gi && k < F.gi_bounces;
+        SlotTicket tk;
+        if (gi_ray) tk.issue(O.next.count, 1u);
 #pragma unroll 1
         for (int t = 0; t < n_shade; t++) {
             const Col w = gi ? mk(1.f, 1.f, 1.f) : Ws;
@@ -598,9 +621,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, w, sb, target, sp, gi ? t : tree);
         }
         if (gi) {
-            if (k < F.gi_bounces) {
-                SlotTicket tk; // the slot of the sample ray is reserved before its direction is drawn
-                tk.issue(O.next.count, 1u);
+            if (gi_ray) {
                 Rng rng;
                 rng.key = F.seed; rng.pixel = 0x61u; rng.path = path; rng.dim = 0;
                 float ox, oy, oz;
@@ -1325,6 +1346,18 @@ template <class K> static int resident_grid(const LaunchCfg &cfg, K kernel, int 
     return cfg.sm_count * *cache;
 }
 
+// the shading kernel has its own residency (SHADE_BLOCKS), independent of the traversal kernels' cfg.blocks_per_sm
+template <class K> static int shade_grid(const LaunchCfg &cfg, K kernel, int *cache)
+{
+    if (*cache == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WAVE_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+        if (n > SHADE_BLOCKS) n = SHADE_BLOCKS;
+        *cache = n;
+    }
+    return cfg.sm_count * *cache;
+}
+
 static WaveOut make_out(const WaveBuffers &B, int out_q, float4 *accum)
 {
     WaveOut O;
@@ -1389,7 +1422,7 @@ void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S
 {
     static int occ = 0;
     WaveOut O = make_out(B, out_q, accum);
-    k_shade<true><<<resident_grid(cfg, k_shade<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, B.q[1 - out_q], B.aux[1 - out_q], B.hits, O,
+    k_shade<true><<<shade_grid(cfg, k_shade<true>, &occ), WAVE_THREADS, 0, st>>>(S, F, s0, B.q[1 - out_q], B.aux[1 - out_q], B.hits, O,
                                                                                    work_counter, B.gi_count);
 }
 
@@ -1423,7 +1456,7 @@ void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 {
     static int occ = 0;
     WaveOut O = make_out(B, 1 - in_q, accum);
-    k_shade<false><<<resident_grid(cfg, k_shade<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, B.q[in_q], B.aux[in_q], B.hits, O, work_counter,
+    k_shade<false><<<shade_grid(cfg, k_shade<false>, &occ), WAVE_THREADS, 0, st>>>(S, F, 0, B.q[in_q], B.aux[in_q], B.hits, O, work_counter,
                                                                                      B.gi_count);
 }
 

@@ -182,7 +182,10 @@ struct SlotTicket {
         stride = __popc(mask);
         rank = __popc(mask & ((1u << lane) - 1u));
         base_in_leader = 0;
-        if (lane == leader) base_in_leader = atomicAdd(counter, stride * n);
+        // inline PTX: nvcc rewrites a plain atomicAdd() here into its own warp-aggregated form, whose shuffle consumes the
+        // result at once and so waits out the whole round trip on the spot
+        if (lane == leader)
+            asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(base_in_leader) : "l"(counter), "r"(stride * n) : "memory");
     }
     // must be called by exactly the lanes that called issue() (still converged or reconverged)
     __device__ __forceinline__ unsigned slot() const { return __shfl_sync(mask, base_in_leader, leader) + rank; }
