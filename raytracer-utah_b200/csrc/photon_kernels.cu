@@ -370,33 +370,47 @@ k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_boun
     Tally tl = {0, 0, 0, 0, 0};
     const unsigned lane = threadIdx.x & 31u;
     const DLight L = S.lights[light];
+    // Every lane carries one photon path and advances it by one segment per round: [bounce off the last hit] -> Trace ->
+    // [store].  A lane whose path ended takes the next path number at the top of the round, so lanes stay busy although
+    // path lengths differ (mean 2.4 segments, maximum max_bounce + 1), and the traversal code exists once.
+    bool alive = false, drained = false, first = false;
+    unsigned k = 0, stored = 0, flag = 0;
+    int bounce = 0;
+    Rng rng;
+    Ray ray;
+    Best B;
+    HitRec H;
+    Col outgoing = mk(0, 0, 0), incoming = mk(0, 0, 0);
     for (;;) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_paths) break;
-        unsigned k = base + lane;
-        if (k >= n_paths) continue;
-        unsigned long long path = path0 + k;
-        Rng rng;
-        rng.key = seed; rng.pixel = 0x9407u ^ (unsigned)(path >> 32); rng.path = (unsigned)path; rng.dim = 0;
-        // PointLight::RandomPhoton (lightFunctions.cpp:19-25)
-        Ray ray;
-        ray.px = L.v[0]; ray.py = L.v[1]; ray.pz = L.v[2];
-        sample_ball(rng, 1.0f, ray.dx, ray.dy, ray.dz);
-        norm3(ray.dx, ray.dy, ray.dz);
-        Best B;
-        B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
-        tl.trace++;
-        unsigned stored = 0, flag = 0;
-        if (scene_hit<false>(S, ray, B, tl, false)) {
-            flag = 0x80u; // photonFromLight++ (RenderFunctions.cpp:357)
-            Col outgoing = mk(L.I[0], L.I[1], L.I[2]);
-            for (int i = 0; i < max_bounce; i++) {
-                Col incoming = outgoing;
-                HitRec H;
-                finalize_hit(S, ray, B, H);
-                if (H.material < 0) break; // the reference would dereference a NULL material
+        const unsigned want = __ballot_sync(0xffffffffu, !alive && !drained);
+        if (want) {
+            unsigned base = 0;
+            const unsigned leader = __ffs(want) - 1;
+            if (lane == leader) base = atomicAdd(work, (unsigned)__popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!alive && !drained) {
+                k = base + __popc(want & ((1u << lane) - 1u));
+                if (k >= n_paths) drained = true;
+                else {
+                    const unsigned long long path = path0 + k;
+                    rng.key = seed; rng.pixel = 0x9407u ^ (unsigned)(path >> 32); rng.path = (unsigned)path; rng.dim = 0;
+                    // PointLight::RandomPhoton (lightFunctions.cpp:19-25)
+                    ray.px = L.v[0]; ray.py = L.v[1]; ray.pz = L.v[2];
+                    sample_ball(rng, 1.0f, ray.dx, ray.dy, ray.dz);
+                    norm3(ray.dx, ray.dy, ray.dz);
+                    B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
+                    stored = 0; flag = 0; bounce = 0;
+                    alive = true; first = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        const bool was_alive = alive;
+        if (alive && !first) {
+            // one iteration of the bounce loop (RenderFunctions.cpp:359-381) up to its Trace()
+            incoming = outgoing;
+            if (H.material < 0) alive = false; // the reference would dereference a NULL material
+            else {
                 const DMaterial &M = S.materials[H.material];
                 // MtlBlinn::RandomPhotonBounce (mtlFunctions.cpp:19-118)
                 Col Kd = texcolor_sample(S, M.diffuse, H.u, H.v, H.w);
@@ -409,32 +423,35 @@ k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_boun
                 float pick = u.x;
                 Ray nr;
                 nr.px = H.px; nr.py = H.py; nr.pz = H.pz;
+                nr.dx = nr.dy = nr.dz = 0.f;
                 if (pick > dG) {
                     if (pick > dG + sG) {
-                        if (pick > (dG + sG) + rG) break; // absorbed
-                        float ox, oy, oz;
-                        sample_ball(rng, M.refr_gloss, ox, oy, oz);
-                        float snx = ((H.px + H.nx) + ox) - H.px, sny = ((H.py + H.ny) + oy) - H.py, snz = ((H.pz + H.nz) + oz) - H.pz;
-                        norm3(snx, sny, snz);
-                        float cos1 = dot3(snx, sny, snz, -ray.dx, -ray.dy, -ray.dz);
-                        float sin1 = (float)sqrt(1.0 - (double)cos1 * (double)cos1);
-                        if (sin1 > 1) sin1 = 1.0f;
-                        if (sin1 < -1) sin1 = -1.0f;
-                        if (cos1 > 1) cos1 = 1.0f;
-                        if (cos1 < -1) cos1 = -1.0f;
-                        float n1 = M.ior, n2 = 1.0f;
-                        if (H.front) { n1 = 1.0f; n2 = M.ior; }
-                        float sin2 = (n1 / n2) * sin1;
-                        float cos2 = sqrtf(1 - sin2 * sin2);
-                        if (cos2 > 1) cos2 = 1.0f;
-                        float cx = sny * (-ray.dz) - snz * (-ray.dy), cy = snz * (-ray.dx) - snx * (-ray.dz), cz = snx * (-ray.dy) - sny * (-ray.dx);
-                        norm3(cx, cy, cz);
-                        float svx = sny * cz - snz * cy, svy = snz * cx - snx * cz, svz = snx * cy - sny * cx;
-                        norm3(svx, svy, svz);
-                        nr.dx = (-snx) * cos2 + svx * sin2; nr.dy = (-sny) * cos2 + svy * sin2; nr.dz = (-snz) * cos2 + svz * sin2;
-                        norm3(nr.dx, nr.dy, nr.dz);
-                        float w = rG / 1.0f;
-                        outgoing = outgoing * mk(Kt.r / w, Kt.g / w, Kt.b / w);
+                        if (pick > (dG + sG) + rG) alive = false; // absorbed
+                        else {
+                            float ox, oy, oz;
+                            sample_ball(rng, M.refr_gloss, ox, oy, oz);
+                            float snx = ((H.px + H.nx) + ox) - H.px, sny = ((H.py + H.ny) + oy) - H.py, snz = ((H.pz + H.nz) + oz) - H.pz;
+                            norm3(snx, sny, snz);
+                            float cos1 = dot3(snx, sny, snz, -ray.dx, -ray.dy, -ray.dz);
+                            float sin1 = (float)sqrt(1.0 - (double)cos1 * (double)cos1);
+                            if (sin1 > 1) sin1 = 1.0f;
+                            if (sin1 < -1) sin1 = -1.0f;
+                            if (cos1 > 1) cos1 = 1.0f;
+                            if (cos1 < -1) cos1 = -1.0f;
+                            float n1 = M.ior, n2 = 1.0f;
+                            if (H.front) { n1 = 1.0f; n2 = M.ior; }
+                            float sin2 = (n1 / n2) * sin1;
+                            float cos2 = sqrtf(1 - sin2 * sin2);
+                            if (cos2 > 1) cos2 = 1.0f;
+                            float cx = sny * (-ray.dz) - snz * (-ray.dy), cy = snz * (-ray.dx) - snx * (-ray.dz), cz = snx * (-ray.dy) - sny * (-ray.dx);
+                            norm3(cx, cy, cz);
+                            float svx = sny * cz - snz * cy, svy = snz * cx - snx * cz, svz = snx * cy - sny * cx;
+                            norm3(svx, svy, svz);
+                            nr.dx = (-snx) * cos2 + svx * sin2; nr.dy = (-sny) * cos2 + svy * sin2; nr.dz = (-snz) * cos2 + svz * sin2;
+                            norm3(nr.dx, nr.dy, nr.dz);
+                            float w = rG / 1.0f;
+                            outgoing = outgoing * mk(Kt.r / w, Kt.g / w, Kt.b / w);
+                        }
                     } else {
                         sample_ball(rng, 1.0f, nr.dx, nr.dy, nr.dz); // unnormalised point of the unit ball (SURVEY A-16)
                         float w = sG / 1.0f;
@@ -446,24 +463,37 @@ k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_boun
                     outgoing = outgoing * mk(Kd.r / w, Kd.g / w, Kd.b / w);
                 }
                 ray = nr;
-                // Trace(r, &rootNode, hInfo) into the SAME HitInfo: its z still holds the previous segment's length, so
-                // only nearer hits are found (SURVEY A-16)
-                tl.trace++;
-                if (!scene_hit<false>(S, ray, B, tl, false)) break;
-                int mtl = __ldg(&S.nodes[B.node].material);
-                if (mtl < 0) break;
-                const DMaterial &M2 = S.materials[mtl];
-                if (gray(mk(M2.diffuse.c[0], M2.diffuse.c[1], M2.diffuse.c[2])) > 0.f) { // IsPhotonSurface (materials.h:48)
-                    HitRec H2;
-                    finalize_hit(S, ray, B, H2);
-                    float dx = ray.dx, dy = ray.dy, dz = ray.dz;
-                    norm3(dx, dy, dz);
-                    encode_photon(staging + (size_t)k * (size_t)max_bounce + stored, H2.px, H2.py, H2.pz, dx, dy, dz, incoming);
-                    stored++;
+            }
+        }
+        if (alive) {
+            // Trace(r, &rootNode, hInfo); after the first segment into the SAME HitInfo: its z still holds the previous
+            // segment's length, so only nearer hits are found (SURVEY A-16)
+            tl.trace++;
+            if (!scene_hit<false>(S, ray, B, tl, false)) alive = false;
+            else {
+                finalize_hit(S, ray, B, H); // serves the store below and the next round's bounce
+                if (first) {
+                    flag = 0x80u; // photonFromLight++ (RenderFunctions.cpp:357)
+                    outgoing = mk(L.I[0], L.I[1], L.I[2]);
+                    first = false;
+                    if (max_bounce <= 0) alive = false;
+                } else {
+                    const int mtl = __ldg(&S.nodes[B.node].material);
+                    if (mtl < 0) alive = false;
+                    else {
+                        const DMaterial &M2 = S.materials[mtl];
+                        if (gray(mk(M2.diffuse.c[0], M2.diffuse.c[1], M2.diffuse.c[2])) > 0.f) { // IsPhotonSurface (materials.h:48)
+                            float dx = ray.dx, dy = ray.dy, dz = ray.dz;
+                            norm3(dx, dy, dz);
+                            encode_photon(staging + (size_t)k * (size_t)max_bounce + stored, H.px, H.py, H.pz, dx, dy, dz, incoming);
+                            stored++;
+                        }
+                        if (++bounce >= max_bounce) alive = false;
+                    }
                 }
             }
         }
-        counts[k] = (unsigned char)(stored | flag);
+        if (was_alive && !alive) counts[k] = (unsigned char)(stored | flag);
     }
     // emission rays are booked with the primary class
     DCounterBlock *c = &counters->k[0];
