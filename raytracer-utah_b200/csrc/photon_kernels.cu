@@ -16,6 +16,10 @@
 #include "shade.cuh"
 #include "camera.cuh"
 
+#ifndef GATHER_STEPS
+#define GATHER_STEPS 8 // tree steps a lane may take before the warp turns to the heap updates
+#endif
+
 #define WAVE_THREADS_PHOTON 256
 
 #define PHOTON_K 100 // photonSampleSize (RenderFunctions.cpp:33)
@@ -61,26 +65,33 @@ struct Gather {
     int found;
 };
 
-// LocatePhotons's per-node part (cyPhotonMap.h:368-423)
-__device__ __forceinline__ void gather_visit(const rtu_photon *map, int index, float qx, float qy, float qz, bool has_n, float nx,
-                                             float ny, float nz, float norm_scale, Gather &G)
+// LocatePhotons's per-node part (cyPhotonMap.h:368-423), in two halves so that the lanes of a warp can run the second one
+// together: gather_test() decides whether photon `index` enters the heap (and with which squared distance),
+// gather_insert() is the heap update.
+__device__ __forceinline__ bool gather_test(const rtu_photon *map, int index, float qx, float qy, float qz, bool has_n, float nx,
+                                            float ny, float nz, float norm_scale, const Gather &G, float &dist2)
 {
     const PhotonRec p = load_photon(map, index);
     float fx = p.x - qx, fy = p.y - qy, fz = p.z - qz;
-    float dist2 = dot3(fx, fy, fz, fx, fy, fz);
-    if (!(dist2 < G.d2[0])) return;
+    dist2 = dot3(fx, fy, fz, fx, fy, fz);
+    if (!(dist2 < G.d2[0])) return false;
     if (has_n) {
         float dx, dy, dz;
         photon_direction(p, dx, dy, dz);
-        if (dot3(dx, dy, dz, nx, ny, nz) >= 0.f) return;
+        if (dot3(dx, dy, dz, nx, ny, nz) >= 0.f) return false;
         if (norm_scale > 0.f) {
             float perp = dot3(fx, fy, fz, nx, ny, nz);
             float s = perp * norm_scale;
             fx = fx + nx * s; fy = fy + ny * s; fz = fz + nz * s;
             dist2 = dot3(fx, fy, fz, fx, fy, fz);
-            if (dist2 >= G.d2[0]) return;
+            if (dist2 >= G.d2[0]) return false;
         }
     }
+    return true;
+}
+
+__device__ __forceinline__ void gather_insert(int index, float dist2, Gather &G)
+{
     if (G.found < PHOTON_K) {
         G.found++;
         G.d2[G.found] = dist2;
@@ -134,36 +145,49 @@ __device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx,
         int top = 0;
         frame[0] = 1u;
         fdist[0] = 0.f;
-        while (top >= 0) {
-            unsigned f = frame[top];
-            int index = (int)(f & 0x0fffffffu);
-            unsigned state = f >> 28;
-            if (state == 0) {
-                if (index < PM.half) {
-                    const PhotonRec p = load_photon(PM.map, index);
-                    unsigned axis = (p.packed0 >> 24) & 0x3u;
-                    float dist = (axis == 0 ? qx : (axis == 1 ? qy : qz)) - (axis == 0 ? p.x : (axis == 1 ? p.y : p.z));
-                    fdist[top] = dist;
-                    frame[top] = (unsigned)index | (1u << 28);
-                    int near_child = dist > 0 ? 2 * index + 1 : 2 * index;
-                    top++;
-                    frame[top] = (unsigned)near_child;
-                    continue;
+        // Lanes walk until they hold a photon that enters the heap (at most GATHER_STEPS tree steps per round), then the
+        // lanes that hold one update their heaps side by side; each lane still sees its photons in LocatePhotons order.
+        bool pending = false;
+        int pidx = 0;
+        float pd2 = 0.f;
+        while (top >= 0 || pending) {
+#pragma unroll 1
+            for (int step = 0; step < GATHER_STEPS && top >= 0 && !pending; step++) {
+                unsigned f = frame[top];
+                int index = (int)(f & 0x0fffffffu);
+                unsigned state = f >> 28;
+                if (state == 0) {
+                    if (index < PM.half) {
+                        const PhotonRec p = load_photon(PM.map, index);
+                        unsigned axis = (p.packed0 >> 24) & 0x3u;
+                        float dist = (axis == 0 ? qx : (axis == 1 ? qy : qz)) - (axis == 0 ? p.x : (axis == 1 ? p.y : p.z));
+                        fdist[top] = dist;
+                        frame[top] = (unsigned)index | (1u << 28);
+                        int near_child = dist > 0 ? 2 * index + 1 : 2 * index;
+                        top++;
+                        frame[top] = (unsigned)near_child;
+                        continue;
+                    }
+                    state = 2;
                 }
-                state = 2;
-            }
-            if (state == 1) {
-                float dist = fdist[top];
-                frame[top] = (unsigned)index | (2u << 28);
-                if (dist * dist < G.d2[0]) {
-                    int far_child = dist > 0 ? 2 * index : 2 * index + 1;
-                    top++;
-                    frame[top] = (unsigned)far_child;
-                    continue;
+                if (state == 1) {
+                    float dist = fdist[top];
+                    frame[top] = (unsigned)index | (2u << 28);
+                    if (dist * dist < G.d2[0]) {
+                        int far_child = dist > 0 ? 2 * index : 2 * index + 1;
+                        top++;
+                        frame[top] = (unsigned)far_child;
+                        continue;
+                    }
                 }
+                pending = gather_test(PM.map, index, qx, qy, qz, has_n, nx, ny, nz, norm_scale, G, pd2);
+                pidx = index;
+                top--;
             }
-            gather_visit(PM.map, index, qx, qy, qz, has_n, nx, ny, nz, norm_scale, G);
-            top--;
+            if (pending) {
+                gather_insert(pidx, pd2, G);
+                pending = false;
+            }
         }
     }
     irrad = mk(0, 0, 0);
