@@ -16,6 +16,14 @@
 #include "shade.cuh"
 #include "camera.cuh"
 
+#ifndef PGATHER_MIN_CTAS
+#define PGATHER_MIN_CTAS 16 // same for k_photon_gather (final gathering traces its sample rays in the kernel)
+#endif
+
+#ifndef GATHER_MIN_CTAS
+#define GATHER_MIN_CTAS 16 // resident 128-thread CTAs per SM the estimate kernels are compiled for
+#endif
+
 #ifndef GATHER_STEPS
 #define GATHER_STEPS 8 // tree steps a lane may take before the warp turns to the heap updates
 #endif
@@ -213,7 +221,7 @@ __device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx,
     found = G.found;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, GATHER_MIN_CTAS)
 k_estimate(DPhotonMap PM, const float *pos, const float *normal, long long n, float radius, float norm_scale, float *irrad,
            float *direction, int *found)
 {
@@ -263,7 +271,7 @@ __device__ __forceinline__ Col photon_mapping(const DScene &S, const DPhotonMap 
 }
 
 // RTU_MODE_PHOTON: PhotonMapping per primary hit of the hit queue.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, GATHER_MIN_CTAS)
 k_photon_shade(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float4 *accum)
 {
     unsigned total = *hq.count;
@@ -295,7 +303,7 @@ k_photon_shade(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float
 // Whitted radiance the other kernels produce.  Up to gi_bounces cosine samples of the hemisphere of the SAME first hit; the
 // HitInfo of the sample rays is never reset, so a later sample only finds what is nearer than the previous sample's hit;
 // a sample that finds nothing adds the background and ends the loop; the sum is divided by the samples taken.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PGATHER_MIN_CTAS)
 k_photon_gather(DScene S, FrameSetup F, int s0, HitQueue hq, DPhotonMap PM, float4 *accum, DCounters *counters)
 {
     Tally tl = {0, 0, 0, 0, 0};
