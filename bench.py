@@ -33,7 +33,7 @@ MODE = "whitted"
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # dram bytes per launch of the dominant kernel from profiles/ (ncu --set full); None until captured
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 1142886000  # dram read+write of the wave-0 k_shadow_wave launch of a 64-spp frame (profiles/r01_final_ncu_summary.txt)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1144421000  # dram read+write of the wave-0 k_shadow_wave launch of a 64-spp frame (profiles/r01_final_ncu_summary.txt)
 
 
 def measured_peaks():
