@@ -326,7 +326,7 @@ def test_path_mode_matches_reference_head_render(rtu, gpu_ctx, tag):
         hs.close()
 
 
-@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "spheres_1000", "dupmesh"])
+@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "spheres_1000", "dupmesh", "manymtl"])
 def test_synthetic_scenes(rtu, gpu_ctx, name):
     """SURVEY section 8d shapes: a 1 M-triangle mesh (707 640-node BVH) and flat lists of 100 / 1000 spheres with
     mirrors and glass; expectations from the unmodified reference on the same generated files."""

@@ -113,7 +113,7 @@ def test_path_mode_matches_reference_head_render(rtu, oracle, tag):
     assert np.abs(a - b).mean() < 2.5
 
 
-@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "dupmesh"])
+@pytest.mark.parametrize("name", ["grid1M", "spheres_100", "dupmesh", "manymtl"])
 def test_synthetic_scenes_match_reference(rtu, oracle, name):
     """The section-8d generated scenes (1 M-triangle mesh through our OBJ loader + BVH builder; flat sphere lists)."""
     from conftest import synthetic_scene

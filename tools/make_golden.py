@@ -65,7 +65,7 @@ FULL = {
 LOADER = ["Project1Example.xml", "Project4.xml", "Project5/scene.xml", "Project7/scene.xml", "Project9/scene.xml",
           "Project10/scene.xml", "Project11/scene_86.xml", "Project13/scene.xml", "Teapot/scene.xml", "Teapot/scene2.xml"]
 # generated scenes of section 8d (tools/make_synthetic.py): 1 M-triangle mesh, flat lists of spheres
-SYNTHETIC = {"grid1M": (240, 135), "spheres_100": (240, 135), "spheres_1000": (240, 135), "dupmesh": (480, 270)}
+SYNTHETIC = {"grid1M": (240, 135), "spheres_100": (240, 135), "spheres_1000": (240, 135), "dupmesh": (480, 270), "manymtl": (240, 135)}
 TEX = {"Project7/scene.xml": "p7", "Project9/scene.xml": "p9", "Project10/scene.xml": "p10"}
 
 

@@ -146,6 +146,34 @@ def write_spheres(path, n, w=1920, h=1080):
         f.write("  </scene>\n" + CAMERA % dict(dist=34, height=12, w=w, h=h) + "</xml>\n")
 
 
+def write_manymtl(path, n_mtl=48, n_light=24, w=1920, h=1080):
+    """More lights and materials than the shading kernel stages in shared memory (16 / 32): 96 spheres over a floor,
+    every sphere with its own Blinn material (every fifth a mirror, every seventh glass), point lights on a ring."""
+    rng = np.random.default_rng(SEED + 4242)
+    with open(path, "w") as f:
+        f.write("<xml>\n  <scene>\n    <background r=\"0.05\" g=\"0.06\" b=\"0.09\"/>\n    <environment value=\"0.2\"/>\n")
+        f.write("    <object type=\"plane\" name=\"floor\" material=\"m0\"><scale value=\"40\"/><translate z=\"-6\"/></object>\n")
+        for i in range(96):
+            c = rng.uniform(-8, 8, 3)
+            f.write("    <object type=\"sphere\" name=\"s%d\" material=\"m%d\"><scale value=\"%.4f\"/><translate x=\"%.4f\" y=\"%.4f\" z=\"%.4f\"/></object>\n"
+                    % (i, i % n_mtl, rng.uniform(0.6, 1.4), c[0], c[1], c[2] * 0.6))
+        for i in range(n_mtl):
+            d = rng.uniform(0.1, 0.9, 3)
+            f.write("    <material type=\"blinn\" name=\"m%d\">\n      <diffuse r=\"%.3f\" g=\"%.3f\" b=\"%.3f\"/>\n      <specular value=\"%.3f\"/>\n      <glossiness value=\"%d\"/>\n"
+                    % (i, d[0], d[1], d[2], rng.uniform(0.1, 0.8), int(rng.integers(5, 120))))
+            if i % 5 == 3:
+                f.write("      <reflection value=\"%.3f\"/>\n" % rng.uniform(0.3, 0.8))
+            if i % 7 == 5:
+                f.write("      <refraction index=\"%.3f\" value=\"%.3f\"/>\n" % (rng.uniform(1.2, 1.8), rng.uniform(0.4, 0.8)))
+            f.write("    </material>\n")
+        f.write("    <light type=\"ambient\" name=\"amb\"><intensity value=\"0.1\"/></light>\n")
+        for i in range(n_light - 1):
+            a = 2 * np.pi * i / (n_light - 1)
+            f.write("    <light type=\"point\" name=\"l%d\"><intensity value=\"%.3f\"/><position x=\"%.4f\" y=\"%.4f\" z=\"%.4f\"/></light>\n"
+                    % (i, rng.uniform(30, 80), 14 * np.cos(a), 14 * np.sin(a), rng.uniform(8, 16)))
+        f.write("  </scene>\n" + CAMERA % dict(dist=34, height=12, w=w, h=h) + "</xml>\n")
+
+
 def ensure(names=("grid1M", "spheres_100", "spheres_1000", "spheres_10000")):
     """Creates the requested synthetic scenes if missing; returns {name: xml path relative to scenes/}."""
     os.makedirs(OUT, exist_ok=True)
@@ -158,6 +186,9 @@ def ensure(names=("grid1M", "spheres_100", "spheres_1000", "spheres_10000")):
                 {"grid1M": write_grid, "soup1M": write_soup, "dupmesh": write_dupmesh}[n](obj)
             if not os.path.exists(xml):
                 write_mesh_scene(xml, n + ".obj", 3840, 2160, 22 if n != "soup1M" else 40, 12)
+        elif n == "manymtl":
+            if not os.path.exists(xml):
+                write_manymtl(xml)
         elif n.startswith("spheres_"):
             if not os.path.exists(xml):
                 write_spheres(xml, int(n.split("_")[1]))
