@@ -99,15 +99,25 @@ __device__ __forceinline__ void extend_finish(const DScene &S, const FrameSetup 
     }
 }
 
-// A tile none of whose camera rays can reach any object (FrameSetup::tile_empty): the ray is not built at all; it books
-// what Trace() books for a ray whose every node fails its bound-box gate, and adds the background (RenderFunctions.cpp:145).
+// A tile none of whose camera rays can reach any object (FrameSetup::tile_empty): no ray is built.  The work item of the
+// chunk's FIRST sample does the tile's pixel for all `ns` samples of the chunk: it books what Trace() books for rays whose every
+// node fails its bound-box gate and adds the background (RenderFunctions.cpp:145; a function of the pixel only) once per
+// sample, in order, like the reference's sample loop; the items of the other samples return at once.  Nobody else touches the
+// accumulator of such a pixel while the primary wave runs, so the sum is kept in registers (no atomics, one texture fetch).
 __device__ __forceinline__ void primary_miss_fast(const DScene &S, const FrameSetup &F, const PrimaryMap &pm, float4 *accum, int x,
-                                                  int y, Tally &tl)
+                                                  int y, int s, int s0, int ns, Tally &tl)
 {
-    tl.trace++;
-    tl.node += F.n_obj;
-    tl.box += F.n_obj;
-    accum_add(accum, y * pm.W + x, background_sample(S, x, y, pm.W, F.cam.height));
+    if (s != s0) return;
+    tl.trace += (unsigned)ns;
+    tl.node += (unsigned)(ns * F.n_obj);
+    tl.box += (unsigned)(ns * F.n_obj);
+    const Col c = background_sample(S, x, y, pm.W, F.cam.height);
+    float4 a = accum[y * pm.W + x];
+#pragma unroll 1
+    for (int i = 0; i < ns; i++) {
+        a.x += c.r; a.y += c.g; a.z += c.b;
+    }
+    accum[y * pm.W + x] = a;
 }
 
 // ------------------------------------------------------------------ closest hit
@@ -140,7 +150,7 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         if (PRIMARY) {
             int s;
             if (!pm.decode(idx, s0, s, x, y)) continue;
-            if (F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, tl); continue; }
+            if (F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl); continue; }
             pixel = y * pm.W + x;
             ray = primary_ray(F, s, x, y, pixel);
         } else {
@@ -420,7 +430,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 have = pm.decode(idx, s0, s, x, y);
                 pixel = y * pm.W + x;
                 if (have && i0 == 1 && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { // warp-uniform: a ticket is one tile
-                    primary_miss_fast(S, F, pm, accum, x, y, tl);
+                    primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl);
                     have = false;
                 }
                 if (have) ray = primary_ray(F, s, x, y, pixel);
@@ -1219,7 +1229,7 @@ k_extend_top(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux,
             if (PRIMARY) {
                 int s;
                 have = pm.decode(idx, s0, s, x, y);
-                if (have && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, tl); have = false; }
+                if (have && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl); have = false; }
                 pixel = y * pm.W + x;
                 if (have) ray = primary_ray(F, s, x, y, pixel);
             } else {
