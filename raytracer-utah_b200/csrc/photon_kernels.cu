@@ -67,11 +67,24 @@ __device__ __forceinline__ void photon_direction(const PhotonRec &p, float &dx, 
     if ((p.packed0 >> 24) & 0x8u) dz = -dz;
 }
 
-struct Gather {
-    float d2[PHOTON_K + 1];
-    int idx[PHOTON_K + 1];
-    int found;
+// The reference's heap arrays dist2[] / index[] as one array of (distance, photon) pairs: the two children of a heap slot
+// are 16 adjacent, aligned bytes, so a sift step is ONE 128-bit local-memory load instead of two dependent round trips
+// (distances, then the index to move).  r2 = the current search radius^2 (the reference's maxDist2, its slot 0).
+struct __align__(8) HeapEnt {
+    float d2;
+    int idx;
 };
+struct Gather {
+    __align__(16) HeapEnt e[PHOTON_K + 2]; // slots 1..PHOTON_K; slot PHOTON_K+1 is only ever loaded, never used
+    int found;
+    float r2;
+};
+__device__ __forceinline__ void heap_children(const Gather &G, int j, HeapEnt &a, HeapEnt &b)
+{
+    const float4 v = *reinterpret_cast<const float4 *>(&G.e[j]); // j is even
+    a.d2 = v.x; a.idx = __float_as_int(v.y);
+    b.d2 = v.z; b.idx = __float_as_int(v.w);
+}
 
 // LocatePhotons's per-node part (cyPhotonMap.h:368-423), in two halves so that the lanes of a warp can run the second one
 // together: gather_test() decides whether photon `index` enters the heap (and with which squared distance),
@@ -82,7 +95,7 @@ __device__ __forceinline__ bool gather_test(const rtu_photon *map, int index, fl
     const PhotonRec p = load_photon(map, index);
     float fx = p.x - qx, fy = p.y - qy, fz = p.z - qz;
     dist2 = dot3(fx, fy, fz, fx, fy, fz);
-    if (!(dist2 < G.d2[0])) return false;
+    if (!(dist2 < G.r2)) return false;
     if (has_n) {
         float dx, dy, dz;
         photon_direction(p, dx, dy, dz);
@@ -92,7 +105,7 @@ __device__ __forceinline__ bool gather_test(const rtu_photon *map, int index, fl
             float s = perp * norm_scale;
             fx = fx + nx * s; fy = fy + ny * s; fz = fz + nz * s;
             dist2 = dot3(fx, fy, fz, fx, fy, fz);
-            if (dist2 >= G.d2[0]) return false;
+            if (dist2 >= G.r2) return false;
         }
     }
     return true;
@@ -102,39 +115,41 @@ __device__ __forceinline__ void gather_insert(int index, float dist2, Gather &G)
 {
     if (G.found < PHOTON_K) {
         G.found++;
-        G.d2[G.found] = dist2;
-        G.idx[G.found] = index;
+        G.e[G.found].d2 = dist2;
+        G.e[G.found].idx = index;
         if (G.found == PHOTON_K) { // build the max-heap (:385-401)
-            const int half = G.found >> 1;
+            const int half = PHOTON_K >> 1;
             for (int k = half; k >= 1; k--) {
                 int parent = k;
-                int ti = G.idx[k];
-                float td = G.d2[k];
+                const HeapEnt t = G.e[k];
                 while (parent <= half) {
                     int j = parent + parent;
-                    if (j < G.found && G.d2[j] < G.d2[j + 1]) j++;
-                    if (td >= G.d2[j]) break;
-                    G.d2[parent] = G.d2[j];
-                    G.idx[parent] = G.idx[j];
+                    HeapEnt a, b;
+                    heap_children(G, j, a, b);
+                    if (j < PHOTON_K && a.d2 < b.d2) { j++; a = b; }
+                    if (t.d2 >= a.d2) break;
+                    G.e[parent] = a;
                     parent = j;
                 }
-                G.idx[parent] = ti;
-                G.d2[parent] = td;
+                G.e[parent] = t;
             }
         }
     } else { // replace the farthest (:403-418)
         int parent = 1, j = 2;
-        while (j <= G.found) {
-            if (j < G.found && G.d2[j] < G.d2[j + 1]) j++;
-            if (dist2 > G.d2[j]) break;
-            G.d2[parent] = G.d2[j];
-            G.idx[parent] = G.idx[j];
+        float top = dist2; // what ends up in slot 1
+        while (j <= PHOTON_K) {
+            HeapEnt a, b;
+            heap_children(G, j, a, b);
+            if (j < PHOTON_K && a.d2 < b.d2) { j++; a = b; }
+            if (dist2 > a.d2) break;
+            G.e[parent] = a;
+            if (parent == 1) top = a.d2;
             parent = j;
             j <<= 1;
         }
-        G.idx[parent] = index;
-        G.d2[parent] = dist2;
-        G.d2[0] = G.d2[1];
+        G.e[parent].idx = index;
+        G.e[parent].d2 = dist2;
+        G.r2 = top; // maxDist2 = dist2[1]
     }
 }
 
@@ -145,7 +160,7 @@ __device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx,
 {
     Gather G;
     G.found = 0;
-    G.d2[0] = radius * radius;
+    G.r2 = radius * radius;
     if (PM.n > 0) {
         // explicit form of the recursion: frame = node | state << 28; state 0 = entered, 1 = near child done, 2 = both done
         unsigned frame[32];
@@ -181,7 +196,7 @@ __device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx,
                 if (state == 1) {
                     float dist = fdist[top];
                     frame[top] = (unsigned)index | (2u << 28);
-                    if (dist * dist < G.d2[0]) {
+                    if (dist * dist < G.r2) {
                         int far_child = dist > 0 ? 2 * index : 2 * index + 1;
                         top++;
                         frame[top] = (unsigned)far_child;
@@ -201,7 +216,7 @@ __device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx,
     irrad = mk(0, 0, 0);
     ox = oy = oz = 0.f;
     for (int i = 1; i <= G.found; i++) {
-        const PhotonRec p = load_photon(PM.map, G.idx[i]);
+        const PhotonRec p = load_photon(PM.map, G.e[i].idx);
         Col pw = mk((float)(p.packed0 & 0xffu) / 255.0f, (float)((p.packed0 >> 8) & 0xffu) / 255.0f, (float)((p.packed0 >> 16) & 0xffu) / 255.0f) * p.power;
         const float filter = 1.f;
         irrad = irrad + pw * filter;
@@ -211,7 +226,7 @@ __device__ __noinline__ void estimate_irradiance(const DPhotonMap &PM, float qx,
         ox = ox + dx * w; oy = oy + dy * w; oz = oz + dz * w;
     }
     if (G.found > 0) {
-        float area = 3.14159274101257324f * G.d2[0]; // (float)M_PI
+        float area = 3.14159274101257324f * G.r2; // (float)M_PI
         if (area > 0.f) {
             const float inv = 1.0f / area;
             irrad = irrad * inv;
