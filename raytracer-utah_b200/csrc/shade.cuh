@@ -272,7 +272,7 @@ struct ShadeParams {
 //           with unit intensity; the caller multiplies the accumulated factor by its intensity later.
 __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P, const WaveOut &O, float dirx, float diry,
                                           float dirz, const HitRec &H, Col Wt, int bounce, int pixel, unsigned path,
-                                          int tree = 0)
+                                          int tree = 0, bool fresh_slot = false)
 {
     if (H.material < 0) { // node without material: the reference would dereference NULL
         accum_add(O.accum, pixel, Wt);
@@ -364,7 +364,15 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
             }
         }
     }
-    accum_add(O.accum, pixel, local * Wt);
+    if (fresh_slot) {
+        // a GI vertex's own slot still holds the zeros it was opened with (its shadow rays and child rays come later):
+        // 0 + v = v, so the sum is stored; an atomic here would be a DRAM read-modify-write, the record left L2 waves ago
+        const Col v = local * Wt;
+        float *a = reinterpret_cast<float *>(O.accum + pixel);
+        a[0] = v.r; a[1] = v.g; a[2] = v.b;
+    } else {
+        accum_add(O.accum, pixel, local * Wt);
+    }
 
     if (bounce <= 0) return;
     Col Kt = texcolor_sample(S, M.refraction, H.u, H.v, H.w);
