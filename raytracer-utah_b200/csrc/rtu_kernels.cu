@@ -526,11 +526,13 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
     __shared__ DMaterial s_materials[SHADE_SMEM_MATERIALS];
     if (S.n_lights <= SHADE_SMEM_LIGHTS) {
         const int words = S.n_lights * (int)(sizeof(DLight) / 4);
+#pragma unroll 1
         for (int i = threadIdx.x; i < words; i += WAVE_THREADS) ((unsigned *)s_lights)[i] = ((const unsigned *)S.lights)[i];
         S.lights = s_lights;
     }
     if (S.n_materials <= SHADE_SMEM_MATERIALS) {
         const int words = S.n_materials * (int)(sizeof(DMaterial) / 4);
+#pragma unroll 1
         for (int i = threadIdx.x; i < words; i += WAVE_THREADS) ((unsigned *)s_materials)[i] = ((const unsigned *)S.materials)[i];
         S.materials = s_materials;
     }
