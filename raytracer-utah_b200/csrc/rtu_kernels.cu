@@ -501,9 +501,6 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
 #ifndef SHADE_BLOCKS
 #define SHADE_BLOCKS 3 // resident CTAs per SM of the shading kernel (80 registers; measured best of 2/3/4 over Teapot, Project10, Project11)
 #endif
-#ifndef SHADE_FRESH_STORE
-#define SHADE_FRESH_STORE 1
-#endif
 #define SHADE_SMEM_LIGHTS 16     // scenes with no more lights / materials than this shade out of shared-memory copies
 #define SHADE_SMEM_MATERIALS 32
 template <bool PRIMARY>
@@ -591,7 +588,8 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             k = kind == RK_PRIMARY ? 0 : gidepth;
             if (kind == RK_PRIMARY) {
                 rec = (int)h * (gi_end + 1);
-                for (int j = 0; j <= gi_end; j++) O.accum[rec + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // no zero fill: every vertex stores both of its slots when it is shaded (fresh_slot), k_gi_combine reads the
+                // slots of shaded vertices only, and the End slot is always written (terminal vertex or missed sample ray)
                 O.accum[rec].w = __int_as_float(pixel);
             } else {
                 rec = pixel;
@@ -633,7 +631,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             const int sb = gi ? F.shade_bounces : bounce;
             const int target = gi ? rec + 2 * k + (t ? 0 : 1) : pixel;
             const unsigned sp = gi ? child_path(path, 8u + (unsigned)t) : path;
-            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, w, sb, target, sp, gi ? t : tree, SHADE_FRESH_STORE && gi);
+            shade_hit(S, SP, O, ray.dx, ray.dy, ray.dz, H, w, sb, target, sp, gi ? t : tree, gi);
         }
         if (gi) {
             if (gi_ray) {

@@ -275,7 +275,12 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
                                           int tree = 0, bool fresh_slot = false)
 {
     if (H.material < 0) { // node without material: the reference would dereference NULL
-        accum_add(O.accum, pixel, Wt);
+        if (fresh_slot) {
+            float *a = reinterpret_cast<float *>(O.accum + pixel);
+            a[0] = Wt.r; a[1] = Wt.g; a[2] = Wt.b;
+        } else {
+            accum_add(O.accum, pixel, Wt);
+        }
         return;
     }
     const DMaterial &M = S.materials[H.material];
