@@ -1075,7 +1075,7 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
     const bool path_mode = F.mode == RTU_MODE_PATH;
     float4 *target = accum; // the array ray slots index: pixels, or GI records folded into pixels per chunk
     if (path_mode) {
-        if ((rc = ensure_gi(c, (size_t)c->wb.hits.cap * (size_t)(2 * (F.gi_bounces + 1) + 1)))) return rc;
+        if ((rc = ensure_gi(c, (size_t)c->wb.hits.cap * (size_t)(2 * (F.gi_bounces + 1) + 2)))) return rc;
         target = c->gi;
     }
     CU(cudaEventRecord(c->ev0, c->stream));

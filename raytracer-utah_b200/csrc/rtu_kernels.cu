@@ -587,7 +587,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             // k_gi_combine once all waves are done: L_k = D_k + A_k * L_{k+1}.
             k = kind == RK_PRIMARY ? 0 : gidepth;
             if (kind == RK_PRIMARY) {
-                rec = (int)h * (gi_end + 1);
+                rec = (int)h * (gi_end + 2); // stride kept even: a vertex's two slots are one aligned 32-byte sector
                 // no zero fill: every vertex stores both of its slots when it is shaded (fresh_slot), k_gi_combine reads the
                 // slots of shaded vertices only, and the End slot is always written (terminal vertex or missed sample ray)
                 O.accum[rec].w = __int_as_float(pixel);
@@ -1519,7 +1519,7 @@ __global__ void k_gi_combine(const float4 *gi, const unsigned *count, unsigned c
     if (n > cap) n = cap;
     const int end_slot = 2 * (gi_bounces + 1);
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const float4 *rec = gi + (size_t)r * (end_slot + 1);
+        const float4 *rec = gi + (size_t)r * (end_slot + 2);
         float4 e = rec[end_slot];
         int end = (int)e.w;
         if (end > gi_bounces + 1) end = gi_bounces + 1;
