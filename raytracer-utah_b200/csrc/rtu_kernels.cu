@@ -590,7 +590,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
                 rec = (int)h * (gi_end + 2); // stride kept even: a vertex's two slots are one aligned 32-byte sector
                 // no zero fill: every vertex stores both of its slots when it is shaded (fresh_slot), k_gi_combine reads the
                 // slots of shaded vertices only, and the End slot is always written (terminal vertex or missed sample ray)
-                O.accum[rec].w = __int_as_float(pixel);
+                O.accum[rec + gi_end + 1] = make_float4(__int_as_float(pixel), 0.f, 0.f, 0.f); // the record's pixel, in its pad slot
             } else {
                 rec = pixel;
             }
@@ -1528,7 +1528,7 @@ __global__ void k_gi_combine(const float4 *gi, const unsigned *count, unsigned c
             float4 a = rec[2 * k], d = rec[2 * k + 1];
             L = mk(d.x, d.y, d.z) + mk(a.x, a.y, a.z) * L;
         }
-        accum_add(accum, __float_as_int(rec[0].w), L);
+        accum_add(accum, __float_as_int(rec[end_slot + 1].x), L);
     }
 }
 

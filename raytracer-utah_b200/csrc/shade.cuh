@@ -7,6 +7,10 @@
 // (directions, origins) is evaluated with the reference's operation order so that secondary
 // rays hit the same primitives; colour factors are within float rounding of the reference.
 #pragma once
+#ifndef ACCUM_VECTOR_RED
+#define ACCUM_VECTOR_RED 1
+#endif
+
 #include "intersect.cuh"
 
 struct Col {
@@ -199,12 +203,19 @@ struct WaveOut {
     DCounters *counters;
 };
 
+// One 16-byte vector reduction per contribution (red.global.add.v4.f32) instead of three scalar ones: a third of the L2
+// atomic traffic.  The .w lane only ever receives +0: no accumulator keeps anything but zero there (the pixel index of a GI
+// record lives in the record's last slot, which is never added to).
 __device__ __forceinline__ void accum_add(float4 *accum, int pixel, Col c)
 {
+#if ACCUM_VECTOR_RED
+    if (c.r != 0.f || c.g != 0.f || c.b != 0.f) atomicAdd(accum + pixel, make_float4(c.r, c.g, c.b, 0.f));
+#else
     float *a = reinterpret_cast<float *>(accum + pixel);
     if (c.r != 0.f) atomicAdd(a, c.r);
     if (c.g != 0.f) atomicAdd(a + 1, c.g);
     if (c.b != 0.f) atomicAdd(a + 2, c.b);
+#endif
 }
 
 // ray meta word: kind (3 bits) | bounceCount left (4) | tree (1) | GI depth (3) | parent material (21)
@@ -276,8 +287,7 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
 {
     if (H.material < 0) { // node without material: the reference would dereference NULL
         if (fresh_slot) {
-            float *a = reinterpret_cast<float *>(O.accum + pixel);
-            a[0] = Wt.r; a[1] = Wt.g; a[2] = Wt.b;
+            O.accum[pixel] = make_float4(Wt.r, Wt.g, Wt.b, 0.f);
         } else {
             accum_add(O.accum, pixel, Wt);
         }
@@ -373,8 +383,7 @@ __device__ __forceinline__ void shade_hit(const DScene &S, const ShadeParams &P,
         // a GI vertex's own slot still holds the zeros it was opened with (its shadow rays and child rays come later):
         // 0 + v = v, so the sum is stored; an atomic here would be a DRAM read-modify-write, the record left L2 waves ago
         const Col v = local * Wt;
-        float *a = reinterpret_cast<float *>(O.accum + pixel);
-        a[0] = v.r; a[1] = v.g; a[2] = v.b;
+        O.accum[pixel] = make_float4(v.r, v.g, v.b, 0.f);
     } else {
         accum_add(O.accum, pixel, local * Wt);
     }
