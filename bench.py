@@ -65,9 +65,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_alive(self, timeout=5.0):
+        """nvidia-smi can take most of a second to print its first row: block until it has, so that a short timed
+        region is not over before the sampler runs."""
+        t0 = time.monotonic()
+        while self.proc and not self.rows and time.monotonic() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        return time.monotonic()
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,8 +85,12 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
+        window = "timed region"
+        if not rows:  # nothing fell inside the window: report what was sampled under the warm-up load instead
+            rows, window = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -86,7 +100,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def _mode_id(R):
@@ -206,25 +220,29 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so that it is certainly printing when the timed region begins
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    if rank == 0:
+        sampler.wait_alive()
     st = sc.stats()
     rays_rank = st["trace_rays"] + st["shadow_rays"]
     launches_step = st["kernel_launches"]
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_begin = sampler.mark()
     for a, b in ev:
         flush.zero_()          # L2 flush, outside the timed bracket
         a.record()
         step()
         b.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = sampler.mark()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms_total, float(rays_rank)], dtype=torch.float64, device="cuda")
     if world > 1:
