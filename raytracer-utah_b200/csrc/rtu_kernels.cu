@@ -513,7 +513,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
     unsigned total = *hq.count;
     if (total > hq.cap) total = hq.cap;
     const bool path_mode = F.mode == RTU_MODE_PATH;
-    const int gi_end = 2 * (F.gi_bounces + 1); // GI record: A_0, D_0, ..., A_K-1, D_K-1, End
+    const int gi_end = 2 * (F.gi_bounces + 1); // GI record: A_0, D_0, ..., A_K, D_K, End, pad (.x = pixel)
     if (PRIMARY && path_mode && blockIdx.x == 0 && threadIdx.x == 0) *gi_count = total; // one GI record per primary hit
     ShadeParams SP;
     SP.flags = F.flags;
