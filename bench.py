@@ -85,10 +85,15 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
+        return self.summarise(self.rows, t_begin, t_end)
+
+    @staticmethod
+    def summarise(stamped_rows, t_begin=None, t_end=None):
+        """Median SM clock, maximum clock and throttle reasons of the rows that arrived inside [t_begin, t_end]."""
+        rows = [r for t, r in stamped_rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
         window = "timed region"
         if not rows:  # nothing fell inside the window: report what was sampled under the warm-up load instead
-            rows, window = [r for _, r in self.rows], "warm-up + timed region"
+            rows, window = [r for _, r in stamped_rows], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:

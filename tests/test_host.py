@@ -209,3 +209,20 @@ def test_photon_direction_integer_sqrt_shortcut():
         while (z + 1) * (z + 1) <= v:
             z += 1
         assert z == bitwise(v), x
+
+
+def test_bench_clock_sampler_window():
+    """bench.py keeps the nvidia-smi rows that arrived during the timed region; if the region was too short to catch
+    one, the rows of the warm-up load are reported and labelled as such."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700.0", "0x0", "Not Active", "Not Active", "Not Active", cap]
+    rows = [(1.0, row(900, "Not Active")), (2.0, row(1965, "Not Active")), (2.1, row(1950, "Active")), (3.5, row(800, "Not Active"))]
+    inside = bench.ClockSampler.summarise(rows, 1.9, 2.2)
+    assert inside["samples"] == 2 and inside["sm_mhz"] == 1957.5 and inside["sm_max_mhz"] == 1965.0
+    assert inside["reasons"] == ["sw_power_cap"] and inside["window"] == "timed region"
+    missed = bench.ClockSampler.summarise(rows, 5.0, 5.1)
+    assert missed["samples"] == 4 and missed["window"] == "warm-up + timed region"
+    assert bench.ClockSampler.summarise([], 0.0, 1.0)["sm_mhz"] is None
