@@ -8,7 +8,9 @@
 //   k_extend_pool<queue>     same for the rays of the previous wave's queue (reflection / refraction / Fresnel / GI
 //                            rays); misses add the environment term their parent would have added
 //   k_shade<..>              one MtlBlinn::Shade step per compacted hit: evaluates the hit record, appends shadow rays
-//                            (radiance-if-unoccluded) and the next wave's secondary rays; GI records in RTU_MODE_PATH
+//                            (radiance-if-unoccluded) and the next wave's secondary rays; GI records in RTU_MODE_PATH.
+//                            One inlined shade_hit() site, CTA rounds of 256 hits behind a barrier (instruction cache),
+//                            lights / materials in shared memory, 3 CTAs per SM
 //   k_shadow_wave            any-hit (ShadowTrace) over the shadow queue with pooled mesh walks; adds the unoccluded
 //                            contributions to the accumulator
 //   k_extend / k_shadow_wave_simple      the same waves with one walk per lane (meshes beyond the pool's item encoding)
@@ -19,7 +21,8 @@
 // Traversal and shading are separate kernels so that the traversal kernels stay small (2 resident CTAs of 256 threads
 // per SM, measured best) and shading runs on dense warps of hits only.
 // Work distribution replaces PixelIterator's atomic ticket counter (PixelIterator.h:25-38): each warp takes 32
-// consecutive tickets from a global counter until the wave is drained.  Grids are SM-count multiples (148 x resident
+// consecutive tickets from a global counter until the wave is drained (256 per atomic in a primary wave whose tiles are
+// mostly empty, 256 per CTA in k_shade).  Grids are SM-count multiples (148 x resident
 // CTAs per SM, from the occupancy API); CTAs stay resident for the whole wave.
 #include <cstdio>
 #include <cstdlib>
