@@ -17,9 +17,22 @@ void set_error(const std::string &msg);
 
 namespace {
 
+// What the selection moves around: the position it compares and where the photon came from (16 bytes instead of the
+// 24-byte record: a third less memory traffic in the partition passes, which are all this build does).
+struct Item {
+    float position[3];
+    uint32_t src; // index into the caller's array
+};
+
 struct Balancer {
-    rtu_photon *work; // 1-based; partitioned in place
-    rtu_photon *out;              // 1-based heap order
+    Item *work;           // 1-based; partitioned in place
+    const rtu_photon *in; // the caller's photons (0-based)
+    rtu_photon *out;      // 1-based heap order
+    void place(int slot, const Item &it, int axis_bits)
+    {
+        out[slot] = in[it.src];
+        if (axis_bits >= 0) out[slot].plane_dirz = (uint8_t)((out[slot].plane_dirz & 0x8) | axis_bits);
+    }
 
     // Position of the median that leaves a complete left subtree (cyPhotonMap.h:233-241)
     static int median_of(int start, int end)
@@ -63,15 +76,14 @@ struct Balancer {
             axis = 1;
         }
         select(axis, start, end, median);
-        out[index] = work[median];
-        out[index].plane_dirz = (uint8_t)((out[index].plane_dirz & 0x8) | axis);
-        const float split = out[index].position[axis];
+        place(index, work[median], axis);
+        const float split = work[median].position[axis];
         float h2[3] = {hi[0], hi[1], hi[2]}, l2[3] = {lo[0], lo[1], lo[2]};
         h2[axis] = split;
         l2[axis] = split;
         const bool left_rec = median > start && start < median - 1, right_rec = median < end && median + 1 < end;
-        if (median > start && !left_rec) out[2 * index] = work[start];
-        if (median < end && !right_rec) out[2 * index + 1] = work[end];
+        if (median > start && !left_rec) place(2 * index, work[start], -1);
+        if (median < end && !right_rec) place(2 * index + 1, work[end], -1);
         if (left_rec && right_rec && fork_levels > 0 && end - start > 4096) {
             std::thread t([&]() { segment(lo, h2, 2 * index, start, median - 1, fork_levels - 1); });
             segment(l2, hi, 2 * index + 1, median + 1, end, fork_levels - 1);
@@ -92,9 +104,10 @@ extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_ph
     std::memset(out, 0, sizeof(rtu_photon)); // slot 0; every slot 1..n is assigned exactly once by the recursion
     if (n == 0) return RTU_OK;
     Balancer b;
-    std::unique_ptr<rtu_photon[]> work(new rtu_photon[(size_t)n + 1]); // not value-initialised: 24 MB less to write
+    std::unique_ptr<Item[]> work(new Item[(size_t)n + 1]); // not value-initialised
     b.work = work.get();
-    std::memset(&b.work[0], 0, sizeof(rtu_photon));
+    std::memset(&b.work[0], 0, sizeof(Item));
+    b.in = in;
     b.out = out;
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
@@ -107,11 +120,12 @@ extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_ph
         for (unsigned t = 0; t < slices; t++) {
             auto job = [&, t]() {
                 const size_t a = 1 + (size_t)n * t / slices, e = 1 + (size_t)n * (t + 1) / slices;
-                std::memcpy(&b.work[a], in + (a - 1), sizeof(rtu_photon) * (e - a));
                 float l[3] = {0, 0, 0}, h[3] = {0, 0, 0};
                 for (size_t i = a; i < e; i++)
                     for (int k = 0; k < 3; k++) {
-                        const float v = b.work[i].position[k];
+                        const float v = in[i - 1].position[k];
+                        b.work[i].position[k] = v;
+                        b.work[i].src = (uint32_t)(i - 1);
                         if (l[k] > v) l[k] = v;
                         if (h[k] < v) h[k] = v;
                     }
