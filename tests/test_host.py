@@ -188,6 +188,28 @@ def test_photon_map_balancing_matches_reference(rtu):
     assert rtu.balance_photons(pin[:0]).shape == (1,)
 
 
+def test_photon_map_balancing_sizes_and_ties(rtu):
+    """The threaded paths of rtu_host_balance_photons (sliced copy above 65 536 photons, forked subtrees above 4 096) and
+    its small cases against the C restatement (itself pinned on the reference's map above): photons on an axis-aligned
+    wall share one coordinate exactly, so medians fall on ties and the result depends on the reference's partition order."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as oracle  # the checker (tests/ may use it; the product may not)
+    oracle.lib()
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 3, 4, 5, 7, 8, 100, 4097, 70001):
+        ph = np.zeros(n, dtype=rtu.PHOTON_DTYPE)
+        ph["position"] = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+        ph["position"][: n // 2, 1] = 1.5
+        ph["power"] = rng.uniform(0, 1, n).astype(np.float32)
+        ph["plane_dirz"] = rng.integers(0, 16, n).astype(np.uint8)
+        ph["dir_x"] = rng.integers(-30000, 30000, n)
+        ph["dir_y"] = rng.integers(-30000, 30000, n)
+        ours = rtu.balance_photons(ph)
+        ref = oracle.balance_photons(ph.astype(oracle.PHOTON_DTYPE))
+        assert ours.tobytes() == ref.tobytes(), n
+
+
 def test_photon_direction_integer_sqrt_shortcut():
     """Photon::GetDirection (cyPhotonMap.h:166-178) takes floor(sqrt(0x3FFF0001 - dirX^2)) with a 16-round bitwise
     routine; the device code uses sqrtf plus a correction step.  Equal for every reachable argument."""
