@@ -239,6 +239,7 @@ static void ModeWhitted(const Opts &o)
     bool center = o.pattern == "center";
     int spp = o.spp;
     float pixelIncrement = 1.0 / spp;   // RenderFunctions.cpp:71
+    srand((unsigned)o.seed);            // the stochastic branches (soft lights, glossy lobes, lens) draw from rand(); Render() seeds by wall clock (:60)
     double t0 = Now();
     ParallelRows(y0, y1, o.threads, [&](int y, int tid) {
         for (int x = x0; x < x1; x++) {
@@ -251,7 +252,14 @@ static void ModeWhitted(const Opts &o)
                     ox = cur + Halton(s, 4);                   // :84,96
                     oy = cur + Halton(s, 5);                   // :85,96
                 }
-                Ray r = CameraRay(x, y, ox, oy, 0, 0);
+                float camOffsetX = 0, camOffsetY = 0;
+                if (camera.dof > 0) {                          // the lens sample of Render(), :88-91 (two rand() draws)
+                    float sampleX = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+                    float sampleTheta = static_cast<float>(rand()) / (static_cast<float>(RAND_MAX / (2 * M_PI)));
+                    camOffsetX = sqrt(sampleX * camera.dof * camera.dof) * cos(sampleTheta);
+                    camOffsetY = sqrt(sampleX * camera.dof * camera.dof) * sin(sampleTheta);
+                }
+                Ray r = CameraRay(x, y, ox, oy, camOffsetX, camOffsetY);
                 HitInfo h;
                 Color c(0.0, 0.0, 0.0);
                 if (Trace(r, &rootNode, h)) {

@@ -92,3 +92,40 @@ def synthetic_scene(name, meta):
         got = hashlib.sha256(open(os.path.join(SCENES, "synthetic", f), "rb").read()).hexdigest()
         assert got == want, "generated %s differs from the one the fixture was made from" % f
     return os.path.join(SCENES, rel)
+
+
+STOCHASTIC_CASES = ["p9_dof", "teapot1_soft", "p10", "p11_glossy_soft", "p11_glossy"]
+
+
+def check_stochastic(img, g, meta):
+    """A Monte-Carlo image against the reference's 256-spp Whitted mean of the same scene (tests/golden/stochastic_*.npz,
+    two rand() seeds).  The streams are unrelated, so the comparison is statistical, with the reference's own seed-to-seed
+    difference as yardstick: image mean within 1 %, RMSE <= 1.5 x the seed-to-seed RMSE, and - so that a bias hidden in the
+    per-pixel noise cannot pass - the same bar on 8x8 block means against the mean of the two reference runs."""
+    a = np.asarray(img, np.float64)
+    r0, r1 = g["rgb0"].astype(np.float64), g["rgb1"].astype(np.float64)
+    if "crop" in meta and list(meta["crop"]) != [0, 0, meta["width"], meta["height"]] and a.shape != r0.shape:
+        x0, y0, x1, y1 = meta["crop"]
+        a = a[y0:y1, x0:x1]
+    assert a.shape == r0.shape
+    assert np.isfinite(a).all()
+    assert abs(a.mean() - r0.mean()) <= 0.01 * r0.mean() + abs(r0.mean() - r1.mean()), (a.mean(), r0.mean(), r1.mean())
+    noise = np.sqrt(np.mean((r0 - r1) ** 2))
+    rmse = np.sqrt(np.mean((a - r0) ** 2))
+    assert noise > 0
+    assert rmse <= 1.5 * noise, "RMSE %.4g vs the reference's seed-to-seed RMSE %.4g" % (rmse, noise)
+
+    def pool(x):
+        h, w = (x.shape[0] // 8) * 8, (x.shape[1] // 8) * 8
+        return x[:h, :w].reshape(h // 8, 8, w // 8, 8, 3).mean(axis=(1, 3))
+
+    def trimmed_rms(x):
+        # rare "fireflies" (one sample in millions: a back-face Fresnel factor of ~30, mtlFunctions.cpp:236-237) put a whole
+        # run's squared error into one block on either side; the 2 % largest blocks are left out of both sums
+        e = np.sort((x ** 2).sum(axis=2).ravel())
+        return np.sqrt(e[:max(1, int(0.98 * e.size))].mean())
+
+    pn = trimmed_rms(pool(r0 - r1))
+    pe = trimmed_rms(pool(a - 0.5 * (r0 + r1)))
+    assert pe <= 1.5 * pn + 1e-6, "block-mean RMSE %.4g vs the reference's %.4g" % (pe, pn)
+    return rmse, noise, pe, pn

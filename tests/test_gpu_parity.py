@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, bits_equal, load_golden, single_object_scene
+from conftest import SCENES, STOCHASTIC_CASES, bits_equal, check_stochastic, load_golden, single_object_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -321,6 +321,38 @@ def test_path_mode_matches_reference_head_render(rtu, gpu_ctx, tag):
         # same seed, same frame: the counter-based RNG makes the render reproducible (up to float summation order)
         again = sc.render(p, want=("rgb",))["rgb"]
         assert np.allclose(again, out["rgb"], rtol=1e-4, atol=1e-6)
+    finally:
+        sc.close()
+        hs.close()
+
+
+@pytest.mark.parametrize("tag", STOCHASTIC_CASES)
+def test_stochastic_branches_match_reference(rtu, gpu_ctx, tag):
+    """The rand()-driven branches on the device (Philox streams): thin-lens depth of field (RenderFunctions.cpp:88-97,
+    Project9), soft shadows = one disk sample per shadow ray (lightFunctions.cpp:39-84; Teapot/scene.xml, Project10,
+    scene_glossy_soft) and glossy reflection / refraction lobes (mtlFunctions.cpp:163-165, 225-227, 276-278; Project10,
+    scene_glossy*) against 256-spp Whitted means rendered by the UNMODIFIED reference with two rand() seeds
+    (tests/golden/stochastic_*.npz).  Bars: conftest.check_stochastic."""
+    g, meta = load_golden("stochastic_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=rtu.PATTERN_REFERENCE,
+                               mode=rtu.MODE_WHITTED, shade_bounces=5, seed=2026)
+        out = sc.render(p, want=("rgb",))
+        check_stochastic(out["rgb"], g, meta)
+        x0, y0, x1, y1 = meta["crop"]
+        if [x0, y0, x1, y1] == [0, 0, meta["width"], meta["height"]]:
+            # as many root-level rays as the reference's recursion, up to the spread of the stochastic branches themselves
+            st = sc.stats()
+            ref = meta["trace_rays"][0] + meta["shadow_rays"][0]
+            assert abs(st["trace_rays"] + st["shadow_rays"] - ref) <= 0.01 * ref
+        # a second seed is a different image, the same seed the same image
+        again = sc.render(p, want=("rgb",))["rgb"]
+        assert np.allclose(again, out["rgb"], rtol=1e-4, atol=1e-6)
+        p.seed = 2027
+        other = sc.render(p, want=("rgb",))["rgb"]
+        assert not np.allclose(other, out["rgb"], rtol=1e-4, atol=1e-6)
     finally:
         sc.close()
         hs.close()

@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT, SCENES, bits_equal, load_golden, single_object_scene
+from conftest import ROOT, SCENES, STOCHASTIC_CASES, bits_equal, check_stochastic, load_golden, single_object_scene
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
@@ -111,6 +111,24 @@ def test_path_mode_matches_reference_head_render(rtu, oracle, tag):
     a, b = o["rgb8"].astype(np.float64), g["rgb8"].astype(np.float64)
     assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
     assert np.abs(a - b).mean() < 2.5
+
+
+@pytest.mark.parametrize("tag", STOCHASTIC_CASES)
+def test_stochastic_branches_match_reference(rtu, oracle, tag):
+    """Depth of field (RenderFunctions.cpp:88-97), soft shadows (lightFunctions.cpp:39-84) and glossy reflection /
+    refraction lobes (mtlFunctions.cpp:163-165, 225-227, 276-278; SampleSphere RenderFunctions.cpp:282-302) of the
+    restatement against 256-spp Whitted means rendered by the UNMODIFIED reference (two rand() seeds)."""
+    g, meta = load_golden("stochastic_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    p = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=rtu.PATTERN_REFERENCE,
+                           mode=rtu.MODE_WHITTED, shade_bounces=5, seed=77)
+    o = oracle.render(hs.desc, params=p, want=("rgb",), crop=meta["crop"])
+    check_stochastic(o["rgb"], g, meta)
+    # the reference's recursion and the restatement trace the same number of rays up to the stochastic branches' own
+    # spread (a glossy lobe decides whether a bounce hits or misses)
+    rays = o["stats"]["trace_rays"] + o["stats"]["shadow_rays"]
+    ref = meta["trace_rays"][0] + meta["shadow_rays"][0]
+    assert abs(rays - ref) <= 0.01 * ref
 
 
 @pytest.mark.parametrize("name", ["grid1M", "spheres_100", "dupmesh", "manymtl"])

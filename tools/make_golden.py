@@ -11,6 +11,7 @@ never regenerates them.
   primary_<scene>.npz   pixel-centre Trace(): z, node, face, front, p, N, uvw
   whitted_<scene>.npz   Trace + Shade(ray,h,lights,5): linear RGB, RGB8, ray counts
   tex_<scene>.npz       TexturedColor::Sample / SampleEnvironment on seeded inputs
+  stochastic_<scene>.npz  256-spp Whitted means of the scenes with depth of field / soft lights / glossy lobes, two seeds
 """
 import glob
 import json
@@ -67,6 +68,17 @@ LOADER = ["Project1Example.xml", "Project4.xml", "Project5/scene.xml", "Project7
 # generated scenes of section 8d (tools/make_synthetic.py): 1 M-triangle mesh, flat lists of spheres
 SYNTHETIC = {"grid1M": (240, 135), "spheres_100": (240, 135), "spheres_1000": (240, 135), "dupmesh": (480, 270), "manymtl": (240, 135)}
 TEX = {"Project7/scene.xml": "p7", "Project9/scene.xml": "p9", "Project10/scene.xml": "p10"}
+# stochastic branches of Shade / Render (rand()-driven in the reference): thin-lens depth of field (RenderFunctions.cpp:88-97),
+# soft shadows = one disk sample of radius `size` per shadow ray (lightFunctions.cpp:39-84), glossy reflection / refraction
+# lobes = SampleSphere offsets of the normal (mtlFunctions.cpp:163-165, 225-227, 276-278).  Converged means at 256 spp of
+# the reference's sample pattern, two rand() seeds each: the second one is the noise yardstick.
+STOCHASTIC = {
+    "Project9/scene.xml": ("p9_dof", (160, 120), 256, None),
+    "Teapot/scene.xml": ("teapot1_soft", (640, 360), 256, (272, 196, 432, 292)),   # the teapot and its soft shadows; the rest is background
+    "Project10/scene.xml": ("p10", (160, 120), 256, None),
+    "Project11/scene_glossy_soft.xml": ("p11_glossy_soft", (160, 120), 256, None),
+    "Project11/scene_glossy.xml": ("p11_glossy", (160, 120), 256, None),
+}
 
 
 def run(scene, mode, prefix, *extra):
@@ -185,6 +197,18 @@ def main():
                 stats["meta%d" % run_i] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
             save("photon_Project13", stats, dict(scene="Project13/scene.xml", width=160, height=120, bins=[8, 8, 8],
                                                  range=[[-32, 32], [-32, 32], [-20, 44]]))
+        if want("stochastic"):
+            for sc, (tag, (w, h), spp, crop) in STOCHASTIC.items():
+                arrs, metas = {}, []
+                for i, seed in enumerate((101, 202)):
+                    pre = os.path.join(tmp, "st%d" % i)
+                    # one thread: rand() is process-wide state, so a multi-threaded run is not reproducible
+                    meta = run(sc, "whitted", pre, "--width", w, "--height", h, "--spp", spp, "--pattern", "ref", "--threads", 1, "--seed", seed,
+                               *(("--crop",) + crop if crop else ()))
+                    arrs["rgb%d" % i] = collect(pre)["rgb"]
+                    metas.append(meta)
+                save("stochastic_" + tag, arrs, dict(metas[0], scene=sc, seeds=[101, 202], trace_rays=[m["trace_rays"] for m in metas],
+                                                     shadow_rays=[m["shadow_rays"] for m in metas]))
         if want("tex"):
             for sc, tag in TEX.items():
                 pre = os.path.join(tmp, "tx")
