@@ -217,6 +217,8 @@ typedef struct rtu_stats {
     rtu_kernel_stats shadow_waves;  /* k_shadow_wave: any-hit */
     rtu_kernel_stats shade_kernels; /* k_shade: MtlBlinn::Shade steps on the compacted hits (launches, ms only) */
     uint64_t scene_device_bytes;    /* bytes rtu_scene_upload copied host -> device */
+    uint64_t queue_retries;         /* frames this context rendered again because a ray queue overflowed (the scene then
+                                       remembers the larger queues, so a steady state shows no new retries) */
 } rtu_stats;
 
 typedef struct rtu_context rtu_context; /* one per GPU / host thread */
@@ -268,15 +270,35 @@ int rtu_selftest_division(rtu_context *ctx, uint32_t numerators_per_divisor, uin
 
 /* Frame level.  rtu_render: the whole Render() job with HOST output buffers (the e2e path).
  * rtu_render_device: same work, result left in device memory (accum: W*H float4 = sum of
- * radiance over the rendered samples, .w = sample count); accum may be a caller-owned device
- * pointer (e.g. a torch tensor, so that NCCL can reduce it) or NULL for the internal one.
- * rtu_resolve: accum -> mean, gamma, Color24, z image; writes HOST buffers. */
+ * radiance over the rendered samples in .xyz; .w stays 0); accum may be a caller-owned device
+ * pointer or NULL for the internal one.  clear_accum == 0 ADDS the frame to what accum holds
+ * (spp slices / row ranges rendered by separate calls); the frame is added only once it is known
+ * to be complete, so a failed call never leaves accum half written.
+ * rtu_resolve: accum -> mean over params->spp, gamma, Color24, z image; writes HOST buffers. */
 void rtu_params_default(rtu_params *p);
 int rtu_render(rtu_scene *scene, const rtu_params *params, rtu_image *out);
 int rtu_render_device(rtu_scene *scene, const rtu_params *params, float *d_accum, int32_t clear_accum);
 int rtu_resolve(rtu_scene *scene, const rtu_params *params, const float *d_accum, rtu_image *out);
 int rtu_get_stats(const rtu_scene *scene, rtu_stats *out);
 int rtu_synchronize(rtu_context *ctx);
+
+/* ---- Multi-GPU: one process or host thread per GPU, each with its own context.  The path shards by
+ * independent units; the only data-path communication is the step that brings the partial images together on one rank.
+ * The communicator wraps an NCCL communicator created from a 128-byte unique id: rank 0 calls rtu_comm_unique_id and hands
+ * the bytes to the other ranks by whatever means the host program has (the reference has none: it is a single process). */
+#define RTU_COMM_ID_BYTES 128
+typedef struct rtu_comm rtu_comm;
+int rtu_comm_unique_id(uint8_t id[RTU_COMM_ID_BYTES]);
+int rtu_comm_create(rtu_context *ctx, const uint8_t id[RTU_COMM_ID_BYTES], int32_t rank, int32_t world, rtu_comm **out);
+void rtu_comm_destroy(rtu_comm *comm);
+/* spp slices: every rank rendered samples [sample_begin,sample_end) of ALL pixels (rtu_render_device) into d_accum (NULL =
+ * the context's own accumulator).  RGB planes -> one ncclReduce(sum, FP32) onto `root` -> resolve (mean over params->spp,
+ * gamma, Color24) -> the root's HOST buffers, all on the context's stream.  Collective: every rank calls it; `out` is only
+ * read on the root, the other ranks return as soon as their part is enqueued. */
+int rtu_reduce_resolve(rtu_scene *scene, rtu_comm *comm, const rtu_params *params, const float *d_accum, int32_t root, rtu_image *out);
+/* row ranges: every rank rendered ALL samples of rows [row_begin,row_end) (disjoint, covering the image); each rank resolves
+ * its rows and sends them to the root, which assembles Result.png's pixels.  No reduction. */
+int rtu_gather_resolve(rtu_scene *scene, rtu_comm *comm, const rtu_params *params, const float *d_accum, int32_t root, rtu_image *out);
 
 /* ---- Photon map (dead code at the reference's HEAD, main.cpp:31) -------------------------------
  * rtu_photon is cyPhotonMap::Photon (cyPhotonMap.h:47-66) byte for byte: a balanced array can be exchanged with the

@@ -7,28 +7,23 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <functional>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../host/hmath.h"
 #include "../host/host_scene.h"
 #include "rtu_internal.h"
+#include "rtu_objects.h"
 
 using rtu::V3;
 
 namespace {
 
-#define CU(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess) {                                                                        \
-            rtu::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
-            return e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RTU_ERR_NO_DEVICE : RTU_ERR_CUDA; \
-        }                                                                                               \
-    } while (0)
-
 thread_local size_t g_upload_bytes = 0; // host->device bytes of the scene upload in progress
+std::atomic<uint64_t> g_scene_serial{1}; // identifies an uploaded scene in the per-context frame-setup cache
 
 template <class T> int dev_upload(const std::vector<T> &h, T **d, cudaStream_t st, std::vector<void *> &owned)
 {
@@ -42,70 +37,6 @@ template <class T> int dev_upload(const std::vector<T> &h, T **d, cudaStream_t s
 }
 
 } // namespace
-
-struct rtu_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    LaunchCfg cfg;
-    size_t chunk_rays = 1u << 27;  // primary rays per wave chunk (~300 B of queue space each): a 64-spp 1080p frame is one chunk
-    double queue_factor = 1.0;
-    // scratch (lazily sized)
-    WaveBuffers wb;
-    size_t q_cap = 0, shadow_cap = 0;
-    std::vector<void *> scratch;
-    unsigned *work = nullptr;
-    size_t work_n = 0;
-    unsigned *zmm = nullptr;
-    float4 *gi = nullptr;  // GI records of the current chunk (RTU_MODE_PATH): one per primary hit
-    size_t gi_n = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // optional per-launch timing (RTU_FLAG_TIME_KERNELS)
-    std::vector<cudaEvent_t> kt_ev;
-    std::vector<int> kt_cls;
-    size_t kt_used = 0;
-    bool kt_on = false;
-    uint64_t cls_launches[4] = {0, 0, 0, 0}; // primary extend, queue extend, shadow, shade
-    // frame buffers: owned by the context so that re-uploading a scene every frame (the e2e
-    // path) does not re-allocate them
-    struct FrameBuffers {
-        float4 *accum = nullptr;
-        size_t accum_n = 0;
-        float *d_rgb = nullptr;
-        unsigned char *d_rgb8 = nullptr;
-        float *d_z = nullptr;
-        unsigned char *d_z8 = nullptr;
-        int *d_node = nullptr, *d_face = nullptr;
-        size_t img_n = 0;
-        float2 *d_offsets = nullptr;
-        size_t offsets_n = 0;
-        unsigned char *d_tile = nullptr; // FrameSetup::tile_empty
-        size_t tile_n = 0;
-    } fb;
-};
-
-struct rtu_scene {
-    rtu_context *ctx = nullptr;
-    DScene S;
-    rtu_camera cam;
-    std::vector<void *> owned;
-    size_t device_bytes = 0;
-    int n_shadow_lights = 0;
-    uint64_t launches = 0;
-    bool timed = false;
-    // photon map (balanced, n+1 records, record 0 unused) and the parameters it was made with
-    struct Footprint { double c[8][3]; bool finite; int node; }; // world-space corners of an object's bound box
-    std::vector<Footprint> footprints;
-    size_t chunk_limit = 0;       // set after a queue overflow: later frames of this scene start with smaller chunks ...
-    double queue_boost = 1.0;     // ... or with more queue entries per primary ray
-    size_t last_chunk_cap = 0;    // primary rays per chunk of the last frame
-    bool root_identity = true;
-    int n_obj = 0;                // nodes whose object Trace() tests (what a ray that misses everything books)
-    int h_light0_kind = -1;       // lights[0]: the only light GeneratePhotonMap emits from
-    float h_light0_I[3] = {0, 0, 0};
-    rtu_photon *d_photons = nullptr;
-    uint32_t n_photons = 0;
-    rtu_photon_params photon_params;
-};
 
 namespace {
 
@@ -158,6 +89,7 @@ int ensure_scratch(rtu_context *c, size_t q_cap, size_t shadow_cap)
     CU(cudaStreamSynchronize(c->stream));
     free_list(c->scratch);
     c->q_cap = c->shadow_cap = 0;
+    memset(&c->wb, 0, sizeof c->wb); // nothing may point into the freed block if an allocation below fails
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(p, bytes);
         if (e == cudaSuccess) c->scratch.push_back(*p);
@@ -430,18 +362,25 @@ int rtu_context_create(int32_t device, void *stream, rtu_context **out)
     rtu_context *c = new rtu_context;
     c->device = device;
     c->stream = (cudaStream_t)stream;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    c->cfg.sm_count = prop.multiProcessorCount;
+    int sm_count = 0;
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_count < 1) sm_count = 148;
+    c->cfg.sm_count = sm_count;
     c->cfg.blocks_per_sm = 2;
     c->cfg.threads = 256;
     if (const char *s = getenv("RTU_CHUNK_RAYS")) { long long v = atoll(s); if (v >= 1024) c->chunk_rays = (size_t)v; }
     if (const char *s = getenv("RTU_QUEUE_FACTOR")) { double v = atof(s); if (v >= 1.0 && v <= 8.0) c->queue_factor = v; }
     if (const char *s = getenv("RTU_BLOCKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= 8) c->cfg.blocks_per_sm = v; }
     memset(&c->wb, 0, sizeof c->wb);
-    CU(cudaMalloc((void **)&c->zmm, 2 * sizeof(unsigned)));
-    CU(cudaEventCreate(&c->ev0));
-    CU(cudaEventCreate(&c->ev1));
+    auto bail = [&](cudaError_t e, const char *what) {
+        rtu::set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        rtu_context_destroy(c);
+        return RTU_ERR_CUDA;
+    };
+    cudaError_t e2;
+    if ((e2 = cudaMalloc((void **)&c->zmm, 2 * sizeof(unsigned))) != cudaSuccess) return bail(e2, "cudaMalloc");
+    if ((e2 = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(e2, "cudaEventCreate");
+    if ((e2 = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e2, "cudaEventCreate");
+    if ((e2 = cudaHostAlloc((void **)&c->h_flag, 64, cudaHostAllocDefault)) != cudaSuccess) return bail(e2, "cudaHostAlloc");
     *out = c;
     return RTU_OK;
 }
@@ -458,9 +397,12 @@ void rtu_context_destroy(rtu_context *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->kt_ev) cudaEventDestroy(e);
-    void *fbp[] = {c->fb.accum, c->fb.d_rgb, c->fb.d_rgb8, c->fb.d_z, c->fb.d_z8, c->fb.d_node, c->fb.d_face, c->fb.d_offsets};
+    void *fbp[] = {c->fb.accum, c->fb.accum2, c->fb.d_rgb, c->fb.d_rgb8, c->fb.d_z, c->fb.d_z8, c->fb.d_node, c->fb.d_face, c->fb.d_offsets};
     for (void *p : fbp) if (p) cudaFree(p);
     if (c->fb.d_tile) cudaFree(c->fb.d_tile);
+    c->stage_off.release();
+    c->stage_tile.release();
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     delete c;
 }
 
@@ -475,6 +417,11 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
 {
     if (!c || !d || !out) { rtu::set_error("rtu_scene_upload: null argument"); return RTU_ERR_INVALID; }
     if (d->n_nodes < 1 || !d->nodes) { rtu::set_error("rtu_scene_upload: scene has no root node"); return RTU_ERR_INVALID; }
+    if (d->n_meshes < 0 || d->n_materials < 0 || d->n_lights < 0 || d->n_texmaps < 0 || (d->n_meshes > 0 && !d->meshes) ||
+        (d->n_materials > 0 && !d->materials) || (d->n_lights > 0 && !d->lights) || (d->n_texmaps > 0 && !d->texmaps)) {
+        rtu::set_error("rtu_scene_upload: a non-empty array of the scene description is NULL");
+        return RTU_ERR_INVALID;
+    }
     CU(cudaSetDevice(c->device));
     std::unique_ptr<rtu_scene> sc(new rtu_scene);
     sc->ctx = c;
@@ -483,6 +430,11 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     memset(&sc->S, 0, sizeof sc->S);
     int rc;
     auto fail = [&](int code) { free_list_async(sc->owned, c->stream); return code; };
+    auto cuda_fail = [&](cudaError_t e, const char *what) {
+        rtu::set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        return fail(RTU_ERR_CUDA);
+    };
+    sc->serial = g_scene_serial.fetch_add(1);
 
     // nodes
     std::vector<DNode> nodes(d->n_nodes);
@@ -671,9 +623,11 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
             for (auto &pr : pix) if (pr.first == t.rgb8) dp = pr.second;
             if (!dp) {
                 size_t bytes = (size_t)t.width * t.height * 3;
-                CU(cudaMallocAsync((void **)&dp, bytes, c->stream));
+                cudaError_t te = cudaMallocAsync((void **)&dp, bytes, c->stream);
+                if (te != cudaSuccess) return cuda_fail(te, "rtu_scene_upload: texture allocation");
                 sc->owned.push_back(dp);
-                CU(cudaMemcpyAsync(dp, t.rgb8, bytes, cudaMemcpyHostToDevice, c->stream));
+                te = cudaMemcpyAsync(dp, t.rgb8, bytes, cudaMemcpyHostToDevice, c->stream);
+                if (te != cudaSuccess) return cuda_fail(te, "rtu_scene_upload: texture copy");
                 pix.push_back({t.rgb8, dp});
                 g_upload_bytes += bytes;
             }
@@ -684,9 +638,13 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     if ((rc = dev_upload(tms, &dt, c->stream, sc->owned))) return fail(rc);
     // materials
     std::vector<DMaterial> mats(d->n_materials);
+    bool any_refl = false, any_refr = false;
     for (int i = 0; i < d->n_materials; i++) {
         const rtu_material &m = d->materials[i];
         DMaterial &o = mats[i];
+        // Kr / Kt are colour x texture sample: a black colour can never spawn a ray (mtlFunctions.cpp:160, 273)
+        any_refl = any_refl || m.reflection.color[0] != 0.f || m.reflection.color[1] != 0.f || m.reflection.color[2] != 0.f;
+        any_refr = any_refr || m.refraction.color[0] != 0.f || m.refraction.color[1] != 0.f || m.refraction.color[2] != 0.f;
         o.diffuse = pack_tc(m.diffuse, d->n_texmaps);
         o.specular = pack_tc(m.specular, d->n_texmaps);
         o.reflection = pack_tc(m.reflection, d->n_texmaps);
@@ -714,7 +672,11 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     }
     DLight *dl = nullptr;
     if ((rc = dev_upload(lts, &dl, c->stream, sc->owned))) return fail(rc);
-    CU(cudaStreamSynchronize(c->stream));
+    {
+        cudaError_t se = cudaStreamSynchronize(c->stream);
+        if (se != cudaSuccess) return cuda_fail(se, "rtu_scene_upload: cudaStreamSynchronize");
+    }
+    sc->tree_waves = any_refr ? 2 : (any_refl ? 1 : 0);
 
     DScene &S = sc->S;
     S.nodes = dn;
@@ -880,7 +842,7 @@ bool image_footprints(const rtu_scene *s, const DCamera &C, std::vector<TileObje
     return true;
 }
 
-int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, int *s_end)
+int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, int *s_end, bool *mask_launched)
 {
     int W, H, rc;
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
@@ -906,32 +868,57 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     F->gi_bounces = p->gi_bounces;
     F->flags = p->flags;
     F->seed = make_uint2((unsigned)(p->seed & 0xffffffffu), (unsigned)(p->seed >> 32));
-    // sub-pixel offsets of every sample (RenderFunctions.cpp:71,81-85,96)
-    std::vector<float2> off(p->spp);
-    if (p->pattern == RTU_PATTERN_CENTER) {
-        off[0] = make_float2(0.5f, 0.5f);
-    } else {
-        float pixelIncrement = 1.0 / p->spp;
-        for (int i = 0; i < p->spp; i++) {
-            float cur = i * pixelIncrement;
-            off[i] = make_float2(cur + halton(i, 4), cur + halton(i, 5));
+    // sub-pixel offsets of every sample (RenderFunctions.cpp:71,81-85,96); uploaded only when the pattern changes
+    rtu_context *c = s->ctx;
+    if (c->off_spp != p->spp || c->off_pattern != p->pattern) {
+        c->off_spp = c->off_pattern = -1;
+        c->tile_key = rtu_context::TileKey();
+        std::vector<float2> &off = c->h_offsets;
+        off.resize(p->spp);
+        if (p->pattern == RTU_PATTERN_CENTER) {
+            off[0] = make_float2(0.5f, 0.5f);
+        } else {
+            float pixelIncrement = 1.0 / p->spp;
+            for (int i = 0; i < p->spp; i++) {
+                float cur = i * pixelIncrement;
+                off[i] = make_float2(cur + halton(i, 4), cur + halton(i, 5));
+            }
         }
+        if ((size_t)p->spp > c->fb.offsets_n) {
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->fb.d_offsets) cudaFree(c->fb.d_offsets);
+            c->fb.d_offsets = nullptr;
+            c->fb.offsets_n = 0;
+            CU(cudaMalloc((void **)&c->fb.d_offsets, (size_t)p->spp * sizeof(float2)));
+            c->fb.offsets_n = p->spp;
+        }
+        void *stage = c->stage_off.acquire(off.size() * sizeof(float2));
+        if (!stage) { rtu::set_error("page-locked staging allocation failed"); return RTU_ERR_CUDA; }
+        memcpy(stage, off.data(), off.size() * sizeof(float2));
+        CU(cudaMemcpyAsync(c->fb.d_offsets, stage, off.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        c->stage_off.submitted(c->stream);
+        c->off_spp = p->spp;
+        c->off_pattern = p->pattern;
     }
-    if ((size_t)p->spp > s->ctx->fb.offsets_n) {
-        CU(cudaStreamSynchronize(s->ctx->stream));
-        if (s->ctx->fb.d_offsets) cudaFree(s->ctx->fb.d_offsets);
-        s->ctx->fb.d_offsets = nullptr;
-        CU(cudaMalloc((void **)&s->ctx->fb.d_offsets, (size_t)p->spp * sizeof(float2)));
-        s->ctx->fb.offsets_n = p->spp;
-    }
-    CU(cudaMemcpyAsync(s->ctx->fb.d_offsets, off.data(), off.size() * sizeof(float2), cudaMemcpyHostToDevice, s->ctx->stream));
-    CU(cudaStreamSynchronize(s->ctx->stream)); // `off` is a local
-    F->sample_offsets = s->ctx->fb.d_offsets;
+    const std::vector<float2> &off = c->h_offsets;
+    F->sample_offsets = c->fb.d_offsets;
     // tiles of the primary wave that no camera ray of the rendered samples can leave with a hit
     F->tile_empty = nullptr;
+    F->n_empty_tiles = nullptr;
+    F->n_tiles = 0;
     F->n_obj = s->n_obj;
-    F->ticket_block = 32;
+    *mask_launched = false;
     if (!getenv("RTU_NO_TILE_MASK") && s->cam.dof <= 0.f && s->root_identity) {
+        rtu_context::TileKey key;
+        key.scene = s->serial; key.W = W; key.H = H; key.row0 = F->row_begin; key.row1 = F->row_end;
+        key.s0 = *s_begin; key.s1 = *s_end; key.spp = p->spp; key.pattern = p->pattern;
+        if (c->tile_mask && key == c->tile_key) { // same scene, camera, size and samples as the last frame: the mask is still on the device
+            F->tile_empty = c->tile_mask;
+            F->n_empty_tiles = c->tile_count;
+            F->n_tiles = c->tile_total;
+            return RTU_OK;
+        }
+        c->tile_mask = nullptr;
         float ox0 = off[*s_begin].x, ox1 = ox0, oy0 = off[*s_begin].y, oy1 = oy0;
         for (int i = *s_begin; i < *s_end; i++) {
             ox0 = std::min(ox0, off[i].x); ox1 = std::max(ox1, off[i].x);
@@ -941,29 +928,39 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
         std::vector<float4> edges;
         if (image_footprints(s, F->cam, &objs, &edges)) {
             size_t tiles = (size_t)((W + 7) / 8) * (size_t)((F->row_end - F->row_begin + 3) / 4);
-            size_t need = tiles + objs.size() * sizeof(TileObject) + edges.size() * sizeof(float4) + 128;
-            if (need > s->ctx->fb.tile_n) {
-                CU(cudaStreamSynchronize(s->ctx->stream));
-                if (s->ctx->fb.d_tile) cudaFree(s->ctx->fb.d_tile);
-                s->ctx->fb.d_tile = nullptr;
-                s->ctx->fb.tile_n = 0;
-                CU(cudaMalloc((void **)&s->ctx->fb.d_tile, need));
-                s->ctx->fb.tile_n = need;
+            const size_t objs_b = ((objs.size() * sizeof(TileObject) + 15) / 16) * 16, edges_b = edges.size() * sizeof(float4);
+            size_t need = tiles + objs_b + edges_b + 128;
+            if (need > c->fb.tile_n) {
+                CU(cudaStreamSynchronize(c->stream));
+                if (c->fb.d_tile) cudaFree(c->fb.d_tile);
+                c->fb.d_tile = nullptr;
+                c->fb.tile_n = 0;
+                CU(cudaMalloc((void **)&c->fb.d_tile, need));
+                c->fb.tile_n = need;
             }
-            // layout: [objects][edges][mask]
-            unsigned char *base = s->ctx->fb.d_tile;
+            // layout: [objects][edges][mask][count]; objects and edges go up in one copy from page-locked staging
+            unsigned char *base = c->fb.d_tile;
             TileObject *d_objs = (TileObject *)base;
-            float4 *d_edges = (float4 *)(base + ((objs.size() * sizeof(TileObject) + 15) / 16) * 16);
-            unsigned char *d_mask = (unsigned char *)(d_edges + edges.size());
-            if (!objs.empty()) CU(cudaMemcpyAsync(d_objs, objs.data(), objs.size() * sizeof(TileObject), cudaMemcpyHostToDevice, s->ctx->stream));
-            if (!edges.empty()) CU(cudaMemcpyAsync(d_edges, edges.data(), edges.size() * sizeof(float4), cudaMemcpyHostToDevice, s->ctx->stream));
-            unsigned *d_count = (unsigned *)(base + ((size_t)(d_mask - base) + tiles + 15) / 16 * 16);
-            launch_tile_mask(s->ctx->stream, *F, d_objs, (int)objs.size(), d_edges, ox0, ox1, oy0, oy1, d_mask, d_count);
-            unsigned n_empty = 0;
-            CU(cudaMemcpyAsync(&n_empty, d_count, sizeof n_empty, cudaMemcpyDeviceToHost, s->ctx->stream));
-            CU(cudaStreamSynchronize(s->ctx->stream)); // objs / edges are locals
+            float4 *d_edges = (float4 *)(base + objs_b);
+            unsigned char *d_mask = base + objs_b + edges_b;
+            unsigned *d_count = (unsigned *)(base + ((objs_b + edges_b + tiles + 15) / 16) * 16);
+            if (objs_b + edges_b > 0) {
+                unsigned char *stage = (unsigned char *)c->stage_tile.acquire(objs_b + edges_b);
+                if (!stage) { rtu::set_error("page-locked staging allocation failed"); return RTU_ERR_CUDA; }
+                if (!objs.empty()) memcpy(stage, objs.data(), objs.size() * sizeof(TileObject));
+                if (!edges.empty()) memcpy(stage + objs_b, edges.data(), edges_b);
+                CU(cudaMemcpyAsync(base, stage, objs_b + edges_b, cudaMemcpyHostToDevice, c->stream));
+                c->stage_tile.submitted(c->stream);
+            }
+            launch_tile_mask(c->stream, *F, d_objs, (int)objs.size(), d_edges, ox0, ox1, oy0, oy1, d_mask, d_count);
+            *mask_launched = true;
             F->tile_empty = d_mask;
-            if ((size_t)n_empty * 2 > tiles) F->ticket_block = 256; // mostly empty tiles: hand them out in blocks
+            F->n_empty_tiles = d_count;
+            F->n_tiles = (unsigned)tiles;
+            c->tile_key = key;
+            c->tile_mask = d_mask;
+            c->tile_count = d_count;
+            c->tile_total = (unsigned)tiles;
             if (getenv("RTU_TILE_DEBUG")) {
                 std::vector<unsigned char> hm(tiles);
                 cudaMemcpy(hm.data(), d_mask, tiles, cudaMemcpyDeviceToHost);
@@ -978,16 +975,19 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
 }
 
 // the waves that follow a first wave whose output is in q[out_q]
-int wave_count(const FrameSetup &F)
+int wave_count(const FrameSetup &F, int tree_waves)
 {
-    // a Fresnel ray starts one wave after its sibling at every level; every GI vertex restarts a Shade tree
-    return 2 * F.shade_bounces + 1 + (F.mode == RTU_MODE_PATH ? F.gi_bounces : 0);
+    // Waves one Shade tree can last: none when no material of the scene reflects or refracts (nothing is ever spawned),
+    // one per bounce with mirrors only; with refraction a Fresnel ray starts one wave after its sibling at every level.
+    // Every GI vertex restarts a Shade tree.
+    const int tree = tree_waves == 0 ? 0 : (tree_waves == 1 ? F.shade_bounces : 2 * F.shade_bounces + 1);
+    return tree + (F.mode == RTU_MODE_PATH ? F.gi_bounces : 0);
 }
 
-int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_t *work_i)
+int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_t *work_i, int tree_waves)
 {
     rtu_context *c = s->ctx;
-    int n_waves = wave_count(F);
+    int n_waves = wave_count(F, tree_waves);
     kt_begin(c, 2);
     launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
     kt_end(c);
@@ -1038,21 +1038,15 @@ int check_overflow(rtu_scene *s, DCounters *host)
 
 extern "C" {
 
-static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
+static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, int32_t clear_accum)
 {
-    if (!s || !p) { rtu::set_error("rtu_render_device: null argument"); return RTU_ERR_INVALID; }
     rtu_context *c = s->ctx;
-    CU(cudaSetDevice(c->device));
     FrameSetup F;
     int s0, s1, rc;
-    if ((rc = setup_frame(s, p, &F, &s0, &s1))) return rc;
+    bool mask_launched = false;
+    if ((rc = setup_frame(s, p, &F, &s0, &s1, &mask_launched))) return rc;
     int W = F.cam.width, H = F.cam.height;
     size_t npix = (size_t)W * H;
-    float4 *accum = (float4 *)d_accum;
-    if (!accum) {
-        if ((rc = ensure_accum(s, npix))) return rc;
-        accum = s->ctx->fb.accum;
-    }
     int rows = F.row_end - F.row_begin;
     size_t per_sample = (size_t)((W + 7) / 8) * ((rows + 3) / 4) * 32;
     size_t chunk_rays = c->chunk_rays;
@@ -1062,15 +1056,15 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
     size_t chunk_cap = std::max(per_sample, chunk_samples * per_sample);
     if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
     // Queue capacities: one entry per primary ray of a chunk.  A hit can spawn up to 3 rays, so no
-    // fixed factor is a bound; overflow is detected on the device (DCounters::overflow) and reported,
-    // and rtu_render retries with smaller chunks.  Scenes whose every pixel is glass need RTU_QUEUE_FACTOR=2.
+    // fixed factor is a bound; overflow is detected on the device (DCounters::overflow) and the frame is
+    // rendered again with larger queues / smaller chunks (render_checked).
     s->last_chunk_cap = chunk_cap;
     size_t q_cap = (size_t)((double)chunk_cap * c->queue_factor * s->queue_boost);
     if (q_cap < chunk_cap) q_cap = chunk_cap;
     size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
     if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
     size_t n_chunks = ((size_t)(s1 - s0) + chunk_samples - 1) / chunk_samples;
-    size_t launches_per_chunk = 3 + 3 * (size_t)wave_count(F);
+    size_t launches_per_chunk = 3 + 3 * (size_t)wave_count(F, s->tree_waves);
     if ((rc = ensure_work(c, n_chunks * launches_per_chunk + 8))) return rc;
     const bool path_mode = F.mode == RTU_MODE_PATH;
     float4 *target = accum; // the array ray slots index: pixels, or GI records folded into pixels per chunk
@@ -1081,7 +1075,7 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
     CU(cudaEventRecord(c->ev0, c->stream));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
     if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * sizeof(float4), c->stream));
-    s->launches = F.tile_empty ? 1 : 0; // k_tile_mask ran in setup_frame
+    s->launches = mask_launched ? 1 : 0; // k_tile_mask ran in setup_frame
     kt_reset(c, (p->flags & RTU_FLAG_TIME_KERNELS) != 0);
     size_t wi = 0;
     for (int a = s0; a < s1; a += (int)chunk_samples) {
@@ -1105,7 +1099,7 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
         }
         kt_end(c);
         s->launches += 3;
-        if ((rc = run_waves(s, F, target, 0, &wi))) return rc;
+        if ((rc = run_waves(s, F, target, 0, &wi, s->tree_waves))) return rc;
         if (path_mode) {
             launch_gi_combine(c->stream, c->gi, c->wb.gi_count, c->wb.hits.cap, F.gi_bounces, accum);
             s->launches++;
@@ -1117,82 +1111,165 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float *d_accum,
     return RTU_OK;
 }
 
-// The queues hold one entry per primary ray of a chunk; a scene whose hits spawn more rays than that (glossy rooms in
-// RTU_MODE_PATH) overflows them.  The device flags it; a frame that started from a cleared accumulator is then rendered
-// again with half the chunk, and the scene remembers the smaller chunk for its next frames.
-int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
+// After a queue overflow: more queue entries per primary ray (up to ~64 GB of queues), after that smaller chunks; the scene
+// remembers the setting for its next frames.  Returns RTU_OK when another attempt makes sense.
+static int grow_queues(rtu_scene *s, int attempt)
 {
-    for (int attempt = 0;; attempt++) {
-        int rc = render_device_once(s, p, d_accum, clear_accum);
-        if (rc || !clear_accum) return rc;
-        rtu_context *c = s->ctx;
-        uint32_t overflow = 0;
-        CU(cudaMemcpyAsync(&overflow, &c->wb.counters->overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        if (!overflow) return RTU_OK;
-        // the queues hold queue_factor x queue_boost entries per primary ray of a chunk: a scene whose hits spawn more
-        // rays than that needs more entries per ray (up to ~64 GB of queues), after that smaller chunks
-        const double bytes_per_entry = 300.0 * std::max(1, s->n_shadow_lights);
-        const double doubled = (double)s->last_chunk_cap * c->queue_factor * s->queue_boost * 2.0 * bytes_per_entry;
-        if (attempt >= 10) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS or raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
-        if (doubled <= 64e9 && s->queue_boost < 16.0) s->queue_boost *= 2.0;
-        else if (s->last_chunk_cap > 65536) s->chunk_limit = s->last_chunk_cap / 2;
-        else { rtu::set_error("ray queue overflow: raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
-    }
+    rtu_context *c = s->ctx;
+    const double bytes_per_entry = 300.0 * std::max(1, s->n_shadow_lights);
+    const double doubled = (double)s->last_chunk_cap * c->queue_factor * s->queue_boost * 2.0 * bytes_per_entry;
+    if (attempt >= 10) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS or raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
+    if (doubled <= 64e9 && s->queue_boost < 16.0) s->queue_boost *= 2.0;
+    else if (s->last_chunk_cap > 65536) s->chunk_limit = s->last_chunk_cap / 2;
+    else { rtu::set_error("ray queue overflow: raise RTU_QUEUE_FACTOR"); return RTU_ERR_UNSUPPORTED; }
+    c->queue_retries++;
+    return RTU_OK;
 }
 
-int rtu_resolve(rtu_scene *s, const rtu_params *p, const float *d_accum, rtu_image *out)
+// the overflow flag of the frame just enqueued, read through the page-locked word (waits for the frame)
+static int frame_overflowed(rtu_context *c, bool *overflow)
 {
-    if (!s || !p || !out) { rtu::set_error("rtu_resolve: null argument"); return RTU_ERR_INVALID; }
+    CU(cudaMemcpyAsync(c->h_flag, &c->wb.counters->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *overflow = *c->h_flag != 0;
+    return RTU_OK;
+}
+
+
+// Renders into `accum`; the queues hold one entry per primary ray of a chunk, and a scene whose hits spawn more rays than
+// that (glossy rooms in RTU_MODE_PATH) overflows them: the device flags it and the frame is rendered again with larger
+// queues.  That needs a frame that starts from zero, so a call that ADDS to the caller's accumulator (clear_accum == 0: the
+// spp-sliced / row-sliced path) renders into the context's second accumulator and adds that to the caller's once it is
+// known to be complete: an overflow never leaves a caller's accumulator half written.
+// `out`: resolve + device->host copies enqueued behind the frame, covered by the same wait as the overflow flag.
+static int render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum, rtu_image *out)
+{
+    if (!s || !p) { rtu::set_error("rtu_render_device: null argument"); return RTU_ERR_INVALID; }
     rtu_context *c = s->ctx;
     CU(cudaSetDevice(c->device));
     int W, H, rc;
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
+    const size_t npix = (size_t)W * H;
+    float4 *dst = (float4 *)d_accum;
+    if (!dst) {
+        if ((rc = ensure_accum(s, npix))) return rc;
+        dst = c->fb.accum;
+    }
+    float4 *render_into = dst;
+    if (!clear_accum) {
+        if (npix > c->fb.accum2_n) {
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->fb.accum2) cudaFree(c->fb.accum2);
+            c->fb.accum2 = nullptr;
+            c->fb.accum2_n = 0;
+            CU(cudaMalloc((void **)&c->fb.accum2, npix * sizeof(float4)));
+            c->fb.accum2_n = npix;
+        }
+        render_into = c->fb.accum2;
+    }
+    for (int attempt = 0;; attempt++) {
+        if ((rc = render_device_once(s, p, render_into, 1))) return rc;
+        if (out && clear_accum && (rc = rtu_resolve_enqueue(s, p, dst, out))) return rc; // optimistic: dropped if the frame overflowed
+        bool overflow = false;
+        if ((rc = frame_overflowed(c, &overflow))) return rc;
+        if (!overflow) break;
+        if ((rc = grow_queues(s, attempt))) return rc;
+    }
+    if (!clear_accum) {
+        launch_accum_add(c->stream, dst, render_into, npix);
+        s->launches++;
+        if (out) {
+            if ((rc = rtu_resolve_enqueue(s, p, dst, out))) return rc;
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    }
+    CU(cudaGetLastError());
+    return RTU_OK;
+}
+
+int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
+{
+    return rtu::guarded("rtu_render_device", [&]() -> int { return render_checked(s, p, d_accum, clear_accum, nullptr); });
+}
+
+} // extern "C"
+
+int rtu_frame_dims(const rtu_scene *s, const rtu_params *p, int *W, int *H) { return frame_dims(s, p, W, H); }
+int rtu_ensure_image(rtu_scene *s, size_t npix) { return ensure_image(s, npix); }
+
+// accum -> device images -> host buffers, enqueued on the context's stream (no wait)
+
+int rtu_resolve_enqueue(rtu_scene *s, const rtu_params *p, const float4 *accum, rtu_image *out)
+{
+    rtu_context *c = s->ctx;
+    int W, H, rc;
+    if ((rc = frame_dims(s, p, &W, &H))) return rc;
+    if (p->spp < 1) { rtu::set_error("rtu_resolve: spp must be at least 1"); return RTU_ERR_INVALID; }
     size_t npix = (size_t)W * H;
     if ((rc = ensure_image(s, npix))) return rc;
-    const float4 *accum = d_accum ? (const float4 *)d_accum : s->ctx->fb.accum;
     if (out->rgb || out->rgb8) {
         if (!accum) { rtu::set_error("rtu_resolve: nothing rendered yet"); return RTU_ERR_INVALID; }
-        launch_resolve(c->stream, accum, (int)npix, 0.f, p->spp, out->rgb ? s->ctx->fb.d_rgb : nullptr, out->rgb8 ? s->ctx->fb.d_rgb8 : nullptr);
-        if (out->rgb) CU(cudaMemcpyAsync(out->rgb, s->ctx->fb.d_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, s->ctx->fb.d_rgb8, npix * 3, cudaMemcpyDeviceToHost, c->stream));
+        if (accum == c->fb.accum && npix > c->fb.accum_n) { rtu::set_error("rtu_resolve: the last frame rendered into the internal accumulator was smaller than this image"); return RTU_ERR_INVALID; }
+        launch_resolve(c->stream, accum, (int)npix, 0.f, p->spp, out->rgb ? c->fb.d_rgb : nullptr, out->rgb8 ? c->fb.d_rgb8 : nullptr);
+        if (out->rgb) CU(cudaMemcpyAsync(out->rgb, c->fb.d_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, c->fb.d_rgb8, npix * 3, cudaMemcpyDeviceToHost, c->stream));
     }
     if (out->z || out->z8 || out->node_id || out->face_id) {
         DCamera cam;
         make_camera(s->cam, W, H, &cam);
-        // visibility at pixel centres: the z the reference meant to store (SURVEY A-3)
+        // visibility at pixel centres: the z the reference meant to store (SURVEY A-3); always the whole image, whatever
+        // row range the frame's samples covered
         if (!c->wb.counters) { if ((rc = ensure_scratch(c, 1024, 1024))) return rc; }
-        launch_primary_ids(c->cfg, c->stream, s->S, cam, s->ctx->fb.d_z, s->ctx->fb.d_node, s->ctx->fb.d_face, c->wb.counters);
-        if (out->z8) launch_zimage(c->stream, s->ctx->fb.d_z, (int)npix, c->zmm, s->ctx->fb.d_z8);
-        if (out->z) CU(cudaMemcpyAsync(out->z, s->ctx->fb.d_z, npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (out->z8) CU(cudaMemcpyAsync(out->z8, s->ctx->fb.d_z8, npix, cudaMemcpyDeviceToHost, c->stream));
-        if (out->node_id) CU(cudaMemcpyAsync(out->node_id, s->ctx->fb.d_node, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (out->face_id) CU(cudaMemcpyAsync(out->face_id, s->ctx->fb.d_face, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        launch_primary_ids(c->cfg, c->stream, s->S, cam, c->fb.d_z, c->fb.d_node, c->fb.d_face, c->wb.counters);
+        if (out->z8) launch_zimage(c->stream, c->fb.d_z, (int)npix, c->zmm, c->fb.d_z8);
+        if (out->z) CU(cudaMemcpyAsync(out->z, c->fb.d_z, npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->z8) CU(cudaMemcpyAsync(out->z8, c->fb.d_z8, npix, cudaMemcpyDeviceToHost, c->stream));
+        if (out->node_id) CU(cudaMemcpyAsync(out->node_id, c->fb.d_node, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (out->face_id) CU(cudaMemcpyAsync(out->face_id, c->fb.d_face, npix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaGetLastError());
     return RTU_OK;
+}
+
+extern "C" {
+
+int rtu_resolve(rtu_scene *s, const rtu_params *p, const float *d_accum, rtu_image *out)
+{
+    if (!s || !p || !out) { rtu::set_error("rtu_resolve: null argument"); return RTU_ERR_INVALID; }
+    return rtu::guarded("rtu_resolve", [&]() -> int {
+        rtu_context *c = s->ctx;
+        CU(cudaSetDevice(c->device));
+        int rc = rtu_resolve_enqueue(s, p, d_accum ? (const float4 *)d_accum : c->fb.accum, out);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        return RTU_OK;
+    });
 }
 
 int rtu_render(rtu_scene *s, const rtu_params *p, rtu_image *out)
 {
     if (!s || !p || !out) { rtu::set_error("rtu_render: null argument"); return RTU_ERR_INVALID; }
-    int rc;
-    if (p->mode == RTU_MODE_PRIMARY) {
-        rtu_image o = *out;
-        o.rgb = nullptr;
-        o.rgb8 = nullptr;
-        if ((rc = ensure_scratch(s->ctx, 1024, 1024))) return rc;
-        CU(cudaMemsetAsync(s->ctx->wb.counters, 0, sizeof(DCounters), s->ctx->stream));
-        CU(cudaEventRecord(s->ctx->ev0, s->ctx->stream));
-        rc = rtu_resolve(s, p, nullptr, &o);
-        CU(cudaEventRecord(s->ctx->ev1, s->ctx->stream));
-        s->timed = true;
-        return rc;
-    }
-    rc = rtu_render_device(s, p, nullptr, 1); // retries with smaller chunks if a queue overflows
-    if (rc) return rc;
-    return rtu_resolve(s, p, nullptr, out);
+    return rtu::guarded("rtu_render", [&]() -> int {
+        int rc;
+        if (p->mode == RTU_MODE_PRIMARY) {
+            rtu_image o = *out;
+            o.rgb = nullptr;
+            o.rgb8 = nullptr;
+            if ((rc = ensure_scratch(s->ctx, 1024, 1024))) return rc;
+            CU(cudaMemsetAsync(s->ctx->wb.counters, 0, sizeof(DCounters), s->ctx->stream));
+            CU(cudaEventRecord(s->ctx->ev0, s->ctx->stream));
+            rc = rtu_resolve_enqueue(s, p, nullptr, &o);
+            CU(cudaEventRecord(s->ctx->ev1, s->ctx->stream));
+            s->timed = true;
+            s->launches = o.z8 ? 3 : 1;
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(s->ctx->stream));
+            CU(cudaGetLastError());
+            return RTU_OK;
+        }
+        // frame, resolve and device->host copies are enqueued together: one wait covers the images and the overflow flag
+        return render_checked(s, p, nullptr, 1, out);
+    });
 }
 
 int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
@@ -1225,6 +1302,7 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
         if (cudaEventElapsedTime(&ms, c->kt_ev[i * 2], c->kt_ev[i * 2 + 1]) == cudaSuccess) ks[c->kt_cls[i]]->ms += ms;
     }
     out->scene_device_bytes = s->device_bytes;
+    out->queue_retries = c->queue_retries;
     out->kernel_launches = s->launches;
     if (s->timed) {
         float ms = 0;
@@ -1386,7 +1464,7 @@ int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n,
         s->launches = 2;
         launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, nullptr);
         launch_shade_batch(c->cfg, c->stream, s->S, F, dr, dh, n, c->wb, 0, acc);
-        rc = run_waves(s, F, acc, 0, &wi);
+        rc = run_waves(s, F, acc, 0, &wi, s->tree_waves);
         if (rc == RTU_OK) e = cudaMemcpyAsync(host_acc.data(), acc, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

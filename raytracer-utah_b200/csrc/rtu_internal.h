@@ -19,7 +19,10 @@ struct FrameSetup {
     // bounding sphere of any object; such rays book n_obj culled nodes each and add the background (may be NULL)
     const unsigned char *tile_empty;
     int n_obj;
-    int ticket_block;    // work items a warp of the primary wave takes per atomic: 256 when most tiles are empty, else 32
+    // number of empty tiles (device word written by k_tile_mask) and of tiles: a warp of the primary wave takes 256 work
+    // items per atomic when most tiles are empty, else 32.  Read on the device so that the host never waits for the mask.
+    const unsigned *n_empty_tiles;
+    unsigned n_tiles;
 };
 
 struct LaunchCfg {
@@ -77,6 +80,10 @@ void launch_selftest_div(cudaStream_t st, unsigned per_thread, unsigned long lon
                          unsigned long long *tested);
 // accum -> mean, gamma 1/2.2, Color24 (RenderFunctions.cpp:152-159)
 void launch_resolve(cudaStream_t st, const float4 *accum, int npix, float inv_unused, int spp, float *rgb, unsigned char *rgb8);
+void launch_accum_add(cudaStream_t st, float4 *dst, const float4 *src, size_t npix);
+// multi-GPU: accumulator -> three planes of RGB sums (what the collective moves); resolve of reduced planes
+void launch_pack_rgb(cudaStream_t st, const float4 *accum, size_t npix, float *planes);
+void launch_resolve_planes(cudaStream_t st, const float *planes, size_t npix, int spp, float *rgb, unsigned char *rgb8);
 // RenderImage::ComputeZBufferImage (scene.h:590-612)
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8);
 

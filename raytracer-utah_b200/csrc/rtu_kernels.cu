@@ -227,9 +227,9 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
     unsigned t_next = 0, t_end = 0; // this warp's block of work items: large waves take TICKET_BLOCK items per atomic,
     unsigned t_block;               // small ones fewer, so that every resident warp still gets several blocks
     {
-        // blocks only pay where most work items are nearly free (frames whose tiles are mostly empty, FrameSetup::ticket_block);
+        // blocks only pay where most work items are nearly free (frames whose tiles are mostly empty, FrameSetup::n_empty_tiles);
         // heavy items are better handed out 32 at a time
-        const unsigned want = PRIMARY ? (unsigned)F.ticket_block : 32u;
+        const unsigned want = (PRIMARY && F.n_empty_tiles && 2u * __ldg(F.n_empty_tiles) > F.n_tiles) ? 256u : 32u;
         const unsigned per_warp = total / (gridDim.x * (WAVE_THREADS / 32) * 8u);
         t_block = per_warp >= want ? want : (per_warp < 32u ? 32u : (per_warp & ~31u));
     }
@@ -1084,6 +1084,48 @@ __global__ void k_resolve(const float4 *accum, int npix, int spp, float *rgb, un
     }
 }
 
+// dst += src (a frame that was rendered on its own and is now known to be complete; see render_checked in rtu_api.cu)
+__global__ void k_accum_add(float4 *dst, const float4 *src, size_t npix)
+{
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dst[p];
+        const float4 b = src[p];
+        a.x += b.x; a.y += b.y; a.z += b.z;
+        dst[p] = a;
+    }
+}
+
+// The RGB sums of the accumulator as three planes of npix floats: what a collective has to move (the .w lane carries nothing)
+__global__ void k_pack_rgb(const float4 *accum, size_t npix, float *planes)
+{
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = accum[p];
+        planes[p] = a.x;
+        planes[npix + p] = a.y;
+        planes[2 * npix + p] = a.z;
+    }
+}
+
+// k_resolve on reduced planes (RenderFunctions.cpp:152-159); rows [row0,row1) only when a rank resolves its own tile rows
+__global__ void k_resolve_planes(const float *planes, size_t npix, int spp, float *rgb, unsigned char *rgb8)
+{
+    size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float n = (float)spp;
+    float c[3] = {planes[p] / n, planes[npix + p] / n, planes[2 * npix + p] / n};
+    if (rgb) { rgb[p * 3] = c[0]; rgb[p * 3 + 1] = c[1]; rgb[p * 3 + 2] = c[2]; }
+    if (rgb8) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float gmm = (float)pow((double)c[k], 1 / 2.2);
+            float s = gmm * 255;
+            int v = (s == s) ? (int)s : 0;
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            rgb8[p * 3 + k] = (unsigned char)v;
+        }
+    }
+}
+
 __global__ void k_zminmax(const float *z, int npix, unsigned *mm)
 {
     // zmin / zmax over hit pixels (scene.h:596-601); positive floats order like their bit patterns
@@ -1628,6 +1670,21 @@ void launch_camera_rays(cudaStream_t st, const DCamera &cam, float ox, float oy,
 void launch_resolve(cudaStream_t st, const float4 *accum, int npix, float, int spp, float *rgb, unsigned char *rgb8)
 {
     k_resolve<<<(npix + 255) / 256, 256, 0, st>>>(accum, npix, spp, rgb, rgb8);
+}
+
+void launch_accum_add(cudaStream_t st, float4 *dst, const float4 *src, size_t npix)
+{
+    k_accum_add<<<148 * 8, 256, 0, st>>>(dst, src, npix);
+}
+
+void launch_pack_rgb(cudaStream_t st, const float4 *accum, size_t npix, float *planes)
+{
+    k_pack_rgb<<<148 * 8, 256, 0, st>>>(accum, npix, planes);
+}
+
+void launch_resolve_planes(cudaStream_t st, const float *planes, size_t npix, int spp, float *rgb, unsigned char *rgb8)
+{
+    k_resolve_planes<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(planes, npix, spp, rgb, rgb8);
 }
 
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8)

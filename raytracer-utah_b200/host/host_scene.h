@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -44,6 +46,22 @@ bool encode_png(const char *path, const uint8_t *px, int w, int h, int channels,
 
 void set_error(const std::string &msg);
 const std::string &last_error();
+
+// Body of an extern "C" entry point: no exception (std::bad_alloc from a vector sized by a file header, std::system_error
+// from std::thread, ...) may cross the C ABI; it becomes a status and a message like every other failure.
+template <class F> int guarded(const char *what, F body)
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        set_error(std::string(what) + ": out of host memory");
+    } catch (const std::exception &e) {
+        set_error(std::string(what) + ": " + e.what());
+    } catch (...) {
+        set_error(std::string(what) + ": unknown exception");
+    }
+    return RTU_ERR_INVALID;
+}
 
 } // namespace rtu
 

@@ -9,11 +9,7 @@
 #include <utility>
 #include <vector>
 
-#include "rtu.h"
-
-namespace rtu {
-void set_error(const std::string &msg);
-}
+#include "host_scene.h"
 
 namespace {
 
@@ -103,6 +99,7 @@ extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_ph
     if (n >= (1u << 30)) { rtu::set_error("rtu_host_balance_photons: too many photons"); return RTU_ERR_INVALID; }
     std::memset(out, 0, sizeof(rtu_photon)); // slot 0; every slot 1..n is assigned exactly once by the recursion
     if (n == 0) return RTU_OK;
+    return rtu::guarded("rtu_host_balance_photons", [&]() -> int {
     Balancer b;
     std::unique_ptr<Item[]> work(new Item[(size_t)n + 1]); // not value-initialised
     b.work = work.get();
@@ -145,6 +142,7 @@ extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_ph
     while ((1u << (fork_levels + 1)) <= hw && fork_levels < 6) fork_levels++;
     b.segment(lo, hi, 1, 1, (int)n, fork_levels);
     return RTU_OK;
+    });
 }
 
 extern "C" void rtu_photon_params_default(rtu_photon_params *p)

@@ -66,6 +66,8 @@ bool decode_png_rgb8(const char *path, std::vector<uint8_t> *rgb, int *w, int *h
         pos += 12 + (size_t)len;
     }
     if (W == 0 || H == 0) return fail("missing IHDR");
+    // the header is untrusted input: the same limit frame_dims() applies to images (2^28 pixels), and 16-bit sides
+    if (W > 65535u || H > 65535u || (uint64_t)W * H > (1ull << 28)) return fail("image dimensions out of range");
     if (interlace != 0) return fail("interlaced PNG not supported");
     int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!channels) return fail("bad colour type");

@@ -437,6 +437,7 @@ int rtu_version(void) { return 1; }
 int rtu_host_load_xml(const char *xml_path, const char *asset_root, rtu_host_scene **out)
 {
     if (!xml_path || !out) { rtu::set_error("rtu_host_load_xml: null argument"); return RTU_ERR_INVALID; }
+    return rtu::guarded("rtu_host_load_xml", [&]() -> int {
     std::unique_ptr<rtu_host_scene> hs(new rtu_host_scene);
     memset(&hs->desc, 0, sizeof hs->desc);
     rtu::Loader L;
@@ -455,6 +456,7 @@ int rtu_host_load_xml(const char *xml_path, const char *asset_root, rtu_host_sce
     }
     *out = hs.release();
     return RTU_OK;
+    });
 }
 
 const rtu_scene_desc *rtu_host_scene_desc(const rtu_host_scene *hs) { return hs ? &hs->desc : nullptr; }
@@ -467,6 +469,7 @@ int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t 
     if (!v || !f || !boxes || !data || !elements || !n_nodes) { rtu::set_error("rtu_host_build_bvh: null argument"); return RTU_ERR_INVALID; }
     for (uint32_t i = 0; i < nf * 3; i++)
         if (f[i] >= nv) { rtu::set_error("rtu_host_build_bvh: face index out of range"); return RTU_ERR_INVALID; }
+    return rtu::guarded("rtu_host_build_bvh", [&]() -> int {
     std::vector<float> b;
     std::vector<uint32_t> d, e;
     rtu::build_bvh(v, f, nf, max_per_leaf, &b, &d, &e);
@@ -475,14 +478,17 @@ int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t 
     memcpy(elements, e.data(), e.size() * sizeof(uint32_t));
     *n_nodes = (uint32_t)d.size();
     return RTU_OK;
+    });
 }
 
 int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels)
 {
     std::string err;
     if (!path || !pixels) { rtu::set_error("rtu_write_png: null argument"); return RTU_ERR_INVALID; }
-    if (!rtu::encode_png(path, pixels, width, height, channels, &err)) { rtu::set_error(err); return RTU_ERR_IO; }
-    return RTU_OK;
+    return rtu::guarded("rtu_write_png", [&]() -> int {
+        if (!rtu::encode_png(path, pixels, width, height, channels, &err)) { rtu::set_error(err); return RTU_ERR_IO; }
+        return RTU_OK;
+    });
 }
 
 } // extern "C"

@@ -101,7 +101,8 @@ class Stats(C.Structure):
     _fields_ = [("trace_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("box_tests", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("primary_wave", KernelStats), ("secondary_waves", KernelStats),
-                ("shadow_waves", KernelStats), ("shade_kernels", KernelStats), ("scene_device_bytes", C.c_uint64)]
+                ("shadow_waves", KernelStats), ("shade_kernels", KernelStats), ("scene_device_bytes", C.c_uint64),
+                ("queue_retries", C.c_uint64)]
 
     def as_dict(self):
         out = {}
@@ -275,6 +276,37 @@ class Context:
             self._h = C.c_void_p()
 
 
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rtu_comm_unique_id: 128 bytes rank 0 hands to the other ranks (any transport) before rtu_comm_create."""
+    L = lib()
+    buf = (u8 * COMM_ID_BYTES)()
+    _check(L.rtu_comm_unique_id(buf), "rtu_comm_unique_id")
+    return bytes(buf)
+
+
+class Comm:
+    """rtu_comm: this rank's end of the NCCL communicator the multi-GPU entry points use (one context per rank)."""
+
+    def __init__(self, ctx, unique_id, rank, world):
+        L = lib()
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        buf = (u8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        L.rtu_comm_create.argtypes = [C.c_void_p, C.c_void_p, i32, i32, C.POINTER(C.c_void_p)]
+        _check(L.rtu_comm_create(ctx._h, buf, rank, world, C.byref(self._h)), "rtu_comm_create")
+
+    def close(self):
+        if self._h:
+            L = lib()
+            L.rtu_comm_destroy.argtypes = [C.c_void_p]
+            L.rtu_comm_destroy.restype = None
+            L.rtu_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 class Scene:
     """Device-resident scene (rtu_scene_upload) with the batched operator calls."""
 
@@ -364,6 +396,46 @@ class Scene:
         L = lib()
         L.rtu_render_device.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, i32]
         _check(L.rtu_render_device(self._h, C.byref(params), C.c_void_p(d_accum), 1 if clear else 0), "rtu_render_device")
+
+    def _image(self, params, want, out=None):
+        w, h = self._dims(params)
+        spec = {"rgb8": ((h, w, 3), "u1", u8), "rgb": ((h, w, 3), "f4", f32), "z": ((h, w), "f4", f32),
+                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
+        bufs, img = {}, Image()
+        for k in want:
+            shp, dt, ct = spec[k]
+            if out is not None and k in out:
+                a = out[k]
+                if a.shape != shp or a.dtype != np.dtype(dt) or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (k, dt, shp))
+                bufs[k] = a
+            else:
+                bufs[k] = np.zeros(shp, dt)
+            setattr(img, k, _ptr(bufs[k], ct))
+        return bufs, img
+
+    def reduce_resolve(self, comm, params, d_accum=0, root=0, want=("rgb8",), out=None):
+        """rtu_reduce_resolve: spp slices -> one ncclReduce of the RGB sums onto `root` -> resolve -> host buffers.
+        Collective; returns the buffers on the root, None elsewhere."""
+        L = lib()
+        L.rtu_reduce_resolve.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, i32, C.POINTER(Image)]
+        if comm.rank == root:
+            bufs, img = self._image(params, want, out)
+            _check(L.rtu_reduce_resolve(self._h, comm._h, C.byref(params), C.c_void_p(d_accum), root, C.byref(img)), "rtu_reduce_resolve")
+            return bufs
+        _check(L.rtu_reduce_resolve(self._h, comm._h, C.byref(params), C.c_void_p(d_accum), root, None), "rtu_reduce_resolve")
+        return None
+
+    def gather_resolve(self, comm, params, d_accum=0, root=0, want=("rgb8",), out=None):
+        """rtu_gather_resolve: row ranges -> every rank resolves its rows and sends them to `root`."""
+        L = lib()
+        L.rtu_gather_resolve.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, i32, C.POINTER(Image)]
+        if comm.rank == root:
+            bufs, img = self._image(params, want, out)
+            _check(L.rtu_gather_resolve(self._h, comm._h, C.byref(params), C.c_void_p(d_accum), root, C.byref(img)), "rtu_gather_resolve")
+            return bufs
+        _check(L.rtu_gather_resolve(self._h, comm._h, C.byref(params), C.c_void_p(d_accum), root, None), "rtu_gather_resolve")
+        return None
 
     def resolve(self, params, d_accum=0, want=("rgb8", "rgb")):
         L = lib()
