@@ -710,6 +710,9 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
 #ifndef SHADOW_BLOCKS
 #define SHADOW_BLOCKS EXT_BLOCKS
 #endif
+#ifndef SHADOW_PRUNE_TMAX
+#define SHADOW_PRUNE_TMAX 1 // any-hit walks skip boxes entered beyond the light (result-neutral, see k_shadow_wave)
+#endif
 
 struct SpWarp {
     float4 o[32];                // mesh-local origin, t_max
@@ -831,6 +834,15 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                             bool h1 = slab_fast(r, I, a.x, a.y, a.z, a.w, b.x, b.y, RTU_BIG, e1);
                             bool h2 = slab_fast(r, I, b.z, b.w, c.x, c.y, c.z, c.w, RTU_BIG, e2);
                             tl.box += 2;
+#if SHADOW_PRUNE_TMAX
+                            // Only the boolean is observable: a box the ray enters well beyond the light holds no triangle
+                            // that can pass `t < t_max` (objFunctions.cpp:270; the reference walks such boxes because it
+                            // hands BIGFLOAT to BVHBoxIntersection, :358-359).  "Well beyond": 1 % + 0.01, orders of
+                            // magnitude above the rounding of a triangle's own t against its box's tEntry.
+                            const float tlim = o.w * 1.01f + 0.01f;
+                            h1 = h1 && !(e1 > tlim);
+                            h2 = h2 && !(e2 > tlim);
+#endif
                             if (h1) c1 = __float_as_uint(dd.x);
                             if (h2) c2 = __float_as_uint(dd.y);
                         }

@@ -11,6 +11,14 @@
 
 namespace rtu {
 
+// The any-hit hierarchy of a mesh (occlusion_bvh.cpp): binned-SAH binary tree in the device pair layout
+struct OccBvh {
+    std::vector<float> pairs;    // 16 words per internal node: child boxes (min xyz, max xyz) x 2, child words x 2, 2 unused
+    std::vector<uint32_t> slots; // leaf-ordered cyBVH slots (indices into bvh_elements)
+    uint32_t root = 0;           // child word of the root
+};
+void build_occlusion_bvh(const float *v, const uint32_t *f, const uint32_t *elements, uint32_t nf, OccBvh *out);
+
 // cyTriMesh arrays + cyBVH arrays of one TriObj (objects.h:46-66)
 struct HostMesh {
     std::string name;
@@ -19,6 +27,7 @@ struct HostMesh {
     std::vector<float> bvh_boxes;        // (n_nodes) x 6, node 0 unused
     std::vector<uint32_t> bvh_data;
     std::vector<uint32_t> bvh_elements;
+    OccBvh occ;                          // any-hit hierarchy over the same triangles (built at load time)
     float bound_min[3] = {1, 1, 1}, bound_max[3] = {0, 0, 0}; // cyTriMesh.h:128 "not ready" box
     uint32_t nf() const { return (uint32_t)(f.size() / 3); }
 };

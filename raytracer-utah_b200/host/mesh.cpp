@@ -174,6 +174,7 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
     if (m->vn.empty()) compute_vertex_normals(m); // objects.h:56
     compute_bounds(m);                             // objects.h:57
     build_bvh(m->v.data(), m->f.data(), nf, 4, &m->bvh_boxes, &m->bvh_data, &m->bvh_elements); // objects.h:58
+    build_occlusion_bvh(m->v.data(), m->f.data(), m->bvh_elements.data(), nf, &m->occ);       // any-hit hierarchy (not in the reference)
     return true;
 }
 

@@ -412,6 +412,12 @@ void rtu_host_scene::finalize()
         d.bvh_data = m->bvh_data.data();
         d.bvh_nodes = (uint32_t)m->bvh_data.size();
         d.bvh_elements = m->bvh_elements.data();
+        if (!m->occ.slots.empty()) {
+            d.occ_pairs = m->occ.pairs.empty() ? nullptr : m->occ.pairs.data();
+            d.occ_n_pairs = (uint32_t)(m->occ.pairs.size() / 16);
+            d.occ_root = m->occ.root;
+            d.occ_slots = m->occ.slots.data();
+        }
         memcpy(d.bound_min, m->bound_min, sizeof d.bound_min);
         memcpy(d.bound_max, m->bound_max, sizeof d.bound_max);
         mesh_descs.push_back(d);
@@ -478,6 +484,25 @@ int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t 
     memcpy(elements, e.data(), e.size() * sizeof(uint32_t));
     *n_nodes = (uint32_t)d.size();
     return RTU_OK;
+    });
+}
+
+int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t nf, const uint32_t *bvh_elements,
+                                 float *pairs, uint32_t *n_pairs, uint32_t *root, uint32_t *slots)
+{
+    if (!v || !f || !bvh_elements || !pairs || !n_pairs || !root || !slots) { rtu::set_error("rtu_host_build_occlusion_bvh: null argument"); return RTU_ERR_INVALID; }
+    for (uint32_t i = 0; i < nf * 3; i++)
+        if (f[i] >= nv) { rtu::set_error("rtu_host_build_occlusion_bvh: face index out of range"); return RTU_ERR_INVALID; }
+    for (uint32_t i = 0; i < nf; i++)
+        if (bvh_elements[i] >= nf) { rtu::set_error("rtu_host_build_occlusion_bvh: element out of range"); return RTU_ERR_INVALID; }
+    return rtu::guarded("rtu_host_build_occlusion_bvh", [&]() -> int {
+        rtu::OccBvh o;
+        rtu::build_occlusion_bvh(v, f, bvh_elements, nf, &o);
+        memcpy(pairs, o.pairs.data(), o.pairs.size() * sizeof(float));
+        memcpy(slots, o.slots.data(), o.slots.size() * sizeof(uint32_t));
+        *n_pairs = (uint32_t)(o.pairs.size() / 16);
+        *root = o.root;
+        return RTU_OK;
     });
 }
 
