@@ -72,9 +72,9 @@ typedef struct rtu_mesh {
     float bound_min[3], bound_max[3]; /* cyTriMesh::boundMin/Max */
     /* Optional: the any-hit hierarchy of rtu_host_build_occlusion_bvh over the same triangles (what shadow rays walk on the
      * device; the cyBVH above still decides every answer).  All zero / NULL: rtu_scene_upload builds it itself. */
-    const float *occ_pairs;           /* occ_n_pairs x 16 words */
+    const float *occ_nodes;           /* occ_n_nodes x 32 words: 4-wide nodes */
     const uint32_t *occ_slots;        /* nf indices into bvh_elements, in the hierarchy's leaf order */
-    uint32_t occ_n_pairs;
+    uint32_t occ_n_nodes;
     uint32_t occ_root;
 } rtu_mesh;
 
@@ -246,10 +246,10 @@ void rtu_host_scene_destroy(rtu_host_scene *hs);
 int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t nf,
                        uint32_t max_per_leaf, float *boxes, uint32_t *data, uint32_t *elements,
                        uint32_t *n_nodes);
-/* Binned-SAH any-hit hierarchy over the triangles of a mesh (not in the reference: ShadowTrace walks the cyBVH there).
- * pairs: room for nf x 16 words, slots: nf words; *n_pairs <= nf - 1 internal nodes are written. */
+/* Binned-SAH any-hit hierarchy over the triangles of a mesh, 4-wide nodes (not in the reference: ShadowTrace walks the
+ * cyBVH there).  nodes: room for nf x 32 words, slots: nf words; *n_nodes < nf nodes are written. */
 int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t nf, const uint32_t *bvh_elements,
-                                 float *pairs, uint32_t *n_pairs, uint32_t *root, uint32_t *slots);
+                                 float *nodes, uint32_t *n_nodes, uint32_t *root, uint32_t *slots);
 /* Result.png / ZBuffer.png writers (RenderImage::SaveImage/SaveZImage, scene.h:638-654). */
 int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels);
 

@@ -38,7 +38,18 @@ struct __align__(16) BvhPair {
     float b1[6];    // child 1 box: min xyz, max xyz
     float b2[6];    // child 2 box
     uint32_t c1, c2;
-    uint32_t pad[2];
+    uint32_t up;    // cyBVH pairs only: the pair that holds this node's own box | (1u << 31 if it is that pair's child 2);
+                    // 0xffffffff for the root's pair (the root's box is never tested, objFunctions.cpp:343)
+    uint32_t pad;
+};
+
+// One node of a mesh's any-hit hierarchy (host/occlusion_bvh.cpp): the boxes of up to four children, one coordinate of all
+// four per float4, and their child words; an unused slot has an inverted box and the word 0x7fffffff.  One visit = one
+// 128-byte line.
+struct __align__(16) OccNode {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    uint32_t child[4];
+    uint32_t pad[4];
 };
 
 struct __align__(16) TriRec {
@@ -64,6 +75,14 @@ struct DMesh {
     float bmin[3], bmax[3];
     uint32_t empty;      // no faces: cyTriMesh's "not ready" box never intersects
     uint32_t coords_ok;  // every box coordinate of the mesh is 0 or at least 2^-36 in magnitude (see mesh_invdir)
+    // any-hit hierarchy (host/occlusion_bvh.cpp): 4-wide binned-SAH nodes over the same triangles, its triangle records in
+    // ITS leaf order (fbits: projection axis << 30 | cyBVH slot), and per cyBVH slot the pair that holds the box of the
+    // slot's leaf (| 1u << 31: child 2) - the start of the ancestor chain ref_reaches() climbs
+    const OccNode *occ_nodes;
+    const TriRec *occ_tris;
+    const uint32_t *tri_up;
+    uint32_t occ_root;
+    float occ_scale;     // largest |coordinate| of the mesh's bound box (scale of the per-ray conservative margin)
 };
 
 struct DTexMap {

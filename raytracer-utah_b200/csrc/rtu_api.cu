@@ -232,7 +232,24 @@ int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *
         memcpy(P.b1, m.bvh_boxes + (size_t)c1 * 6, 6 * sizeof(float));
         memcpy(P.b2, m.bvh_boxes + (size_t)(c1 + 1) * 6, 6 * sizeof(float));
         if (!child_word(c1, &P.c1) || !child_word(c1 + 1, &P.c2)) { rtu::set_error("rtu_scene_upload: BVH leaf range out of bounds"); return RTU_ERR_INVALID; }
-        P.pad[0] = P.pad[1] = 0;
+        P.up = 0xffffffffu;
+        P.pad = 0;
+    }
+    // ancestor links: pair i holds the boxes of the two children of internal node order[i]; a child that is internal has its
+    // own pair, whose `up` points back here; a child that is a leaf hands the link to its triangles (tri_up)
+    std::vector<uint32_t> tri_up(m.nf, 0xffffffffu);
+    for (size_t i = 0; i < order.size(); i++) {
+        const uint32_t c1 = m.bvh_data[order[i]] & 0x7fffffffu;
+        for (uint32_t k = 0; k < 2; k++) {
+            const uint32_t c = c1 + k, link = (uint32_t)i | (k << 31);
+            const uint32_t dw = m.bvh_data[c];
+            if (dw & LEAF) {
+                const uint32_t off = dw & 0x0fffffffu, cnt = ((dw >> 28) & 7u) + 1u;
+                for (uint32_t t = 0; t < cnt; t++) tri_up[off + t] = link;
+            } else {
+                pairs[pair_of[c]].up = link;
+            }
+        }
     }
     if (!child_word(1, &out->root)) { rtu::set_error("rtu_scene_upload: BVH root leaf out of bounds"); return RTU_ERR_INVALID; }
     // depth bound for the traversal stack (depth-first, both children pushed: depth+1 entries)
@@ -292,17 +309,70 @@ int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *
             }
         }
     }
+    // any-hit hierarchy: the caller's (built once at load time by rtu_host_load_xml / rtu_host_build_occlusion_bvh), else built here
+    rtu::OccBvh built;
+    const float *onodes = m.occ_nodes;
+    const uint32_t *oslots = m.occ_slots;
+    uint32_t on_nodes = m.occ_n_nodes, oroot = m.occ_root;
+    if (!oslots) {
+        rtu::build_occlusion_bvh(m.v, m.f, m.bvh_elements, m.nf, &built);
+        onodes = built.nodes.data();
+        oslots = built.slots.data();
+        on_nodes = (uint32_t)(built.nodes.size() / 32);
+        oroot = built.root;
+    }
+    static_assert(sizeof(OccNode) == 128, "any-hit node layout");
+    std::vector<OccNode> occ(on_nodes);
+    if (on_nodes) {
+        if (!onodes) { rtu::set_error("rtu_scene_upload: occ_n_nodes without occ_nodes"); return RTU_ERR_INVALID; }
+        memcpy(occ.data(), onodes, (size_t)on_nodes * sizeof(OccNode));
+    }
+    {   // validate what the device will index with: child words of the hierarchy and the slot permutation
+        auto word_ok = [&](uint32_t w) {
+            if (w == 0x7fffffffu) return true; // unused child slot
+            if (w & LEAF) return (uint64_t)(w & 0x0fffffffu) + (((w >> 28) & 7u) + 1u) <= m.nf;
+            return w < on_nodes;
+        };
+        bool ok = word_ok(oroot) && oroot != 0x7fffffffu && on_nodes < (1u << 27);
+        for (uint32_t i = 0; i < on_nodes && ok; i++)
+            for (int k = 0; k < 4; k++) ok = ok && word_ok(occ[i].child[k]);
+        std::vector<unsigned char> seen(m.nf, 0);
+        for (uint32_t i = 0; i < m.nf && ok; i++) { ok = oslots[i] < m.nf && !seen[oslots[i]]; if (ok) seen[oslots[i]] = 1; }
+        if (!ok) { rtu::set_error("rtu_scene_upload: malformed any-hit hierarchy (occ_nodes / occ_slots)"); return RTU_ERR_INVALID; }
+    }
+    std::vector<TriRec> otris(m.nf);
+    for (uint32_t i = 0; i < m.nf; i++) {
+        otris[i] = tris[oslots[i]];
+        uint32_t fb;
+        memcpy(&fb, &otris[i].fbits, 4);
+        fb = (fb & 0xc0000000u) | oslots[i]; // keep the projection axis, carry the cyBVH slot instead of the face id
+        memcpy(&otris[i].fbits, &fb, 4);
+    }
     BvhPair *dp = nullptr;
-    TriRec *dt = nullptr;
+    OccNode *dop = nullptr;
+    TriRec *dt = nullptr, *dot = nullptr;
     TriShade *ds = nullptr;
+    uint32_t *dup = nullptr;
     int rc;
     if ((rc = dev_upload(pairs, &dp, st, owned))) return rc;
     if ((rc = dev_upload(tris, &dt, st, owned))) return rc;
     if ((rc = dev_upload(shade, &ds, st, owned))) return rc;
+    if ((rc = dev_upload(occ, &dop, st, owned))) return rc;
+    if ((rc = dev_upload(otris, &dot, st, owned))) return rc;
+    if ((rc = dev_upload(tri_up, &dup, st, owned))) return rc;
     CU(cudaStreamSynchronize(st)); // host vectors go out of scope
     out->pairs = dp;
     out->tris = dt;
     out->shade = ds;
+    out->occ_nodes = dop;
+    out->occ_tris = dot;
+    out->tri_up = dup;
+    out->occ_root = oroot;
+    {
+        float sc = 0.f;
+        for (int k = 0; k < 3; k++) sc = std::max(sc, std::max(std::fabs(m.bound_min[k]), std::fabs(m.bound_max[k])));
+        out->occ_scale = sc;
+    }
     out->n_pairs = (uint32_t)pairs.size();
     out->n_tris = m.nf;
     {   // box coordinates that are 0 or >= 2^-36 in magnitude: then "bound - origin" is 0 or >= 2^-60 for every such
@@ -1347,25 +1417,35 @@ int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int6
 {
     if (!s || (n > 0 && (!rays || !t_max || !occluded)) || n < 0) { rtu::set_error("rtu_shadow_trace: bad argument"); return RTU_ERR_INVALID; }
     if (n == 0) return RTU_OK;
+    if (n >= (1ll << 30)) { rtu::set_error("rtu_shadow_trace: batch too large"); return RTU_ERR_UNSUPPORTED; }
     rtu_context *c = s->ctx;
     CU(cudaSetDevice(c->device));
+    // The operator runs the kernel the frames run (k_shadow_wave: pooled walks of the any-hit hierarchy); RTU_SHADOW_TRACE=exact
+    // selects the plain per-lane walk of the cyBVH instead (k_shadow_batch), which the tests use as the cross-check.
+    const char *sel = getenv("RTU_SHADOW_TRACE");
+    const bool wave = !(sel && sel[0] == 'e');
     int rc;
-    if ((rc = ensure_scratch(c, std::max<size_t>(c->q_cap, 1024), std::max<size_t>(c->shadow_cap, 1024)))) return rc;
+    if ((rc = ensure_scratch(c, std::max<size_t>(c->q_cap, 1024), std::max<size_t>(c->shadow_cap, wave ? (size_t)n : 1024)))) return rc;
+    if ((rc = ensure_work(c, 8))) return rc;
     rtu_ray *dr = nullptr;
     float *dt = nullptr;
     unsigned char *docc = nullptr;
+    float4 *acc = nullptr;
     CU(cudaMalloc((void **)&dr, n * sizeof(rtu_ray)));
     cudaError_t e = cudaMalloc((void **)&dt, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&docc, n);
+    if (e == cudaSuccess && wave) e = cudaMalloc((void **)&acc, n * sizeof(float4));
+    if (e == cudaSuccess && wave) e = cudaMemsetAsync(acc, 0, n * sizeof(float4), c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dr, rays, n * sizeof(rtu_ray), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dt, t_max, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream);
     if (e == cudaSuccess) {
         cudaEventRecord(c->ev0, c->stream);
-        launch_shadow_batch(c->cfg, c->stream, s->S, dr, dt, n, docc, c->wb.counters);
+        if (wave) launch_shadow_batch_wave(c->cfg, c->stream, s->S, dr, dt, n, docc, c->wb, acc, c->work);
+        else launch_shadow_batch(c->cfg, c->stream, s->S, dr, dt, n, docc, c->wb.counters);
         cudaEventRecord(c->ev1, c->stream);
         s->timed = true;
-        s->launches = 1;
+        s->launches = wave ? 3 : 1;
         e = cudaMemcpyAsync(occluded, docc, n, cudaMemcpyDeviceToHost, c->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1373,6 +1453,7 @@ int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int6
     cudaFree(dr);
     if (dt) cudaFree(dt);
     if (docc) cudaFree(docc);
+    if (acc) cudaFree(acc);
     CU(e);
     return RTU_OK;
 }

@@ -72,6 +72,9 @@ void launch_trace_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
                         rtu_hit *hits, DCounters *counters);
 void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
                          long long n, unsigned char *occ, DCounters *counters);
+// the same operator through the frame's own any-hit kernel (launch_shadow_wave): accum = n zeroed float4
+void launch_shadow_batch_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
+                              long long n, unsigned char *occ, const WaveBuffers &B, float4 *accum, unsigned *work_counter);
 // Shade(ray, hit, lights, bounces) for caller-provided hits: first step, then the usual waves
 void launch_shade_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const rtu_ray *rays,
                         const rtu_hit *hits, long long n, const WaveBuffers &B, int out_q, float4 *accum);

@@ -706,9 +706,12 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
 #ifndef SP_POOL
 #define SP_POOL 512  // internal-node items: slot << 27 | pair index
 #endif
-#define SP_LEAF 128  // leaf items: slot << 27 | (count - 1) << 24 | first triangle
+#define SP_LEAF 192  // leaf items: slot << 27 | (count - 1) << 24 | first triangle (one iteration can add 128, 31 may wait)
 #ifndef SHADOW_BLOCKS
 #define SHADOW_BLOCKS EXT_BLOCKS
+#endif
+#ifndef SHADOW_OCC
+#define SHADOW_OCC 1 // any-hit walks use the mesh's binned-SAH occlusion hierarchy with conservative box tests (intersect.cuh)
 #endif
 #ifndef SHADOW_PRUNE_TMAX
 #define SHADOW_PRUNE_TMAX 1 // any-hit walks skip boxes entered beyond the light (result-neutral, see k_shadow_wave)
@@ -717,8 +720,18 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
 struct SpWarp {
     float4 o[32];                // mesh-local origin, t_max
     float4 d[32];                // mesh-local direction, InvDir::ok
-    float4 y[32];                // hoisted reciprocals
-    const BvhPair *pairs[32];
+    float4 y[32];                // hoisted reciprocals (exact slab tests: cyBVH walk, ref_reaches)
+#if SHADOW_OCC
+    float4 ci[32];               // OccRay: 1/d, tlim
+    float4 cn[32];               // OccRay: near-plane offsets
+    float4 cf[32];               // OccRay: far-plane offsets
+    const DMesh *mesh[32];
+#endif
+#if SHADOW_OCC
+    const OccNode *nodes[32];    // the hierarchy the pool walks: the mesh's 4-wide any-hit hierarchy
+#else
+    const BvhPair *pairs[32];    // ... or its cyBVH
+#endif
     const TriRec *tris[32];
     unsigned idx[32], node[32];  // shadow-queue entry and mesh node of the slot
     unsigned pool[SP_POOL];
@@ -751,6 +764,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
             const unsigned take = njobs < 32u ? njobs : 32u;
             njobs -= take;
             unsigned rootw = NONE;
+            bool decided = false; // occluded before the pool starts (rays that do not use the hierarchy)
             if (lane < take) {
                 uint2 j = W.jobs[njobs + lane];
                 float4 o = Q.o[j.x], d = Q.d[j.x];
@@ -765,17 +779,33 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 W.o[lane] = make_float4(lr.px, lr.py, lr.pz, d.w);
                 W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
                 W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
-                W.pairs[lane] = M.pairs;
-                W.tris[lane] = M.tris;
                 W.idx[lane] = j.x;
                 W.node[lane] = j.y;
+#if SHADOW_OCC
+                const OccRay oc = occ_setup(lr, M.occ_scale, d.w);
+                W.ci[lane] = make_float4(oc.ix, oc.iy, oc.iz, oc.tlim);
+                W.cn[lane] = make_float4(oc.nx, oc.ny, oc.nz, 0.f);
+                W.cf[lane] = make_float4(oc.fx, oc.fy, oc.fz, 0.f);
+                W.mesh[lane] = &M;
+                W.nodes[lane] = M.occ_nodes;
+                W.tris[lane] = M.occ_tris;
+                rootw = M.occ_root;
+                if (!oc.ok) { // non-finite / huge components: the exact walk of the cyBVH decides
+                    decided = bvh_walk_any_fallback(M, lr, I, d.w, tl);
+                    rootw = NONE;
+                }
+#else
+                W.pairs[lane] = M.pairs;
+                W.tris[lane] = M.tris;
                 rootw = M.root;
+#endif
             }
             unsigned bi = __ballot_sync(FULL, rootw < NONE), bl = __ballot_sync(FULL, rootw > NONE);
             if (rootw < NONE) W.pool[__popc(bi & lt)] = (lane << 27) | rootw;
             if (rootw > NONE) W.leaf[__popc(bl & lt)] = (lane << 27) | (((rootw >> 28) & 7u) << 24) | (rootw & 0x00ffffffu);
             unsigned pool_n = __popc(bi), leaf_n = __popc(bl);
-            if (lane == 0) W.occl = 0u;
+            const unsigned dec = __ballot_sync(FULL, decided);
+            if (lane == 0) W.occl = dec;
             __syncwarp();
             for (;;) {
                 const bool do_leaf = leaf_n >= 32u || (pool_n == 0u && leaf_n > 0u);
@@ -792,6 +822,14 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                             r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                             const TriRec *tris = W.tris[sl];
                             const unsigned first = it & 0x00ffffffu, cnt = ((it >> 24) & 7u) + 1u;
+#if SHADOW_OCC
+                            const float4 yv = W.y[sl];
+                            InvDir I;
+                            I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                            const DMesh *M = W.mesh[sl];
+                            for (unsigned i = 0; i < cnt; i++)
+                                if (occ_candidate(*M, tris + first + i, r, I, o.w, tl)) { atomicOr(&W.occl, 1u << sl); break; }
+#else
                             for (unsigned i = 0; i < cnt; i++) {
                                 const float4 *q = reinterpret_cast<const float4 *>(tris + first + i);
                                 float4 x = __ldg(q), yv = __ldg(q + 1), w4 = __ldg(q + 2);
@@ -804,11 +842,71 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                                 int fr;
                                 if (tri_hit(T, r, z, fr, b1, b2, b3)) { atomicOr(&W.occl, 1u << sl); break; }
                             }
+#endif
                         }
                     }
                     __syncwarp();
                     continue;
                 }
+#if SHADOW_OCC
+                // one item = one 4-wide node: up to four children go back to the pools
+                const bool finish = pool_n > SP_POOL - 128u; // no room to expand 32 items: walk them to the end instead
+                const unsigned n = pool_n < 32u ? pool_n : 32u;
+                pool_n -= n;
+                unsigned sl = 0, hit = 0;
+                uint4 ch = make_uint4(NONE, NONE, NONE, NONE);
+                if (lane < n) {
+                    const unsigned it = W.pool[pool_n + lane];
+                    sl = it >> 27;
+                    if (!((occl >> sl) & 1u)) {
+                        const float4 ci = W.ci[sl], cn = W.cn[sl], cf = W.cf[sl];
+                        OccRay oc;
+                        oc.ix = ci.x; oc.iy = ci.y; oc.iz = ci.z; oc.tlim = ci.w;
+                        oc.nx = cn.x; oc.ny = cn.y; oc.nz = cn.z;
+                        oc.fx = cf.x; oc.fy = cf.y; oc.fz = cf.z;
+                        oc.ok = true;
+                        if (finish) {
+                            const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
+                            Ray r;
+                            r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                            InvDir I;
+                            I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                            if (occ_walk(*W.mesh[sl], it & 0x07ffffffu, r, I, oc, o.w, tl)) atomicOr(&W.occl, 1u << sl);
+                        } else {
+                            hit = occ_node(oc, W.nodes[sl] + (it & 0x07ffffffu), ch);
+                            tl.box += 4;
+                        }
+                    }
+                }
+                // every lane pushes its hit children: internal nodes to the item pool, leaves to the leaf pool; positions from
+                // one packed warp scan (internal count in the low half, leaf count in the high half)
+                const unsigned w0 = (hit & 1u) ? ch.x : NONE, w1 = (hit & 2u) ? ch.y : NONE, w2 = (hit & 4u) ? ch.z : NONE, w3 = (hit & 8u) ? ch.w : NONE;
+                const unsigned mine = (unsigned)(w0 < NONE) + (w1 < NONE) + (w2 < NONE) + (w3 < NONE) +
+                                      (((unsigned)(w0 > NONE) + (w1 > NONE) + (w2 > NONE) + (w3 > NONE)) << 16);
+                unsigned incl = mine;
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const unsigned v = __shfl_up_sync(FULL, incl, o2);
+                    if (lane >= (unsigned)o2) incl += v;
+                }
+                const unsigned tot = __shfl_sync(FULL, incl, 31);
+                unsigned pi = pool_n + ((incl - mine) & 0xffffu), li = leaf_n + ((incl - mine) >> 16);
+                const unsigned tag = sl << 27;
+#define RTU_PUSH(WORD)                                                                                                           \
+                if (WORD < NONE) W.pool[pi++] = tag | WORD;                                                                      \
+                else if (WORD > NONE) W.leaf[li++] = tag | (((WORD >> 28) & 7u) << 24) | (WORD & 0x00ffffffu);
+                RTU_PUSH(w3)
+                RTU_PUSH(w2)
+                RTU_PUSH(w1)
+                RTU_PUSH(w0)
+#undef RTU_PUSH
+                pool_n += tot & 0xffffu;
+                leaf_n += tot >> 16;
+#ifdef RTU_DEBUG_BOUNDS
+                if (pool_n > SP_POOL || leaf_n > SP_LEAF) counters->overflow = 0xBAD4;
+#endif
+                __syncwarp();
+#else
                 const bool finish = pool_n > SP_POOL - 64u; // no room to expand 32 items: walk them to the end instead
                 const unsigned n = pool_n < 32u ? pool_n : 32u;
                 pool_n -= n;
@@ -817,12 +915,12 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                     const unsigned it = W.pool[pool_n + lane];
                     sl = it >> 27;
                     if (!((occl >> sl) & 1u)) {
+                        const BvhPair *pairs = W.pairs[sl];
                         const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
                         Ray r;
                         r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                         InvDir I;
                         I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                        const BvhPair *pairs = W.pairs[sl];
                         if (finish) {
                             float z = o.w, b1, b2, b3;
                             int fr, tslot;
@@ -861,6 +959,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 if (pool_n > SP_POOL || leaf_n > SP_LEAF) counters->overflow = 0xBAD4;
 #endif
                 __syncwarp();
+#endif
             }
             // rays that were not stopped by their mesh go on with the node behind it
             const unsigned occl = *(volatile unsigned *)&W.occl;
@@ -1040,6 +1139,23 @@ k_shadow_batch(DScene S, const rtu_ray *rays, const float *tmax, long long n, un
         occ[i] = (h && B.z > 0.0f) ? 1 : 0;
     }
     flush_tally(tl, counters, 2);
+}
+
+// rtu_shadow_trace through the frame's own any-hit kernel: caller rays become shadow-queue entries whose contribution is 1
+// for "pixel" i, so accum[i].x stays 0 exactly where ray i is occluded.
+__global__ void k_fill_shadow_queue(const rtu_ray *rays, const float *tmax, long long n, ShadowQueue Q)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Q.o[i] = make_float4(rays[i].p[0], rays[i].p[1], rays[i].p[2], __int_as_float((int)i));
+        Q.d[i] = make_float4(rays[i].dir[0], rays[i].dir[1], rays[i].dir[2], tmax[i]);
+        Q.c[i] = make_float4(1.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *Q.count = (unsigned)n;
+}
+__global__ void k_occluded_from_accum(const float4 *accum, long long n, unsigned char *occ)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        occ[i] = accum[i].x == 0.f ? 1 : 0;
 }
 
 // First Shade() step on caller-provided hits (rtu_shade); pixel index = ray index.
@@ -1618,6 +1734,14 @@ void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
 {
     static int occ = 0;
     k_shadow_batch<<<resident_grid(cfg, k_shadow_batch, &occ), WAVE_THREADS, 0, st>>>(S, rays, tmax, n, occl, counters);
+}
+
+void launch_shadow_batch_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
+                              long long n, unsigned char *occl, const WaveBuffers &B, float4 *accum, unsigned *work_counter)
+{
+    k_fill_shadow_queue<<<148 * 4, 256, 0, st>>>(rays, tmax, n, B.shadow);
+    launch_shadow_wave(cfg, st, S, B, accum, work_counter);
+    k_occluded_from_accum<<<148 * 4, 256, 0, st>>>(accum, n, occl);
 }
 
 void launch_shade_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const rtu_ray *rays,

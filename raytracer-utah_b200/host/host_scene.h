@@ -11,17 +11,29 @@
 
 namespace rtu {
 
-// The any-hit hierarchy of a mesh (occlusion_bvh.cpp): binned-SAH binary tree in the device pair layout
+// The any-hit hierarchy of a mesh (occlusion_bvh.cpp): binned-SAH tree collapsed to 4-wide nodes, device layout
 struct OccBvh {
-    std::vector<float> pairs;    // 16 words per internal node: child boxes (min xyz, max xyz) x 2, child words x 2, 2 unused
+    std::vector<float> nodes;    // 32 words per node: lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] child[4] pad[4]
     std::vector<uint32_t> slots; // leaf-ordered cyBVH slots (indices into bvh_elements)
-    uint32_t root = 0;           // child word of the root
+    uint32_t root = 0;           // child word of the root: node 0, or a leaf word for a mesh of at most 4 triangles
 };
 void build_occlusion_bvh(const float *v, const uint32_t *f, const uint32_t *elements, uint32_t nf, OccBvh *out);
+
+// cyTriMesh::Mtl (cyTriMesh.h:74-103): one material of an OBJ's .mtl library, with the constructor's defaults
+struct ObjMtl {
+    std::string name;
+    float Ka[3] = {0, 0, 0}, Kd[3] = {1, 1, 1}, Ks[3] = {0, 0, 0}, Tf[3] = {0, 0, 0};
+    float Ns = 0, Ni = 1;
+    int illum = 2;
+    std::string map_Kd, map_Ks;
+    bool has_map_Kd = false, has_map_Ks = false; // Str::data != nullptr: the command appeared
+};
 
 // cyTriMesh arrays + cyBVH arrays of one TriObj (objects.h:46-66)
 struct HostMesh {
     std::string name;
+    std::vector<ObjMtl> mtls;            // cyTriMesh::m, only when the OBJ was loaded with loadMtl (xmlload.cpp:204)
+    std::vector<int> mcfc;               // material cumulative face count (faces are grouped by material, cyTriMesh.h:468-493)
     std::vector<float> v, vn, vt;        // xyz triples
     std::vector<uint32_t> f, fn, ft;     // index triples
     std::vector<float> bvh_boxes;        // (n_nodes) x 6, node 0 unused
@@ -43,7 +55,8 @@ struct HostTexture {
 // Loads an OBJ with the parsing rules of cyTriMesh::LoadFromFileObj (cyTriMesh.h:263-547),
 // then TriObj::Load's post-steps (objects.h:52-60): ComputeNormals if none, bounding box,
 // BVH with max 4 elements per leaf.  Returns false if the file cannot be opened.
-bool load_obj_mesh(const char *path, HostMesh *out, std::string *err);
+// load_mtl: TriObj::Load(name, loadMtl) - usemtl / mtllib are honoured only then (cyTriMesh.h:439-448, 499-544).
+bool load_obj_mesh(const char *path, HostMesh *out, std::string *err, bool load_mtl = false);
 void compute_vertex_normals(HostMesh *m);
 void compute_bounds(HostMesh *m);
 // cyBVH::Build (cyBVH.h:122-142) + BVHTriMesh element callbacks (:356-375)
@@ -51,6 +64,7 @@ void build_bvh(const float *v, const uint32_t *f, uint32_t nf, uint32_t max_per_
                std::vector<float> *boxes, std::vector<uint32_t> *data, std::vector<uint32_t> *elements);
 
 bool decode_png_rgb8(const char *path, std::vector<uint8_t> *rgb, int *w, int *h, std::string *err);
+bool decode_ppm_rgb8(const char *path, std::vector<uint8_t> *rgb, int *w, int *h, std::string *err); // LoadPPM, texture.cpp:32-55
 bool encode_png(const char *path, const uint8_t *px, int w, int h, int channels, std::string *err);
 
 void set_error(const std::string &msg);

@@ -82,7 +82,7 @@ struct LineReader {
 
 } // namespace
 
-bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
+bool load_obj_mesh(const char *path, HostMesh *m, std::string *err, bool load_mtl)
 {
     FILE *fp = fopen(path, "rb");
     if (!fp) {
@@ -98,7 +98,16 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
     }
     m->name = path;
     m->v.clear(); m->vn.clear(); m->vt.clear(); m->f.clear(); m->fn.clear(); m->ft.clear();
+    m->mtls.clear(); m->mcfc.clear();
     bool has_tex = false, has_nrm = false;
+    // usemtl / mtllib state (cyTriMesh.h:326-358): materials in order of first use, per face the material current when the
+    // face was read, per material its first face and how many faces were read while it was current
+    struct MtlData { std::string name; uint32_t first_face = 0, face_count = 0; };
+    std::vector<MtlData> mtl_data;
+    std::vector<std::string> mtl_files;
+    std::vector<int> face_mtl;
+    int current_mtl = -1;
+    auto mtl_index = [&](const char *name) { for (size_t i = 0; i < mtl_data.size(); i++) if (mtl_data[i].name == name) return (int)i; return -1; };
     LineReader lr(text.data(), text.data() + text.size());
     while (int rb = lr.next()) {
         float t[3];
@@ -116,6 +125,7 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
         } else if (lr.is_cmd("f")) {
             // corner state machine of cyTriMesh.h:379-438
             uint32_t fv[3] = {0, 0, 0}, ftx[3] = {0, 0, 0}, fnr[3] = {0, 0, 0};
+            const size_t faces_before = m->f.size() / 3;
             int corner = -1;
             bool inspace = true, negative = false;
             int type = 0;
@@ -124,6 +134,7 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
                 m->f.insert(m->f.end(), fv, fv + 3);
                 if (has_tex) m->ft.insert(m->ft.end(), ftx, ftx + 3);
                 if (has_nrm) m->fn.insert(m->fn.end(), fnr, fnr + 3);
+                face_mtl.push_back(current_mtl);
             };
             for (int i = 2; i < rb; i++) {
                 char ch = lr.buf[i];
@@ -150,9 +161,27 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
                 }
             }
             emit();
+            if (current_mtl >= 0) mtl_data[current_mtl].face_count += (uint32_t)(m->f.size() / 3 - faces_before);
+        } else if (load_mtl) {
+            // only when the node names no material in the XML: TriObj::Load(name, mtlName==NULL) (xmlload.cpp:204)
+            if (lr.is_cmd("usemtl")) {                      // MtlList::CreateMtl(buffer.Data(7), _f.size())
+                const char *name = lr.len > 7 ? lr.buf + 7 : "";
+                if (name[0] == '\0') {
+                    current_mtl = mtl_data.empty() ? -1 : 0; // CreateMtl("") returns 0
+                } else {
+                    int i = mtl_index(name);
+                    if (i < 0) {
+                        MtlData d;
+                        d.name = name;
+                        d.first_face = (uint32_t)(m->f.size() / 3);
+                        mtl_data.push_back(d);
+                        i = (int)mtl_data.size() - 1;
+                    }
+                    current_mtl = i;
+                }
+            }
+            if (lr.is_cmd("mtllib") && lr.len > 7) mtl_files.push_back(lr.buf + 7);
         }
-        // usemtl / mtllib: every node in the shipped scenes names its material in the XML, so
-        // TriObj::Load is called with loadMtl=false (xmlload.cpp:204) and these are ignored.
         if (lr.eof()) break;
     }
     if (m->f.empty()) { // cyTriMesh.h:455: nothing is allocated, the mesh stays empty
@@ -162,6 +191,79 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err)
     uint32_t nf = m->nf();
     if (!m->vt.empty()) m->ft.resize((size_t)nf * 3, 0); else m->ft.clear();
     if (!m->vn.empty()) m->fn.resize((size_t)nf * 3, 0); else m->fn.clear();
+    if (!mtl_data.empty()) {
+        // faces grouped by material, materials in order of first use, faces without a material last (cyTriMesh.h:468-493;
+        // the scan of a material starts at its first face and ends after face_count matches)
+        std::vector<uint32_t> f2, ft2, fn2;
+        f2.reserve(m->f.size());
+        auto take = [&](uint32_t i) {
+            f2.insert(f2.end(), m->f.begin() + (size_t)i * 3, m->f.begin() + (size_t)i * 3 + 3);
+            if (!m->ft.empty()) ft2.insert(ft2.end(), m->ft.begin() + (size_t)i * 3, m->ft.begin() + (size_t)i * 3 + 3);
+            if (!m->fn.empty()) fn2.insert(fn2.end(), m->fn.begin() + (size_t)i * 3, m->fn.begin() + (size_t)i * 3 + 3);
+        };
+        m->mcfc.assign(mtl_data.size(), 0);
+        for (size_t k = 0; k < mtl_data.size(); k++) {
+            for (uint32_t i = mtl_data[k].first_face, j = 0; j < mtl_data[k].face_count && i < nf; i++)
+                if (face_mtl[i] == (int)k) { take(i); j++; }
+            m->mcfc[k] = (int)(f2.size() / 3);
+        }
+        if (f2.size() / 3 < nf)
+            for (uint32_t i = 0; i < nf; i++)
+                if (face_mtl[i] < 0) take(i);
+        if (f2.size() == m->f.size()) { // (always, unless a material's faces were not all found by its scan)
+            m->f.swap(f2);
+            if (!m->ft.empty()) m->ft.swap(ft2);
+            if (!m->fn.empty()) m->fn.swap(fn2);
+        }
+        // the .mtl libraries, looked up next to the OBJ (cyTriMesh.h:499-544)
+        m->mtls.resize(mtl_data.size());
+        std::string dir;
+        {
+            const char *e1 = strrchr(path, '\\'), *e2 = e1 ? e1 : strrchr(path, '/');
+            if (e2) dir.assign(path, e2 - path + 1);
+        }
+        for (const std::string &lib : mtl_files) {
+            FILE *mf = fopen((dir + lib).c_str(), "rb");
+            if (!mf) continue; // "ERROR: Cannot open file": the materials keep their defaults
+            std::vector<char> mt;
+            char tmp[1 << 14];
+            size_t n;
+            while ((n = fread(tmp, 1, sizeof tmp, mf)) > 0) mt.insert(mt.end(), tmp, tmp + n);
+            fclose(mf);
+            LineReader ml(mt.data(), mt.data() + mt.size());
+            int id = -1;
+            auto float3 = [&](float out[3]) { // Buffer::ReadFloat3: one value fills all three
+                out[0] = out[1] = out[2] = 0.f;
+                if (ml.len < 2) return;
+                int got = sscanf(ml.buf + 2, "%f %f %f", &out[0], &out[1], &out[2]);
+                if (got == 1) out[2] = out[1] = out[0];
+            };
+            auto copy_from = [&](int start) { // Buffer::Copy: skip blanks from `start`
+                if (ml.len < start) return std::string();
+                const char *q = ml.buf + start;
+                while (*q != '\0' && *q <= ' ') q++;
+                return std::string(q);
+            };
+            while (ml.next()) {
+                if (ml.is_cmd("newmtl")) {
+                    id = ml.len > 7 ? mtl_index(ml.buf + 7) : -1;
+                    if (id >= 0) m->mtls[id].name = copy_from(7);
+                } else if (id >= 0) {
+                    ObjMtl &M = m->mtls[id];
+                    if (ml.is_cmd("Ka")) float3(M.Ka);
+                    else if (ml.is_cmd("Kd")) float3(M.Kd);
+                    else if (ml.is_cmd("Ks")) float3(M.Ks);
+                    else if (ml.is_cmd("Tf")) float3(M.Tf);
+                    else if (ml.is_cmd("Ns")) { if (ml.len >= 2) sscanf(ml.buf + 2, "%f", &M.Ns); }
+                    else if (ml.is_cmd("Ni")) { if (ml.len >= 2) sscanf(ml.buf + 2, "%f", &M.Ni); }
+                    else if (ml.is_cmd("illum")) { if (ml.len >= 5) sscanf(ml.buf + 5, "%d", &M.illum); }
+                    else if (ml.is_cmd("map_Kd")) { M.map_Kd = copy_from(7); M.has_map_Kd = true; }
+                    else if (ml.is_cmd("map_Ks")) { M.map_Ks = copy_from(7); M.has_map_Ks = true; }
+                }
+                if (ml.eof()) break;
+            }
+        }
+    }
     // validate indices so the device never reads out of bounds
     auto check = [&](const std::vector<uint32_t> &idx, size_t n, const char *what) {
         for (uint32_t i : idx)

@@ -7,8 +7,9 @@
 // ref_reaches() in csrc/intersect.cuh).  That leaves the shape of the search structure open, and the cyBVH - midpoint splits
 // of the widest axis, cyBVH.h:295-328 - is a poor one for rays that skim a mesh.  This file builds a binned-SAH binary
 // hierarchy over the same triangles (Wald 2007: 16 bins per axis, cost = 1 + (A_l N_l + A_r N_r) / A), leaves of up to 4
-// triangles, emitted in the device layout of the cyBVH pairs (device_scene.h BvhPair: both child boxes + both child words
-// per internal node, breadth first) so that the pooled walk of k_shadow_wave runs on either structure.
+// triangles, and collapses it into 4-wide nodes (device_scene.h OccNode: the boxes of four children as six float4 + four
+// child words = one 128-byte line per visit).  The any-hit kernel is bound by the latency of one pool iteration (shared
+// memory pop -> node fetch -> tests -> push), not by its arithmetic: a 4-wide node halves the iterations per ray.
 //
 // Boxes are the exact float bounds of the triangles' vertices; the conservative margin that covers the rounding of a
 // triangle's computed hit point is applied per ray on the device (occ_setup in csrc/intersect.cuh).
@@ -125,7 +126,7 @@ struct Builder {
 
 void build_occlusion_bvh(const float *v, const uint32_t *f, const uint32_t *elements, uint32_t nf, OccBvh *out)
 {
-    out->pairs.clear();
+    out->nodes.clear();
     out->slots.clear();
     out->root = 0;
     if (nf == 0) return;
@@ -143,30 +144,62 @@ void build_occlusion_bvh(const float *v, const uint32_t *f, const uint32_t *elem
     B.build(0, nf);
     out->slots.resize(nf);
     for (uint32_t i = 0; i < nf; i++) out->slots[i] = B.prims[i].slot;
-    // breadth-first numbering of the internal nodes = pair indices (top levels first: they stay cache resident)
-    auto word = [&](int n, const std::vector<uint32_t> &pair_of) -> uint32_t {
-        const TempNode &t = B.nodes[n];
-        if (t.left < 0) return 0x80000000u | ((t.count - 1u) << 28) | t.first;
-        return pair_of[n];
-    };
-    std::vector<uint32_t> pair_of(B.nodes.size(), 0xffffffffu);
-    std::vector<int> order;
-    if (B.nodes[0].left >= 0) { pair_of[0] = 0; order.push_back(0); }
-    for (size_t h = 0; h < order.size(); h++) {
-        const TempNode &t = B.nodes[order[h]];
-        for (int c : {t.left, t.right})
-            if (B.nodes[c].left >= 0) { pair_of[c] = (uint32_t)order.size(); order.push_back(c); }
+    const uint32_t NONE = 0x7fffffffu;
+    auto leaf_word = [&](const TempNode &t) { return 0x80000000u | ((t.count - 1u) << 28) | t.first; };
+    if (B.nodes[0].left < 0) { out->root = leaf_word(B.nodes[0]); return; }
+    // Collapse the binary tree into 4-wide nodes: a wide node starts with the two children of a binary node and keeps
+    // replacing its largest internal child by that child's two children until it has four (or only leaves are left).
+    // Breadth-first numbering: the top levels come first and stay cache resident.
+    struct Wide { int child[4]; int n; };
+    std::vector<Wide> wide;
+    std::vector<int> wide_of_binary; // binary node index -> wide node index (for children that stay internal)
+    wide_of_binary.assign(B.nodes.size(), -1);
+    std::vector<int> queue;          // binary nodes that become wide nodes, in BFS order
+    queue.push_back(0);
+    wide_of_binary[0] = 0;
+    for (size_t h = 0; h < queue.size(); h++) {
+        const TempNode &t = B.nodes[queue[h]];
+        Wide w;
+        w.child[0] = t.left; w.child[1] = t.right; w.n = 2;
+        while (w.n < 4) {
+            int pick = -1;
+            double best = -1.0;
+            for (int k = 0; k < w.n; k++) {
+                const TempNode &c = B.nodes[w.child[k]];
+                if (c.left < 0) continue;
+                const double a = c.box.half_area();
+                if (a > best) { best = a; pick = k; }
+            }
+            if (pick < 0) break;
+            const TempNode &c = B.nodes[w.child[pick]];
+            w.child[pick] = c.left;
+            w.child[w.n++] = c.right;
+        }
+        for (int k = 0; k < w.n; k++)
+            if (B.nodes[w.child[k]].left >= 0) {
+                wide_of_binary[w.child[k]] = (int)queue.size();
+                queue.push_back(w.child[k]);
+            }
+        wide.push_back(w);
     }
-    out->pairs.resize(order.size() * 16);
-    for (size_t i = 0; i < order.size(); i++) {
-        const TempNode &t = B.nodes[order[i]];
-        float *P = &out->pairs[i * 16];
-        const Box3 &a = B.nodes[t.left].box, &b = B.nodes[t.right].box;
-        for (int k = 0; k < 3; k++) { P[k] = a.lo[k]; P[3 + k] = a.hi[k]; P[6 + k] = b.lo[k]; P[9 + k] = b.hi[k]; }
-        uint32_t w[4] = {word(t.left, pair_of), word(t.right, pair_of), 0u, 0u};
-        memcpy(P + 12, w, sizeof w);
+    // device layout (device_scene.h OccNode, 32 words): lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] child[4] pad[4];
+    // an unused child slot has an inverted box (never hit) and the word NONE
+    out->nodes.assign(wide.size() * 32, 0.f);
+    for (size_t i = 0; i < wide.size(); i++) {
+        float *N = &out->nodes[i * 32];
+        uint32_t words[8] = {NONE, NONE, NONE, NONE, 0u, 0u, 0u, 0u};
+        for (int k = 0; k < 4; k++) {
+            if (k < wide[i].n) {
+                const TempNode &c = B.nodes[wide[i].child[k]];
+                for (int a = 0; a < 3; a++) { N[a * 4 + k] = c.box.lo[a]; N[12 + a * 4 + k] = c.box.hi[a]; }
+                words[k] = c.left < 0 ? leaf_word(c) : (uint32_t)wide_of_binary[wide[i].child[k]];
+            } else {
+                for (int a = 0; a < 3; a++) { N[a * 4 + k] = 3.0e38f; N[12 + a * 4 + k] = -3.0e38f; }
+            }
+        }
+        memcpy(N + 24, words, sizeof words);
     }
-    out->root = word(0, pair_of);
+    out->root = 0; // wide node 0
 }
 
 } // namespace rtu

@@ -132,6 +132,42 @@ bool decode_png_rgb8(const char *path, std::vector<uint8_t> *rgb, int *w, int *h
     return true;
 }
 
+// LoadPPM (texture.cpp:18-55): binary P6; the header is read line by line (a line ends at \n, \r or after 1024 characters),
+// '#' lines are skipped before the size line and before the maxval line, the pixels follow the maxval line directly.
+// Like the reference, the magic is only rejected when BOTH of its characters are wrong and the maxval is not looked at.
+bool decode_ppm_rgb8(const char *path, std::vector<uint8_t> *rgb, int *w, int *h, std::string *err)
+{
+    auto fail = [&](const char *m) { if (err) *err = std::string(path) + ": " + m; return false; };
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail("cannot open file");
+    char buf[1024];
+    auto read_line = [&]() {
+        int i;
+        for (i = 0; i < 1024; i++) {
+            int c = fgetc(fp);
+            buf[i] = (char)c;
+            if (c == EOF || c == '\n' || c == '\r') { buf[i] = '\0'; return; }
+        }
+        buf[1023] = '\0';
+    };
+    read_line();
+    if (buf[0] != 'P' && buf[1] != '6') { fclose(fp); return fail("not a PPM file"); }
+    read_line();
+    while (buf[0] == '#') read_line();
+    int W = 0, H = 0;
+    sscanf(buf, "%d %d", &W, &H);
+    read_line();
+    while (buf[0] == '#') read_line();
+    if (W <= 0 || H <= 0 || W > 65535 || H > 65535 || (long long)W * H > (1ll << 28)) { fclose(fp); return fail("image dimensions out of range"); }
+    rgb->assign((size_t)W * H * 3, 0);
+    size_t got = fread(rgb->data(), 3, (size_t)W * H, fp);
+    (void)got; // a short file leaves the rest of the pixels as they were allocated (zero here)
+    fclose(fp);
+    *w = W;
+    *h = H;
+    return true;
+}
+
 bool encode_png(const char *path, const uint8_t *px, int w, int h, int channels, std::string *err)
 {
     auto fail = [&](const char *m) { if (err) *err = std::string(path) + ": " + m; return false; };

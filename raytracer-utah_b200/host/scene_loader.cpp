@@ -101,7 +101,8 @@ struct Loader {
         if (len >= 3) {
             char ext[4] = {(char)tolower(name[len - 3]), (char)tolower(name[len - 2]), (char)tolower(name[len - 1]), 0};
             if (!strcmp(ext, "png")) ok = decode_png_rgb8(resolve(name).c_str(), &t->rgb8, &t->width, &t->height, &err);
-            else err = "unsupported texture format"; // PPM (texture.cpp:32-53) is not used by any shipped scene
+            else if (!strcmp(ext, "ppm")) ok = decode_ppm_rgb8(resolve(name).c_str(), &t->rgb8, &t->width, &t->height, &err);
+            else err = "unsupported texture format"; // TextureFile::Load knows png and ppm (texture.cpp:71-88)
         }
         if (!ok) {
             warnings.push_back(std::string("texture \"") + name + "\" not loaded: " + err);
@@ -150,6 +151,63 @@ struct Loader {
         }
         hs->texmaps.push_back(m);
         return (int)hs->texmaps.size() - 1;
+    }
+
+    // new TextureMap(ReadTexture(filename)) (xmlload.cpp:221-225): identity transform; a file that fails to load leaves a
+    // map without texture, which samples black (scene.h:382)
+    int file_texmap(const char *file)
+    {
+        int tex = file_texture(file);
+        Xform x;
+        rtu_texmap m;
+        memset(&m, 0, sizeof m);
+        m.kind = RTU_TEX_NULL;
+        memcpy(m.itm, x.itm.d, sizeof m.itm);
+        if (tex >= 0) {
+            const HostTexture &t = *hs->textures[tex];
+            m.kind = t.kind;
+            memcpy(m.color1, t.color1, sizeof m.color1);
+            memcpy(m.color2, t.color2, sizeof m.color2);
+            m.rgb8 = t.rgb8.empty() ? nullptr : t.rgb8.data();
+            m.width = t.width;
+            m.height = t.height;
+        }
+        hs->texmaps.push_back(m);
+        return (int)hs->texmaps.size() - 1;
+    }
+
+    // The MultiMtl xmlload.cpp:208-241 generates for an OBJ that brought its own materials, as the only sub-material that
+    // can ever shade: hInfo.mtlID is never set by IntersectTriangle, so MultiMtl::Shade (materials.h:66) always takes
+    // mtls[0].  The textures of every sub-material are still read, in order, like the reference does (textureList order).
+    void obj_multi_material(const HostMesh &hm, const char *name, int node)
+    {
+        for (const std::string &n : hs->material_names) if (n == name) return; // materials.Find(name) != NULL
+        rtu_material first;
+        bool have = false;
+        for (const ObjMtl &mtl : hm.mtls) {
+            rtu_material m; // MtlBlinn() defaults, materials.h:23-25
+            m.diffuse = texcolor(mtl.Kd[0], mtl.Kd[1], mtl.Kd[2]);
+            m.specular = texcolor(mtl.Ks[0], mtl.Ks[1], mtl.Ks[2]);
+            m.reflection = texcolor(0, 0, 0);
+            m.refraction = texcolor(0, 0, 0);
+            m.emission = texcolor(0, 0, 0);
+            m.glossiness = mtl.Ns;
+            m.absorption[0] = m.absorption[1] = m.absorption[2] = 0;
+            m.ior = mtl.Ni;
+            m.reflection_glossiness = m.refraction_glossiness = 0;
+            if (mtl.has_map_Kd) m.diffuse.texmap = file_texmap(mtl.map_Kd.c_str());
+            if (mtl.has_map_Ks) m.diffuse.texmap = file_texmap(mtl.map_Ks.c_str()); // sic: SetDiffuseTexture (xmlload.cpp:222, SURVEY A-19)
+            if (mtl.illum > 2 && mtl.illum <= 7) {
+                m.reflection = texcolor(mtl.Ks[0], mtl.Ks[1], mtl.Ks[2]);
+                if (mtl.has_map_Ks) m.reflection.texmap = file_texmap(mtl.map_Ks.c_str());
+                if (mtl.illum >= 6) m.refraction = texcolor(1 - mtl.Tf[0], 1 - mtl.Tf[1], 1 - mtl.Tf[2]);
+            }
+            if (!have) { first = m; have = true; }
+        }
+        if (!have) return;
+        hs->materials.push_back(first);
+        hs->material_names.push_back(name);
+        node_mtl.push_back({node, name});
     }
 
     static rtu_texcolor texcolor(float r, float g, float b)
@@ -284,8 +342,9 @@ struct Loader {
                 } else {
                     std::unique_ptr<HostMesh> hm(new HostMesh);
                     std::string err;
-                    if (load_obj_mesh(resolve(name).c_str(), hm.get(), &err)) {
+                    if (load_obj_mesh(resolve(name).c_str(), hm.get(), &err, mtl == nullptr)) {
                         hm->name = name;
+                        if (!hm->mtls.empty()) obj_multi_material(*hm, name, me); // only on the first load of this OBJ (xmlload.cpp:201-241)
                         hs->meshes.push_back(std::move(hm));
                         mesh = (int)hs->meshes.size() - 1;
                         mesh_by_name[name] = mesh;
@@ -413,8 +472,8 @@ void rtu_host_scene::finalize()
         d.bvh_nodes = (uint32_t)m->bvh_data.size();
         d.bvh_elements = m->bvh_elements.data();
         if (!m->occ.slots.empty()) {
-            d.occ_pairs = m->occ.pairs.empty() ? nullptr : m->occ.pairs.data();
-            d.occ_n_pairs = (uint32_t)(m->occ.pairs.size() / 16);
+            d.occ_nodes = m->occ.nodes.empty() ? nullptr : m->occ.nodes.data();
+            d.occ_n_nodes = (uint32_t)(m->occ.nodes.size() / 32);
             d.occ_root = m->occ.root;
             d.occ_slots = m->occ.slots.data();
         }
@@ -488,9 +547,9 @@ int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t 
 }
 
 int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t nf, const uint32_t *bvh_elements,
-                                 float *pairs, uint32_t *n_pairs, uint32_t *root, uint32_t *slots)
+                                 float *nodes, uint32_t *n_nodes, uint32_t *root, uint32_t *slots)
 {
-    if (!v || !f || !bvh_elements || !pairs || !n_pairs || !root || !slots) { rtu::set_error("rtu_host_build_occlusion_bvh: null argument"); return RTU_ERR_INVALID; }
+    if (!v || !f || !bvh_elements || !nodes || !n_nodes || !root || !slots) { rtu::set_error("rtu_host_build_occlusion_bvh: null argument"); return RTU_ERR_INVALID; }
     for (uint32_t i = 0; i < nf * 3; i++)
         if (f[i] >= nv) { rtu::set_error("rtu_host_build_occlusion_bvh: face index out of range"); return RTU_ERR_INVALID; }
     for (uint32_t i = 0; i < nf; i++)
@@ -498,9 +557,9 @@ int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f,
     return rtu::guarded("rtu_host_build_occlusion_bvh", [&]() -> int {
         rtu::OccBvh o;
         rtu::build_occlusion_bvh(v, f, bvh_elements, nf, &o);
-        memcpy(pairs, o.pairs.data(), o.pairs.size() * sizeof(float));
+        memcpy(nodes, o.nodes.data(), o.nodes.size() * sizeof(float));
         memcpy(slots, o.slots.data(), o.slots.size() * sizeof(uint32_t));
-        *n_pairs = (uint32_t)(o.pairs.size() / 16);
+        *n_nodes = (uint32_t)(o.nodes.size() / 32);
         *root = o.root;
         return RTU_OK;
     });

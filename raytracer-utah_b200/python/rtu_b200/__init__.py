@@ -40,7 +40,7 @@ class Mesh(C.Structure):
                 ("f", PU), ("fn", PU), ("ft", PU), ("nf", u32),
                 ("bvh_boxes", PF), ("bvh_data", PU), ("bvh_nodes", u32), ("bvh_elements", PU),
                 ("bound_min", f32 * 3), ("bound_max", f32 * 3),
-                ("occ_pairs", PF), ("occ_slots", PU), ("occ_n_pairs", u32), ("occ_root", u32)]
+                ("occ_nodes", PF), ("occ_slots", PU), ("occ_n_nodes", u32), ("occ_root", u32)]
 
 
 class TexMap(C.Structure):

@@ -82,7 +82,72 @@ def test_kat_mesh(rtu, gpu_ctx):
     check_kat(rtu, gpu_ctx, "mesh", rtu.OBJ_MESH, hs)
 
 
-PRIMARY_CASES = ["p1example", "p1test", "p4", "p5", "p5low", "p7", "p11", "p13", "teapot1", "teapot2",
+def _occlusion_rays(bmin, bmax, surface, n, seed):
+    """Seeded any-hit rays around a mesh: origins on the surface (self-shadow rays, offset 0 as in Shade), inside and around
+    the bound box; directions towards random points, along axes and skimming the box; t_max BIG, long and short."""
+    rng = np.random.default_rng(seed)
+    ext = (bmax - bmin).astype(np.float64)
+    o = np.empty((n, 3)); d = np.empty((n, 3))
+    k = n // 4
+    o[:k] = surface[rng.integers(0, len(surface), k)]                              # on the mesh
+    o[k:2 * k] = bmin + rng.random((k, 3)) * ext                                    # inside the box
+    o[2 * k:] = bmin - ext + rng.random((n - 2 * k, 3)) * 3 * ext                   # around it
+    target = bmin - 0.1 * ext + rng.random((n, 3)) * 1.2 * ext
+    d[:] = target - o
+    ax = rng.integers(0, n, n // 16)
+    d[ax] = np.eye(3)[rng.integers(0, 3, len(ax))] * rng.choice([-1.0, 1.0], (len(ax), 1))   # zero direction components
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    t = np.full(n, 1.0e30, "f4")
+    short = rng.random(n) < 0.5
+    t[short] = (rng.random(short.sum()) ** 2 * 2.5 * np.linalg.norm(ext)).astype("f4")
+    import rtu_b200 as R
+    r = np.zeros(n, R.RAY_DTYPE)
+    r["p"] = o.astype("f4")
+    r["dir"] = d.astype("f4")
+    return r, t
+
+
+@pytest.mark.parametrize("which", ["teapot", "grid1M"])
+def test_any_hit_hierarchy_gives_the_reference_answer(rtu, gpu_ctx, which, monkeypatch):
+    """ShadowTrace on a mesh three ways: the frames' kernel (k_shadow_wave: pooled walk of the binned-SAH any-hit hierarchy,
+    conservative box tests, exact triangle test, accepted triangles confirmed against the exact slab tests of their cyBVH
+    ancestors), the plain per-lane walk of the cyBVH in the reference's order, and the C restatement of the reference
+    (pinned by kat_mesh).  The boolean must be IDENTICAL for every ray, skimming and self-shadow rays included."""
+    import sys
+    from conftest import ROOT, synthetic_scene
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    if which == "teapot":
+        hs = rtu.HostScene(os.path.join(SCENES, "Teapot/scene2.xml"))
+        n = 1 << 19
+    else:
+        g, meta = load_golden("synthetic_grid1M")
+        hs = rtu.HostScene(synthetic_scene("grid1M", meta))
+        n = 1 << 18
+    desc = single_object_scene(rtu, rtu.OBJ_MESH, hs)
+    m = hs.mesh(0)
+    surface = m["v"][m["f"]].mean(axis=1)           # triangle centroids
+    rays, tmax = _occlusion_rays(m["bound"][:3].astype(np.float64), m["bound"][3:].astype(np.float64), surface.astype(np.float64), n, 20261019)
+    sc = rtu.Scene(gpu_ctx, desc)
+    try:
+        monkeypatch.delenv("RTU_SHADOW_TRACE", raising=False)
+        wave = sc.shadow_trace(rays, tmax)
+        st = sc.stats()
+        monkeypatch.setenv("RTU_SHADOW_TRACE", "exact")
+        exact = sc.shadow_trace(rays, tmax)
+        monkeypatch.delenv("RTU_SHADOW_TRACE", raising=False)
+        assert np.array_equal(wave, exact), "%d of %d rays differ between the any-hit hierarchy and the cyBVH walk" % (int((wave != exact).sum()), n)
+        assert 0.1 < wave.mean() < 0.9
+        assert st["shadow_rays"] == n
+        sub = slice(0, 1 << 15)
+        ref = oracle_py.shadow_trace(desc, rays[sub], tmax[sub])
+        assert np.array_equal(wave[sub], ref)
+    finally:
+        sc.close()
+        hs.close()
+
+
+PRIMARY_CASES = ["p1example", "p1test", "p4", "p5", "p5low", "p7", "p11", "p13", "teapot1", "teapot2", "objmtl",
                  "p1example_full", "p4_full", "teapot2_1080p"]
 
 
@@ -119,7 +184,7 @@ def within_tol(a, b):
     return np.abs(a - b) <= REL_TOL * np.maximum(np.abs(a), np.abs(b)) + ABS_FLOOR
 
 
-WHITTED_CASES = ["p2", "p3simple", "p3box", "p4", "p5", "p7", "p11", "p13", "teapot2", "p4_spp4", "teapot2_spp4",
+WHITTED_CASES = ["p2", "p3simple", "p3box", "p4", "p5", "p7", "p11", "p13", "teapot2", "p4_spp4", "teapot2_spp4", "objmtl",
                  "p4_full", "teapot2_1080p"]
 
 

@@ -11,7 +11,7 @@ import pytest
 
 from conftest import ROOT, SCENES, bits_equal, load_golden
 
-LOADER_CASES = ["Project1Example", "Project4", "Project5_scene", "Project7_scene", "Project9_scene", "Project10_scene",
+LOADER_CASES = ["ObjMtl_scene", "Project1Example", "Project4", "Project5_scene", "Project7_scene", "Project9_scene", "Project10_scene",
                 "Project11_scene_86", "Project13_scene", "Teapot_scene", "Teapot_scene2"]
 
 
@@ -248,3 +248,37 @@ def test_bench_clock_sampler_window():
     missed = bench.ClockSampler.summarise(rows, 5.0, 5.1)
     assert missed["samples"] == 4 and missed["window"] == "warm-up + timed region"
     assert bench.ClockSampler.summarise([], 0.0, 1.0)["sm_mhz"] is None
+
+
+def test_obj_material_library_becomes_a_multimtl(rtu):
+    """An OBJ node without a material attribute loads the OBJ's own materials (TriObj::Load(name, loadMtl=true),
+    xmlload.cpp:204): faces are regrouped by material in order of first use (cyTriMesh.h:468-493), the node's material is
+    the generated MultiMtl - represented by sub-material 0, the only one MultiMtl::Shade can reach (materials.h:66) - and
+    map_Kd names a binary PPM (texture.cpp:32-55).  Bit-identical to the reference's loader (loader_ObjMtl_scene.npz)."""
+    hs = rtu.HostScene(os.path.join(SCENES, "ObjMtl/scene.xml"))
+    assert hs.warnings == ""
+    d = hs.desc
+    assert d.n_materials == 2 and d.n_meshes == 1
+    meta = hs.nodes()["meta"]
+    assert meta[2][1] == rtu.OBJ_MESH and meta[2][3] == 0      # the MultiMtl comes first: it is created while the node is read
+    m = d.materials[0]
+    assert m.diffuse.texmap >= 0 and d.texmaps[m.diffuse.texmap].kind == rtu.TEX_FILE
+    t = d.texmaps[m.diffuse.texmap]
+    assert (t.width, t.height) == (8, 8)
+    px = np.ctypeslib.as_array(t.rgb8, shape=(8 * 8 * 3,))
+    raw = open(os.path.join(SCENES, "ObjMtl/tex.ppm"), "rb").read()
+    assert bytes(px) == raw[-192:]
+    assert abs(m.ior - 1.3) < 1e-6 and m.glossiness == 30.0
+    hs.close()
+
+
+def test_ppm_loader_limits(rtu, tmp_path):
+    """The PPM header is untrusted input like a PNG's: absurd sizes are rejected, a short file is zero-filled."""
+    import shutil
+    root = tmp_path / "scenes"
+    shutil.copytree(os.path.join(SCENES, "ObjMtl"), root / "ObjMtl")
+    (root / "ObjMtl" / "tex.ppm").write_bytes(b"P6\n70000 70000\n255\n" + b"\0" * 16)
+    hs = rtu.HostScene(str(root / "ObjMtl" / "scene.xml"), asset_root=str(root))
+    assert "dimensions out of range" in hs.warnings
+    assert hs.desc.texmaps[hs.desc.materials[0].diffuse.texmap].kind == rtu.TEX_NULL
+    hs.close()

@@ -58,7 +58,7 @@ def test_primitive_kats_bit_exact(rtu, oracle, prim, kind):
         assert np.array_equal(hits["face"][m], g["face"][fresh][m])
 
 
-@pytest.mark.parametrize("tag", ["p1example", "p4", "p5", "p7", "p11", "teapot1", "teapot2", "p1example_full"])
+@pytest.mark.parametrize("tag", ["p1example", "p4", "p5", "p7", "p11", "teapot1", "teapot2", "p1example_full", "objmtl"])
 def test_primary_bit_exact(rtu, oracle, tag):
     g, meta = load_golden("primary_" + tag)
     hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
@@ -69,7 +69,7 @@ def test_primary_bit_exact(rtu, oracle, tag):
     assert o["stats"]["trace_rays"] == meta["rays"]
 
 
-@pytest.mark.parametrize("tag", ["p2", "p3box", "p4", "p5", "p7", "p11", "p13", "teapot2", "p4_spp4", "teapot2_spp4"])
+@pytest.mark.parametrize("tag", ["p2", "p3box", "p4", "p5", "p7", "p11", "p13", "teapot2", "p4_spp4", "teapot2_spp4", "objmtl"])
 def test_whitted_matches_reference(rtu, oracle, tag):
     g, meta = load_golden("whitted_" + tag)
     hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))

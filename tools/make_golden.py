@@ -39,6 +39,7 @@ PRIMARY = {
     "Project13/scene.xml": ("p13", (240, 180)),
     "Teapot/scene.xml": ("teapot1", (480, 270)),
     "Teapot/scene2.xml": ("teapot2", (480, 270)),
+    "ObjMtl/scene.xml": ("objmtl", (320, 240)),           # OBJ with usemtl / mtllib -> MultiMtl, PPM texture
 }
 # deterministic Whitted scenes: no soft lights, no glossy reflection/refraction, no DOF
 WHITTED = {
@@ -51,6 +52,7 @@ WHITTED = {
     "Project11/scene.xml": ("p11", (240, 180), 1),
     "Project13/scene.xml": ("p13", (240, 180), 1),
     "Teapot/scene2.xml": ("teapot2", (480, 270), 1),
+    "ObjMtl/scene.xml": ("objmtl", (320, 240), 1),
 }
 # multi-sample (reference Halton pattern) fixtures
 WHITTED_SPP = {
@@ -63,7 +65,7 @@ FULL = {
     "Project4.xml": ("p4_full", (800, 600)),
     "Teapot/scene2.xml": ("teapot2_1080p", (1920, 1080)),
 }
-LOADER = ["Project1Example.xml", "Project4.xml", "Project5/scene.xml", "Project7/scene.xml", "Project9/scene.xml",
+LOADER = ["ObjMtl/scene.xml", "Project1Example.xml", "Project4.xml", "Project5/scene.xml", "Project7/scene.xml", "Project9/scene.xml",
           "Project10/scene.xml", "Project11/scene_86.xml", "Project13/scene.xml", "Teapot/scene.xml", "Teapot/scene2.xml"]
 # generated scenes of section 8d (tools/make_synthetic.py): 1 M-triangle mesh, flat lists of spheres
 SYNTHETIC = {"grid1M": (240, 135), "spheres_100": (240, 135), "spheres_1000": (240, 135), "dupmesh": (480, 270), "manymtl": (240, 135)}
@@ -126,7 +128,7 @@ def main():
                     os.remove(f)
                 meta = run(sc, "dump", pre)
                 arrs = collect(pre)
-                if sc not in ("Teapot/scene2.xml", "Project5/scene.xml"):   # the same teapot.obj everywhere else
+                if sc not in ("Teapot/scene2.xml", "Project5/scene.xml", "ObjMtl/scene.xml"):   # the same teapot.obj everywhere else
                     arrs = {k: v for k, v in arrs.items() if not k.startswith("mesh")}
                 save("loader_" + sc.replace("/", "_").replace(".xml", ""), arrs, dict(meta, scene=sc))
         if want("primary"):
