@@ -35,7 +35,8 @@ typedef enum {
     RTU_ERR_CUDA = 2,      /* CUDA runtime error (message has the cudaError string) */
     RTU_ERR_IO = 3,        /* file missing / unreadable / unparsable */
     RTU_ERR_NO_DEVICE = 4, /* no CUDA device: there is NO CPU fallback */
-    RTU_ERR_UNSUPPORTED = 5
+    RTU_ERR_UNSUPPORTED = 5,
+    RTU_ERR_CANCELLED = 6  /* rtu_job_cancel (StopRender) ended the frame */
 } rtu_status;
 
 /* ------------------------------------------------------------------ scene description */
@@ -171,7 +172,10 @@ enum {
 enum {
     RTU_FLAG_CULL_NULL_SHADOW_RAYS = 1, /* skip shadow rays whose contribution is exactly 0 (the reference traces them) */
     RTU_FLAG_CULL_ZERO_WEIGHT_RAYS = 2, /* skip secondary rays whose throughput is exactly 0 (e.g. absorbed TIR; the reference traces them) */
-    RTU_FLAG_TIME_KERNELS = 4           /* bracket every wave kernel with CUDA events (fills rtu_kernel_stats.ms) */
+    RTU_FLAG_TIME_KERNELS = 4,          /* bracket every wave kernel with CUDA events (fills rtu_kernel_stats.ms) */
+    RTU_FLAG_REFERENCE_WALK = 8         /* mesh walks through the cyBVH with the reference's own box / triangle tests and no pruning, so
+                                           that the counters book exactly the work Trace() does (the figure SURVEY 8d builds the
+                                           algorithmic bytes from).  Default: the meshes' own 4-wide hierarchies (same image, less work). */
 };
 
 typedef struct rtu_params {
@@ -291,6 +295,22 @@ int rtu_render_device(rtu_scene *scene, const rtu_params *params, float *d_accum
 int rtu_resolve(rtu_scene *scene, const rtu_params *params, const float *d_accum, rtu_image *out);
 int rtu_get_stats(const rtu_scene *scene, rtu_stats *out);
 int rtu_synchronize(rtu_context *ctx);
+
+/* ---- Non-blocking frame + progress (BeginRender / StopRender / numRenderedPixels: viewport.cpp:36,443,447, main.cpp:66-72,
+ * scene.h:585-588) and the PNG writer that overlaps the next frame (RenderImage::SaveImage, scene.h:638-654).
+ * rtu_render_async returns at once; a worker thread renders the frame in slices (groups of samples, or row blocks when
+ * there are few samples).  After every slice - when a callback is given - and at the end, `out`'s buffers hold the mean over
+ * what is done so far, the counter moves and the callback runs on the worker thread.  The scene's context must not be used by
+ * other calls until rtu_job_wait returns.  pixels_done reaches width*height at the end like numRenderedPixels. */
+typedef struct rtu_job rtu_job;
+typedef void (*rtu_progress_fn)(void *user, int64_t pixels_done, int64_t pixels_total);
+int rtu_render_async(rtu_scene *scene, const rtu_params *params, const rtu_image *out, rtu_progress_fn progress, void *user, rtu_job **job);
+int rtu_job_progress(const rtu_job *job, int64_t *pixels_done, int64_t *pixels_total, int32_t *finished);
+void rtu_job_cancel(rtu_job *job);   /* StopRender(): the frame ends after the slice in flight, rtu_job_wait returns RTU_ERR_CANCELLED */
+int rtu_job_wait(rtu_job *job);      /* joins the worker; the job's status (message in rtu_last_error) */
+void rtu_job_destroy(rtu_job *job);  /* waits if needed */
+/* Encodes on a worker thread; the pixels are copied first, so the caller may render the next frame into the same buffer. */
+int rtu_write_png_async(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels, rtu_job **job);
 
 /* ---- Multi-GPU: one process or host thread per GPU, each with its own context.  The path shards by
  * independent units; the only data-path communication is the step that brings the partial images together on one rank.

@@ -51,7 +51,8 @@ void RefGeneratePhotonMap();
 Color RefPhotonMapping(const Ray &r, const HitInfo &h);
 cyPhotonMap *RefPhotonMap();
 Color RefMonteCarloPhoton(const HitInfo &h, int x, int y, int n);
-int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pattern, double *device_ms, unsigned long long *rays);
+int RtuBeginRender(const char *lib_path, int estimator, int spp, int bounces, int gi_bounces, bool reference_pattern, double *device_ms,
+                   unsigned long long *rays);
 
 // ---------------------------------------------------------------- npy output
 static void WriteNpy(const std::string &path, const void *data, const char *descr,
@@ -162,7 +163,7 @@ static Ray CameraRay(int x, int y, float offX, float offY, float camOffsetX, flo
 
 // ---------------------------------------------------------------- options
 struct Opts {
-    std::string scene, root = ".", mode = "primary", out = "out", pattern = "center", lib = "raytracer-utah_b200/librtu_b200.so";
+    std::string scene, root = ".", mode = "primary", out = "out", pattern = "center", lib = "raytracer-utah_b200/librtu_b200.so", estimator = "whitted";
     int width = 0, height = 0, spp = 1, threads = 1, bounces = 5, n = 100000, seed = 1;
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
     int s0 = 0, s1 = -1;   // --samples a b: only samples [a,b) of the spp-sample pattern (bounded CPU-baseline runs)
@@ -553,8 +554,11 @@ static void ModeGpu(const Opts &o)
 {
     double ms = 0;
     unsigned long long rays = 0;
-    int rc = RtuBeginRender(o.lib.c_str(), o.spp, o.bounces, o.pattern != "center", &ms, &rays);
+    // --estimator head (default of the binding): what Render() computes at HEAD; whitted: Shade(ray,h,lights,5) alone
+    const bool head = o.estimator == "head";
+    int rc = RtuBeginRender(o.lib.c_str(), head ? 2 /* RTU_MODE_PATH */ : 1 /* RTU_MODE_WHITTED */, o.spp, o.bounces, 4, head || o.pattern != "center", &ms, &rays);
     if (rc) exit(rc);
+    if (renderImage.GetNumRenderedPixels() != camera.imgWidth * camera.imgHeight) { fprintf(stderr, "progress counter ended at %d\n", renderImage.GetNumRenderedPixels()); exit(4); }
     int W = camera.imgWidth, H = camera.imgHeight;
     renderImage.SaveImage((o.out + "_Result.png").c_str());        // main.cpp:59
     renderImage.ComputeZBufferImage();                             // main.cpp:60
@@ -728,6 +732,7 @@ int main(int argc, char **argv)
         else if (a == "--crop") { o.x0 = atoi(next()); o.y0 = atoi(next()); o.x1 = atoi(next()); o.y1 = atoi(next()); }
         else if (a == "--verbose") o.quiet = false;
         else if (a == "--lib") o.lib = next();
+        else if (a == "--estimator") o.estimator = next();
         else if (a[0] != '-') o.scene = a;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }

@@ -184,9 +184,23 @@ template <class F> F sym(void *lib, const char *name)
 
 } // namespace
 
-// Replacement of SpawnRenderThreads() (main.cpp:29-64).  spp / pattern / bounces are the constants the
-// reference hard-codes (RenderFunctions.cpp:27,134); here they are parameters.
-int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pattern, double *device_ms, unsigned long long *rays)
+// Replacement of SpawnRenderThreads() (main.cpp:29-64).  The reference hard-codes what Render() estimates: at HEAD it is the
+// Monte-Carlo estimator of RenderFunctions.cpp:129-135 (MonteCarlo() with 4 bounces folded into an ambient light, then two
+// Shade calls) at maxSampleSize = 1024 samples of the Halton(4,5) pattern, bounceCount 5 (RenderFunctions.cpp:26-31,134).
+// Those constants are the defaults here: estimator = RTU_MODE_PATH, spp = 1024, bounces = 5, gi_bounces = 4.  The frame runs
+// on the library's worker thread (rtu_render_async, "renderer must run in a separate thread", viewport.cpp:36); the progress
+// callback moves renderImage's numRenderedPixels, which the viewport polls (scene.h:585-588, viewport.cpp:390-410), and the
+// image in renderImage is refreshed after every slice like the reference's threads fill it pixel by pixel.
+struct RtuProgress { long long last; };
+static void RtuOnProgress(void *user, int64_t done, int64_t total)
+{
+    RtuProgress *pr = (RtuProgress *)user;
+    (void)total;
+    if (done > pr->last) { renderImage.IncrementNumRenderPixel((int)(done - pr->last)); pr->last = done; }
+}
+
+int RtuBeginRender(const char *lib_path, int estimator, int spp, int bounces, int gi_bounces, bool reference_pattern, double *device_ms,
+                   unsigned long long *rays)
 {
     void *lib = dlopen(lib_path, RTLD_NOW | RTLD_LOCAL);
     if (!lib) { fprintf(stderr, "cannot load %s: %s\n", lib_path, dlerror()); return 3; }
@@ -196,7 +210,9 @@ int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pa
     auto upload = sym<int (*)(rtu_context *, const rtu_scene_desc *, rtu_scene **)>(lib, "rtu_scene_upload");
     auto destroy = sym<void (*)(rtu_scene *)>(lib, "rtu_scene_destroy");
     auto params_default = sym<void (*)(rtu_params *)>(lib, "rtu_params_default");
-    auto render = sym<int (*)(rtu_scene *, const rtu_params *, rtu_image *)>(lib, "rtu_render");
+    auto render_async = sym<int (*)(rtu_scene *, const rtu_params *, const rtu_image *, rtu_progress_fn, void *, rtu_job **)>(lib, "rtu_render_async");
+    auto job_wait = sym<int (*)(rtu_job *)>(lib, "rtu_job_wait");
+    auto job_destroy = sym<void (*)(rtu_job *)>(lib, "rtu_job_destroy");
     auto get_stats = sym<int (*)(const rtu_scene *, rtu_stats *)>(lib, "rtu_get_stats");
 
     Packed P;
@@ -210,15 +226,19 @@ int RtuBeginRender(const char *lib_path, int spp, int bounces, bool reference_pa
     params_default(&p);
     p.spp = spp;
     p.shade_bounces = bounces;
+    p.gi_bounces = gi_bounces;
     p.pattern = reference_pattern ? RTU_PATTERN_REFERENCE : RTU_PATTERN_CENTER;
-    p.mode = RTU_MODE_WHITTED;
+    p.mode = estimator;
     rtu_image img;
     memset(&img, 0, sizeof img);
     img.rgb8 = &renderImage.GetPixels()[0].r;   // Color24[W*H], row 0 first (scene.h:542,578)
     img.z = renderImage.GetZBuffer();           // float[W*H], BIGFLOAT on miss (scene.h:543,579)
-    rc = render(sc, &p, &img);
-    if (rc) { fprintf(stderr, "rtu_render: %s\n", last_error()); return rc; }
-    renderImage.IncrementNumRenderPixel(renderImage.GetWidth() * renderImage.GetHeight()); // progress bar (scene.h:587)
+    RtuProgress pr = {0};
+    rtu_job *job = nullptr;
+    rc = render_async(sc, &p, &img, RtuOnProgress, &pr, &job);   // BeginRender() returns here; the viewport keeps polling
+    if (!rc) rc = job_wait(job);                                 // (this headless caller has nothing else to do)
+    if (rc) { fprintf(stderr, "rtu_render_async: %s\n", last_error()); return rc; }
+    job_destroy(job);
     rtu_stats st;
     get_stats(sc, &st);
     if (device_ms) *device_ms = st.device_ms;

@@ -82,6 +82,7 @@ struct DMesh {
     const TriRec *occ_tris;
     const uint32_t *tri_up;
     uint32_t occ_root;
+    uint32_t nested;     // every cyBVH box contains the boxes of its children (then a leaf's box implies its ancestors', ref_reaches)
     float occ_scale;     // largest |coordinate| of the mesh's bound box (scale of the per-ray conservative margin)
 };
 

@@ -309,6 +309,16 @@ int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *
             }
         }
     }
+    // does every box contain its children's boxes?  cyBVH::Build's do (a node's box is the min / max over its elements)
+    bool nested = true;
+    for (size_t i = 0; i < pairs.size() && nested; i++) {
+        const BvhPair &P = pairs[i];
+        if (P.up == 0xffffffffu) continue; // the root's own box is never tested (objFunctions.cpp:343)
+        const BvhPair &U = pairs[P.up & 0x7fffffffu];
+        const float *outer = (P.up >> 31) ? U.b2 : U.b1;
+        for (const float *inner : {P.b1, P.b2})
+            for (int k = 0; k < 3 && nested; k++) nested = inner[k] >= outer[k] && inner[3 + k] <= outer[3 + k]; // (false for NaN)
+    }
     // any-hit hierarchy: the caller's (built once at load time by rtu_host_load_xml / rtu_host_build_occlusion_bvh), else built here
     rtu::OccBvh built;
     const float *onodes = m.occ_nodes;
@@ -368,6 +378,7 @@ int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *
     out->occ_tris = dot;
     out->tri_up = dup;
     out->occ_root = oroot;
+    out->nested = nested ? 1u : 0u;
     {
         float sc = 0.f;
         for (int k = 0; k < 3; k++) sc = std::max(sc, std::max(std::fabs(m.bound_min[k]), std::fabs(m.bound_max[k])));
@@ -1059,7 +1070,8 @@ int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_
     rtu_context *c = s->ctx;
     int n_waves = wave_count(F, tree_waves);
     kt_begin(c, 2);
-    launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
+    const bool refwalk = (F.flags & RTU_FLAG_REFERENCE_WALK) != 0;
+    launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++, refwalk);
     kt_end(c);
     s->launches++;
     int in_q = out_q;
@@ -1072,7 +1084,7 @@ int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_
         launch_shade_queue(c->cfg, c->stream, s->S, F, c->wb, in_q, accum, c->work + (*work_i)++);
         kt_end(c);
         kt_begin(c, 2);
-        launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++);
+        launch_shadow_wave(c->cfg, c->stream, s->S, c->wb, accum, c->work + (*work_i)++, refwalk);
         kt_end(c);
         s->launches += 4;
         in_q = 1 - in_q;
@@ -1212,6 +1224,10 @@ static int frame_overflowed(rtu_context *c, bool *overflow)
 // spp-sliced / row-sliced path) renders into the context's second accumulator and adds that to the caller's once it is
 // known to be complete: an overflow never leaves a caller's accumulator half written.
 // `out`: resolve + device->host copies enqueued behind the frame, covered by the same wait as the overflow flag.
+static int render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum, rtu_image *out);
+} // extern "C"
+int rtu_render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum, rtu_image *out) { return render_checked(s, p, d_accum, clear_accum, out); }
+extern "C" {
 static int render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum, rtu_image *out)
 {
     if (!s || !p) { rtu::set_error("rtu_render_device: null argument"); return RTU_ERR_INVALID; }
@@ -1386,10 +1402,18 @@ int rtu_trace(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
 {
     if (!s || (n > 0 && (!rays || !hits)) || n < 0) { rtu::set_error("rtu_trace: bad argument"); return RTU_ERR_INVALID; }
     if (n == 0) return RTU_OK;
+    if (n >= (1ll << 30)) { rtu::set_error("rtu_trace: batch too large"); return RTU_ERR_UNSUPPORTED; }
     rtu_context *c = s->ctx;
     CU(cudaSetDevice(c->device));
+    // The operator runs the kernel the frames run (k_extend_pool on the meshes' own hierarchies).  RTU_TRACE=reference walks
+    // the cyBVH with the reference's tests inside the same kernel, RTU_TRACE=exact selects the plain per-lane walk of the cyBVH
+    // in the reference's order (k_trace_batch): the tests use both as cross-checks.
+    const char *sel = getenv("RTU_TRACE");
+    const bool exact = sel && sel[0] == 'e', refwalk = sel && sel[0] == 'r';
     int rc;
-    if ((rc = ensure_scratch(c, std::max<size_t>(c->q_cap, 1024), std::max<size_t>(c->shadow_cap, 1024)))) return rc;
+    if ((rc = ensure_scratch(c, std::max<size_t>(c->q_cap, exact ? 1024 : (size_t)n), std::max<size_t>(c->shadow_cap, 1024)))) return rc;
+    if ((rc = ensure_work(c, 8))) return rc;
+    if ((rc = ensure_accum(s, 1))) return rc;
     rtu_ray *dr = nullptr;
     rtu_hit *dh = nullptr;
     CU(cudaMalloc((void **)&dr, n * sizeof(rtu_ray)));
@@ -1399,10 +1423,15 @@ int rtu_trace(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
     if (e == cudaSuccess) e = cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream);
     if (e == cudaSuccess) {
         cudaEventRecord(c->ev0, c->stream);
-        launch_trace_batch(c->cfg, c->stream, s->S, dr, n, dh, c->wb.counters);
+        if (exact) {
+            launch_trace_batch(c->cfg, c->stream, s->S, dr, n, dh, c->wb.counters);
+        } else {
+            launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, c->wb.hits.count);
+            launch_trace_batch_wave(c->cfg, c->stream, s->S, dr, n, dh, c->wb, c->fb.accum, c->work, refwalk);
+        }
         cudaEventRecord(c->ev1, c->stream);
         s->timed = true;
-        s->launches = 1;
+        s->launches = exact ? 1 : 4;
         e = cudaMemcpyAsync(hits, dh, n * sizeof(rtu_hit), cudaMemcpyDeviceToHost, c->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

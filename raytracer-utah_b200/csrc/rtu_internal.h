@@ -59,8 +59,10 @@ void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
 void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
                         int in_q, float4 *accum, unsigned *work_counter);
 // any-hit over the shadow queue, adds unoccluded contributions to accum
+// reference_walk (RTU_FLAG_REFERENCE_WALK): mesh walks go through the cyBVH with the reference's own box tests instead of the
+// meshes' any-hit hierarchies
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
-                        unsigned *work_counter);
+                        unsigned *work_counter, bool reference_walk = false);
 void launch_gi_combine(cudaStream_t st, const float4 *gi, const unsigned *count, unsigned cap, int gi_bounces, float4 *accum);
 void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d);
 
@@ -72,6 +74,9 @@ void launch_trace_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
                         rtu_hit *hits, DCounters *counters);
 void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
                          long long n, unsigned char *occ, DCounters *counters);
+// Trace() of caller rays through the frame's own closest-hit kernel (launch_extend_queue); scratch_accum: one float4 (never written)
+void launch_trace_batch_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, long long n, rtu_hit *hits,
+                             const WaveBuffers &B, float4 *scratch_accum, unsigned *work_counter, bool reference_walk);
 // the same operator through the frame's own any-hit kernel (launch_shadow_wave): accum = n zeroed float4
 void launch_shadow_batch_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
                               long long n, unsigned char *occ, const WaveBuffers &B, float4 *accum, unsigned *work_counter);

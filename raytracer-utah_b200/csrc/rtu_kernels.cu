@@ -26,6 +26,7 @@
 // CTAs per SM, from the occupancy API); CTAs stay resident for the whole wave.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "rtu_internal.h"
 #include "shade.cuh"
@@ -183,13 +184,16 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
 #ifndef XP_POOL
 #define XP_POOL 512
 #endif
-#define XP_LEAF 128
+#define XP_LEAF 192 // one iteration of the 4-wide walk can add 128 leaves while 31 wait
 
 struct XpWarp {
     float4 o[32];                  // mesh-local origin, z of the HitInfo when the mesh was entered
     float4 d[32];                  // mesh-local direction, InvDir::ok
     float4 y[32];                  // hoisted reciprocals
-    const BvhPair *pairs[32];
+    float4 ci[32], cn[32], cf[32]; // OccRay: 1/d, near-plane offsets, far-plane offsets (OCC)
+    const DMesh *mesh[32];
+    const OccNode *nodes[32];      // OCC: the mesh's 4-wide hierarchy; tris = its triangle records in ITS leaf order
+    const BvhPair *pairs[32];      // !OCC: the cyBVH; tris = the cyBVH's triangle records
     const TriRec *tris[32];
     unsigned long long zkey[32];   // (closest z so far) << 32 | triangle, merged with atomicMin
     unsigned pool[XP_POOL];
@@ -206,7 +210,14 @@ __device__ __forceinline__ void tri_load(const TriRec *p, TriRec &T)
     T.cau = w4.x; T.cav = w4.y; T.bau = w4.z; T.bav = w4.w;
 }
 
-template <bool PRIMARY, bool FLAT>
+__device__ __forceinline__ bool ref_reaches_lane(const DMesh &M, unsigned slot, const Ray &r, bool inv_ok, const float4 yv, Tally &tl)
+{
+    InvDir I;
+    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = inv_ok;
+    return ref_reaches(M, slot, r, I, tl);
+}
+
+template <bool PRIMARY, bool FLAT, bool OCC>
 __global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
               DCounters *counters, unsigned *work, float4 *park)
@@ -243,6 +254,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
             const unsigned take = njobs < 32u ? njobs : 32u;
             njobs -= take;
             unsigned rootw = NONE, idx = 0, node = 0;
+            bool direct = false;
             Best B;
             B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
             if (lane < take) {
@@ -268,16 +280,29 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 W.o[lane] = make_float4(lr.px, lr.py, lr.pz, B.z);
                 W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
                 W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
-                W.pairs[lane] = M.pairs;
-                W.tris[lane] = M.tris;
+                W.mesh[lane] = &M;
                 W.zkey[lane] = ((unsigned long long)__float_as_uint(B.z) << 32) | 0xffffffffull;
-                rootw = M.root;
+                if constexpr (OCC) {
+                    const OccRay oc = occ_setup(lr, M.occ_scale, B.z);
+                    W.ci[lane] = make_float4(oc.ix, oc.iy, oc.iz, 0.f);
+                    W.cn[lane] = make_float4(oc.nx, oc.ny, oc.nz, 0.f);
+                    W.cf[lane] = make_float4(oc.fx, oc.fy, oc.fz, 0.f);
+                    W.nodes[lane] = M.occ_nodes;
+                    W.tris[lane] = M.occ_tris;
+                    rootw = M.occ_root;
+                    if (!oc.ok) { direct = true; rootw = NONE; } // non-finite / huge components: walked in the reference's order below
+                } else {
+                    W.pairs[lane] = M.pairs;
+                    W.tris[lane] = M.tris;
+                    rootw = M.root;
+                }
             }
             unsigned bi = __ballot_sync(FULL, rootw < NONE), bl = __ballot_sync(FULL, rootw > NONE);
             if (rootw < NONE) W.pool[__popc(bi & lt)] = (lane << 27) | rootw;
             if (rootw > NONE) W.leaf[__popc(bl & lt)] = (lane << 27) | (((rootw >> 28) & 7u) << 24) | (rootw & 0x00ffffffu);
             unsigned pool_n = __popc(bi), leaf_n = __popc(bl);
-            if (lane == 0) W.tie = 0u;
+            const unsigned dmask = __ballot_sync(FULL, direct);
+            if (lane == 0) W.tie = dmask; // a ray that does not use the hierarchy takes the path of a tie: the reference-order walk
             __syncwarp();
             for (;;) {
                 const bool do_leaf = leaf_n >= 32u || (pool_n == 0u && leaf_n > 0u);
@@ -292,6 +317,13 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                         r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                         const TriRec *tris = W.tris[sl];
                         const unsigned first = it & 0x00ffffffu, cnt = ((it >> 24) & 7u) + 1u;
+                        if constexpr (OCC) {
+                            const float4 yv = W.y[sl];
+                            InvDir I;
+                            I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                            const DMesh *M = W.mesh[sl];
+                            for (unsigned i = 0; i < cnt; i++) occ_candidate_closest(*M, tris + first + i, r, I, o.w, &W.zkey[sl], &W.tie, 1u << sl, tl);
+                        } else
                         for (unsigned i = 0; i < cnt; i++) {
                             TriRec T;
                             tri_load(tris + first + i, T);
@@ -310,6 +342,62 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                     __syncwarp();
                     continue;
                 }
+                if constexpr (OCC) {
+                // one item = one 4-wide node; boxes entered beyond the best z so far are skipped
+                const bool finish = pool_n > XP_POOL - 128u; // no room to expand 32 items: walk them to the end instead
+                const unsigned n = pool_n < 32u ? pool_n : 32u;
+                pool_n -= n;
+                unsigned sl = 0, hit = 0;
+                uint4 ch = make_uint4(NONE, NONE, NONE, NONE);
+                if (lane < n) {
+                    const unsigned it = W.pool[pool_n + lane];
+                    sl = it >> 27;
+                    const float4 ci = W.ci[sl], cn = W.cn[sl], cf = W.cf[sl];
+                    OccRay oc;
+                    oc.ix = ci.x; oc.iy = ci.y; oc.iz = ci.z;
+                    oc.nx = cn.x; oc.ny = cn.y; oc.nz = cn.z;
+                    oc.fx = cf.x; oc.fy = cf.y; oc.fz = cf.z;
+                    oc.tlim = __uint_as_float((unsigned)(*(volatile unsigned long long *)&W.zkey[sl] >> 32));
+                    oc.ok = true;
+                    if (finish) {
+                        const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
+                        Ray r;
+                        r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                        InvDir I;
+                        I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                        occ_walk_closest(*W.mesh[sl], it & 0x07ffffffu, r, I, oc, o.w, &W.zkey[sl], &W.tie, 1u << sl, tl);
+                    } else {
+                        hit = occ_node(oc, W.nodes[sl] + (it & 0x07ffffffu), ch);
+                        tl.box += 4;
+                    }
+                }
+                const unsigned w0 = (hit & 1u) ? ch.x : NONE, w1 = (hit & 2u) ? ch.y : NONE, w2 = (hit & 4u) ? ch.z : NONE, w3 = (hit & 8u) ? ch.w : NONE;
+                const unsigned mine = (unsigned)(w0 < NONE) + (w1 < NONE) + (w2 < NONE) + (w3 < NONE) +
+                                      (((unsigned)(w0 > NONE) + (w1 > NONE) + (w2 > NONE) + (w3 > NONE)) << 16);
+                unsigned incl = mine;
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const unsigned v = __shfl_up_sync(FULL, incl, o2);
+                    if (lane >= (unsigned)o2) incl += v;
+                }
+                const unsigned tot = __shfl_sync(FULL, incl, 31);
+                unsigned pi = pool_n + ((incl - mine) & 0xffffu), li = leaf_n + ((incl - mine) >> 16);
+                const unsigned tag = sl << 27;
+#define RTU_PUSH(WORD)                                                                                                           \
+                if (WORD < NONE) W.pool[pi++] = tag | WORD;                                                                      \
+                else if (WORD > NONE) W.leaf[li++] = tag | (((WORD >> 28) & 7u) << 24) | (WORD & 0x00ffffffu);
+                RTU_PUSH(w3)
+                RTU_PUSH(w2)
+                RTU_PUSH(w1)
+                RTU_PUSH(w0)
+#undef RTU_PUSH
+                pool_n += tot & 0xffffu;
+                leaf_n += tot >> 16;
+#ifdef RTU_DEBUG_BOUNDS
+                if (pool_n > XP_POOL || leaf_n > XP_LEAF) counters->overflow = 0xBAD1;
+#endif
+                __syncwarp();
+                } else {
                 const bool finish = pool_n > XP_POOL - 64u; // no room to expand 32 items: walk them to the end instead
                 const unsigned n = pool_n < 32u ? pool_n : 32u;
                 pool_n -= n;
@@ -355,6 +443,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 if (pool_n > XP_POOL || leaf_n > XP_LEAF) counters->overflow = 0xBAD1;
 #endif
                 __syncwarp();
+                }
             }
             // every slot's ray takes the closest triangle into its HitInfo and goes on with the node behind the mesh
             if (lane < take) {
@@ -362,16 +451,23 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 const float4 o = W.o[lane], d = W.d[lane];
                 Ray r;
                 r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                const DMesh *M = W.mesh[lane];
                 if ((*(volatile unsigned *)&W.tie >> lane) & 1u) {
                     // two triangles at the same distance: the first one in the reference's visiting order wins
                     const float4 yv = W.y[lane];
                     InvDir I;
                     I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
                     Tally scratch = {0, 0, 0, 0, 0}; // this walk repeats tests that are already booked
-                    if (bvh_walk<false>(W.pairs[lane], W.tris[lane], rootw, r, I, B.z, B.front, B.slot, B.bc1, B.bc2, B.bc3, scratch)) B.node = (int)node;
+                    if (bvh_walk<false>(M->pairs, M->tris, M->root, r, I, B.z, B.front, B.slot, B.bc1, B.bc2, B.bc3, scratch)) B.node = (int)node;
+                } else if ((unsigned)key != 0xffffffffu && OCC && !ref_reaches_lane(*M, (unsigned)key, r, d.w != 0.f, W.y[lane], tl)) {
+                    // the winner's leaf box rejects the ray in the reference's own test: the reference-order walk decides
+                    const float4 yv = W.y[lane];
+                    InvDir I;
+                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                    if (bvh_walk<false>(M->pairs, M->tris, M->root, r, I, B.z, B.front, B.slot, B.bc1, B.bc2, B.bc3, tl)) B.node = (int)node;
                 } else if ((unsigned)key != 0xffffffffu) {
                     TriRec T;
-                    tri_load(W.tris[lane] + (unsigned)key, T);
+                    tri_load(M->tris + (unsigned)key, T); // the key carries the cyBVH slot in both walks
                     float z = RTU_BIG;
                     tri_hit(T, r, z, B.front, B.bc1, B.bc2, B.bc3); // front / barycentrics of the winner; z is the merged one
                     B.z = __uint_as_float((unsigned)(key >> 32));
@@ -710,9 +806,6 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
 #ifndef SHADOW_BLOCKS
 #define SHADOW_BLOCKS EXT_BLOCKS
 #endif
-#ifndef SHADOW_OCC
-#define SHADOW_OCC 1 // any-hit walks use the mesh's binned-SAH occlusion hierarchy with conservative box tests (intersect.cuh)
-#endif
 #ifndef SHADOW_PRUNE_TMAX
 #define SHADOW_PRUNE_TMAX 1 // any-hit walks skip boxes entered beyond the light (result-neutral, see k_shadow_wave)
 #endif
@@ -721,17 +814,13 @@ struct SpWarp {
     float4 o[32];                // mesh-local origin, t_max
     float4 d[32];                // mesh-local direction, InvDir::ok
     float4 y[32];                // hoisted reciprocals (exact slab tests: cyBVH walk, ref_reaches)
-#if SHADOW_OCC
     float4 ci[32];               // OccRay: 1/d, tlim
     float4 cn[32];               // OccRay: near-plane offsets
     float4 cf[32];               // OccRay: far-plane offsets
     const DMesh *mesh[32];
-#endif
-#if SHADOW_OCC
-    const OccNode *nodes[32];    // the hierarchy the pool walks: the mesh's 4-wide any-hit hierarchy
-#else
-    const BvhPair *pairs[32];    // ... or its cyBVH
-#endif
+    unsigned hitslot[32];        // cyBVH slot of the triangle that (tentatively) occludes the slot's ray
+    const OccNode *nodes[32];    // the hierarchy the pool walks: the mesh's 4-wide any-hit hierarchy (OCC) ...
+    const BvhPair *pairs[32];    // ... or its cyBVH in the reference's own tests (RTU_FLAG_REFERENCE_WALK)
     const TriRec *tris[32];
     unsigned idx[32], node[32];  // shadow-queue entry and mesh node of the slot
     unsigned pool[SP_POOL];
@@ -741,7 +830,7 @@ struct SpWarp {
     unsigned occl;               // bit s: the ray in slot s is occluded
 };
 
-template <bool FLAT>
+template <bool FLAT, bool OCC>
 __global__ void __launch_bounds__(WAVE_THREADS, SHADOW_BLOCKS)
 k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
 {
@@ -781,12 +870,13 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
                 W.idx[lane] = j.x;
                 W.node[lane] = j.y;
-#if SHADOW_OCC
+                if constexpr (OCC) {
                 const OccRay oc = occ_setup(lr, M.occ_scale, d.w);
                 W.ci[lane] = make_float4(oc.ix, oc.iy, oc.iz, oc.tlim);
                 W.cn[lane] = make_float4(oc.nx, oc.ny, oc.nz, 0.f);
                 W.cf[lane] = make_float4(oc.fx, oc.fy, oc.fz, 0.f);
                 W.mesh[lane] = &M;
+                W.hitslot[lane] = 0xffffffffu;
                 W.nodes[lane] = M.occ_nodes;
                 W.tris[lane] = M.occ_tris;
                 rootw = M.occ_root;
@@ -794,11 +884,11 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                     decided = bvh_walk_any_fallback(M, lr, I, d.w, tl);
                     rootw = NONE;
                 }
-#else
+                } else {
                 W.pairs[lane] = M.pairs;
                 W.tris[lane] = M.tris;
                 rootw = M.root;
-#endif
+                }
             }
             unsigned bi = __ballot_sync(FULL, rootw < NONE), bl = __ballot_sync(FULL, rootw > NONE);
             if (rootw < NONE) W.pool[__popc(bi & lt)] = (lane << 27) | rootw;
@@ -822,14 +912,12 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                             r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                             const TriRec *tris = W.tris[sl];
                             const unsigned first = it & 0x00ffffffu, cnt = ((it >> 24) & 7u) + 1u;
-#if SHADOW_OCC
-                            const float4 yv = W.y[sl];
-                            InvDir I;
-                            I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                            const DMesh *M = W.mesh[sl];
-                            for (unsigned i = 0; i < cnt; i++)
-                                if (occ_candidate(*M, tris + first + i, r, I, o.w, tl)) { atomicOr(&W.occl, 1u << sl); break; }
-#else
+                            if constexpr (OCC) {
+                            for (unsigned i = 0; i < cnt; i++) {
+                                const unsigned cs = occ_candidate(tris + first + i, r, o.w, tl);
+                                if (cs != 0xffffffffu) { W.hitslot[sl] = cs; atomicOr(&W.occl, 1u << sl); break; } // tentative: confirmed below
+                            }
+                            } else {
                             for (unsigned i = 0; i < cnt; i++) {
                                 const float4 *q = reinterpret_cast<const float4 *>(tris + first + i);
                                 float4 x = __ldg(q), yv = __ldg(q + 1), w4 = __ldg(q + 2);
@@ -842,13 +930,13 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                                 int fr;
                                 if (tri_hit(T, r, z, fr, b1, b2, b3)) { atomicOr(&W.occl, 1u << sl); break; }
                             }
-#endif
+                            }
                         }
                     }
                     __syncwarp();
                     continue;
                 }
-#if SHADOW_OCC
+                if constexpr (OCC) {
                 // one item = one 4-wide node: up to four children go back to the pools
                 const bool finish = pool_n > SP_POOL - 128u; // no room to expand 32 items: walk them to the end instead
                 const unsigned n = pool_n < 32u ? pool_n : 32u;
@@ -906,7 +994,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 if (pool_n > SP_POOL || leaf_n > SP_LEAF) counters->overflow = 0xBAD4;
 #endif
                 __syncwarp();
-#else
+                } else {
                 const bool finish = pool_n > SP_POOL - 64u; // no room to expand 32 items: walk them to the end instead
                 const unsigned n = pool_n < 32u ? pool_n : 32u;
                 pool_n -= n;
@@ -959,11 +1047,24 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 if (pool_n > SP_POOL || leaf_n > SP_LEAF) counters->overflow = 0xBAD4;
 #endif
                 __syncwarp();
-#endif
+                }
             }
             // rays that were not stopped by their mesh go on with the node behind it
             const unsigned occl = *(volatile unsigned *)&W.occl;
-            const bool go_on = lane < take && !((occl >> lane) & 1u);
+            bool stopped = lane < take && ((occl >> lane) & 1u);
+            if constexpr (OCC) {
+                // one lane per ray: the triangle that stopped the ray is confirmed by the exact box test of its cyBVH leaf; a
+                // rejection (hit point within rounding of the box) hands the ray to the exact walk of the cyBVH
+                if (stopped && W.hitslot[lane] != 0xffffffffu) {
+                    const float4 o = W.o[lane], d = W.d[lane], yv = W.y[lane];
+                    Ray r;
+                    r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                    InvDir I;
+                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                    if (!ref_reaches(*W.mesh[lane], W.hitslot[lane], r, I, tl)) stopped = bvh_walk_any_fallback(*W.mesh[lane], r, I, o.w, tl);
+                }
+            }
+            const bool go_on = lane < take && !stopped;
             const unsigned m = __ballot_sync(FULL, go_on);
             if (go_on) W.res[nres + __popc(m & lt)] = make_uint2(W.idx[lane], W.node[lane] + 1u);
             nres += __popc(m);
@@ -1156,6 +1257,52 @@ __global__ void k_occluded_from_accum(const float4 *accum, long long n, unsigned
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         occ[i] = accum[i].x == 0.f ? 1 : 0;
+}
+
+// rtu_trace through the frame's own closest-hit kernel: caller rays become queue entries of a kind whose miss adds nothing
+// (RK_TIR with zero weight); the compacted hits are expanded to HitInfo records afterwards, every other ray keeps the
+// record of a miss.
+__global__ void k_fill_ray_queue(const rtu_ray *rays, long long n, RayQueue Q, rtu_hit *out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Q.o[i] = make_float4(rays[i].p[0], rays[i].p[1], rays[i].p[2], __int_as_float((int)i));
+        Q.d[i] = make_float4(rays[i].dir[0], rays[i].dir[1], rays[i].dir[2], __uint_as_float(pack_meta(RK_TIR, 0, 0)));
+        Q.w[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        Q.path[i] = 0u;
+        rtu_hit o; // HitInfo::Init (scene.h:162)
+        o.z = RTU_BIG;
+        o.p[0] = o.p[1] = o.p[2] = 0.f;
+        o.N[0] = o.N[1] = o.N[2] = 0.f;
+        o.uvw[0] = o.uvw[1] = o.uvw[2] = 0.5f;
+        o.node = -1; o.face = -1; o.front = 1;
+        out[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *Q.count = (unsigned)n;
+}
+__global__ void __launch_bounds__(WAVE_THREADS, 2)
+k_hits_to_records(DScene S, RayQueue Q, HitQueue hq, rtu_hit *out)
+{
+    unsigned total = *hq.count;
+    if (total > hq.cap) total = hq.cap;
+    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < total; h += gridDim.x * blockDim.x) {
+        const float4 ha = hq.a[h], hb = hq.b[h];
+        Best B;
+        B.z = ha.x; B.node = __float_as_int(ha.y); B.front = __float_as_int(ha.z); B.slot = __float_as_int(ha.w);
+        B.bc1 = hb.x; B.bc2 = hb.y; B.bc3 = hb.z;
+        const unsigned idx = __float_as_uint(hb.w);
+        const float4 o = Q.o[idx], d = Q.d[idx];
+        Ray ray;
+        ray.px = o.x; ray.py = o.y; ray.pz = o.z; ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+        HitRec H;
+        finalize_hit(S, ray, B, H);
+        rtu_hit r;
+        r.z = H.z;
+        r.p[0] = H.px; r.p[1] = H.py; r.p[2] = H.pz;
+        r.N[0] = H.nx; r.N[1] = H.ny; r.N[2] = H.nz;
+        r.uvw[0] = H.u; r.uvw[1] = H.v; r.uvw[2] = H.w;
+        r.node = H.node; r.face = H.face; r.front = H.front;
+        out[idx] = r;
+    }
 }
 
 // First Shade() step on caller-provided hits (rtu_shade); pixel index = ray index.
@@ -1578,18 +1725,31 @@ template <class K> static int pooled_grid(const LaunchCfg &cfg, K kernel, size_t
     return cfg.sm_count * *cache;
 }
 
+// <PRIMARY, FLAT, OCC>: OCC walks the meshes' 4-wide hierarchies with pruning; !OCC (RTU_FLAG_REFERENCE_WALK) walks the cyBVH
+// with the reference's own tests and books exactly the work Trace() does
+template <bool PRIMARY> static void launch_extend_pooled(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
+                                                         const RayQueue &q, const AuxPool &aux, const WaveBuffers &B, float4 *pixel_accum, float4 *accum,
+                                                         unsigned *work_counter)
+{
+    static int occ[4] = {0, 0, 0, 0};
+    const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
+    const bool ref = (F.flags & RTU_FLAG_REFERENCE_WALK) != 0;
+#define RTU_LAUNCH_XP(FLAT_, OCC_, SLOT)                                                                                                \
+    k_extend_pool<PRIMARY, FLAT_, OCC_><<<pooled_grid(cfg, k_extend_pool<PRIMARY, FLAT_, OCC_>, smem, &occ[SLOT]), WAVE_THREADS, smem, st>>>( \
+        S, F, s0, s1, q, aux, B.hits, pixel_accum, accum, B.counters, work_counter, B.park)
+    if (S.flat && !ref) RTU_LAUNCH_XP(true, true, 0);
+    else if (S.flat) RTU_LAUNCH_XP(true, false, 1);
+    else if (!ref) RTU_LAUNCH_XP(false, true, 2);
+    else RTU_LAUNCH_XP(false, false, 3);
+#undef RTU_LAUNCH_XP
+}
+
 void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, int s1,
                            const WaveBuffers &B, float4 *pixel_accum, float4 *accum, unsigned *work_counter)
 {
-    static int occ = 0, occ_f = 0, occ_n = 0;
-    const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
+    static int occ = 0;
     if (extend_mode() == 1 && S.pool_ok && S.n_top == 0) { // many-node scenes: plain kernels with top-level nomination
-        if (S.flat)
-            k_extend_pool<true, true><<<pooled_grid(cfg, k_extend_pool<true, true>, smem, &occ_f), WAVE_THREADS, smem, st>>>(
-                S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter, B.park);
-        else
-            k_extend_pool<true, false><<<pooled_grid(cfg, k_extend_pool<true, false>, smem, &occ_n), WAVE_THREADS, smem, st>>>(
-                S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum, B.counters, work_counter, B.park);
+        launch_extend_pooled<true>(cfg, st, S, F, s0, s1, B.q[1], B.aux[1], B, pixel_accum, accum, work_counter);
         return;
     }
     if (S.n_top > 0 && extend_mode() == 1) {
@@ -1615,15 +1775,9 @@ void launch_shade_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &S
 void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B,
                          int in_q, float4 *accum, unsigned *work_counter)
 {
-    static int occ = 0, occ_f = 0, occ_n = 0;
-    const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
+    static int occ = 0;
     if (extend_mode() == 1 && S.pool_ok && S.n_top == 0) { // many-node scenes: plain kernels with top-level nomination
-        if (S.flat)
-            k_extend_pool<false, true><<<pooled_grid(cfg, k_extend_pool<false, true>, smem, &occ_f), WAVE_THREADS, smem, st>>>(
-                S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter, B.park);
-        else
-            k_extend_pool<false, false><<<pooled_grid(cfg, k_extend_pool<false, false>, smem, &occ_n), WAVE_THREADS, smem, st>>>(
-                S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum, B.counters, work_counter, B.park);
+        launch_extend_pooled<false>(cfg, st, S, F, 0, 0, B.q[in_q], B.aux[in_q], B, accum, accum, work_counter);
         return;
     }
     if (S.n_top > 0 && extend_mode() == 1) {
@@ -1646,39 +1800,38 @@ void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
                                                                                      B.gi_count);
 }
 
-void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
-                        unsigned *work_counter)
+template <class K> static int shadow_grid(const LaunchCfg &cfg, K kernel, size_t smem, int *cache)
 {
-    static int occ = 0, occ_simple = 0, mode = -1;
+    if (*cache == 0) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WAVE_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+        if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
+        *cache = n;
+    }
+    return cfg.sm_count * *cache;
+}
+
+void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
+                        unsigned *work_counter, bool reference_walk)
+{
+    static int occ[4] = {0, 0, 0, 0}, occ_simple = 0, mode = -1;
     if (mode < 0) { // RTU_SHADOW_KERNEL=simple selects the plain kernel (A/B measurements)
         const char *e = getenv("RTU_SHADOW_KERNEL");
         mode = (e && e[0] == 's') ? 0 : 1;
     }
     if (mode == 1 && S.pool_ok && S.n_top == 0) {
         const size_t smem = sizeof(SpWarp) * (WAVE_THREADS / 32);
-        if (occ == 0) {
-            cudaFuncSetAttribute(k_shadow_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_shadow_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int n = 0, n2 = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow_wave<true>, WAVE_THREADS, smem) != cudaSuccess || n < 1) n = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, k_shadow_wave<false>, WAVE_THREADS, smem) != cudaSuccess || n2 < 1) n2 = 1;
-            if (n2 < n) n = n2;
-            if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
-            occ = n;
-        }
-        if (S.flat) k_shadow_wave<true><<<cfg.sm_count * occ, WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
-        else k_shadow_wave<false><<<cfg.sm_count * occ, WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        // <FLAT, OCC>: OCC walks the meshes' any-hit hierarchies; the other instantiation walks the cyBVH with the reference's
+        // own box tests (RTU_FLAG_REFERENCE_WALK: it books what ShadowTrace's walk tests, up to the any-hit early out)
+        if (S.flat && !reference_walk) k_shadow_wave<true, true><<<shadow_grid(cfg, k_shadow_wave<true, true>, smem, &occ[0]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        else if (S.flat) k_shadow_wave<true, false><<<shadow_grid(cfg, k_shadow_wave<true, false>, smem, &occ[1]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        else if (!reference_walk) k_shadow_wave<false, true><<<shadow_grid(cfg, k_shadow_wave<false, true>, smem, &occ[2]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        else k_shadow_wave<false, false><<<shadow_grid(cfg, k_shadow_wave<false, false>, smem, &occ[3]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
     } else if (S.n_top > 0 && mode == 1) {
         static int occ_t = 0;
         const size_t tsmem = sizeof(TopWarp) * (WAVE_THREADS / 32);
-        if (occ_t == 0) {
-            cudaFuncSetAttribute(k_shadow_wave_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-            int n = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow_wave_top, WAVE_THREADS, tsmem) != cudaSuccess || n < 1) n = 1;
-            if (cfg.blocks_per_sm > 0 && n > cfg.blocks_per_sm) n = cfg.blocks_per_sm;
-            occ_t = n;
-        }
-        k_shadow_wave_top<<<cfg.sm_count * occ_t, WAVE_THREADS, tsmem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        k_shadow_wave_top<<<shadow_grid(cfg, k_shadow_wave_top, tsmem, &occ_t), WAVE_THREADS, tsmem, st>>>(S, B.shadow, accum, B.counters, work_counter);
     } else {
         k_shadow_wave_simple<<<resident_grid(cfg, k_shadow_wave_simple, &occ_simple), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
     }
@@ -1736,11 +1889,22 @@ void launch_shadow_batch(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
     k_shadow_batch<<<resident_grid(cfg, k_shadow_batch, &occ), WAVE_THREADS, 0, st>>>(S, rays, tmax, n, occl, counters);
 }
 
+void launch_trace_batch_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, long long n, rtu_hit *hits,
+                             const WaveBuffers &B, float4 *scratch_accum, unsigned *work_counter, bool reference_walk)
+{
+    FrameSetup F;
+    memset(&F, 0, sizeof F);
+    F.flags = reference_walk ? RTU_FLAG_REFERENCE_WALK : 0u;
+    k_fill_ray_queue<<<148 * 4, 256, 0, st>>>(rays, n, B.q[0], hits);
+    launch_extend_queue(cfg, st, S, F, B, 0, scratch_accum, work_counter);
+    k_hits_to_records<<<148 * 2, WAVE_THREADS, 0, st>>>(S, B.q[0], B.hits, hits);
+}
+
 void launch_shadow_batch_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const rtu_ray *rays, const float *tmax,
                               long long n, unsigned char *occl, const WaveBuffers &B, float4 *accum, unsigned *work_counter)
 {
     k_fill_shadow_queue<<<148 * 4, 256, 0, st>>>(rays, tmax, n, B.shadow);
-    launch_shadow_wave(cfg, st, S, B, accum, work_counter);
+    launch_shadow_wave(cfg, st, S, B, accum, work_counter, false);
     k_occluded_from_accum<<<148 * 4, 256, 0, st>>>(accum, n, occl);
 }
 

@@ -139,3 +139,5 @@ int rtu_frame_dims(const rtu_scene *s, const rtu_params *p, int *W, int *H);
 int rtu_ensure_image(rtu_scene *s, size_t npix);
 // accum -> device images -> host buffers, enqueued on the context's stream (no wait)
 int rtu_resolve_enqueue(rtu_scene *s, const rtu_params *p, const float4 *accum, rtu_image *out);
+// frame into d_accum (NULL: the context's accumulator) with the overflow check / retry; out != NULL: resolve + copies behind it
+int rtu_render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum, rtu_image *out);

@@ -25,6 +25,7 @@ PATTERN_CENTER, PATTERN_REFERENCE = 0, 1
 FLAG_CULL_NULL_SHADOW_RAYS = 1
 FLAG_CULL_ZERO_WEIGHT_RAYS = 2
 FLAG_TIME_KERNELS = 4
+FLAG_REFERENCE_WALK = 8
 
 f32, i32, u32, u8 = C.c_float, C.c_int32, C.c_uint32, C.c_uint8
 PF, PU, PB = C.POINTER(f32), C.POINTER(u32), C.POINTER(u8)
@@ -277,6 +278,60 @@ class Context:
             self._h = C.c_void_p()
 
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
+ERR_CANCELLED = 6
+
+
+class Job:
+    """rtu_job: a frame (rtu_render_async) or a PNG file (rtu_write_png_async) in flight on a worker thread."""
+
+    def __init__(self, buffers=None):
+        self._h = C.c_void_p()
+        self.buffers = buffers
+
+    def progress(self):
+        """(pixels_done, pixels_total, finished) - numRenderedPixels / IsRenderDone of RenderImage (scene.h:585-588)."""
+        L = lib()
+        d, t, f = C.c_int64(0), C.c_int64(0), i32(0)
+        L.rtu_job_progress.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
+        _check(L.rtu_job_progress(self._h, C.byref(d), C.byref(t), C.byref(f)), "rtu_job_progress")
+        return d.value, t.value, bool(f.value)
+
+    def cancel(self):
+        L = lib()
+        L.rtu_job_cancel.argtypes = [C.c_void_p]
+        L.rtu_job_cancel.restype = None
+        L.rtu_job_cancel(self._h)
+
+    def wait(self):
+        """Joins the worker; raises RtuError if the job failed or was cancelled.  Returns the frame's buffers."""
+        L = lib()
+        L.rtu_job_wait.argtypes = [C.c_void_p]
+        rc = L.rtu_job_wait(self._h)
+        self.status = rc
+        _check(rc, "rtu_job_wait")
+        return self.buffers
+
+    def close(self):
+        if self._h:
+            L = lib()
+            L.rtu_job_destroy.argtypes = [C.c_void_p]
+            L.rtu_job_destroy.restype = None
+            L.rtu_job_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def write_png_async(path, pixels):
+    """rtu_write_png_async: the encode runs on a worker thread; the pixels are copied before this returns."""
+    L = lib()
+    px = np.ascontiguousarray(pixels, "u1")
+    ch = 1 if px.ndim == 2 else px.shape[2]
+    job = Job()
+    L.rtu_write_png_async.argtypes = [C.c_char_p, C.c_void_p, i32, i32, i32, C.POINTER(C.c_void_p)]
+    _check(L.rtu_write_png_async(os.fsencode(path), px.ctypes.data, px.shape[1], px.shape[0], ch, C.byref(job._h)), "rtu_write_png_async")
+    return job
+
+
 COMM_ID_BYTES = 128
 
 
@@ -437,6 +492,19 @@ class Scene:
             return bufs
         _check(L.rtu_gather_resolve(self._h, comm._h, C.byref(params), C.c_void_p(d_accum), root, None), "rtu_gather_resolve")
         return None
+
+    def render_async(self, params, want=("rgb8",), out=None, progress=None):
+        """rtu_render_async (BeginRender): returns a Job at once; `progress(pixels_done, pixels_total)` runs on the worker
+        thread after every slice, when the buffers hold the mean over what is done so far."""
+        L = lib()
+        bufs, img = self._image(params, want, out)
+        job = Job(bufs)
+        job._keep = (img, params)
+        cb = PROGRESS_FN(lambda user, done, total: progress(done, total)) if progress is not None else C.cast(None, PROGRESS_FN)
+        job._cb = cb
+        L.rtu_render_async.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Image), PROGRESS_FN, C.c_void_p, C.POINTER(C.c_void_p)]
+        _check(L.rtu_render_async(self._h, C.byref(params), C.byref(img), cb, None, C.byref(job._h)), "rtu_render_async")
+        return job
 
     def resolve(self, params, d_accum=0, want=("rgb8", "rgb")):
         L = lib()

@@ -147,6 +147,61 @@ def test_any_hit_hierarchy_gives_the_reference_answer(rtu, gpu_ctx, which, monke
         hs.close()
 
 
+@pytest.mark.parametrize("which", ["teapot", "grid1M", "dupmesh"])
+def test_closest_hit_hierarchy_gives_the_reference_answer(rtu, gpu_ctx, which, monkeypatch):
+    """Trace() on a mesh four ways: the frames' kernel on the mesh's own 4-wide hierarchy (conservative box tests, pruning by
+    the best z, exact triangle test, leaf-box confirmation, exact ties re-walked in the reference's order), the same kernel
+    on the cyBVH with the reference's tests, the plain per-lane walk in the reference's order, and the C restatement of the
+    reference.  z, front, p, N bit for bit and the winning FACE - also where every hit is an exact tie (dupmesh: every
+    triangle exists twice)."""
+    import sys
+    from conftest import ROOT, synthetic_scene
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    if which == "teapot":
+        hs = rtu.HostScene(os.path.join(SCENES, "Teapot/scene2.xml"))
+        n = 1 << 19
+    else:
+        g, meta = load_golden("synthetic_" + which)
+        hs = rtu.HostScene(synthetic_scene(which, meta))
+        n = 1 << 18
+    desc = single_object_scene(rtu, rtu.OBJ_MESH, hs)
+    m = hs.mesh(0)
+    surface = m["v"][m["f"]].mean(axis=1)
+    rays, _ = _occlusion_rays(m["bound"][:3].astype(np.float64), m["bound"][3:].astype(np.float64), surface.astype(np.float64), n, 20261020)
+    sc = rtu.Scene(gpu_ctx, desc)
+    try:
+        res = {}
+        for name, env in (("fast", None), ("reference", "reference"), ("exact", "exact")):
+            if env is None:
+                monkeypatch.delenv("RTU_TRACE", raising=False)
+            else:
+                monkeypatch.setenv("RTU_TRACE", env)
+            res[name] = sc.trace(rays)
+            if name == "fast":
+                st_fast = sc.stats()
+            if name == "reference":
+                st_ref = sc.stats()
+        monkeypatch.delenv("RTU_TRACE", raising=False)
+        a = res["exact"]
+        hit = a["node"] >= 0
+        assert 0.05 < hit.mean() < 0.95
+        for name in ("fast", "reference"):
+            b = res[name]
+            assert np.array_equal(a["node"], b["node"]), name
+            assert np.array_equal(a["face"], b["face"]), "%s: %d rays with a different face" % (name, int((a["face"] != b["face"]).sum()))
+            assert bits_equal(a["z"], b["z"]), name
+            assert np.array_equal(a["front"][hit], b["front"][hit]), name
+            assert bits_equal(a["p"][hit], b["p"][hit]) and bits_equal(a["N"][hit], b["N"][hit]) and bits_equal(a["uvw"][hit], b["uvw"][hit]), name
+        assert st_fast["box_tests"] + st_fast["tri_tests"] < st_ref["box_tests"] + st_ref["tri_tests"]
+        sub = slice(0, 1 << 14)
+        o = oracle_py.trace(desc, rays[sub])
+        assert np.array_equal(o["node"], a["node"][sub]) and np.array_equal(o["face"], a["face"][sub]) and bits_equal(o["z"], a["z"][sub])
+    finally:
+        sc.close()
+        hs.close()
+
+
 PRIMARY_CASES = ["p1example", "p1test", "p4", "p5", "p5low", "p7", "p11", "p13", "teapot1", "teapot2", "objmtl",
                  "p1example_full", "p4_full", "teapot2_1080p"]
 
@@ -317,6 +372,16 @@ def test_reference_binary_with_our_library(rtu, tmp_path):
     assert np.array_equal(np.load(pre + "_z8.npy"), ref8)
     from PIL import Image
     assert np.array_equal(np.asarray(Image.open(pre + "_Result.png")), rgb8)
+    # BeginRender() as the binding's defaults run it: the estimator Render() computes at HEAD (RenderFunctions.cpp:129-135:
+    # MonteCarlo GI + two Shade calls, 1024 samples of the Halton pattern), on the library's worker thread with
+    # renderImage's progress counter driven by the callback - against the reference's own Render() (head_Project4.npz)
+    gh, mh = load_golden("head_Project4")
+    pre2 = str(tmp_path / "head")
+    subprocess.run([harness, os.path.join(SCENES, mh["scene"]), "--root", SCENES, "--mode", "gpu", "--estimator", "head", "--width", str(mh["width"]),
+                    "--height", str(mh["height"]), "--spp", str(mh["spp"]), "--lib", rtu.LIB_PATH, "--out", pre2], check=True, stdout=subprocess.DEVNULL)
+    a, b = np.load(pre2 + "_rgb8.npy").astype(np.float64), gh["rgb8"].astype(np.float64)
+    assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
+    assert np.abs(a - b).mean() < 2.5
 
 
 def test_errors_are_reported_not_swallowed(rtu, gpu_ctx):
@@ -574,22 +639,32 @@ def test_photon_emission_statistics(rtu, gpu_ctx):
 
 @pytest.mark.parametrize("scene,size", [("Teapot/scene2.xml", (480, 270)), ("Project5/scene.xml", (240, 180)), ("Project4.xml", (240, 180))])
 def test_primary_wave_books_the_reference_work(rtu, gpu_ctx, scene, size):
-    """The closest-hit wave walks meshes as pools of (ray, node) items, skips empty tiles and culls by bounding spheres,
-    yet it books exactly the node visits, box tests and triangle tests the reference's Trace() performs for the same
-    camera rays (the oracle counts them; SURVEY 8d builds the roofline figure from these counters)."""
+    """With RTU_FLAG_REFERENCE_WALK the closest-hit wave walks the cyBVH as pools of (ray, node) items, skips empty tiles and
+    culls by bounding spheres, yet it books exactly the node visits, box tests and triangle tests the reference's Trace()
+    performs for the same camera rays (the oracle counts them; SURVEY 8d builds the roofline figure from these counters)."""
     from oracle import oracle_py as O
     hs = rtu.HostScene(os.path.join(SCENES, scene))
     sc = rtu.Scene(gpu_ctx, hs.desc)
     try:
         w, h = size
         ref = O.render(hs.desc, width=w, height=h, mode=rtu.MODE_PRIMARY, want=("node_id",))["stats"]
-        p = rtu.default_params(width=w, height=h, mode=rtu.MODE_WHITTED, shade_bounces=0)
+        p = rtu.default_params(width=w, height=h, mode=rtu.MODE_WHITTED, shade_bounces=0, flags=rtu.FLAG_REFERENCE_WALK)
         sc.render_device(p)
         st = sc.stats()["primary_wave"]
         assert st["rays"] == w * h == ref["trace_rays"]
         assert st["node_visits"] == ref["node_visits"]
         assert st["box_tests"] == ref["box_tests"]
         assert st["tri_tests"] == ref["tri_tests"]
+        # the default walk (the meshes' own hierarchies, pruned by the best z so far) visits the same nodes and finds the same
+        # image with fewer box and triangle tests
+        ref_img = sc.resolve(p, want=("rgb",))["rgb"]
+        p.flags = 0
+        sc.render_device(p)
+        fast = sc.stats()["primary_wave"]
+        assert fast["rays"] == w * h and fast["node_visits"] == ref["node_visits"]
+        if hs.desc.n_meshes:
+            assert fast["box_tests"] + fast["tri_tests"] < st["box_tests"] + st["tri_tests"]
+        assert within_tol(sc.resolve(p, want=("rgb",))["rgb"], ref_img).all()
     finally:
         sc.close()
         hs.close()
@@ -696,6 +771,58 @@ def test_photon_mode_slices_compose(rtu, gpu_ctx):
         rows = sc.resolve(rtu.default_params(**kw), want=("rgb",))["rgb"]
         assert np.array_equal(np.isnan(full), np.isnan(rows))
         assert within_tol(full[m], rows[m]).all()
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_async_frame_reports_progress_and_equals_the_blocking_frame(rtu, gpu_ctx, tmp_path):
+    """rtu_render_async = BeginRender(): returns at once, the progress counter moves like numRenderedPixels (scene.h:585-588),
+    the partial images are means over what is done so far, the finished frame equals rtu_render's; rtu_job_cancel =
+    StopRender(); rtu_write_png_async writes Result.png from a copy while the caller's buffer is already being reused."""
+    from PIL import Image
+    hs = rtu.HostScene(os.path.join(SCENES, "Project4.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=320, height=240, spp=32, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_WHITTED)
+        ref = sc.render(p, want=("rgb", "rgb8"))
+        seen = []
+        job = sc.render_async(p, want=("rgb", "rgb8"), progress=lambda d, t: seen.append((d, t)))
+        out = job.wait()
+        done, total, fin = job.progress()
+        job.close()
+        assert fin and done == total == 320 * 240
+        assert len(seen) == 16 and seen[-1] == (total, total) and all(a[0] < b[0] for a, b in zip(seen, seen[1:]))
+        assert within_tol(out["rgb"], ref["rgb"]).all()
+        assert np.abs(out["rgb8"].astype(np.int32) - ref["rgb8"].astype(np.int32)).max() <= 1
+        # few samples: the frame is cut into row blocks, the partial image is complete for the rows that are done
+        p1 = rtu.default_params(width=320, height=240, spp=1, mode=rtu.MODE_WHITTED)
+        ref1 = sc.render(p1, want=("rgb",))["rgb"]
+        parts = []
+        job = sc.render_async(p1, want=("rgb",), progress=lambda d, t: parts.append(d))
+        out1 = job.wait()
+        job.close()
+        assert len(parts) == 8 and parts[-1] == 320 * 240
+        assert within_tol(out1["rgb"], ref1).all()
+        # StopRender()
+        big = rtu.default_params(width=1280, height=960, spp=256, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_WHITTED)
+        job = sc.render_async(big, want=("rgb8",), progress=lambda d, t: None)
+        job.cancel()
+        with pytest.raises(rtu.RtuError):
+            job.wait()
+        assert job.status == rtu.ERR_CANCELLED
+        d, t, fin = job.progress()
+        assert fin and d < t
+        job.close()
+        # the context is usable again, and the PNG writer works from its own copy of the pixels
+        again = sc.render(p, want=("rgb8",))["rgb8"]
+        path = str(tmp_path / "Result.png")
+        w = rtu.write_png_async(path, again)
+        keep = again.copy()
+        again[:] = 0
+        w.wait()
+        w.close()
+        assert np.array_equal(np.asarray(Image.open(path)), keep)
     finally:
         sc.close()
         hs.close()
