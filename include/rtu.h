@@ -77,7 +77,14 @@ typedef struct rtu_mesh {
     const uint32_t *occ_slots;        /* nf indices into bvh_elements, in the hierarchy's leaf order */
     uint32_t occ_n_nodes;
     uint32_t occ_root;
+    uint32_t flags;                   /* RTU_MESH_* */
 } rtu_mesh;
+
+/* rtu_mesh::flags.  RTU_MESH_DEVICE_BVH: the mesh carries no cyBVH (bvh_* and occ_* are ignored and may be NULL);
+ * rtu_scene_upload builds an LBVH over its triangles on the device and every walk runs on that.  Results are the
+ * reference's except where its own tree decides: of two triangles at exactly the same distance the lower face index wins
+ * (the reference keeps the one its walk visits first), and RTU_FLAG_REFERENCE_WALK has nothing to walk. */
+enum { RTU_MESH_DEVICE_BVH = 1 };
 
 enum { RTU_TEX_NULL = 0, RTU_TEX_CHECKER = 1, RTU_TEX_FILE = 2 };
 
@@ -227,6 +234,7 @@ typedef struct rtu_stats {
     rtu_kernel_stats shadow_waves;  /* k_shadow_wave: any-hit */
     rtu_kernel_stats shade_kernels; /* k_shade: MtlBlinn::Shade steps on the compacted hits (launches, ms only) */
     uint64_t scene_device_bytes;    /* bytes rtu_scene_upload copied host -> device */
+    double bvh_build_ms;            /* device time of the LBVH builds of the scene's upload (RTU_MESH_DEVICE_BVH meshes), else 0 */
     uint64_t queue_retries;         /* frames this context rendered again because a ray queue overflowed (the scene then
                                        remembers the larger queues, so a steady state shows no new retries) */
 } rtu_stats;
@@ -243,6 +251,10 @@ int rtu_version(void);
  * + TextureFile::Load (texture.cpp:57-91).  asset_root is prepended to relative object /
  * texture paths (the reference resolves them against the CWD). */
 int rtu_host_load_xml(const char *xml_path, const char *asset_root, rtu_host_scene **out);
+/* flags: RTU_LOAD_DEVICE_BVH skips both host hierarchy builds (cyBVH::Build is seconds for a million triangles) and marks
+ * every mesh RTU_MESH_DEVICE_BVH. */
+enum { RTU_LOAD_DEVICE_BVH = 1 };
+int rtu_host_load_xml_ex(const char *xml_path, const char *asset_root, uint32_t flags, rtu_host_scene **out);
 const rtu_scene_desc *rtu_host_scene_desc(const rtu_host_scene *hs);
 void rtu_host_scene_destroy(rtu_host_scene *hs);
 /* cyBVH build (cyBVH.h:122-142, BVHTriMesh 339-379) on caller arrays; fills caller-provided

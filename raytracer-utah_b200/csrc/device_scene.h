@@ -82,6 +82,8 @@ struct DMesh {
     const TriRec *occ_tris;
     const uint32_t *tri_up;
     uint32_t occ_root;
+    uint32_t no_ref;     // RTU_MESH_DEVICE_BVH: no cyBVH (pairs, tri_up are NULL); occ_* is an LBVH built on the device, tris / shade
+                         // are in FACE order and a triangle's slot is its face index
     uint32_t nested;     // every cyBVH box contains the boxes of its children (then a leaf's box implies its ancestors', ref_reaches)
     float occ_scale;     // largest |coordinate| of the mesh's bound box (scale of the per-ray conservative margin)
 };
@@ -149,6 +151,7 @@ struct DScene {
     const TopNode *top;
     const int32_t *top_items;
     const int32_t *obj_rank; // per node: number of object nodes with index <= that node
+    int32_t any_no_ref;  // some mesh has no cyBVH: RTU_FLAG_REFERENCE_WALK cannot be honoured
     int32_t pool_ok;     // 1: every mesh fits the item encoding of the pooled shadow kernel (<= 2^24 triangles, < 2^27 pairs)
     const DMesh *meshes;
     const DMaterial *materials;

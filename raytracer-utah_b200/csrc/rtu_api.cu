@@ -189,10 +189,107 @@ float halton(int index, int base) // scene.h:130-139
 }
 
 // ---- mesh packing
-int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *> &owned)
+// The ray-independent part of IntersectTriangle (objFunctions.cpp:259-300) and the winner's attributes (:317-320) of one
+// face, evaluated with the reference's float operations; `slot`: where the record goes (cyBVH leaf order, or face order)
+int triangle_records(const rtu_mesh &m, uint32_t face, TriRec &T, TriShade &Sh)
+{
+    auto P3 = [&](const float *a, uint32_t i) { return V3(a[(size_t)i * 3], a[(size_t)i * 3 + 1], a[(size_t)i * 3 + 2]); };
+    uint32_t i0 = m.f[face * 3], i1 = m.f[face * 3 + 1], i2 = m.f[face * 3 + 2];
+    if (i0 >= m.nv || i1 >= m.nv || i2 >= m.nv) { rtu::set_error("rtu_scene_upload: vertex index out of range"); return RTU_ERR_INVALID; }
+    V3 A = P3(m.v, i0), B = P3(m.v, i1), C = P3(m.v, i2);
+    V3 N = rtu::normalized(rtu::cross(B - A, C - A));                       // objFunctions.cpp:263
+    float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z);
+    float mxy = (ax < ay) ? ay : ax;                                        // std::max (:274)
+    float mx = (mxy < az) ? az : mxy;
+    unsigned axis = mx == ax ? 0u : (mx == ay ? 1u : (mx == az ? 2u : 3u)); // :278-295
+    float Au, Av, Bu, Bv, Cu, Cv;
+    if (axis == 0) { Au = A.y; Av = A.z; Bu = B.y; Bv = B.z; Cu = C.y; Cv = C.z; }
+    else if (axis == 1) { Au = A.x; Av = A.z; Bu = B.x; Bv = B.z; Cu = C.x; Cv = C.z; }
+    else { Au = A.x; Av = A.y; Bu = B.x; Bv = B.y; Cu = C.x; Cv = C.y; }
+    T.nx = N.x; T.ny = N.y; T.nz = N.z;
+    T.ax = A.x; T.ay = A.y; T.az = A.z;
+    T.cau = Cu - Au; T.cav = Cv - Av; T.bau = Bu - Au; T.bav = Bv - Av;
+    float cr = (-T.cav) * T.bau + T.cau * T.bav;                            // Point2::Cross (cyPoint.h:248)
+    T.area = (float)((double)cr / 2.0);                                     // :298
+    uint32_t fb = (face & 0x3fffffffu) | (axis << 30);
+    memcpy(&T.fbits, &fb, 4);
+    memset(&Sh, 0, sizeof Sh);
+    for (int k = 0; k < 3; k++) {
+        uint32_t vi = m.f[face * 3 + k];
+        uint32_t ni = m.fn[face * 3 + k];
+        if (ni >= m.nvn) { rtu::set_error("rtu_scene_upload: normal index out of range"); return RTU_ERR_INVALID; }
+        for (int c = 0; c < 3; c++) { Sh.v[k * 3 + c] = m.v[(size_t)vi * 3 + c]; Sh.vn[k * 3 + c] = m.vn[(size_t)ni * 3 + c]; }
+        if (m.ft && m.vt) {
+            uint32_t ti = m.ft[face * 3 + k];
+            if (ti >= m.nvt) { rtu::set_error("rtu_scene_upload: texture index out of range"); return RTU_ERR_INVALID; }
+            for (int c = 0; c < 3; c++) Sh.vt[k * 3 + c] = m.vt[(size_t)ti * 3 + c];
+        }
+    }
+    return RTU_OK;
+}
+
+bool coords_fine(const float *bmin, const float *bmax, const float *extra, size_t n_extra)
+{
+    auto fine = [](float v) { return v == 0.f || (std::fabs(v) >= 1.4551915228366852e-11f && std::isfinite(v)); };
+    bool ok = true;
+    for (size_t i = 0; i < n_extra && ok; i++) ok = fine(extra[i]);
+    for (int k = 0; k < 3; k++) ok = ok && fine(bmin[k]) && fine(bmax[k]);
+    return ok;
+}
+
+// RTU_MESH_DEVICE_BVH: triangle records in FACE order (a triangle's slot is its face index), the hierarchy built on the device
+int pack_mesh_device_bvh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *> &owned, double *build_ms)
+{
+    if (m.nf == 0) { out->empty = 1; return RTU_OK; }
+    if (!m.v || !m.f || !m.vn || !m.fn) { rtu::set_error("rtu_scene_upload: mesh with missing arrays"); return RTU_ERR_INVALID; }
+    if (m.nf > (1u << 24)) { rtu::set_error("rtu_scene_upload: RTU_MESH_DEVICE_BVH handles up to 2^24 triangles per mesh"); return RTU_ERR_UNSUPPORTED; }
+    std::vector<TriRec> tris(m.nf);
+    std::vector<TriShade> shade(m.nf);
+    int rc;
+    for (uint32_t face = 0; face < m.nf; face++)
+        if ((rc = triangle_records(m, face, tris[face], shade[face]))) return rc;
+    TriRec *dt = nullptr;
+    TriShade *ds = nullptr;
+    if ((rc = dev_upload(tris, &dt, st, owned))) return rc;
+    if ((rc = dev_upload(shade, &ds, st, owned))) return rc;
+    // vertices and faces go up for the builder only
+    float *dv = nullptr;
+    uint32_t *df = nullptr;
+    CU(cudaMallocAsync((void **)&dv, sizeof(float) * 3 * (size_t)m.nv, st));
+    cudaError_t e = cudaMallocAsync((void **)&df, sizeof(uint32_t) * 3 * (size_t)m.nf, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv, m.v, sizeof(float) * 3 * (size_t)m.nv, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(df, m.f, sizeof(uint32_t) * 3 * (size_t)m.nf, cudaMemcpyHostToDevice, st);
+    g_upload_bytes += sizeof(float) * 3 * (size_t)m.nv + sizeof(uint32_t) * 3 * (size_t)m.nf;
+    float ms = 0.f;
+    rc = RTU_OK;
+    if (e == cudaSuccess) rc = rtu_lbvh_build(st, dv, df, m.nf, m.bound_min, m.bound_max, dt, owned, &out->occ_nodes, &out->occ_tris, &out->occ_root, &ms);
+    cudaFreeAsync(dv, st);
+    if (df) cudaFreeAsync(df, st);
+    CU(e);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st)); // host vectors go out of scope
+    if (build_ms) *build_ms += ms;
+    out->pairs = nullptr;
+    out->tris = dt;
+    out->shade = ds;
+    out->tri_up = nullptr;
+    out->root = 0x7fffffffu;
+    out->n_pairs = 0;
+    out->n_tris = m.nf;
+    out->no_ref = 1u;
+    out->nested = 0u;
+    out->coords_ok = coords_fine(out->bmin, out->bmax, nullptr, 0) ? 1u : 0u;
+    float sc = 0.f;
+    for (int k = 0; k < 3; k++) sc = std::max(sc, std::max(std::fabs(m.bound_min[k]), std::fabs(m.bound_max[k])));
+    out->occ_scale = sc;
+    return RTU_OK;
+}
+
+int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *> &owned, double *build_ms)
 {
     memset(out, 0, sizeof *out);
     for (int k = 0; k < 3; k++) { out->bmin[k] = m.bound_min[k]; out->bmax[k] = m.bound_max[k]; }
+    if (m.flags & RTU_MESH_DEVICE_BVH) return pack_mesh_device_bvh(m, out, st, owned, build_ms);
     if (m.nf == 0 || m.bvh_nodes < 2) { out->empty = 1; return RTU_OK; }
     if (!m.v || !m.f || !m.vn || !m.fn || !m.bvh_boxes || !m.bvh_data || !m.bvh_elements) {
         rtu::set_error("rtu_scene_upload: mesh with missing arrays");
@@ -269,45 +366,13 @@ int pack_mesh(const rtu_mesh &m, DMesh *out, cudaStream_t st, std::vector<void *
         }
         if (maxd + 2 > RTU_STACK) { rtu::set_error("rtu_scene_upload: BVH deeper than the traversal stack"); return RTU_ERR_UNSUPPORTED; }
     }
-    auto P3 = [&](const float *a, uint32_t i) { return V3(a[(size_t)i * 3], a[(size_t)i * 3 + 1], a[(size_t)i * 3 + 2]); };
     std::vector<TriRec> tris(m.nf);
     std::vector<TriShade> shade(m.nf);
-    for (uint32_t s = 0; s < m.nf; s++) {
-        uint32_t face = m.bvh_elements[s];
+    for (uint32_t slot = 0; slot < m.nf; slot++) {
+        uint32_t face = m.bvh_elements[slot];
         if (face >= m.nf) { rtu::set_error("rtu_scene_upload: BVH element out of range"); return RTU_ERR_INVALID; }
-        uint32_t i0 = m.f[face * 3], i1 = m.f[face * 3 + 1], i2 = m.f[face * 3 + 2];
-        if (i0 >= m.nv || i1 >= m.nv || i2 >= m.nv) { rtu::set_error("rtu_scene_upload: vertex index out of range"); return RTU_ERR_INVALID; }
-        V3 A = P3(m.v, i0), B = P3(m.v, i1), C = P3(m.v, i2);
-        V3 N = rtu::normalized(rtu::cross(B - A, C - A));                       // objFunctions.cpp:263
-        float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z);
-        float mxy = (ax < ay) ? ay : ax;                                        // std::max (:274)
-        float mx = (mxy < az) ? az : mxy;
-        unsigned axis = mx == ax ? 0u : (mx == ay ? 1u : (mx == az ? 2u : 3u)); // :278-295
-        float Au, Av, Bu, Bv, Cu, Cv;
-        if (axis == 0) { Au = A.y; Av = A.z; Bu = B.y; Bv = B.z; Cu = C.y; Cv = C.z; }
-        else if (axis == 1) { Au = A.x; Av = A.z; Bu = B.x; Bv = B.z; Cu = C.x; Cv = C.z; }
-        else { Au = A.x; Av = A.y; Bu = B.x; Bv = B.y; Cu = C.x; Cv = C.y; }
-        TriRec &T = tris[s];
-        T.nx = N.x; T.ny = N.y; T.nz = N.z;
-        T.ax = A.x; T.ay = A.y; T.az = A.z;
-        T.cau = Cu - Au; T.cav = Cv - Av; T.bau = Bu - Au; T.bav = Bv - Av;
-        float cr = (-T.cav) * T.bau + T.cau * T.bav;                            // Point2::Cross (cyPoint.h:248)
-        T.area = (float)((double)cr / 2.0);                                     // :298
-        uint32_t fb = (face & 0x3fffffffu) | (axis << 30);
-        memcpy(&T.fbits, &fb, 4);
-        TriShade &Sh = shade[s];
-        memset(&Sh, 0, sizeof Sh);
-        for (int k = 0; k < 3; k++) {
-            uint32_t vi = m.f[face * 3 + k];
-            uint32_t ni = m.fn[face * 3 + k];
-            if (ni >= m.nvn) { rtu::set_error("rtu_scene_upload: normal index out of range"); return RTU_ERR_INVALID; }
-            for (int c = 0; c < 3; c++) { Sh.v[k * 3 + c] = m.v[(size_t)vi * 3 + c]; Sh.vn[k * 3 + c] = m.vn[(size_t)ni * 3 + c]; }
-            if (m.ft && m.vt) {
-                uint32_t ti = m.ft[face * 3 + k];
-                if (ti >= m.nvt) { rtu::set_error("rtu_scene_upload: texture index out of range"); return RTU_ERR_INVALID; }
-                for (int c = 0; c < 3; c++) Sh.vt[k * 3 + c] = m.vt[(size_t)ti * 3 + c];
-            }
-        }
+        int trc = triangle_records(m, face, tris[slot], shade[slot]);
+        if (trc) return trc;
     }
     // does every box contain its children's boxes?  cyBVH::Build's do (a node's box is the min / max over its elements)
     bool nested = true;
@@ -551,7 +616,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
         if (n.kind == RTU_OBJ_PLANE) { lo[2] = hi[2] = 0; }
         if (n.kind == RTU_OBJ_MESH) {
             const rtu_mesh &m = d->meshes[n.mesh];
-            if (m.nf == 0 || m.bvh_nodes < 2) { bounds[i].w = -2.f; continue; }
+            if (m.nf == 0 || (m.bvh_nodes < 2 && !(m.flags & RTU_MESH_DEVICE_BVH))) { bounds[i].w = -2.f; continue; }
             for (int k = 0; k < 3; k++) { lo[k] = m.bound_min[k]; hi[k] = m.bound_max[k]; }
         }
         auto to_root = [&](double p[3]) { // FromNodeCoords chain up to (not including) the root
@@ -681,7 +746,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     // meshes
     std::vector<DMesh> meshes(d->n_meshes);
     for (int i = 0; i < d->n_meshes; i++)
-        if ((rc = pack_mesh(d->meshes[i], &meshes[i], c->stream, sc->owned))) return fail(rc);
+        if ((rc = pack_mesh(d->meshes[i], &meshes[i], c->stream, sc->owned, &sc->bvh_build_ms))) return fail(rc);
     DMesh *dm = nullptr;
     if ((rc = dev_upload(meshes, &dm, c->stream, sc->owned))) return fail(rc);
     // textures (pixel arrays de-duplicated by host pointer)
@@ -769,6 +834,8 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.top = dtop;
     S.top_items = dtop_items;
     S.obj_rank = drank;
+    S.any_no_ref = 0;
+    for (int m = 0; m < d->n_meshes; m++) if (d->meshes[m].flags & RTU_MESH_DEVICE_BVH) S.any_no_ref = 1;
     S.pool_ok = d->n_meshes > 0 ? 1 : 0; // without meshes nothing would ever be pooled
     for (int m = 0; m < d->n_meshes; m++)
         if (d->meshes[m].nf > (1u << 24) || d->meshes[m].bvh_nodes >= (1u << 27)) S.pool_ok = 0;
@@ -1363,7 +1430,10 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
     if (!s || !out) { rtu::set_error("rtu_get_stats: null argument"); return RTU_ERR_INVALID; }
     rtu_context *c = s->ctx;
     memset(out, 0, sizeof *out);
-    if (!c->wb.counters) return RTU_OK;
+    out->scene_device_bytes = s->device_bytes;
+    out->bvh_build_ms = s->bvh_build_ms;
+    out->queue_retries = c->queue_retries;
+    if (!c->wb.counters) return RTU_OK; // nothing has run on this context yet
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     DCounters hc;
@@ -1389,6 +1459,7 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
     }
     out->scene_device_bytes = s->device_bytes;
     out->queue_retries = c->queue_retries;
+    out->bvh_build_ms = s->bvh_build_ms;
     out->kernel_launches = s->launches;
     if (s->timed) {
         float ms = 0;

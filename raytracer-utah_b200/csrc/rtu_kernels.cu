@@ -452,7 +452,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 Ray r;
                 r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                 const DMesh *M = W.mesh[lane];
-                if ((*(volatile unsigned *)&W.tie >> lane) & 1u) {
+                if (((*(volatile unsigned *)&W.tie >> lane) & 1u) && !M->no_ref) { // (no cyBVH: the lower face index has won the atomicMin)
                     // two triangles at the same distance: the first one in the reference's visiting order wins
                     const float4 yv = W.y[lane];
                     InvDir I;
@@ -1733,7 +1733,7 @@ template <bool PRIMARY> static void launch_extend_pooled(const LaunchCfg &cfg, c
 {
     static int occ[4] = {0, 0, 0, 0};
     const size_t smem = sizeof(XpWarp) * (WAVE_THREADS / 32);
-    const bool ref = (F.flags & RTU_FLAG_REFERENCE_WALK) != 0;
+    const bool ref = (F.flags & RTU_FLAG_REFERENCE_WALK) != 0 && !S.any_no_ref;
 #define RTU_LAUNCH_XP(FLAT_, OCC_, SLOT)                                                                                                \
     k_extend_pool<PRIMARY, FLAT_, OCC_><<<pooled_grid(cfg, k_extend_pool<PRIMARY, FLAT_, OCC_>, smem, &occ[SLOT]), WAVE_THREADS, smem, st>>>( \
         S, F, s0, s1, q, aux, B.hits, pixel_accum, accum, B.counters, work_counter, B.park)
@@ -1820,6 +1820,7 @@ void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
         const char *e = getenv("RTU_SHADOW_KERNEL");
         mode = (e && e[0] == 's') ? 0 : 1;
     }
+    if (S.any_no_ref) reference_walk = false; // a mesh without cyBVH has nothing else to walk
     if (mode == 1 && S.pool_ok && S.n_top == 0) {
         const size_t smem = sizeof(SpWarp) * (WAVE_THREADS / 32);
         // <FLAT, OCC>: OCC walks the meshes' any-hit hierarchies; the other instantiation walks the cyBVH with the reference's

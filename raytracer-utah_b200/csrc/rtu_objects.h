@@ -113,6 +113,7 @@ struct rtu_scene {
     rtu_camera cam;
     std::vector<void *> owned;
     uint64_t serial = 0;          // unique per upload (frame-setup cache key)
+    double bvh_build_ms = 0;      // device time of the LBVH builds of this upload (RTU_MESH_DEVICE_BVH meshes)
     int tree_waves = 2;           // 0: no material reflects or refracts, 1: mirrors only, 2: refraction present (wave_count)
     size_t device_bytes = 0;
     int n_shadow_lights = 0;
@@ -141,3 +142,7 @@ int rtu_ensure_image(rtu_scene *s, size_t npix);
 int rtu_resolve_enqueue(rtu_scene *s, const rtu_params *p, const float4 *accum, rtu_image *out);
 // frame into d_accum (NULL: the context's accumulator) with the overflow check / retry; out != NULL: resolve + copies behind it
 int rtu_render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum, rtu_image *out);
+// LBVH over the triangles of a mesh, built on the device (lbvh_build.cu); outputs are pushed onto `owned`
+int rtu_lbvh_build(cudaStream_t st, const float *d_v, const unsigned *d_f, unsigned nf, const float bmin[3], const float bmax[3],
+                   const TriRec *by_face, std::vector<void *> &owned, const OccNode **nodes_out, const TriRec **tris_out, uint32_t *root_out,
+                   float *build_ms);

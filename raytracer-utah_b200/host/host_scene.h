@@ -40,6 +40,7 @@ struct HostMesh {
     std::vector<uint32_t> bvh_data;
     std::vector<uint32_t> bvh_elements;
     OccBvh occ;                          // any-hit hierarchy over the same triangles (built at load time)
+    bool device_bvh = false;             // RTU_LOAD_DEVICE_BVH: no host hierarchies, the device builds an LBVH at upload
     float bound_min[3] = {1, 1, 1}, bound_max[3] = {0, 0, 0}; // cyTriMesh.h:128 "not ready" box
     uint32_t nf() const { return (uint32_t)(f.size() / 3); }
 };
@@ -56,7 +57,7 @@ struct HostTexture {
 // then TriObj::Load's post-steps (objects.h:52-60): ComputeNormals if none, bounding box,
 // BVH with max 4 elements per leaf.  Returns false if the file cannot be opened.
 // load_mtl: TriObj::Load(name, loadMtl) - usemtl / mtllib are honoured only then (cyTriMesh.h:439-448, 499-544).
-bool load_obj_mesh(const char *path, HostMesh *out, std::string *err, bool load_mtl = false);
+bool load_obj_mesh(const char *path, HostMesh *out, std::string *err, bool load_mtl = false, bool build_hierarchies = true);
 void compute_vertex_normals(HostMesh *m);
 void compute_bounds(HostMesh *m);
 // cyBVH::Build (cyBVH.h:122-142) + BVHTriMesh element callbacks (:356-375)

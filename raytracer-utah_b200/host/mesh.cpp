@@ -82,7 +82,7 @@ struct LineReader {
 
 } // namespace
 
-bool load_obj_mesh(const char *path, HostMesh *m, std::string *err, bool load_mtl)
+bool load_obj_mesh(const char *path, HostMesh *m, std::string *err, bool load_mtl, bool build_hierarchies)
 {
     FILE *fp = fopen(path, "rb");
     if (!fp) {
@@ -275,6 +275,8 @@ bool load_obj_mesh(const char *path, HostMesh *m, std::string *err, bool load_mt
         return false;
     if (m->vn.empty()) compute_vertex_normals(m); // objects.h:56
     compute_bounds(m);                             // objects.h:57
+    m->device_bvh = !build_hierarchies;
+    if (!build_hierarchies) return true; // RTU_LOAD_DEVICE_BVH: the device builds the only hierarchy at upload
     build_bvh(m->v.data(), m->f.data(), nf, 4, &m->bvh_boxes, &m->bvh_data, &m->bvh_elements); // objects.h:58
     build_occlusion_bvh(m->v.data(), m->f.data(), m->bvh_elements.data(), nf, &m->occ);       // any-hit hierarchy (not in the reference)
     return true;

@@ -1,7 +1,9 @@
 // rtu_render: headless replacement for the reference's main() (main.cpp:74-88) for this path.
 //   rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref]
 //              [--mode whitted|head|photon|gather] [--bounces B] [--gi-bounces G] [--photons N] [--seed S]
-//              [--out Result.png] [--zout ZBuffer.png] [--device D]
+//              [--out Result.png] [--zout ZBuffer.png] [--device D] [--device-bvh] [--progress]
+// --device-bvh skips the host hierarchy builds (cyBVH::Build is seconds for a million triangles): the device builds an LBVH.
+// --progress prints numRenderedPixels-style progress while the frame runs on the library's worker thread (BeginRender()).
 // --mode head is what Render() does at the reference's HEAD (4-bounce GI + direct light; the reference uses 1024 spp);
 // photon / gather are its two commented-out photon-map estimators (RenderFunctions.cpp:137-142).
 // Loads the scene (LoadScene), renders it on the GPU and writes Result.png / ZBuffer.png like
@@ -25,6 +27,7 @@ int main(int argc, char **argv)
     std::string scene, root = ".", out = "Result.png", zout = "ZBuffer.png", pattern = "center", mode = "whitted";
     int width = 0, height = 0, spp = 1, bounces = 5, device = 0, gi_bounces = 4;
     long long photons = 1000000, seed = 0;
+    bool device_bvh = false, progress = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -41,12 +44,14 @@ int main(int argc, char **argv)
         else if (a == "--out") out = next();
         else if (a == "--zout") zout = next();
         else if (a == "--device") device = atoi(next());
+        else if (a == "--device-bvh") device_bvh = true;
+        else if (a == "--progress") progress = true;
         else if (a[0] != '-') scene = a;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     if (scene.empty()) { fprintf(stderr, "usage: rtu_render <scene.xml> [--root DIR] [--width W --height H] [--spp N] [--pattern center|ref] [--mode whitted|head|photon|gather] [--bounces B] [--gi-bounces G] [--photons N] [--seed S] [--out Result.png] [--zout ZBuffer.png]\n"); return 2; }
     rtu_host_scene *hs = nullptr;
-    int rc = rtu_host_load_xml(scene.c_str(), root.c_str(), &hs);
+    int rc = rtu_host_load_xml_ex(scene.c_str(), root.c_str(), device_bvh ? RTU_LOAD_DEVICE_BVH : 0u, &hs);
     if (rc) return die("rtu_host_load_xml", rc);
     if (rtu_last_error()[0]) fprintf(stderr, "%s\n", rtu_last_error());
     rtu_context *ctx = nullptr;
@@ -78,11 +83,22 @@ int main(int argc, char **argv)
     memset(&img, 0, sizeof img);
     img.rgb8 = rgb8.data();
     img.z8 = z8.data();
-    if ((rc = rtu_render(sc, &p, &img))) return die("rtu_render", rc);
+    // BeginRender(): the frame runs on the library's worker thread; this thread could draw the partial image (viewport.cpp:390-410)
+    rtu_job *job = nullptr;
+    auto on_progress = [](void *, int64_t done, int64_t total) { fprintf(stderr, "\r%5.1f %%", 100.0 * (double)done / (double)total); };
+    if ((rc = rtu_render_async(sc, &p, &img, progress ? +on_progress : nullptr, nullptr, &job))) return die("rtu_render_async", rc);
+    if ((rc = rtu_job_wait(job))) return die("rtu_render_async", rc);
+    rtu_job_destroy(job);
+    if (progress) fprintf(stderr, "\n");
     rtu_stats st;
     rtu_get_stats(sc, &st);
-    if ((rc = rtu_write_png(out.c_str(), rgb8.data(), W, H, 3))) return die("rtu_write_png", rc);
-    if ((rc = rtu_write_png(zout.c_str(), z8.data(), W, H, 1))) return die("rtu_write_png", rc);
+    // SaveImage / SaveZImage (main.cpp:59-61), both files encoded at the same time on worker threads
+    rtu_job *w1 = nullptr, *w2 = nullptr;
+    if ((rc = rtu_write_png_async(out.c_str(), rgb8.data(), W, H, 3, &w1))) return die("rtu_write_png_async", rc);
+    if ((rc = rtu_write_png_async(zout.c_str(), z8.data(), W, H, 1, &w2))) return die("rtu_write_png_async", rc);
+    if ((rc = rtu_job_wait(w1)) || (rc = rtu_job_wait(w2))) return die("rtu_write_png_async", rc);
+    rtu_job_destroy(w1);
+    rtu_job_destroy(w2);
     double rays = (double)(st.trace_rays + st.shadow_rays);
     printf("{\"width\":%d,\"height\":%d,\"spp\":%d,\"trace_rays\":%llu,\"shadow_rays\":%llu,\"device_ms\":%.3f,\"mrays_per_s\":%.2f}\n", W, H, spp,
            (unsigned long long)st.trace_rays, (unsigned long long)st.shadow_rays, st.device_ms, st.device_ms > 0 ? rays / st.device_ms * 1e-3 : 0.0);

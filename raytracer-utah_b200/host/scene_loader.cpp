@@ -20,6 +20,7 @@ thread_local std::string g_last_error;
 
 struct Loader {
     rtu_host_scene *hs;
+    uint32_t flags = 0; // RTU_LOAD_*
     std::string root; // asset root for relative paths
     struct Pending { int node; std::string mtl; };
     std::vector<Pending> node_mtl;              // nodeMtlList (xmlload.cpp:54-60)
@@ -342,7 +343,7 @@ struct Loader {
                 } else {
                     std::unique_ptr<HostMesh> hm(new HostMesh);
                     std::string err;
-                    if (load_obj_mesh(resolve(name).c_str(), hm.get(), &err, mtl == nullptr)) {
+                    if (load_obj_mesh(resolve(name).c_str(), hm.get(), &err, mtl == nullptr, !(flags & RTU_LOAD_DEVICE_BVH))) {
                         hm->name = name;
                         if (!hm->mtls.empty()) obj_multi_material(*hm, name, me); // only on the first load of this OBJ (xmlload.cpp:201-241)
                         hs->meshes.push_back(std::move(hm));
@@ -467,10 +468,11 @@ void rtu_host_scene::finalize()
         d.fn = m->fn.empty() ? nullptr : m->fn.data();
         d.ft = m->ft.empty() ? nullptr : m->ft.data();
         d.nf = m->nf();
-        d.bvh_boxes = m->bvh_boxes.data();
-        d.bvh_data = m->bvh_data.data();
+        if (m->device_bvh) d.flags |= RTU_MESH_DEVICE_BVH;
+        d.bvh_boxes = m->bvh_boxes.empty() ? nullptr : m->bvh_boxes.data();
+        d.bvh_data = m->bvh_data.empty() ? nullptr : m->bvh_data.data();
         d.bvh_nodes = (uint32_t)m->bvh_data.size();
-        d.bvh_elements = m->bvh_elements.data();
+        d.bvh_elements = m->bvh_elements.empty() ? nullptr : m->bvh_elements.data();
         if (!m->occ.slots.empty()) {
             d.occ_nodes = m->occ.nodes.empty() ? nullptr : m->occ.nodes.data();
             d.occ_n_nodes = (uint32_t)(m->occ.nodes.size() / 32);
@@ -501,12 +503,18 @@ int rtu_version(void) { return 1; }
 
 int rtu_host_load_xml(const char *xml_path, const char *asset_root, rtu_host_scene **out)
 {
+    return rtu_host_load_xml_ex(xml_path, asset_root, 0u, out);
+}
+
+int rtu_host_load_xml_ex(const char *xml_path, const char *asset_root, uint32_t flags, rtu_host_scene **out)
+{
     if (!xml_path || !out) { rtu::set_error("rtu_host_load_xml: null argument"); return RTU_ERR_INVALID; }
     return rtu::guarded("rtu_host_load_xml", [&]() -> int {
     std::unique_ptr<rtu_host_scene> hs(new rtu_host_scene);
     memset(&hs->desc, 0, sizeof hs->desc);
     rtu::Loader L;
     L.hs = hs.get();
+    L.flags = flags;
     L.root = asset_root ? asset_root : "";
     if (!L.load(xml_path)) return RTU_ERR_IO;
     // texmaps captured rgb8 pointers while the texture list was still growing; the pixel

@@ -26,6 +26,8 @@ FLAG_CULL_NULL_SHADOW_RAYS = 1
 FLAG_CULL_ZERO_WEIGHT_RAYS = 2
 FLAG_TIME_KERNELS = 4
 FLAG_REFERENCE_WALK = 8
+MESH_DEVICE_BVH = 1
+LOAD_DEVICE_BVH = 1
 
 f32, i32, u32, u8 = C.c_float, C.c_int32, C.c_uint32, C.c_uint8
 PF, PU, PB = C.POINTER(f32), C.POINTER(u32), C.POINTER(u8)
@@ -41,7 +43,7 @@ class Mesh(C.Structure):
                 ("f", PU), ("fn", PU), ("ft", PU), ("nf", u32),
                 ("bvh_boxes", PF), ("bvh_data", PU), ("bvh_nodes", u32), ("bvh_elements", PU),
                 ("bound_min", f32 * 3), ("bound_max", f32 * 3),
-                ("occ_nodes", PF), ("occ_slots", PU), ("occ_n_nodes", u32), ("occ_root", u32)]
+                ("occ_nodes", PF), ("occ_slots", PU), ("occ_n_nodes", u32), ("occ_root", u32), ("flags", u32)]
 
 
 class TexMap(C.Structure):
@@ -104,7 +106,7 @@ class Stats(C.Structure):
                 ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("primary_wave", KernelStats), ("secondary_waves", KernelStats),
                 ("shadow_waves", KernelStats), ("shade_kernels", KernelStats), ("scene_device_bytes", C.c_uint64),
-                ("queue_retries", C.c_uint64)]
+                ("bvh_build_ms", C.c_double), ("queue_retries", C.c_uint64)]
 
     def as_dict(self):
         out = {}
@@ -170,11 +172,12 @@ def _ptr(a, ty):
 class HostScene:
     """rtu_host_load_xml: our replacement for LoadScene(const char*) (xmlload.cpp:64)."""
 
-    def __init__(self, xml_path, asset_root=None):
+    def __init__(self, xml_path, asset_root=None, flags=0):
         L = lib()
         self._h = C.c_void_p()
         root = asset_root if asset_root is not None else SCENES
-        _check(L.rtu_host_load_xml(os.fsencode(xml_path), os.fsencode(root), C.byref(self._h)), "rtu_host_load_xml")
+        L.rtu_host_load_xml_ex.argtypes = [C.c_char_p, C.c_char_p, u32, C.POINTER(C.c_void_p)]
+        _check(L.rtu_host_load_xml_ex(os.fsencode(xml_path), os.fsencode(root), flags, C.byref(self._h)), "rtu_host_load_xml_ex")
         self.warnings = L.rtu_last_error().decode("utf-8", "replace")
         self.desc = L.rtu_host_scene_desc(self._h).contents
 
@@ -213,9 +216,9 @@ class HostScene:
 
         return {"v": arr(m.v, m.nv, "f4"), "vn": arr(m.vn, m.nvn, "f4"), "vt": arr(m.vt, m.nvt, "f4"),
                 "f": arr(m.f, m.nf, "u4"), "fn": arr(m.fn, m.nf, "u4"), "ft": arr(m.ft, m.nf, "u4"),
-                "bvh_boxes": np.ctypeslib.as_array(m.bvh_boxes, shape=(m.bvh_nodes * 6,)).reshape(-1, 6).copy(),
-                "bvh_data": np.ctypeslib.as_array(m.bvh_data, shape=(m.bvh_nodes,)).copy(),
-                "bvh_elements": np.ctypeslib.as_array(m.bvh_elements, shape=(m.nf,)).copy(),
+                "bvh_boxes": np.ctypeslib.as_array(m.bvh_boxes, shape=(m.bvh_nodes * 6,)).reshape(-1, 6).copy() if m.bvh_boxes else np.zeros((0, 6), "f4"),
+                "bvh_data": np.ctypeslib.as_array(m.bvh_data, shape=(m.bvh_nodes,)).copy() if m.bvh_data else np.zeros(0, "u4"),
+                "bvh_elements": np.ctypeslib.as_array(m.bvh_elements, shape=(m.nf,)).copy() if m.bvh_elements else np.zeros(0, "u4"),
                 "bound": np.concatenate([np.frombuffer(m.bound_min, "f4"), np.frombuffer(m.bound_max, "f4")])}
 
     def camera(self):
