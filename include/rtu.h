@@ -197,6 +197,17 @@ typedef struct rtu_params {
     int32_t row_begin, row_end;   /* image rows rendered by this call (tile-sliced multi-GPU); 0,0 = all */
     uint32_t flags;               /* RTU_FLAG_* */
     uint64_t seed;                /* counter-based RNG key (soft shadows, glossy, DOF, GI) */
+    /* Adaptive sampling: the reference declares minSampleSize = 8, targetVariance = 0.005, sampleIncrement = 1
+     * (RenderFunctions.cpp:25-28) and never uses them.  adaptive_min_spp > 0 turns it on for rtu_render / rtu_render_async
+     * (RTU_MODE_WHITTED and RTU_MODE_PATH, whole frames): every pixel gets adaptive_min_spp samples of the spp-sample
+     * pattern, then passes of adaptive_step more samples go to the 8x4-pixel tiles that still hold a pixel whose estimated
+     * variance of the MEAN exceeds adaptive_target, until none is left or spp samples are spent.  The estimate comes from
+     * two half-images (even / odd samples): ((mean_even - mean_odd) / 2)^2, largest channel.  A pixel's colour is the mean
+     * over its own sample count (rtu_image::sample_count). */
+    int32_t adaptive_min_spp;     /* 0 = fixed spp (the reference's behaviour) */
+    int32_t adaptive_step;        /* samples per pass after the first; <= 0: 8 */
+    float adaptive_target;        /* variance of the pixel mean to stop at */
+    int32_t reserved_;
 } rtu_params;
 
 /* Host output buffers of one frame; any pointer may be NULL. */
@@ -207,6 +218,8 @@ typedef struct rtu_image {
     uint8_t *z8;      /* W*H    ZBuffer.png greys (RenderImage::ComputeZBufferImage, scene.h:590-612) */
     int32_t *node_id; /* W*H    primary hit node (pre-order index), -1 on miss */
     int32_t *face_id; /* W*H    primary hit face, -1 if not a mesh */
+    uint8_t *sample_count; /* W*H  samples the pixel received, saturating at 255: RenderImage::sampleCount (scene.h:545,581);
+                              constant without adaptive sampling */
 } rtu_image;
 
 /* Counters of the last render/trace call.  A "ray" is one root-level Trace or ShadowTrace
@@ -234,6 +247,7 @@ typedef struct rtu_stats {
     rtu_kernel_stats shadow_waves;  /* k_shadow_wave: any-hit */
     rtu_kernel_stats shade_kernels; /* k_shade: MtlBlinn::Shade steps on the compacted hits (launches, ms only) */
     uint64_t scene_device_bytes;    /* bytes rtu_scene_upload copied host -> device */
+    uint64_t pixel_samples;         /* camera samples the last frame spent (= pixels x spp without adaptive sampling) */
     double bvh_build_ms;            /* device time of the LBVH builds of the scene's upload (RTU_MESH_DEVICE_BVH meshes), else 0 */
     uint64_t queue_retries;         /* frames this context rendered again because a ray queue overflowed (the scene then
                                        remembers the larger queues, so a steady state shows no new retries) */

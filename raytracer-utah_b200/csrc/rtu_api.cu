@@ -548,6 +548,7 @@ void rtu_context_destroy(rtu_context *c)
     if (c->fb.d_tile) cudaFree(c->fb.d_tile);
     c->stage_off.release();
     c->stage_tile.release();
+    for (void *q : {(void *)c->d_tile_done, (void *)c->d_tile_samples, (void *)c->d_n_active, (void *)c->d_scount}) if (q) cudaFree(q);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     delete c;
 }
@@ -1055,6 +1056,8 @@ int setup_frame(rtu_scene *s, const rtu_params *p, FrameSetup *F, int *s_begin, 
     F->n_empty_tiles = nullptr;
     F->n_tiles = 0;
     F->n_obj = s->n_obj;
+    F->tile_done = c->adaptive_on ? c->d_tile_done : nullptr;
+    F->half_split = c->adaptive_on ? (unsigned)((size_t)W * H) : 0u;
     *mask_launched = false;
     if (!getenv("RTU_NO_TILE_MASK") && s->cam.dof <= 0.f && s->root_identity) {
         rtu_context::TileKey key;
@@ -1221,9 +1224,11 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
         if ((rc = ensure_gi(c, (size_t)c->wb.hits.cap * (size_t)(2 * (F.gi_bounces + 1) + 2)))) return rc;
         target = c->gi;
     }
+    c->adaptive_totals_valid = false;
+    c->pixel_samples = (uint64_t)W * (uint64_t)rows * (uint64_t)(s1 - s0);
     CU(cudaEventRecord(c->ev0, c->stream));
     CU(cudaMemsetAsync(c->wb.counters, 0, sizeof(DCounters), c->stream));
-    if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * sizeof(float4), c->stream));
+    if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * (c->adaptive_on ? 2 : 1) * sizeof(float4), c->stream));
     s->launches = mask_launched ? 1 : 0; // k_tile_mask ran in setup_frame
     kt_reset(c, (p->flags & RTU_FLAG_TIME_KERNELS) != 0);
     size_t wi = 0;
@@ -1302,7 +1307,7 @@ static int render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int
     CU(cudaSetDevice(c->device));
     int W, H, rc;
     if ((rc = frame_dims(s, p, &W, &H))) return rc;
-    const size_t npix = (size_t)W * H;
+    const size_t npix = (size_t)W * H * (c->adaptive_on ? 2 : 1); // adaptive frames: even and odd samples side by side
     float4 *dst = (float4 *)d_accum;
     if (!dst) {
         if ((rc = ensure_accum(s, npix))) return rc;
@@ -1340,8 +1345,96 @@ static int render_checked(rtu_scene *s, const rtu_params *p, float *d_accum, int
     return RTU_OK;
 }
 
+// Adaptive sampling (rtu_params::adaptive_min_spp > 0): passes over the tiles that have not converged yet.
+// Every pass is an ordinary frame over a range of sample indices of the spp-sample pattern, added to the split accumulator;
+// after it k_adaptive_update retires the tiles whose worst pixel is at or below the target and counts the rest.
+static int render_adaptive(rtu_scene *s, const rtu_params *p, rtu_image *out)
+{
+    rtu_context *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    int W, H, rc;
+    if ((rc = frame_dims(s, p, &W, &H))) return rc;
+    if (p->mode != RTU_MODE_WHITTED && p->mode != RTU_MODE_PATH) { rtu::set_error("adaptive sampling: RTU_MODE_WHITTED and RTU_MODE_PATH only"); return RTU_ERR_UNSUPPORTED; }
+    if (p->sample_begin || p->sample_end || p->row_begin || p->row_end) { rtu::set_error("adaptive sampling renders whole frames (no sample / row ranges)"); return RTU_ERR_INVALID; }
+    if (p->pattern != RTU_PATTERN_REFERENCE || p->spp < 2 || p->adaptive_min_spp < 2 || p->adaptive_min_spp > p->spp || !(p->adaptive_target >= 0.f)) {
+        rtu::set_error("adaptive sampling: needs RTU_PATTERN_REFERENCE, 2 <= adaptive_min_spp <= spp and adaptive_target >= 0");
+        return RTU_ERR_INVALID;
+    }
+    const size_t tiles = (size_t)((W + 7) / 8) * ((H + 3) / 4), npix = (size_t)W * H;
+    if (tiles > c->adaptive_tiles) {
+        CU(cudaStreamSynchronize(c->stream));
+        for (void *q : {(void *)c->d_tile_done, (void *)c->d_tile_samples, (void *)c->d_n_active}) if (q) cudaFree(q);
+        c->d_tile_done = nullptr; c->d_tile_samples = nullptr; c->d_n_active = nullptr;
+        c->adaptive_tiles = 0;
+        CU(cudaMalloc((void **)&c->d_tile_done, tiles));
+        CU(cudaMalloc((void **)&c->d_tile_samples, tiles * sizeof(int)));
+        CU(cudaMalloc((void **)&c->d_n_active, sizeof(unsigned)));
+        c->adaptive_tiles = tiles;
+    }
+    CU(cudaMemsetAsync(c->d_tile_done, 0, tiles, c->stream));
+    CU(cudaMemsetAsync(c->d_tile_samples, 0, tiles * sizeof(int), c->stream));
+    const int step = p->adaptive_step > 0 ? p->adaptive_step : 8;
+    struct Off { rtu_context *c; ~Off() { c->adaptive_on = false; } } off{c}; // every exit leaves the context in fixed-spp mode
+    c->adaptive_on = true;
+    uint64_t spent = 0, active_tiles = tiles, launches = 0;
+    double device_ms = 0;
+    rtu_stats total;
+    memset(&total, 0, sizeof total);
+    for (int n = 0; n < p->spp && active_tiles > 0;) {
+        const int n_next = n == 0 ? p->adaptive_min_spp : std::min(p->spp, n + step);
+        rtu_params q = *p;
+        q.sample_begin = n;
+        q.sample_end = n_next;
+        q.adaptive_min_spp = 0;
+        if ((rc = render_checked(s, &q, nullptr, n == 0 ? 1 : 0, nullptr))) return rc;
+        launch_adaptive_update(c->stream, c->fb.accum, W, H, n_next, p->spp, p->adaptive_target, c->d_tile_done, c->d_tile_samples, c->d_n_active);
+        CU(cudaMemcpyAsync(c->h_flag + 1, c->d_n_active, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        spent += active_tiles * 32ull * (uint64_t)(n_next - n); // (tiles at the image border count whole)
+        active_tiles = c->h_flag[1];
+        rtu_stats st;
+        if (rtu_get_stats(s, &st) == RTU_OK) { // the counters are per call: add the passes up
+            total.trace_rays += st.trace_rays; total.shadow_rays += st.shadow_rays; total.box_tests += st.box_tests;
+            total.tri_tests += st.tri_tests; total.node_visits += st.node_visits;
+            device_ms += st.device_ms;
+            launches += st.kernel_launches + 1;
+        }
+        n = n_next;
+    }
+    c->adaptive_on = false;
+    c->pixel_samples = spent;
+    c->adaptive_totals = total;
+    c->adaptive_totals.device_ms = device_ms;
+    c->adaptive_totals.kernel_launches = launches;
+    c->adaptive_totals_valid = true;
+    // the pixel's colour: mean over its own sample count
+    if ((rc = ensure_image(s, npix))) return rc;
+    if (out->sample_count && npix > c->scount_n) {
+        if (c->d_scount) cudaFree(c->d_scount);
+        c->d_scount = nullptr;
+        c->scount_n = 0;
+        CU(cudaMalloc((void **)&c->d_scount, npix));
+        c->scount_n = npix;
+    }
+    if (out->rgb || out->rgb8 || out->sample_count) {
+        launch_resolve_adaptive(c->stream, c->fb.accum, W, H, c->d_tile_samples, out->rgb ? c->fb.d_rgb : nullptr, out->rgb8 ? c->fb.d_rgb8 : nullptr,
+                                out->sample_count ? c->d_scount : nullptr);
+        if (out->rgb) CU(cudaMemcpyAsync(out->rgb, c->fb.d_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, c->fb.d_rgb8, npix * 3, cudaMemcpyDeviceToHost, c->stream));
+        if (out->sample_count) CU(cudaMemcpyAsync(out->sample_count, c->d_scount, npix, cudaMemcpyDeviceToHost, c->stream));
+    }
+    rtu_image rest = *out;
+    rest.rgb = nullptr; rest.rgb8 = nullptr; rest.sample_count = nullptr;
+    if (rest.z || rest.z8 || rest.node_id || rest.face_id)
+        if ((rc = rtu_resolve_enqueue(s, p, nullptr, &rest))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return RTU_OK;
+}
+
 int rtu_render_device(rtu_scene *s, const rtu_params *p, float *d_accum, int32_t clear_accum)
 {
+    if (p && p->adaptive_min_spp > 0) { rtu::set_error("rtu_render_device: adaptive sampling goes through rtu_render / rtu_render_async"); return RTU_ERR_UNSUPPORTED; }
     return rtu::guarded("rtu_render_device", [&]() -> int { return render_checked(s, p, d_accum, clear_accum, nullptr); });
 }
 
@@ -1420,6 +1513,7 @@ int rtu_render(rtu_scene *s, const rtu_params *p, rtu_image *out)
             CU(cudaGetLastError());
             return RTU_OK;
         }
+        if (p->adaptive_min_spp > 0) return render_adaptive(s, p, out);
         // frame, resolve and device->host copies are enqueued together: one wait covers the images and the overflow flag
         return render_checked(s, p, nullptr, 1, out);
     });
@@ -1433,6 +1527,7 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
     out->scene_device_bytes = s->device_bytes;
     out->bvh_build_ms = s->bvh_build_ms;
     out->queue_retries = c->queue_retries;
+    out->pixel_samples = c->pixel_samples;
     if (!c->wb.counters) return RTU_OK; // nothing has run on this context yet
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
@@ -1464,6 +1559,11 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
     if (s->timed) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->device_ms = ms;
+    }
+    if (c->adaptive_totals_valid) { // the last call was an adaptive frame: its passes added up
+        const rtu_stats &t = c->adaptive_totals;
+        out->trace_rays = t.trace_rays; out->shadow_rays = t.shadow_rays; out->box_tests = t.box_tests; out->tri_tests = t.tri_tests;
+        out->node_visits = t.node_visits; out->device_ms = t.device_ms; out->kernel_launches = t.kernel_launches;
     }
     if (hc.overflow) { rtu::set_error("ray queue overflow: lower RTU_CHUNK_RAYS"); return RTU_ERR_UNSUPPORTED; }
     return RTU_OK;

@@ -23,7 +23,14 @@ struct FrameSetup {
     // items per atomic when most tiles are empty, else 32.  Read on the device so that the host never waits for the mask.
     const unsigned *n_empty_tiles;
     unsigned n_tiles;
+    // adaptive sampling (rtu_params::adaptive_min_spp > 0): tiles whose pixels have all reached the target variance are no
+    // longer sampled (tile_done[tile] != 0), and the accumulator has two halves of npix entries - even samples go to the
+    // first, odd samples to the second - whose difference is the variance estimate
+    const unsigned char *tile_done;
+    unsigned half_split; // 0, or npix: the offset of the odd samples' half
 };
+
+__host__ __device__ inline int half_slot(const FrameSetup &F, int pixel, int s) { return pixel + ((s & 1) ? (int)F.half_split : 0); }
 
 struct LaunchCfg {
     int sm_count;
@@ -92,6 +99,13 @@ void launch_accum_add(cudaStream_t st, float4 *dst, const float4 *src, size_t np
 // multi-GPU: accumulator -> three planes of RGB sums (what the collective moves); resolve of reduced planes
 void launch_pack_rgb(cudaStream_t st, const float4 *accum, size_t npix, float *planes);
 void launch_resolve_planes(cudaStream_t st, const float *planes, size_t npix, int spp, float *rgb, unsigned char *rgb8);
+// adaptive sampling: after a pass that brought the active tiles to n_now samples, per 8x4 tile the largest estimated variance of
+// a pixel mean, ((A/nA - B/nB) / 2)^2 per channel; tiles at or below `target` (or at max_spp) are done.  *n_active counts the rest.
+void launch_adaptive_update(cudaStream_t st, const float4 *accum, int W, int H, int n_now, int max_spp, float target, unsigned char *tile_done,
+                            int *tile_samples, unsigned *n_active);
+// mean over each pixel's OWN sample count, gamma, Color24; sample_count: RenderImage::sampleCount (scene.h:545), saturating at 255
+void launch_resolve_adaptive(cudaStream_t st, const float4 *accum, int W, int H, const int *tile_samples, float *rgb, unsigned char *rgb8,
+                             unsigned char *sample_count);
 // RenderImage::ComputeZBufferImage (scene.h:590-612)
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8);
 

@@ -116,12 +116,25 @@ __device__ __forceinline__ void primary_miss_fast(const DScene &S, const FrameSe
     tl.node += (unsigned)(ns * F.n_obj);
     tl.box += (unsigned)(ns * F.n_obj);
     const Col c = background_sample(S, x, y, pm.W, F.cam.height);
-    float4 a = accum[y * pm.W + x];
+    // adaptive frames keep even and odd samples apart (FrameSetup::half_split): samples s0 .. s0+ns-1 alternate, so
+    // ns - ns/2 of them go where s0's parity says and ns/2 to the other half
+    const int n_same = F.half_split ? ns - ns / 2 : ns, n_other = F.half_split ? ns / 2 : 0;
+    const int base = half_slot(F, y * pm.W + x, F.half_split ? s0 : 0);
+    float4 a = accum[base];
 #pragma unroll 1
-    for (int i = 0; i < ns; i++) {
+    for (int i = 0; i < n_same; i++) {
         a.x += c.r; a.y += c.g; a.z += c.b;
     }
-    accum[y * pm.W + x] = a;
+    accum[base] = a;
+    if (n_other) {
+        const int other = half_slot(F, y * pm.W + x, s0 + 1);
+        float4 b = accum[other];
+#pragma unroll 1
+        for (int i = 0; i < n_other; i++) {
+            b.x += c.r; b.y += c.g; b.z += c.b;
+        }
+        accum[other] = b;
+    }
 }
 
 // ------------------------------------------------------------------ closest hit
@@ -154,9 +167,11 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         if (PRIMARY) {
             int s;
             if (!pm.decode(idx, s0, s, x, y)) continue;
+            if (F.tile_done && F.tile_done[pm.tile_of(idx)]) continue; // adaptive sampling: the tile has converged
             if (F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl); continue; }
             pixel = y * pm.W + x;
             ray = primary_ray(F, s, x, y, pixel);
+            pixel = half_slot(F, pixel, s); // from here on: the accumulator slot
         } else {
             float4 o = in.o[idx], d = in.d[idx];
             ray.px = o.x; ray.py = o.y; ray.pz = o.z;
@@ -528,11 +543,13 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 int s;
                 have = pm.decode(idx, s0, s, x, y);
                 pixel = y * pm.W + x;
+                if (have && i0 == 1 && F.tile_done && F.tile_done[pm.tile_of(idx)]) have = false; // adaptive sampling: converged tile
                 if (have && i0 == 1 && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { // warp-uniform: a ticket is one tile
                     primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl);
                     have = false;
                 }
                 if (have) ray = primary_ray(F, s, x, y, pixel);
+                pixel = half_slot(F, pixel, s); // from here on: the accumulator slot
             } else {
                 float4 o = in.o[idx], d = in.d[idx];
                 ray.px = o.x; ray.py = o.y; ray.pz = o.z;
@@ -659,6 +676,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
             pixel = y * pm.W + x;
             ray = primary_ray(F, s, x, y, pixel);
             path = primary_path(pixel, s);
+            pixel = half_slot(F, pixel, s); // from here on: the accumulator slot (adaptive frames: odd samples in the second half)
             Wt = mk(1.f, 1.f, 1.f);
             kind = RK_PRIMARY; bounce = F.shade_bounces; mtl = 0; aux = -1;
         } else {
@@ -1401,6 +1419,63 @@ __global__ void k_resolve_planes(const float *planes, size_t npix, int spp, floa
     }
 }
 
+// ---- adaptive sampling (minSampleSize / targetVariance / sampleIncrement, RenderFunctions.cpp:25-28, declared by
+// the reference and never wired up).  One thread per 8x4 tile; see launch_adaptive_update.
+__global__ void k_adaptive_update(const float4 *accum, int W, int H, int n_now, int max_spp, float target, unsigned char *tile_done,
+                                  int *tile_samples, unsigned *n_active)
+{
+    const int tilesX = (W + 7) >> 3, tilesY = (H + 3) >> 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tilesX * tilesY) return;
+    if (tile_done[t]) return;
+    tile_samples[t] = n_now;
+    const int tx = t % tilesX, ty = t / tilesX;
+    const size_t npix = (size_t)W * H;
+    const float nA = (float)(n_now - n_now / 2), nB = (float)(n_now / 2); // even / odd samples of [0, n_now)
+    float worst = 0.f;
+    if (n_now >= 2) {
+        for (int j = 0; j < 4; j++)
+            for (int i = 0; i < 8; i++) {
+                const int x = tx * 8 + i, y = ty * 4 + j;
+                if (x >= W || y >= H) continue;
+                const float4 a = accum[(size_t)y * W + x], b = accum[npix + (size_t)y * W + x];
+                const float dr = 0.5f * (a.x / nA - b.x / nB), dg = 0.5f * (a.y / nA - b.y / nB), db = 0.5f * (a.z / nA - b.z / nB);
+                float v = fmaxf(fmaxf(dr * dr, dg * dg), db * db);
+                if (!(v == v)) v = 0.f; // a NaN pixel never converges by waiting
+                worst = fmaxf(worst, v);
+            }
+    } else {
+        worst = 3.0e38f;
+    }
+    if (worst <= target || n_now >= max_spp) tile_done[t] = 1;
+    else atomicAdd(n_active, 1u);
+}
+
+__global__ void k_resolve_adaptive(const float4 *accum, int W, int H, const int *tile_samples, float *rgb, unsigned char *rgb8,
+                                   unsigned char *sample_count)
+{
+    const size_t npix = (size_t)W * H;
+    const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    const int n = tile_samples[(y >> 2) * ((W + 7) >> 3) + (x >> 3)];
+    const float4 a = accum[p], b = accum[npix + p];
+    const float fn = (float)(n > 0 ? n : 1);
+    float c[3] = {(a.x + b.x) / fn, (a.y + b.y) / fn, (a.z + b.z) / fn};
+    if (rgb) { rgb[p * 3] = c[0]; rgb[p * 3 + 1] = c[1]; rgb[p * 3 + 2] = c[2]; }
+    if (rgb8) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float gmm = (float)pow((double)c[k], 1 / 2.2);
+            float s = gmm * 255;
+            int v = (s == s) ? (int)s : 0;
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            rgb8[p * 3 + k] = (unsigned char)v;
+        }
+    }
+    if (sample_count) sample_count[p] = (unsigned char)(n > 255 ? 255 : n);
+}
+
 __global__ void k_zminmax(const float *z, int npix, unsigned *mm)
 {
     // zmin / zmax over hit pixels (scene.h:596-601); positive floats order like their bit patterns
@@ -1552,9 +1627,11 @@ k_extend_top(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux,
             if (PRIMARY) {
                 int s;
                 have = pm.decode(idx, s0, s, x, y);
+                if (have && F.tile_done && F.tile_done[pm.tile_of(idx)]) have = false; // adaptive sampling: converged tile
                 if (have && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl); have = false; }
                 pixel = y * pm.W + x;
                 if (have) ray = primary_ray(F, s, x, y, pixel);
+                pixel = half_slot(F, pixel, s); // from here on: the accumulator slot
             } else {
                 float4 o = in.o[idx], d = in.d[idx];
                 ray.px = o.x; ray.py = o.y; ray.pz = o.z;
@@ -1986,6 +2063,21 @@ void launch_pack_rgb(cudaStream_t st, const float4 *accum, size_t npix, float *p
 void launch_resolve_planes(cudaStream_t st, const float *planes, size_t npix, int spp, float *rgb, unsigned char *rgb8)
 {
     k_resolve_planes<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(planes, npix, spp, rgb, rgb8);
+}
+
+void launch_adaptive_update(cudaStream_t st, const float4 *accum, int W, int H, int n_now, int max_spp, float target, unsigned char *tile_done,
+                            int *tile_samples, unsigned *n_active)
+{
+    const int tiles = ((W + 7) >> 3) * ((H + 3) >> 2);
+    cudaMemsetAsync(n_active, 0, sizeof(unsigned), st);
+    k_adaptive_update<<<(tiles + 127) / 128, 128, 0, st>>>(accum, W, H, n_now, max_spp, target, tile_done, tile_samples, n_active);
+}
+
+void launch_resolve_adaptive(cudaStream_t st, const float4 *accum, int W, int H, const int *tile_samples, float *rgb, unsigned char *rgb8,
+                             unsigned char *sample_count)
+{
+    const size_t npix = (size_t)W * H;
+    k_resolve_adaptive<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(accum, W, H, tile_samples, rgb, rgb8, sample_count);
 }
 
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8)

@@ -103,6 +103,17 @@ struct rtu_context {
     const unsigned *tile_count = nullptr;
     unsigned tile_total = 0;
     PinnedStage stage_off, stage_tile;
+    // adaptive sampling state of the frame in flight (rtu_params::adaptive_min_spp > 0): consulted by setup_frame
+    unsigned char *d_tile_done = nullptr;
+    int *d_tile_samples = nullptr;
+    unsigned *d_n_active = nullptr;
+    size_t adaptive_tiles = 0;
+    bool adaptive_on = false;        // the frame being set up splits even / odd samples and skips finished tiles
+    uint64_t pixel_samples = 0;      // camera samples of the last frame (rtu_stats::pixel_samples)
+    rtu_stats adaptive_totals;       // counters summed over the passes of the last adaptive frame
+    bool adaptive_totals_valid = false;
+    unsigned char *d_scount = nullptr; // sample-count image
+    size_t scount_n = 0;
     uint32_t *h_flag = nullptr;      // page-locked word the overflow flag is copied into
     uint64_t queue_retries = 0;      // frames re-rendered after a queue overflow (rtu_stats::queue_retries)
 };

@@ -85,12 +85,12 @@ class Params(C.Structure):
     _fields_ = [("width", i32), ("height", i32), ("spp", i32), ("sample_begin", i32),
                 ("sample_end", i32), ("pattern", i32), ("mode", i32), ("shade_bounces", i32),
                 ("gi_bounces", i32), ("row_begin", i32), ("row_end", i32), ("flags", u32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("adaptive_min_spp", i32), ("adaptive_step", i32), ("adaptive_target", f32), ("reserved_", i32)]
 
 
 class Image(C.Structure):
     _fields_ = [("rgb8", PB), ("rgb", PF), ("z", PF), ("z8", PB),
-                ("node_id", C.POINTER(i32)), ("face_id", C.POINTER(i32))]
+                ("node_id", C.POINTER(i32)), ("face_id", C.POINTER(i32)), ("sample_count", PB)]
 
 
 class KernelStats(C.Structure):
@@ -106,7 +106,7 @@ class Stats(C.Structure):
                 ("tri_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("primary_wave", KernelStats), ("secondary_waves", KernelStats),
                 ("shadow_waves", KernelStats), ("shade_kernels", KernelStats), ("scene_device_bytes", C.c_uint64),
-                ("bvh_build_ms", C.c_double), ("queue_retries", C.c_uint64)]
+                ("pixel_samples", C.c_uint64), ("bvh_build_ms", C.c_double), ("queue_retries", C.c_uint64)]
 
     def as_dict(self):
         out = {}
@@ -432,21 +432,7 @@ class Scene:
         """rtu_render: whole frame, host buffers out (the e2e path).  out: optional dict of caller-owned arrays (e.g.
         page-locked ones) to write into instead of fresh numpy arrays."""
         L = lib()
-        w, h = self._dims(params)
-        bufs = {}
-        img = Image()
-        spec = {"rgb8": ((h, w, 3), "u1", u8), "rgb": ((h, w, 3), "f4", f32), "z": ((h, w), "f4", f32),
-                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
-        for k in want:
-            shp, dt, ct = spec[k]
-            if out is not None and k in out:
-                a = out[k]
-                if a.shape != shp or a.dtype != np.dtype(dt) or not a.flags["C_CONTIGUOUS"]:
-                    raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (k, dt, shp))
-                bufs[k] = a
-            else:
-                bufs[k] = np.zeros(shp, dt)
-            setattr(img, k, _ptr(bufs[k], ct))
+        bufs, img = self._image(params, want, out)
         L.rtu_render.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Image)]
         _check(L.rtu_render(self._h, C.byref(params), C.byref(img)), "rtu_render")
         return bufs
@@ -459,7 +445,8 @@ class Scene:
     def _image(self, params, want, out=None):
         w, h = self._dims(params)
         spec = {"rgb8": ((h, w, 3), "u1", u8), "rgb": ((h, w, 3), "f4", f32), "z": ((h, w), "f4", f32),
-                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
+                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32),
+                "sample_count": ((h, w), "u1", u8)}
         bufs, img = {}, Image()
         for k in want:
             shp, dt, ct = spec[k]
@@ -511,15 +498,7 @@ class Scene:
 
     def resolve(self, params, d_accum=0, want=("rgb8", "rgb")):
         L = lib()
-        w, h = self._dims(params)
-        bufs = {}
-        img = Image()
-        spec = {"rgb8": ((h, w, 3), "u1", u8), "rgb": ((h, w, 3), "f4", f32), "z": ((h, w), "f4", f32),
-                "z8": ((h, w), "u1", u8), "node_id": ((h, w), "i4", i32), "face_id": ((h, w), "i4", i32)}
-        for k in want:
-            shp, dt, ct = spec[k]
-            bufs[k] = np.zeros(shp, dt)
-            setattr(img, k, _ptr(bufs[k], ct))
+        bufs, img = self._image(params, want)
         L.rtu_resolve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(Image)]
         _check(L.rtu_resolve(self._h, C.byref(params), C.c_void_p(d_accum), C.byref(img)), "rtu_resolve")
         return bufs

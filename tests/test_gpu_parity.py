@@ -873,3 +873,74 @@ def test_device_built_hierarchy(rtu, gpu_ctx, which):
     finally:
         sc.close()
         hs.close()
+
+
+def test_adaptive_sampling(rtu, gpu_ctx):
+    """SURVEY 8f-4 (minSampleSize / targetVariance / sampleIncrement, RenderFunctions.cpp:25-28, never wired up by the
+    reference).  With target 0 no tile ever converges: the frame is the fixed-spp frame, sample for sample (this pins the
+    even / odd half-accumulators, the per-tile sample counts and the passes).  With a target, smooth regions stop early, the
+    sample-count image says where, and the image stays within the target's error of the converged frame."""
+    hs = rtu.HostScene(os.path.join(SCENES, "Project11/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        kw = dict(width=200, height=152, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=4, seed=4)
+        fixed = sc.render(rtu.default_params(spp=64, **kw), want=("rgb",))["rgb"]
+        st_fixed = sc.stats()
+        same = sc.render(rtu.default_params(spp=64, adaptive_min_spp=8, adaptive_step=8, adaptive_target=0.0, **kw), want=("rgb", "sample_count"))
+        st_same = sc.stats()
+        assert (same["sample_count"] == 64).all()
+        assert st_same["pixel_samples"] == 200 * 152 * 64 and st_same["trace_rays"] == st_fixed["trace_rays"] and st_same["shadow_rays"] == st_fixed["shadow_rays"]
+        assert within_tol(same["rgb"], fixed).all()
+        ref = sc.render(rtu.default_params(spp=1024, **kw), want=("rgb",))["rgb"].astype(np.float64)
+        target = 4e-5
+        ad = sc.render(rtu.default_params(spp=1024, adaptive_min_spp=8, adaptive_step=8, adaptive_target=target, **kw), want=("rgb", "sample_count", "rgb8"))
+        st = sc.stats()
+        cnt = ad["sample_count"]
+        assert cnt.min() >= 8 and cnt.max() == 255 and len(np.unique(cnt)) > 4            # 255 = saturated (up to 1024 samples)
+        assert (cnt[::4, ::8][:, :, None] == cnt.reshape(38, 4, 25, 8).transpose(0, 2, 1, 3).reshape(38, 25, 32)).all()   # constant per 8x4 tile
+        assert st["pixel_samples"] < 0.6 * 200 * 152 * 1024, st["pixel_samples"]
+        assert st["trace_rays"] < 0.6 * (st_fixed["trace_rays"] * 16)
+        a = ad["rgb"].astype(np.float64)
+        assert abs(a.mean() - ref.mean()) <= 0.01 * ref.mean()
+        rmse = np.sqrt(np.mean((a - ref) ** 2))
+        assert rmse <= 2.0 * np.sqrt(target), rmse
+        # tiles that stopped early really are the smooth ones: their error against the converged frame is no larger
+        few = np.repeat(cnt < 64, 3).reshape(a.shape)
+        assert np.sqrt(np.mean((a - ref)[few] ** 2)) <= 2.0 * np.sqrt(target)
+        with pytest.raises(rtu.RtuError):
+            sc.render_device(rtu.default_params(spp=64, adaptive_min_spp=8, **kw))
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_queue_overflow_on_the_accumulate_path_never_corrupts_the_accumulator(rtu):
+    """rtu_render_device(clear_accum=0) - the spp-sliced / row-sliced path - with queues that are too small for the slice:
+    the frame is rendered on the side, re-rendered with larger queues after the device flags the overflow, and only then added,
+    so the caller's accumulator holds exactly slice A + slice B (an overflow there used to be silent)."""
+    ctx = rtu.Context(0)
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    try:
+        kw = dict(width=160, height=120, spp=4, pattern=rtu.PATTERN_REFERENCE, shade_bounces=5, gi_bounces=4, seed=5)
+        pa = rtu.default_params(mode=rtu.MODE_WHITTED, sample_begin=0, sample_end=2, **dict(kw, shade_bounces=0))
+        pb = rtu.default_params(mode=rtu.MODE_PATH, sample_begin=2, sample_end=4, **kw)
+        whole = rtu.default_params(mode=rtu.MODE_PATH, **kw)
+        sc = rtu.Scene(ctx, hs.desc)
+        sc.render_device(pa, clear=True)          # small frame: the queues are sized for it
+        r0 = sc.stats()["queue_retries"]
+        sc.render_device(pb, clear=False)         # spawns several rays per hit: overflows, is retried, then added
+        assert sc.stats()["queue_retries"] > r0
+        both = sc.resolve(whole, want=("rgb",))["rgb"].astype(np.float64)
+        sc.close()
+        sc = rtu.Scene(ctx, hs.desc)
+        sc.render_device(pa, clear=True)
+        a = sc.resolve(whole, want=("rgb",))["rgb"].astype(np.float64)
+        sc.render_device(pb, clear=True)
+        b = sc.resolve(whole, want=("rgb",))["rgb"].astype(np.float64)
+        sc.close()
+        assert np.isfinite(both).all()
+        assert np.allclose(both, a + b, rtol=1e-4, atol=1e-6)
+        assert b.mean() > 5 * a.mean() * 0 + 1e-3
+    finally:
+        hs.close()
+        ctx.close()

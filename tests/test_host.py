@@ -145,15 +145,22 @@ def test_abi_exports_every_declared_symbol(rtu):
     assert L.rtu_version() >= 1
 
 
-def test_struct_layouts_match_the_header(rtu):
-    # sizes the C compiler gives the PODs of include/rtu.h (64-bit): guards the ctypes mirrors
-    assert C.sizeof(rtu.Node) == 21 * 4 + 4 * 4
-    assert C.sizeof(rtu.TexColor) == 16
-    assert C.sizeof(rtu.Material) == 5 * 16 + 7 * 4
-    assert C.sizeof(rtu.Light) == 32
-    assert C.sizeof(rtu.Camera) == 14 * 4
-    assert rtu.RAY_DTYPE.itemsize == 24 and rtu.HIT_DTYPE.itemsize == 52
-    assert C.sizeof(rtu.Params) == 56
+def test_struct_layouts_match_the_header(rtu, tmp_path):
+    """The ctypes mirrors against what the C compiler makes of include/rtu.h: a small C program prints sizeof of every POD."""
+    import subprocess
+    pairs = [("rtu_node", rtu.Node), ("rtu_mesh", rtu.Mesh), ("rtu_texmap", rtu.TexMap), ("rtu_texcolor", rtu.TexColor),
+             ("rtu_material", rtu.Material), ("rtu_light", rtu.Light), ("rtu_camera", rtu.Camera), ("rtu_scene_desc", rtu.SceneDesc),
+             ("rtu_params", rtu.Params), ("rtu_image", rtu.Image), ("rtu_kernel_stats", rtu.KernelStats), ("rtu_stats", rtu.Stats),
+             ("rtu_photon_params", rtu.PhotonParams), ("rtu_photon_stats", rtu.PhotonStats)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "rtu.h"\nint main(void){' +
+                   "".join('printf("%%zu\\n", sizeof(%s));' % n for n, _ in pairs) + "return 0;}\n")
+    exe = str(tmp_path / "sizes")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    for (name, ct), size in zip(pairs, sizes):
+        assert C.sizeof(ct) == size, "%s: ctypes %d, C %d" % (name, C.sizeof(ct), size)
+    assert rtu.RAY_DTYPE.itemsize == 24 and rtu.HIT_DTYPE.itemsize == 52 and rtu.PHOTON_DTYPE.itemsize == 24
 
 
 def test_no_gpu_means_an_error_not_a_fallback(rtu):
