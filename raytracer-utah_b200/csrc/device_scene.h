@@ -206,6 +206,7 @@ enum RayKind {
 // (halfStoredPhotons = n/2 - 1, cyPhotonMap.h:227,356)
 struct DPhotonMap {
     const rtu_photon *map;
+    const float4 *knn_nodes, *knn_dir, *knn_pw; // walk records and per-photon tables of the estimate (photon_kernels.cu)
     int n, half;
     float radius, norm_scale; // photonEstRadius; 1/ellipticity - 1 (0 when ellipticity == 1)
 };

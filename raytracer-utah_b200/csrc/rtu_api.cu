@@ -861,6 +861,7 @@ void rtu_scene_destroy(rtu_scene *s)
     cudaSetDevice(s->ctx->device);
     free_list_async(s->owned, s->ctx->stream); // after everything already queued on the context's stream
     if (s->d_photons) cudaFreeAsync(s->d_photons, s->ctx->stream);
+    if (s->d_knn) cudaFreeAsync(s->d_knn, s->ctx->stream);
     delete s;
 }
 
@@ -1167,6 +1168,9 @@ DPhotonMap photon_map_of(const rtu_scene *s)
 {
     DPhotonMap PM;
     PM.map = s->d_photons;
+    PM.knn_nodes = s->d_knn;
+    PM.knn_dir = s->d_knn ? s->d_knn + 3 * ((size_t)s->n_photons + 1) : nullptr;
+    PM.knn_pw = s->d_knn ? s->d_knn + 4 * ((size_t)s->n_photons + 1) : nullptr;
     PM.n = (int)s->n_photons;
     PM.half = (int)s->n_photons / 2 - 1; // halfStoredPhotons (cyPhotonMap.h:227)
     PM.radius = s->photon_params.est_radius;
@@ -1240,16 +1244,16 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
         kt_end(c);
         if (F.mode == RTU_MODE_PHOTON) { // PhotonMapping(ray, hInfo) per hit; no secondary or shadow rays (bounceCount 0)
             kt_begin(c, 3);
-            launch_photon_shade(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum);
+            CU(launch_photon_shade(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum));
             kt_end(c);
-            s->launches += 3;
+            s->launches += 3 + 3 * (((unsigned)c->wb.hits.cap + (1u << 20) - 1) >> 20);
             continue;
         }
         kt_begin(c, 3);
         launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, target, c->work + wi++);
         if (F.mode == RTU_MODE_PHOTON_GATHER) { // + MonteCarloPhoton per primary hit (the hit queue is still intact)
-            launch_photon_gather(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum);
-            s->launches++;
+            CU(launch_photon_gather(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum));
+            s->launches += 3 + 2 * (unsigned)((c->wb.hits.cap * (size_t)std::max(1, F.gi_bounces) + (1u << 20) - 1) >> 20);
         }
         kt_end(c);
         s->launches += 3;
@@ -1770,8 +1774,11 @@ int install_photon_map(rtu_scene *s, const std::vector<rtu_photon> &balanced, ui
 {
     rtu_context *c = s->ctx;
     if (s->d_photons) { cudaFreeAsync(s->d_photons, c->stream); s->d_photons = nullptr; s->n_photons = 0; }
+    if (s->d_knn) { cudaFreeAsync(s->d_knn, c->stream); s->d_knn = nullptr; }
     CU(cudaMallocAsync((void **)&s->d_photons, sizeof(rtu_photon) * ((size_t)n + 1), c->stream));
+    CU(cudaMallocAsync((void **)&s->d_knn, sizeof(float4) * 5 * ((size_t)n + 1), c->stream));
     CU(cudaMemcpyAsync(s->d_photons, balanced.data(), sizeof(rtu_photon) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+    CU(launch_knn_build(c->stream, s->d_photons, (int)n, (int)n / 2 - 1, s->d_knn, s->d_knn + 3 * ((size_t)n + 1), s->d_knn + 4 * ((size_t)n + 1)));
     CU(cudaStreamSynchronize(c->stream)); // `balanced` is pageable and goes out of scope
     s->n_photons = n;
     s->photon_params = pp;
@@ -1828,8 +1835,7 @@ int rtu_estimate_irradiance(rtu_scene *s, const float *pos, const float *normal,
     if (e == cudaSuccess) {
         DPhotonMap PM = photon_map_of(s);
         float norm_scale = ellipticity == 1.f ? 0.f : 1.f / ellipticity - 1.f;
-        launch_estimate(c->stream, PM, dpos, dn, n, radius, norm_scale, dirr, ddir, dfound);
-        e = cudaGetLastError();
+        e = launch_estimate(c->stream, PM, dpos, dn, n, radius, norm_scale, dirr, ddir, dfound);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(irrad, dirr, b3, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(direction, ddir, b3, cudaMemcpyDeviceToHost, c->stream);

@@ -110,12 +110,14 @@ void launch_resolve_adaptive(cudaStream_t st, const float4 *accum, int W, int H,
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8);
 
 // photon path (photon_kernels.cu)
-void launch_estimate(cudaStream_t st, const DPhotonMap &PM, const float *pos, const float *normal, long long n, float radius,
-                     float norm_scale, float *irrad, float *direction, int *found);
-void launch_photon_shade(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
-                         const DPhotonMap &PM, float4 *accum);
-void launch_photon_gather(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
-                          const DPhotonMap &PM, float4 *accum);
+cudaError_t launch_knn_build(cudaStream_t st, const rtu_photon *map, int n, int half, float4 *nodes, float4 *dir, float4 *pw);
+// (these three allocate their scratch from the stream-ordered pool and return the first CUDA error)
+cudaError_t launch_estimate(cudaStream_t st, const DPhotonMap &PM, const float *pos, const float *normal, long long n, float radius,
+                            float norm_scale, float *irrad, float *direction, int *found);
+cudaError_t launch_photon_shade(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
+                                const DPhotonMap &PM, float4 *accum);
+cudaError_t launch_photon_gather(cudaStream_t st, const DScene &S, const FrameSetup &F, int s0, const WaveBuffers &B, unsigned max_hits,
+                                 const DPhotonMap &PM, float4 *accum);
 void launch_photon_emit(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, unsigned long long path0, unsigned n_paths,
                         int max_bounce, uint2 seed, int light, rtu_photon *staging, unsigned char *counts, DCounters *counters,
                         unsigned *work_counter);

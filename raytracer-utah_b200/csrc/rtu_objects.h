@@ -141,6 +141,7 @@ struct rtu_scene {
     int h_light0_kind = -1;       // lights[0]: the only light GeneratePhotonMap emits from
     float h_light0_I[3] = {0, 0, 0};
     rtu_photon *d_photons = nullptr;
+    float4 *d_knn = nullptr;      // walk records (3 per node) + direction table + power table of the estimate, one allocation
     uint32_t n_photons = 0;
     rtu_photon_params photon_params;
 };
