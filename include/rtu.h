@@ -381,7 +381,8 @@ typedef struct rtu_photon_stats {
     uint64_t stored;           /* photons in the map */
     uint64_t trace_rays;       /* root-level Trace calls of the emission */
     float scale_factor;        /* (lights[0] intensity / photonFromLight).Gray()  (:384) */
-    float emit_ms, build_ms;   /* device time of the emission; host time of the kd-tree balancing + upload */
+    float emit_ms, build_ms;   /* device time of the emission; wall time of the kd-tree balancing (+ the estimate's walk records) */
+    uint32_t device_build;     /* 1: the kd-tree was balanced on the device; 0: on the host (a median tied with a neighbour) */
 } rtu_photon_stats;
 
 void rtu_photon_params_default(rtu_photon_params *p);
@@ -389,8 +390,12 @@ void rtu_photon_params_default(rtu_photon_params *p);
  * powers, balances the kd-tree (RenderFunctions.cpp:341-392).  Paths are numbered; path i draws from its own
  * Philox stream and the map holds exactly what the sequential loop over i = 0,1,2,... would have stored. */
 int rtu_photon_map_generate(rtu_scene *scene, const rtu_photon_params *params, rtu_photon_stats *stats);
-/* Installs caller photons (any order, e.g. the reference's own map): PrepareForIrradianceEstimation + upload. */
+/* Installs caller photons (any order, e.g. the reference's own map): PrepareForIrradianceEstimation.  The tree is balanced on
+ * the device where that is the reference's tree by construction (no median ties with a neighbour along its split axis), else
+ * on the host; either way the array is byte-identical to cyPhotonMap's. */
 int rtu_photon_map_set(rtu_scene *scene, const rtu_photon *photons, uint32_t n, const rtu_photon_params *params);
+/* Number of photons of the scene's map (0: none) and whether the device balanced it. */
+int rtu_photon_map_info(const rtu_scene *scene, uint32_t *n_photons, uint32_t *device_build);
 /* Copies the balanced map out: out[i] = photons[i+1] of cyPhotonMap, *n = number of photons (cap = room in out). */
 int rtu_photon_map_get(rtu_scene *scene, rtu_photon *out, uint32_t cap, uint32_t *n);
 /* cyPhotonMap::EstimateIrradiance<100>(irrad, direction, radius, pos, &normal, ellipticity, FILTER_TYPE_CONSTANT)

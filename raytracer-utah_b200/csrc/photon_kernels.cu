@@ -349,6 +349,9 @@ cudaError_t launch_knn_build(cudaStream_t st, const rtu_photon *map, int n, int 
 #ifndef KNN_WALK
 #define KNN_WALK 2 // node visits per lane and round of k_knn_candidates
 #endif
+#ifndef KNN_BOX_SHIFT
+#define KNN_BOX_SHIFT 0 // inner nodes below half >> this are box-tested on arrival
+#endif
 #ifndef KNN_CTAS
 #define KNN_CTAS 5
 #endif
@@ -418,7 +421,7 @@ k_knn_candidates(DPhotonMap PM, const float *pos, const float *normal, const uns
                 if (up == 0u || cur != cidx) n0 = __ldg(rec);
                 if ((int)cur < PM.half) { cidx = cur; cn0 = n0; }
                 bool process = true;
-                if (up == 0u && (int)cur < PM.half) { // arriving at an inner node from above: can anything at or below it pass the node tests?
+                if (up == 0u && (int)cur < (PM.half >> KNN_BOX_SHIFT)) { // arriving at an inner node from above: can anything at or below it pass the node tests?
                     // (a leaf's box is the photon itself: the node test below says the same)
                     const float4 lo = __ldg(rec + 1), hi = __ldg(rec + 2);
                     const float ax = lo.x - qx, ay = lo.y - qy, az = lo.z - qz, bx = hi.x - qx, by = hi.y - qy, bz = hi.z - qz;

@@ -1770,16 +1770,36 @@ int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n,
 // ---------------------------------------------------------------------------------------------- photon map
 namespace {
 
-int install_photon_map(rtu_scene *s, const std::vector<rtu_photon> &balanced, uint32_t n, const rtu_photon_params &pp)
+// Balances `n` raw photons into the scene's map and builds the estimate's walk records.  d_raw: the photons on the device;
+// h_raw: the same on the host, or NULL (then they are read back if the host has to balance).  The device build
+// (photon_build.cu) is the reference's tree whenever no median ties with a neighbour; with ties it says so and the host build
+// (byte-identical to the reference in every case) takes over.  RTU_PHOTON_BUILD=host skips the device build.
+int install_photon_map(rtu_scene *s, const rtu_photon *d_raw, const rtu_photon *h_raw, uint32_t n, const rtu_photon_params &pp)
 {
     rtu_context *c = s->ctx;
     if (s->d_photons) { cudaFreeAsync(s->d_photons, c->stream); s->d_photons = nullptr; s->n_photons = 0; }
     if (s->d_knn) { cudaFreeAsync(s->d_knn, c->stream); s->d_knn = nullptr; }
     CU(cudaMallocAsync((void **)&s->d_photons, sizeof(rtu_photon) * ((size_t)n + 1), c->stream));
     CU(cudaMallocAsync((void **)&s->d_knn, sizeof(float4) * 5 * ((size_t)n + 1), c->stream));
-    CU(cudaMemcpyAsync(s->d_photons, balanced.data(), sizeof(rtu_photon) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+    const char *how = getenv("RTU_PHOTON_BUILD");
+    unsigned tie = 1;
+    if (!(how && !strcmp(how, "host"))) CU(launch_photon_balance(c->stream, d_raw, n, s->d_photons, &tie));
+    s->photon_device_build = tie == 0;
+    if (tie) {
+        std::vector<rtu_photon> tmp;
+        if (!h_raw) {
+            tmp.resize(n);
+            CU(cudaMemcpyAsync(tmp.data(), d_raw, sizeof(rtu_photon) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            h_raw = tmp.data();
+        }
+        std::vector<rtu_photon> balanced((size_t)n + 1);
+        int rc = rtu_host_balance_photons(h_raw, n, balanced.data());
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s->d_photons, balanced.data(), sizeof(rtu_photon) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream)); // `balanced` is pageable and goes out of scope
+    }
     CU(launch_knn_build(c->stream, s->d_photons, (int)n, (int)n / 2 - 1, s->d_knn, s->d_knn + 3 * ((size_t)n + 1), s->d_knn + 4 * ((size_t)n + 1)));
-    CU(cudaStreamSynchronize(c->stream)); // `balanced` is pageable and goes out of scope
     s->n_photons = n;
     s->photon_params = pp;
     return RTU_OK;
@@ -1796,10 +1816,24 @@ int rtu_photon_map_set(rtu_scene *s, const rtu_photon *photons, uint32_t n, cons
     rtu_photon_params pp;
     rtu_photon_params_default(&pp);
     if (params) pp = *params;
-    std::vector<rtu_photon> balanced((size_t)n + 1);
-    int rc = rtu_host_balance_photons(photons, n, balanced.data());
-    if (rc) return rc;
-    return install_photon_map(s, balanced, n, pp);
+    rtu_context *c = s->ctx;
+    rtu_photon *d_raw = nullptr;
+    if (n) {
+        CU(cudaMallocAsync((void **)&d_raw, sizeof(rtu_photon) * (size_t)n, c->stream));
+        cudaError_t e = cudaMemcpyAsync(d_raw, photons, sizeof(rtu_photon) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { cudaFreeAsync(d_raw, c->stream); CU(e); }
+    }
+    int rc = install_photon_map(s, d_raw, photons, n, pp);
+    if (d_raw) cudaFreeAsync(d_raw, c->stream);
+    return rc;
+}
+
+int rtu_photon_map_info(const rtu_scene *s, uint32_t *n_photons, uint32_t *device_build)
+{
+    if (!s) { rtu::set_error("rtu_photon_map_info: null scene"); return RTU_ERR_INVALID; }
+    if (n_photons) *n_photons = s->d_photons ? s->n_photons : 0;
+    if (device_build) *device_build = s->d_photons && s->photon_device_build ? 1u : 0u;
+    return RTU_OK;
 }
 
 int rtu_photon_map_get(rtu_scene *s, rtu_photon *out, uint32_t cap, uint32_t *n)
@@ -1918,21 +1952,19 @@ int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_p
     float scale = ((s->h_light0_I[0] / fl + s->h_light0_I[1] / fl) + s->h_light0_I[2] / fl) / 3.0f;
     launch_photon_scale(c->stream, d_map, cap, scale);
     cudaEventRecord(ev1, c->stream);
-    std::vector<rtu_photon> raw(cap);
-    e = cudaMemcpyAsync(raw.data(), d_map, sizeof(rtu_photon) * (size_t)cap, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    e = cudaStreamSynchronize(c->stream);
     DCounters hc;
     if (e == cudaSuccess) e = cudaMemcpy(&hc, c->wb.counters, sizeof hc, cudaMemcpyDeviceToHost);
     float emit_ms = 0.f;
     cudaEventElapsedTime(&emit_ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    cleanup();
-    CU(e);
+    if (e != cudaSuccess) { cleanup(); CU(e); }
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<rtu_photon> balanced((size_t)cap + 1);
-    if ((rc = rtu_host_balance_photons(raw.data(), cap, balanced.data()))) return rc;
-    if ((rc = install_photon_map(s, balanced, cap, pp))) return rc;
+    rc = install_photon_map(s, d_map, nullptr, cap, pp);
+    if (rc == RTU_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = RTU_ERR_CUDA;
+    cleanup();
+    if (rc) return rc;
     float build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats) {
         stats->paths = paths;
@@ -1942,6 +1974,7 @@ int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_p
         stats->scale_factor = scale;
         stats->emit_ms = emit_ms;
         stats->build_ms = build_ms;
+        stats->device_build = s->photon_device_build ? 1u : 0u;
     }
     return RTU_OK;
 }

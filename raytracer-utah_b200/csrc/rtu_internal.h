@@ -110,6 +110,8 @@ void launch_resolve_adaptive(cudaStream_t st, const float4 *accum, int W, int H,
 void launch_zimage(cudaStream_t st, const float *z, int npix, unsigned *minmax_bits, unsigned char *z8);
 
 // photon path (photon_kernels.cu)
+// device kd-tree build (photon_build.cu); *tie_host = 1: a median tied with a neighbour, `out` is not the reference's tree
+cudaError_t launch_photon_balance(cudaStream_t st, const rtu_photon *raw, unsigned n, rtu_photon *out, unsigned *tie_host);
 cudaError_t launch_knn_build(cudaStream_t st, const rtu_photon *map, int n, int half, float4 *nodes, float4 *dir, float4 *pw);
 // (these three allocate their scratch from the stream-ordered pool and return the first CUDA error)
 cudaError_t launch_estimate(cudaStream_t st, const DPhotonMap &PM, const float *pos, const float *normal, long long n, float radius,

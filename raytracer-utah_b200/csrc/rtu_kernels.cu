@@ -232,6 +232,48 @@ __device__ __forceinline__ bool ref_reaches_lane(const DMesh &M, unsigned slot, 
     return ref_reaches(M, slot, r, I, tl);
 }
 
+// Rare paths of the pooled closest-hit kernel as real functions: the kernel is ~100 KB of code with them inlined at every use
+// and a quarter of its stall samples were instruction fetch.
+struct RefWalkArgs {
+    float px, py, pz, dx, dy, dz, yx, yy, yz;
+    int ok;
+    float z, bc1, bc2, bc3;
+    int front, slot;
+};
+static __device__ __noinline__ bool walk_reference_ni(const DMesh *M, RefWalkArgs *a, Tally *tl)
+{
+    Ray r;
+    r.px = a->px; r.py = a->py; r.pz = a->pz; r.dx = a->dx; r.dy = a->dy; r.dz = a->dz;
+    InvDir I;
+    I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
+    return bvh_walk<false>(M->pairs, M->tris, M->root, r, I, a->z, a->front, a->slot, a->bc1, a->bc2, a->bc3, *tl);
+}
+static __device__ __noinline__ bool ref_reaches_ni(const DMesh *M, unsigned slot, const RefWalkArgs *a, Tally *tl)
+{
+    Ray r;
+    r.px = a->px; r.py = a->py; r.pz = a->pz; r.dx = a->dx; r.dy = a->dy; r.dz = a->dz;
+    InvDir I;
+    I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
+    return ref_reaches(*M, slot, r, I, *tl);
+}
+static __device__ __noinline__ bool occ_walk_ni(const DMesh *M, unsigned start, const RefWalkArgs *a, const OccRay *oc, float t_max, Tally *tl)
+{
+    Ray r;
+    r.px = a->px; r.py = a->py; r.pz = a->pz; r.dx = a->dx; r.dy = a->dy; r.dz = a->dz;
+    InvDir I;
+    I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
+    return occ_walk(*M, start, r, I, *oc, t_max, *tl);
+}
+static __device__ __noinline__ void occ_walk_closest_ni(const DMesh *M, unsigned start, const RefWalkArgs *a, const OccRay *oc, float z_in,
+                                                        unsigned long long *zkey, unsigned *tie, unsigned tie_bit, Tally *tl)
+{
+    Ray r;
+    r.px = a->px; r.py = a->py; r.pz = a->pz; r.dx = a->dx; r.dy = a->dy; r.dz = a->dz;
+    InvDir I;
+    I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
+    occ_walk_closest(*M, start, r, I, *oc, z_in, zkey, tie, tie_bit, *tl);
+}
+
 template <bool PRIMARY, bool FLAT, bool OCC>
 __global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
@@ -376,11 +418,13 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                     oc.ok = true;
                     if (finish) {
                         const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
-                        Ray r;
-                        r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
-                        InvDir I;
-                        I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                        occ_walk_closest(*W.mesh[sl], it & 0x07ffffffu, r, I, oc, o.w, &W.zkey[sl], &W.tie, 1u << sl, tl);
+                        RefWalkArgs a;
+                        a.px = o.x; a.py = o.y; a.pz = o.z; a.dx = d.x; a.dy = d.y; a.dz = d.z;
+                        a.yx = yv.x; a.yy = yv.y; a.yz = yv.z; a.ok = d.w != 0.f;
+                        Tally t2 = {0, 0, 0, 0, 0};
+                        const OccRay oc2 = oc;
+                        occ_walk_closest_ni(W.mesh[sl], it & 0x07ffffffu, &a, &oc2, o.w, &W.zkey[sl], &W.tie, 1u << sl, &t2);
+                        tl.box += t2.box; tl.tri += t2.tri;
                     } else {
                         hit = occ_node(oc, W.nodes[sl] + (it & 0x07ffffffu), ch);
                         tl.box += 4;
@@ -467,19 +511,27 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 Ray r;
                 r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                 const DMesh *M = W.mesh[lane];
-                if (((*(volatile unsigned *)&W.tie >> lane) & 1u) && !M->no_ref) { // (no cyBVH: the lower face index has won the atomicMin)
-                    // two triangles at the same distance: the first one in the reference's visiting order wins
+                // two triangles at the same distance: the first one in the reference's visiting order wins (this walk repeats
+                // tests that are already booked); the winner's leaf box rejects the ray in the reference's own test: the
+                // reference-order walk decides.  (no cyBVH: the lower face index has won the atomicMin)
+                const bool tied = ((*(volatile unsigned *)&W.tie >> lane) & 1u) && !M->no_ref;
+                bool rewalk = tied;
+                RefWalkArgs a;
+                {
                     const float4 yv = W.y[lane];
-                    InvDir I;
-                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                    Tally scratch = {0, 0, 0, 0, 0}; // this walk repeats tests that are already booked
-                    if (bvh_walk<false>(M->pairs, M->tris, M->root, r, I, B.z, B.front, B.slot, B.bc1, B.bc2, B.bc3, scratch)) B.node = (int)node;
-                } else if ((unsigned)key != 0xffffffffu && OCC && !ref_reaches_lane(*M, (unsigned)key, r, d.w != 0.f, W.y[lane], tl)) {
-                    // the winner's leaf box rejects the ray in the reference's own test: the reference-order walk decides
-                    const float4 yv = W.y[lane];
-                    InvDir I;
-                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                    if (bvh_walk<false>(M->pairs, M->tris, M->root, r, I, B.z, B.front, B.slot, B.bc1, B.bc2, B.bc3, tl)) B.node = (int)node;
+                    a.px = r.px; a.py = r.py; a.pz = r.pz; a.dx = r.dx; a.dy = r.dy; a.dz = r.dz;
+                    a.yx = yv.x; a.yy = yv.y; a.yz = yv.z; a.ok = d.w != 0.f;
+                }
+                // (the confirmation runs once per ray that found a triangle: inlined, a call here cost 8 % of the primary wave)
+                if (!rewalk && (unsigned)key != 0xffffffffu && OCC) rewalk = !ref_reaches_lane(*M, (unsigned)key, r, d.w != 0.f, W.y[lane], tl);
+                if (rewalk) {
+                    a.z = B.z; a.front = B.front; a.slot = B.slot; a.bc1 = B.bc1; a.bc2 = B.bc2; a.bc3 = B.bc3;
+                    Tally t2 = {0, 0, 0, 0, 0}; // (its address is taken: kept apart from the kernel's own tally)
+                    if (walk_reference_ni(M, &a, &t2)) {
+                        B.z = a.z; B.front = a.front; B.slot = a.slot; B.bc1 = a.bc1; B.bc2 = a.bc2; B.bc3 = a.bc3;
+                        B.node = (int)node;
+                    }
+                    if (!tied) { tl.box += t2.box; tl.tri += t2.tri; }
                 } else if ((unsigned)key != 0xffffffffu) {
                     TriRec T;
                     tri_load(M->tris + (unsigned)key, T); // the key carries the cyBVH slot in both walks
@@ -973,11 +1025,13 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                         oc.ok = true;
                         if (finish) {
                             const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
-                            Ray r;
-                            r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
-                            InvDir I;
-                            I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                            if (occ_walk(*W.mesh[sl], it & 0x07ffffffu, r, I, oc, o.w, tl)) atomicOr(&W.occl, 1u << sl);
+                            RefWalkArgs a;
+                            a.px = o.x; a.py = o.y; a.pz = o.z; a.dx = d.x; a.dy = d.y; a.dz = d.z;
+                            a.yx = yv.x; a.yy = yv.y; a.yz = yv.z; a.ok = d.w != 0.f;
+                            Tally t2 = {0, 0, 0, 0, 0};
+                            const OccRay oc2 = oc;
+                            if (occ_walk_ni(W.mesh[sl], it & 0x07ffffffu, &a, &oc2, o.w, &t2)) atomicOr(&W.occl, 1u << sl);
+                            tl.box += t2.box; tl.tri += t2.tri;
                         } else {
                             hit = occ_node(oc, W.nodes[sl] + (it & 0x07ffffffu), ch);
                             tl.box += 4;
@@ -1075,11 +1129,19 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 // rejection (hit point within rounding of the box) hands the ray to the exact walk of the cyBVH
                 if (stopped && W.hitslot[lane] != 0xffffffffu) {
                     const float4 o = W.o[lane], d = W.d[lane], yv = W.y[lane];
-                    Ray r;
-                    r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
-                    InvDir I;
-                    I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
-                    if (!ref_reaches(*W.mesh[lane], W.hitslot[lane], r, I, tl)) stopped = bvh_walk_any_fallback(*W.mesh[lane], r, I, o.w, tl);
+                    RefWalkArgs a;
+                    a.px = o.x; a.py = o.y; a.pz = o.z; a.dx = d.x; a.dy = d.y; a.dz = d.z;
+                    a.yx = yv.x; a.yy = yv.y; a.yz = yv.z; a.ok = d.w != 0.f;
+                    Tally t2 = {0, 0, 0, 0, 0};
+                    const bool reached = ref_reaches_ni(W.mesh[lane], W.hitslot[lane], &a, &t2);
+                    tl.box += t2.box;
+                    if (!reached) {
+                        Ray r;
+                        r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                        InvDir I;
+                        I.yx = yv.x; I.yy = yv.y; I.yz = yv.z; I.ok = d.w != 0.f;
+                        stopped = bvh_walk_any_fallback(*W.mesh[lane], r, I, o.w, tl);
+                    }
                 }
             }
             const bool go_on = lane < take && !stopped;

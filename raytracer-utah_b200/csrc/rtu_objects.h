@@ -143,6 +143,7 @@ struct rtu_scene {
     rtu_photon *d_photons = nullptr;
     float4 *d_knn = nullptr;      // walk records (3 per node) + direction table + power table of the estimate, one allocation
     uint32_t n_photons = 0;
+    bool photon_device_build = false; // the map in d_photons was balanced by photon_build.cu (no tie met)
     rtu_photon_params photon_params;
 };
 

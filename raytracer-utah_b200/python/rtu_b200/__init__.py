@@ -133,7 +133,7 @@ class PhotonParams(C.Structure):
 
 class PhotonStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("from_light", C.c_uint64), ("stored", C.c_uint64), ("trace_rays", C.c_uint64),
-                ("scale_factor", f32), ("emit_ms", f32), ("build_ms", f32)]
+                ("scale_factor", f32), ("emit_ms", f32), ("build_ms", f32), ("device_build", u32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -520,6 +520,14 @@ class Scene:
         pp = photon_params(**kw)
         L.rtu_photon_map_set.argtypes = [C.c_void_p, C.c_void_p, u32, C.POINTER(PhotonParams)]
         _check(L.rtu_photon_map_set(self._h, photons.ctypes.data, photons.shape[0], C.byref(pp)), "rtu_photon_map_set")
+
+    def photon_map_info(self):
+        """(number of photons, whether the kd-tree was balanced on the device)."""
+        L = lib()
+        n, dev = u32(0), u32(0)
+        L.rtu_photon_map_info.argtypes = [C.c_void_p, C.POINTER(u32), C.POINTER(u32)]
+        _check(L.rtu_photon_map_info(self._h, C.byref(n), C.byref(dev)), "rtu_photon_map_info")
+        return n.value, bool(dev.value)
 
     def photon_map_get(self):
         """The balanced map as cyPhotonMap stores it (photons[1..n])."""

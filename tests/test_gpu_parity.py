@@ -553,6 +553,52 @@ def test_photon_map_kat(rtu, gpu_ctx):
         hs.close()
 
 
+def test_photon_tree_device_build_is_the_reference_tree(rtu, gpu_ctx):
+    """The device kd-tree build (photon_build.cu) equals cyPhotonMap's balancing byte for byte: on the reference's own
+    20 000-photon fixture, on small and odd sizes (left-balanced medians), on a 10^6-photon emission (against the host
+    port, itself pinned to the reference in tests/test_host.py) - and a map with tied coordinates falls back to the host."""
+    g, _ = load_golden("kat_photonmap")
+    hs = rtu.HostScene(os.path.join(SCENES, "Project13/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        pin = g["photons_in"].view(rtu.PHOTON_DTYPE).reshape(-1)
+        sc.photon_map_set(pin)
+        n, on_device = sc.photon_map_info()
+        assert n == len(pin) and on_device, "the fixture has no ties: the device build must have been used"
+        assert sc.photon_map_get().tobytes() == g["photons_balanced"].tobytes()
+        for m in (1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 13, 100, 1023, 1024, 1025, 4097):
+            sc.photon_map_set(pin[:m])
+            assert sc.photon_map_info() == (m, True), m
+            assert sc.photon_map_get().tobytes() == rtu.balance_photons(pin[:m])[1:].tobytes(), m
+        # ties: every photon twice -> the selection's swap order decides -> host build, still the reference's array
+        dup = np.concatenate([pin[:500], pin[:500]])
+        sc.photon_map_set(dup)
+        assert sc.photon_map_info() == (1000, False)
+        assert sc.photon_map_get().tobytes() == rtu.balance_photons(dup)[1:].tobytes()
+        # a large map with pairwise distinct coordinates on every axis: all 19 levels on the device
+        rng = np.random.default_rng(7)
+        big = np.zeros(300001, rtu.PHOTON_DTYPE)
+        for k in range(3):
+            big["position"][:, k] = (rng.permutation(len(big)).astype("f4") - 150000.0) * np.float32(0.001 * (k + 1))
+        big["power"] = rng.random(len(big), dtype="f4")
+        big["color"] = rng.integers(0, 256, (len(big), 3), dtype="u1")
+        big["plane_dirz"] = rng.integers(0, 2, len(big), dtype="u1") * 8
+        big["dir_x"] = rng.integers(-20000, 20000, len(big)); big["dir_y"] = rng.integers(-20000, 20000, len(big))
+        sc.photon_map_set(big)
+        assert sc.photon_map_info() == (len(big), True)
+        assert sc.photon_map_get().tobytes() == rtu.balance_photons(big)[1:].tobytes()
+        # the emission of this scene puts hundreds of thousands of photons on axis-aligned walls (equal coordinates): whichever
+        # build ran, the tree is the one the host port builds from the same photons in any input order... when no tie decided
+        st = sc.photon_map_generate(seed=5)
+        assert st["stored"] == 1000000
+        if st["device_build"]:
+            tree = sc.photon_map_get()
+            assert tree.tobytes() == rtu.balance_photons(tree[rng.permutation(len(tree))])[1:].tobytes()
+    finally:
+        sc.close()
+        hs.close()
+
+
 def test_photon_mapping_image_matches_oracle(rtu, gpu_ctx):
     """RTU_MODE_PHOTON = PhotonMapping(ray, hInfo) per sample, on a map emitted by the device; the oracle (bit-exact
     with the reference's PhotonMapping on the reference's map, tests/test_oracle.py) renders with the same map."""
