@@ -4,6 +4,20 @@
 #include "rtu_internal.h"
 #include "shade.cuh"
 
+// The lens point of a depth-of-field camera (RenderFunctions.cpp:272-283).  A real function: the counter-based generator and
+// sinf / cosf are ~250 instructions, the camera ray is built at two places of the pooled primary kernel, and most scenes
+// have no depth of field.
+static __device__ __noinline__ void lens_sample(uint2 key, unsigned pixel, unsigned path, unsigned dim, float dof, float *lx, float *ly)
+{
+    Rng rng;
+    rng.key = key; rng.pixel = pixel; rng.path = path; rng.dim = dim;
+    float4 u = rng.next4();
+    float th = u.y * 6.283185307179586f;
+    float rad = sqrtf(u.x * dof * dof);
+    *lx = rad * cosf(th);
+    *ly = rad * sinf(th);
+}
+
 // Camera ray of pixel (x,y) with sub-pixel offset (ox,oy): RenderFunctions.cpp:88-97, 258-269
 __device__ __forceinline__ Ray camera_ray(const DCamera &C, int x, int y, float ox, float oy, Rng *rng)
 {
@@ -14,10 +28,8 @@ __device__ __forceinline__ Ray camera_ray(const DCamera &C, int x, int y, float 
     Ray r;
     r.px = C.pos[0]; r.py = C.pos[1]; r.pz = C.pos[2];
     if (C.dof > 0.f && rng) {
-        float4 u = rng->next4();
-        float th = u.y * 6.283185307179586f;
-        float rad = sqrtf(u.x * C.dof * C.dof);
-        float lx = rad * cosf(th), ly = rad * sinf(th);
+        float lx, ly;
+        lens_sample(rng->key, rng->pixel, rng->path, rng->dim, C.dof, &lx, &ly);
         r.px = (C.pos[0] + C.lens_y[0] * ly) + C.lens_x[0] * lx;
         r.py = (C.pos[1] + C.lens_y[1] * ly) + C.lens_x[1] * lx;
         r.pz = (C.pos[2] + C.lens_y[2] * ly) + C.lens_x[2] * lx;

@@ -302,6 +302,13 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
         t_block = per_warp >= want ? want : (per_warp < 32u ? 32u : (per_warp & ~31u));
     }
     bool drained = false;
+    // (see the ticket code below) no adaptive frame: its converged tiles are looked up per ticket
+    const bool sparse = PRIMARY && F.tile_empty && !F.tile_done && F.n_empty_tiles && 2u * __ldg(F.n_empty_tiles) > F.n_tiles;
+    unsigned live = 0, live_base = 0, sparse_tickets = 8;
+    if (sparse) { // about four tickets with work per atomic: more would leave the last warps with long tails
+        const unsigned n_live = F.n_tiles - __ldg(F.n_empty_tiles);
+        sparse_tickets = 8u * n_live < F.n_tiles ? 32u : (4u * n_live < F.n_tiles ? 16u : 8u);
+    }
     DNode root;
     load_node(S.nodes, root);
 
@@ -559,7 +566,33 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
         const unsigned k = (nres >= 32u || drained) ? (nres < 32u ? nres : 32u) : 0u;
         unsigned fresh = (k == 0u && !drained) ? 32u : 0u;
         unsigned base = 0;
-        if (fresh) {
+        if (PRIMARY && fresh && sparse) {
+            // a frame of mostly empty tiles: 8 to 32 tickets (= tiles of one sample) per atomic; every lane looks at one ticket's
+            // tile, the warp fills the empty tiles that fall to it (the tickets of the chunk's first sample) and then
+            // takes the tickets that hold work one pass at a time
+            while (live == 0u && !drained) {
+                unsigned blk = 0;
+                if (lane == 0) blk = atomicAdd(work, 32u * sparse_tickets);
+                blk = __shfl_sync(FULL, blk, 0);
+                if (blk >= total) { drained = true; break; }
+                const unsigned mine = blk + 32u * lane;
+                const bool valid = lane < sparse_tickets && mine < total;
+                const bool empty = valid && F.tile_empty[pm.tile_of(mine)];
+                live = __ballot_sync(FULL, valid && !empty);
+                live_base = blk;
+                unsigned fill = __ballot_sync(FULL, empty && mine < pm.perSample);
+                while (fill) {
+                    const unsigned b = __ffs(fill) - 1u;
+                    fill &= fill - 1u;
+                    int s, x, y;
+                    if (pm.decode(blk + 32u * b + lane, s0, s, x, y)) primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl);
+                }
+            }
+            if (live) {
+                base = live_base + 32u * (__ffs(live) - 1u);
+                live &= live - 1u;
+            } else fresh = 0;
+        } else if (fresh) {
             // work items come in blocks of TICKET_BLOCK (8 tiles / 8 x 32 queue entries) per atomic: a wave of mostly empty
             // tiles would otherwise spend its time waiting for the single work counter
             if (t_next >= t_end) {
@@ -596,7 +629,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                 have = pm.decode(idx, s0, s, x, y);
                 pixel = y * pm.W + x;
                 if (have && i0 == 1 && F.tile_done && F.tile_done[pm.tile_of(idx)]) have = false; // adaptive sampling: converged tile
-                if (have && i0 == 1 && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { // warp-uniform: a ticket is one tile
+                if (have && i0 == 1 && !sparse && F.tile_empty && F.tile_empty[pm.tile_of(idx)]) { // warp-uniform: a ticket is one tile
                     primary_miss_fast(S, F, pm, accum, x, y, s, s0, s1 - s0, tl);
                     have = false;
                 }
