@@ -140,11 +140,11 @@ def estimate_irradiance(balanced, pos, normal, radius, ellipticity):
     L = lib()
     balanced = np.ascontiguousarray(balanced, PHOTON_DTYPE)
     pos = np.ascontiguousarray(pos, "f4")
-    normal = np.ascontiguousarray(normal, "f4")
+    normal = None if normal is None else np.ascontiguousarray(normal, "f4")
     nq = pos.shape[0]
     irrad = np.zeros((nq, 3), "f4"); direction = np.zeros((nq, 3), "f4"); found = np.zeros(nq, "i4")
     rc = L.oracle_estimate_irradiance(C.c_void_p(balanced.ctypes.data), C.c_uint32(balanced.shape[0] - 1), C.c_void_p(pos.ctypes.data),
-                                      C.c_void_p(normal.ctypes.data), C.c_int64(nq), C.c_float(radius), C.c_float(ellipticity),
+                                      C.c_void_p(None if normal is None else normal.ctypes.data), C.c_int64(nq), C.c_float(radius), C.c_float(ellipticity),
                                       C.c_void_p(irrad.ctypes.data), C.c_void_p(direction.ctypes.data), C.c_void_p(found.ctypes.data))
     assert rc == 0
     return irrad, direction, found

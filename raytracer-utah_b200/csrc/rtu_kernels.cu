@@ -303,11 +303,14 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
     }
     bool drained = false;
     // (see the ticket code below) no adaptive frame: its converged tiles are looked up per ticket
-    const bool sparse = PRIMARY && F.tile_empty && !F.tile_done && F.n_empty_tiles && 2u * __ldg(F.n_empty_tiles) > F.n_tiles;
+    bool sparse = PRIMARY && F.tile_empty && !F.tile_done && F.n_empty_tiles && 2u * __ldg(F.n_empty_tiles) > F.n_tiles;
     unsigned live = 0, live_base = 0, sparse_tickets = 8;
     if (sparse) { // about four tickets with work per atomic: more would leave the last warps with long tails
         const unsigned n_live = F.n_tiles - __ldg(F.n_empty_tiles);
         sparse_tickets = 8u * n_live < F.n_tiles ? 32u : (4u * n_live < F.n_tiles ? 16u : 8u);
+        // a small wave (few samples) has less than a block per resident warp: the plain tickets serve it better
+        const unsigned per_warp = (total >> 5) / (gridDim.x * (WAVE_THREADS / 32));
+        if (per_warp < 4u * sparse_tickets) sparse = false;
     }
     DNode root;
     load_node(S.nodes, root);
@@ -438,20 +441,16 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                     }
                 }
                 const unsigned w0 = (hit & 1u) ? ch.x : NONE, w1 = (hit & 2u) ? ch.y : NONE, w2 = (hit & 4u) ? ch.z : NONE, w3 = (hit & 8u) ? ch.w : NONE;
-                const unsigned mine = (unsigned)(w0 < NONE) + (w1 < NONE) + (w2 < NONE) + (w3 < NONE) +
-                                      (((unsigned)(w0 > NONE) + (w1 > NONE) + (w2 > NONE) + (w3 > NONE)) << 16);
-                unsigned incl = mine;
-#pragma unroll
-                for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                    const unsigned v = __shfl_up_sync(FULL, incl, o2);
-                    if (lane >= (unsigned)o2) incl += v;
-                }
-                const unsigned tot = __shfl_sync(FULL, incl, 31);
-                unsigned pi = pool_n + ((incl - mine) & 0xffffu), li = leaf_n + ((incl - mine) >> 16);
+                // positions from eight ballots (independent of each other) instead of a five-step shuffle scan (a dependent chain)
+                const unsigned i0 = __ballot_sync(FULL, w0 < NONE), i1 = __ballot_sync(FULL, w1 < NONE), i2 = __ballot_sync(FULL, w2 < NONE), i3 = __ballot_sync(FULL, w3 < NONE);
+                const unsigned l0 = __ballot_sync(FULL, w0 > NONE), l1 = __ballot_sync(FULL, w1 > NONE), l2 = __ballot_sync(FULL, w2 > NONE), l3 = __ballot_sync(FULL, w3 > NONE);
+                unsigned pi = pool_n + __popc(i0 & lt) + __popc(i1 & lt) + __popc(i2 & lt) + __popc(i3 & lt);
+                unsigned li = leaf_n + __popc(l0 & lt) + __popc(l1 & lt) + __popc(l2 & lt) + __popc(l3 & lt);
+                const unsigned tot = (__popc(i0) + __popc(i1) + __popc(i2) + __popc(i3)) | ((__popc(l0) + __popc(l1) + __popc(l2) + __popc(l3)) << 16);
                 const unsigned tag = sl << 27;
 #define RTU_PUSH(WORD)                                                                                                           \
-                if (WORD < NONE) W.pool[pi++] = tag | WORD;                                                                      \
-                else if (WORD > NONE) W.leaf[li++] = tag | (((WORD >> 28) & 7u) << 24) | (WORD & 0x00ffffffu);
+                if (WORD < NONE) { W.pool[pi++] = tag | WORD; }                                  \
+                else if (WORD > NONE) { W.leaf[li++] = tag | (((WORD >> 28) & 7u) << 24) | (WORD & 0x00ffffffu); }
                 RTU_PUSH(w3)
                 RTU_PUSH(w2)
                 RTU_PUSH(w1)
@@ -1074,20 +1073,16 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 // every lane pushes its hit children: internal nodes to the item pool, leaves to the leaf pool; positions from
                 // one packed warp scan (internal count in the low half, leaf count in the high half)
                 const unsigned w0 = (hit & 1u) ? ch.x : NONE, w1 = (hit & 2u) ? ch.y : NONE, w2 = (hit & 4u) ? ch.z : NONE, w3 = (hit & 8u) ? ch.w : NONE;
-                const unsigned mine = (unsigned)(w0 < NONE) + (w1 < NONE) + (w2 < NONE) + (w3 < NONE) +
-                                      (((unsigned)(w0 > NONE) + (w1 > NONE) + (w2 > NONE) + (w3 > NONE)) << 16);
-                unsigned incl = mine;
-#pragma unroll
-                for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                    const unsigned v = __shfl_up_sync(FULL, incl, o2);
-                    if (lane >= (unsigned)o2) incl += v;
-                }
-                const unsigned tot = __shfl_sync(FULL, incl, 31);
-                unsigned pi = pool_n + ((incl - mine) & 0xffffu), li = leaf_n + ((incl - mine) >> 16);
+                // positions from eight ballots (independent of each other) instead of a five-step shuffle scan (a dependent chain)
+                const unsigned i0 = __ballot_sync(FULL, w0 < NONE), i1 = __ballot_sync(FULL, w1 < NONE), i2 = __ballot_sync(FULL, w2 < NONE), i3 = __ballot_sync(FULL, w3 < NONE);
+                const unsigned l0 = __ballot_sync(FULL, w0 > NONE), l1 = __ballot_sync(FULL, w1 > NONE), l2 = __ballot_sync(FULL, w2 > NONE), l3 = __ballot_sync(FULL, w3 > NONE);
+                unsigned pi = pool_n + __popc(i0 & lt) + __popc(i1 & lt) + __popc(i2 & lt) + __popc(i3 & lt);
+                unsigned li = leaf_n + __popc(l0 & lt) + __popc(l1 & lt) + __popc(l2 & lt) + __popc(l3 & lt);
+                const unsigned tot = (__popc(i0) + __popc(i1) + __popc(i2) + __popc(i3)) | ((__popc(l0) + __popc(l1) + __popc(l2) + __popc(l3)) << 16);
                 const unsigned tag = sl << 27;
 #define RTU_PUSH(WORD)                                                                                                           \
-                if (WORD < NONE) W.pool[pi++] = tag | WORD;                                                                      \
-                else if (WORD > NONE) W.leaf[li++] = tag | (((WORD >> 28) & 7u) << 24) | (WORD & 0x00ffffffu);
+                if (WORD < NONE) { W.pool[pi++] = tag | WORD; }                                  \
+                else if (WORD > NONE) { W.leaf[li++] = tag | (((WORD >> 28) & 7u) << 24) | (WORD & 0x00ffffffu); }
                 RTU_PUSH(w3)
                 RTU_PUSH(w2)
                 RTU_PUSH(w1)

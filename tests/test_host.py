@@ -289,3 +289,34 @@ def test_ppm_loader_limits(rtu, tmp_path):
     assert "dimensions out of range" in hs.warnings
     assert hs.desc.texmaps[hs.desc.materials[0].diffuse.texmap].kind == rtu.TEX_NULL
     hs.close()
+
+
+def test_two_phase_photon_estimate_algorithm_matches_the_oracle(rtu, tmp_path):
+    """The algorithm of the device estimate (heap-free candidate walk with a histogram radius and subtree boxes, then a replay
+    against the real heap: csrc/photon_kernels.cu) restated in C (tests/csrc/knn_two_phase.c) equals the oracle's LocatePhotons
+    recursion bit for bit - irradiance, direction, photons found - on the reference's own fixture, with and without normals."""
+    import ctypes as C, subprocess
+    from oracle import oracle_py as O
+    so = str(tmp_path / "knn_two_phase.so")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "csrc", "knn_two_phase.c"), "-lm"])
+    L = C.CDLL(so)
+    g, meta = load_golden("kat_photonmap")
+    bal = np.zeros(len(g["photons_balanced"]) + 1, rtu.PHOTON_DTYPE)
+    bal[1:] = g["photons_balanced"].view(rtu.PHOTON_DTYPE).reshape(-1)
+    n = len(bal) - 1
+    qpos = np.ascontiguousarray(g["qpos"], "f4"); qn = np.ascontiguousarray(g["qnormal"], "f4")
+    cases = list(zip(meta["radius"], meta["ellipticity"], [True] * len(meta["radius"]))) + [(1.0, 0.5, False), (0.25, 1.0, True), (4.0, 0.5, True)]
+    for r, e, with_n in cases:
+        irr = np.zeros_like(qpos); d = np.zeros_like(qpos); found = np.zeros(len(qpos), "i4")
+        steps, lists = C.c_double(0), C.c_double(0)
+        over = L.knn_two_phase_estimate(C.c_void_p(bal.ctypes.data), C.c_int(n), C.c_void_p(qpos.ctypes.data), C.c_void_p(qn.ctypes.data if with_n else None),
+                                        C.c_long(len(qpos)), C.c_float(r), C.c_float(e), C.c_void_p(irr.ctypes.data), C.c_void_p(d.ctypes.data),
+                                        C.c_void_p(found.ctypes.data), C.byref(steps), C.byref(lists))
+        ref_irr, ref_d, ref_found = O.estimate_irradiance(bal, qpos, qn if with_n else None, r, e)
+        ok = np.ones(len(qpos), bool)
+        if over:  # a list longer than 1024 entries goes to the exact one-lane kernel on the device
+            assert r >= 4.0
+            ok = found > 0
+        assert np.array_equal(found[ok], ref_found[ok]), (r, e, with_n)
+        assert np.array_equal(irr.view("u4")[ok], ref_irr.view("u4")[ok]), (r, e, with_n)
+        assert np.array_equal(d.view("u4")[ok], ref_d.view("u4")[ok]), (r, e, with_n)
