@@ -1678,12 +1678,7 @@ __device__ __forceinline__ int warp_nominate(const DScene &S, TopWarp &W, const 
     if (!have) return 0;
     if (nc > RTU_TOP_CAND) return -1;
     int *L = W.list[lane];
-    for (int i = 1; i < nc; i++) { // ascending node order
-        const int v = L[i];
-        int j = i;
-        while (j > 0 && L[j - 1] > v) { L[j] = L[j - 1]; j--; }
-        L[j] = v;
-    }
+    sort_ascending(L, nc); // ascending node order
     return nc;
 }
 
