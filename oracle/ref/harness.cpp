@@ -51,6 +51,7 @@ void RefGeneratePhotonMap();
 Color RefPhotonMapping(const Ray &r, const HitInfo &h);
 cyPhotonMap *RefPhotonMap();
 Color RefMonteCarloPhoton(const HitInfo &h, int x, int y, int n);
+int RtuInstallOperators(const char *lib_path, int what);
 int RtuBeginRender(const char *lib_path, int estimator, int spp, int bounces, int gi_bounces, bool reference_pattern, double *device_ms,
                    unsigned long long *rays);
 
@@ -163,7 +164,7 @@ static Ray CameraRay(int x, int y, float offX, float offY, float camOffsetX, flo
 
 // ---------------------------------------------------------------- options
 struct Opts {
-    std::string scene, root = ".", mode = "primary", out = "out", pattern = "center", lib = "raytracer-utah_b200/librtu_b200.so", estimator = "whitted";
+    std::string scene, root = ".", mode = "primary", out = "out", pattern = "center", lib = "raytracer-utah_b200/librtu_b200.so", estimator = "whitted", operators;
     int width = 0, height = 0, spp = 1, threads = 1, bounces = 5, n = 100000, seed = 1;
     int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
     int s0 = 0, s1 = -1;   // --samples a b: only samples [a,b) of the spp-sample pattern (bounded CPU-baseline runs)
@@ -733,6 +734,7 @@ int main(int argc, char **argv)
         else if (a == "--verbose") o.quiet = false;
         else if (a == "--lib") o.lib = next();
         else if (a == "--estimator") o.estimator = next();
+        else if (a == "--operators") o.operators = next();   // objects | materials | both: the reference's own code on device-backed operators
         else if (a[0] != '-') o.scene = a;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -759,6 +761,12 @@ int main(int argc, char **argv)
     renderImage.Init(camera.imgWidth, camera.imgHeight);
     IndexNodes(&rootNode, -1);
     g_imgOrigin = RefCalculateImageOrigin(camera.focaldist);   // also sets actualWidth/actualHeight
+    if (!o.operators.empty()) {
+        // after IndexNodes (the harness's own node table is by Node*, which the replacement keeps)
+        int rc = RtuInstallOperators(o.lib.c_str(), o.operators == "objects" ? 1 : o.operators == "materials" ? 2 : 3);
+        if (rc) return rc;
+        o.threads = 1; // one context, one host thread
+    }
     if (o.mode == "primary") ModePrimary(o);
     else if (o.mode == "whitted") ModeWhitted(o);
     else if (o.mode == "head") ModeHead(o);

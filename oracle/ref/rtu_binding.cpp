@@ -12,6 +12,7 @@
 // Built into oracle/_ref/ref_harness (mode "gpu"); INTEGRATION.md quotes it.
 #include "std_first.h"
 #include <dlfcn.h>
+#include <map>
 #define private public
 #define protected public
 #include "ExternalLibrary/scene.h"
@@ -246,5 +247,160 @@ int RtuBeginRender(const char *lib_path, int estimator, int spp, int bounces, in
     destroy(sc);
     ctx_destroy(ctx);
     dlclose(lib);
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Operator-level drop-ins (SURVEY 8b "operator surface to preserve").  The reference's own Render() / Trace() / ShadowTrace() /
+// Shade() keep running on the host, unmodified; what goes to the device is ONE virtual call at a time:
+//   RtuObject    : Object   - IntersectRay(ray, hInfo) of a Sphere / Plane / TriObj = rtu_shadow_trace (the boolean for the
+//                             HitInfo's current z, stale-z sphere return included) + rtu_trace (the record) on a scene that
+//                             holds just that object
+//   RtuMaterial  : Material - Shade(ray, hInfo, lights, bounceCount) = rtu_shade on the whole scene
+// One device round trip per call: this is about the interface, not about speed (the frame-level path is RtuBeginRender).
+namespace {
+
+struct RtuOps {
+    void *lib = nullptr;
+    const char *(*last_error)(void) = nullptr;
+    int (*trace)(rtu_scene *, const rtu_ray *, int64_t, rtu_hit *) = nullptr;
+    int (*shadow_trace)(rtu_scene *, const rtu_ray *, const float *, int64_t, uint8_t *) = nullptr;
+    int (*shade)(rtu_scene *, const rtu_ray *, const rtu_hit *, int64_t, int32_t, float *) = nullptr;
+    rtu_context *ctx = nullptr;
+    rtu_scene *whole = nullptr;
+    Packed P;                               // the whole scene (kept alive: the description points into it)
+    std::map<const Node *, int> node_index; // pre-order index = rtu_hit::node
+};
+RtuOps g_ops;
+
+rtu_ray to_rtu(const Ray &r)
+{
+    rtu_ray o;
+    copy3(o.p, r.p);
+    copy3(o.dir, r.dir);
+    return o;
+}
+
+class RtuObject : public Object
+{
+public:
+    const Object *orig = nullptr;
+    rtu_scene *one = nullptr;
+    bool IntersectRay(const Ray &ray, HitInfo &hInfo, int hitSide = HIT_FRONT) const override
+    {
+        (void)hitSide;
+        const rtu_ray r = to_rtu(ray);
+        uint8_t occluded = 0;
+        const float z_in = hInfo.z;
+        if (g_ops.shadow_trace(one, &r, &z_in, 1, &occluded)) { fprintf(stderr, "rtu_shadow_trace: %s\n", g_ops.last_error()); exit(5); }
+        if (!occluded) return false;
+        rtu_hit h;
+        if (g_ops.trace(one, &r, 1, &h)) { fprintf(stderr, "rtu_trace: %s\n", g_ops.last_error()); exit(5); }
+        if (h.node >= 0 && h.z < hInfo.z) { // (a sphere may report a hit without a nearer z: objFunctions.cpp:60-75)
+            hInfo.z = h.z;
+            hInfo.p = Point3(h.p[0], h.p[1], h.p[2]);
+            hInfo.N = Point3(h.N[0], h.N[1], h.N[2]);
+            hInfo.uvw = Point3(h.uvw[0], h.uvw[1], h.uvw[2]);
+            hInfo.front = h.front != 0;
+        }
+        return true;
+    }
+    Box GetBoundBox() const override { return orig->GetBoundBox(); }
+};
+
+class RtuMaterial : public Material
+{
+public:
+    Color Shade(const Ray &ray, const HitInfo &hInfo, const LightList &lts, int bounceCount) const override
+    {
+        (void)lts; // the scene's own light list (what Render() passes at every call site of the Whitted estimator)
+        const rtu_ray r = to_rtu(ray);
+        rtu_hit h;
+        memset(&h, 0, sizeof h);
+        h.z = hInfo.z;
+        copy3(h.p, hInfo.p); copy3(h.N, hInfo.N); copy3(h.uvw, hInfo.uvw);
+        h.node = g_ops.node_index.at(hInfo.node);
+        h.face = -1;
+        h.front = hInfo.front ? 1 : 0;
+        float rgb[3] = {0, 0, 0};
+        if (g_ops.shade(g_ops.whole, &r, &h, 1, bounceCount, rgb)) { fprintf(stderr, "rtu_shade: %s\n", g_ops.last_error()); exit(5); }
+        return Color(rgb[0], rgb[1], rgb[2]);
+    }
+};
+
+void index_nodes(const Node *n, int &next)
+{
+    g_ops.node_index[n] = next++;
+    for (int i = 0; i < n->GetNumChild(); i++) index_nodes(n->GetChild(i), next);
+}
+
+} // namespace
+
+// what: bit 0 = every Node's object becomes an RtuObject, bit 1 = every Node's material becomes an RtuMaterial
+int RtuInstallOperators(const char *lib_path, int what)
+{
+    RtuOps &G = g_ops;
+    G.lib = dlopen(lib_path, RTLD_NOW | RTLD_LOCAL);
+    if (!G.lib) { fprintf(stderr, "cannot load %s: %s\n", lib_path, dlerror()); return 3; }
+    G.last_error = sym<const char *(*)(void)>(G.lib, "rtu_last_error");
+    G.trace = sym<int (*)(rtu_scene *, const rtu_ray *, int64_t, rtu_hit *)>(G.lib, "rtu_trace");
+    G.shadow_trace = sym<int (*)(rtu_scene *, const rtu_ray *, const float *, int64_t, uint8_t *)>(G.lib, "rtu_shadow_trace");
+    G.shade = sym<int (*)(rtu_scene *, const rtu_ray *, const rtu_hit *, int64_t, int32_t, float *)>(G.lib, "rtu_shade");
+    auto ctx_create = sym<int (*)(int32_t, void *, rtu_context **)>(G.lib, "rtu_context_create");
+    auto upload = sym<int (*)(rtu_context *, const rtu_scene_desc *, rtu_scene **)>(G.lib, "rtu_scene_upload");
+    pack_scene(G.P); // before any object is replaced: the description is of the reference's own scene
+    int next = 0;
+    index_nodes(&rootNode, next);
+    int rc = ctx_create(0, nullptr, &G.ctx);
+    if (!rc) rc = upload(G.ctx, &G.P.desc, &G.whole);
+    if (rc) { fprintf(stderr, "rtu: %s\n", G.last_error()); return rc; }
+    std::map<const Object *, RtuObject *> proxies;
+    std::vector<Node *> stack{&rootNode};
+    while (!stack.empty()) {
+        Node *n = stack.back();
+        stack.pop_back();
+        for (int i = 0; i < n->GetNumChild(); i++) stack.push_back(n->GetChild(i));
+        if ((what & 1) && n->GetNodeObj()) {
+            const Object *obj = n->GetNodeObj();
+            RtuObject *&px = proxies[obj];
+            if (!px) {
+                // a scene of its own: the root (identity, no object) and one identity node holding the object
+                static std::vector<std::vector<rtu_node>> keep;
+                keep.emplace_back(2);
+                rtu_node *nd = keep.back().data();
+                for (int k = 0; k < 2; k++) {
+                    memset(&nd[k], 0, sizeof(rtu_node));
+                    nd[k].tm[0] = nd[k].tm[4] = nd[k].tm[8] = 1.f;
+                    nd[k].itm[0] = nd[k].itm[4] = nd[k].itm[8] = 1.f;
+                    nd[k].parent = k - 1;
+                    nd[k].kind = RTU_OBJ_NONE;
+                    nd[k].mesh = -1;
+                    nd[k].material = -1;
+                }
+                rtu_scene_desc d;
+                memset(&d, 0, sizeof d);
+                d.camera = G.P.desc.camera;
+                d.nodes = nd;
+                d.n_nodes = 2;
+                d.background.texmap = d.environment.texmap = -1;
+                nd[1].kind = obj == &theSphere ? RTU_OBJ_SPHERE : obj == &thePlane ? RTU_OBJ_PLANE : RTU_OBJ_MESH;
+                if (nd[1].kind == RTU_OBJ_MESH) {
+                    int m = -1;
+                    for (size_t k = 0; k < G.P.mesh_objs.size(); k++) if (G.P.mesh_objs[k] == obj) m = (int)k;
+                    if (m < 0) { fprintf(stderr, "mesh not packed\n"); return 4; }
+                    d.meshes = &G.P.meshes[m];
+                    d.n_meshes = 1;
+                    nd[1].mesh = 0;
+                }
+                px = new RtuObject;
+                px->orig = obj;
+                rc = upload(G.ctx, &d, &px->one);
+                if (rc) { fprintf(stderr, "rtu_scene_upload: %s\n", G.last_error()); return rc; }
+            }
+            n->SetNodeObj(px);
+        }
+        if ((what & 2) && n->GetMaterial()) n->SetMaterial(new RtuMaterial);
+    }
     return 0;
 }

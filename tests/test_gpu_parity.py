@@ -384,6 +384,31 @@ def test_reference_binary_with_our_library(rtu, tmp_path):
     assert np.abs(a - b).mean() < 2.5
 
 
+@pytest.mark.parametrize("golden,crop", [("whitted_p4", (110, 105, 150, 130)), ("whitted_teapot2", (200, 195, 250, 230))])
+@pytest.mark.parametrize("operators", ["objects", "materials", "both"])
+def test_reference_code_on_device_backed_operators(rtu, tmp_path, golden, crop, operators):
+    """SURVEY 8b "operator surface to preserve": the reference's own Render loop / Trace() / ShadowTrace() / Shade() run unmodified
+    on the host while single virtual calls go to the device - every Node's Object replaced by one whose IntersectRay is
+    rtu_shadow_trace + rtu_trace on a one-object scene, and / or every Material by one whose Shade is rtu_shade
+    (oracle/ref/rtu_binding.cpp RtuInstallOperators).  The image must be the one the reference computes alone."""
+    import subprocess
+    from conftest import ROOT
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        pytest.skip("oracle/_ref/ref_harness was not shipped to this box")
+    g, meta = load_golden(golden)
+    x0, y0, x1, y1 = crop
+    pre = str(tmp_path / "ops")
+    subprocess.run([harness, os.path.join(SCENES, meta["scene"]), "--root", SCENES, "--mode", "whitted", "--width", str(meta["width"]),
+                    "--height", str(meta["height"]), "--crop", str(x0), str(y0), str(x1), str(y1), "--operators", operators,
+                    "--lib", rtu.LIB_PATH, "--out", pre], check=True, stdout=subprocess.DEVNULL, timeout=600)
+    rgb = np.load(pre + "_rgb.npy")
+    ref = g["rgb"][y0:y1, x0:x1]
+    assert ref.std() > 0.02, "the crop must show something"
+    bad = ~within_tol(rgb, ref)
+    assert bad.mean() <= 1e-3, "%d of %d values differ" % (bad.sum(), bad.size)
+
+
 def test_errors_are_reported_not_swallowed(rtu, gpu_ctx):
     hs = rtu.HostScene(os.path.join(SCENES, "Project1Test.xml"))
     sc = rtu.Scene(gpu_ctx, hs.desc)
