@@ -345,7 +345,7 @@ cudaError_t launch_knn_build(cudaStream_t st, const rtu_photon *map, int n, int 
 #define KNN_CAP 1024u        // list entries per query; a longer list sends the query to k_estimate_list (none on Project13)
 #define KNN_THREADS 256
 #define KNN_CHUNK (1u << 20) // queries per pass (8 GB of lists)
-#define KNN_REPLAY_WARPS 8
+#define KNN_REPLAY_WARPS 11
 #ifndef KNN_WALK
 #define KNN_WALK 2 // node visits per lane and round of k_knn_candidates
 #endif
@@ -511,12 +511,13 @@ k_knn_candidates(DPhotonMap PM, const float *pos, const float *normal, const uns
     }
 }
 
-// cyPhotonMap's insert on shared-memory columns: D[k * 32] / I[k * 32] = heap slot k + 1 of this lane.
+// cyPhotonMap's insert on shared-memory columns: D[k * 32] / I[k * 32] = heap slot k + 1 of this lane.  The heap holds a
+// photon as its position in the query's candidate list (16 bits: 6 bytes per entry, 11 warps per SM instead of 8).
 struct ColumnHeap {
     float *D;
-    int *I;
+    unsigned short *I;
     __device__ __forceinline__ float &d(int slot) { return D[(slot - 1) * 32]; }
-    __device__ __forceinline__ int &i(int slot) { return I[(slot - 1) * 32]; }
+    __device__ __forceinline__ unsigned short &i(int slot) { return I[(slot - 1) * 32]; }
 };
 
 __global__ void __launch_bounds__(KNN_REPLAY_WARPS * 32, 1)
@@ -526,8 +527,8 @@ k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_
     extern __shared__ __align__(16) unsigned char knn_raw[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
     ColumnHeap Hp;
-    Hp.D = reinterpret_cast<float *>(knn_raw) + (size_t)warp * (2 * PHOTON_K * 32) + lane;
-    Hp.I = reinterpret_cast<int *>(Hp.D + PHOTON_K * 32);
+    Hp.D = reinterpret_cast<float *>(knn_raw + (size_t)warp * (PHOTON_K * 32 * 6)) + lane;
+    Hp.I = reinterpret_cast<unsigned short *>(knn_raw + (size_t)warp * (PHOTON_K * 32 * 6) + PHOTON_K * 32 * 4) + lane;
     unsigned n = n_max;
     if (n_ptr) { const unsigned long long m = (unsigned long long)__ldg(n_ptr) * n_mult; if (m < n) n = (unsigned)m; }
     n = n > q0 ? n - q0 : 0u;
@@ -552,7 +553,7 @@ k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_
             if (i < head) {
                 const uint2 e = row[(size_t)i * 32u];
                 Hp.d((int)i + 1) = __uint_as_float(e.x);
-                Hp.i((int)i + 1) = (int)(e.y & 0x7fffffffu); // (both tests were made against the caller's radius)
+                Hp.i((int)i + 1) = (unsigned short)i; // (both tests were made against the caller's radius)
             }
         nfound = (int)head;
         if (head == (unsigned)PHOTON_K) { // build the max-heap (:385-401)
@@ -560,7 +561,7 @@ k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_
             for (int k = half; k >= 1; k--) {
                 int parent = k;
                 const float td = Hp.d(k);
-                const int ti = Hp.i(k);
+                const unsigned short ti = Hp.i(k);
                 while (parent <= half) {
                     int j = parent + parent;
                     float a = Hp.d(j);
@@ -608,7 +609,7 @@ k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_
                         j <<= 1;
                     }
                     Hp.d(parent) = dist2;
-                    Hp.i(parent) = (int)(e[u].y & 0x7fffffffu);
+                    Hp.i(parent) = (unsigned short)(i0 + u);
                     r2 = top;
                 }
             }
@@ -619,7 +620,7 @@ k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_
         float ox = 0.f, oy = 0.f, oz = 0.f;
 #pragma unroll 4
         for (int i = 1; i <= nfound; i++) {
-            const int k = Hp.i(i);
+            const int k = (int)(row[(size_t)Hp.i(i) * 32u].y & 0x7fffffffu);
             const float4 pwv = __ldg(PM.knn_pw + k), dv = __ldg(PM.knn_dir + k); // GetPower, GetDirection
             const float filter = 1.f;
             irr = irr + mk(pwv.x, pwv.y, pwv.z) * filter;
@@ -764,7 +765,7 @@ k_gather_trace(DScene S, FrameSetup F, int s0, HitQueue hq, float *qpos, float *
             norm3(sr.dx, sr.dy, sr.dz);
             actual++;
             tl.trace++;
-            if (scene_hit<false>(S, sr, Bs, tl, false)) {
+            if (scene_hit<false, true>(S, sr, Bs, tl, false)) {
                 HitRec Hs;
                 finalize_hit(S, sr, Bs, Hs);
                 qpos[o] = Hs.px; qpos[o + 1] = Hs.py; qpos[o + 2] = Hs.pz;
@@ -961,7 +962,7 @@ k_photon_emit(DScene S, unsigned long long path0, unsigned n_paths, int max_boun
             // Trace(r, &rootNode, hInfo); after the first segment into the SAME HitInfo: its z still holds the previous
             // segment's length, so only nearer hits are found (SURVEY A-16)
             tl.trace++;
-            if (!scene_hit<false>(S, ray, B, tl, false)) alive = false;
+            if (!scene_hit<false, true>(S, ray, B, tl, false)) alive = false;
             else {
                 finalize_hit(S, ray, B, H); // serves the store below and the next round's bounce
                 if (first) {
@@ -1047,7 +1048,7 @@ static cudaError_t run_estimate(cudaStream_t st, const DPhotonMap &PM, const flo
 {
     if (n_max == 0) return cudaSuccess;
     static bool attr_set = false;
-    const size_t replay_smem = (size_t)KNN_REPLAY_WARPS * 32 * PHOTON_K * 8;
+    const size_t replay_smem = (size_t)KNN_REPLAY_WARPS * 32 * PHOTON_K * 6;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_knn_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)replay_smem);
         if (e != cudaSuccess) return e;
