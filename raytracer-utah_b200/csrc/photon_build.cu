@@ -212,6 +212,13 @@ cudaError_t launch_photon_balance(cudaStream_t st, const rtu_photon *raw, unsign
             cur ^= 1;
             k_bal_split<<<G, 256, 0, st>>>(raw, n, seg, src[cur], meta[lv & 1], meta[(lv & 1) ^ 1], out, flags + 6);
             k_bal_assign<<<G, 256, 0, st>>>(n, seg, meta[lv & 1]);
+            // maps that tie mostly do so at once (photons on axis-aligned walls): look at the flag after the first levels
+            // instead of building twenty levels of a tree nobody will use
+            if ((lv == 1 || lv == 5) && lv + 1 < levels && e == cudaSuccess) {
+                e = cudaMemcpyAsync(tie_host, flags + 6, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e == cudaSuccess && *tie_host) break;
+            }
         }
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(tie_host, flags + 6, sizeof(unsigned), cudaMemcpyDeviceToHost, st);

@@ -548,6 +548,8 @@ void rtu_context_destroy(rtu_context *c)
     if (c->fb.d_tile) cudaFree(c->fb.d_tile);
     c->stage_off.release();
     c->stage_tile.release();
+    c->stage_photon_raw.release();
+    c->stage_photon_bal.release();
     for (void *q : {(void *)c->d_tile_done, (void *)c->d_tile_samples, (void *)c->d_n_active, (void *)c->d_scount}) if (q) cudaFree(q);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     delete c;
@@ -1786,18 +1788,21 @@ int install_photon_map(rtu_scene *s, const rtu_photon *d_raw, const rtu_photon *
     if (!(how && !strcmp(how, "host"))) CU(launch_photon_balance(c->stream, d_raw, n, s->d_photons, &tie));
     s->photon_device_build = tie == 0;
     if (tie) {
-        std::vector<rtu_photon> tmp;
+        // page-locked staging kept by the context: fresh pageable vectors of this size cost more (first-touch faults, slow copies)
+        // than the balancing's top level
         if (!h_raw) {
-            tmp.resize(n);
-            CU(cudaMemcpyAsync(tmp.data(), d_raw, sizeof(rtu_photon) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            rtu_photon *raw = (rtu_photon *)c->stage_photon_raw.acquire(sizeof(rtu_photon) * (size_t)n);
+            if (!raw) { rtu::set_error("page-locked staging allocation failed"); return RTU_ERR_CUDA; }
+            CU(cudaMemcpyAsync(raw, d_raw, sizeof(rtu_photon) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
-            h_raw = tmp.data();
+            h_raw = raw;
         }
-        std::vector<rtu_photon> balanced((size_t)n + 1);
-        int rc = rtu_host_balance_photons(h_raw, n, balanced.data());
+        rtu_photon *balanced = (rtu_photon *)c->stage_photon_bal.acquire(sizeof(rtu_photon) * ((size_t)n + 1));
+        if (!balanced) { rtu::set_error("page-locked staging allocation failed"); return RTU_ERR_CUDA; }
+        int rc = rtu_host_balance_photons(h_raw, n, balanced);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s->d_photons, balanced.data(), sizeof(rtu_photon) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream)); // `balanced` is pageable and goes out of scope
+        CU(cudaMemcpyAsync(s->d_photons, balanced, sizeof(rtu_photon) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+        c->stage_photon_bal.submitted(c->stream);
     }
     CU(launch_knn_build(c->stream, s->d_photons, (int)n, (int)n / 2 - 1, s->d_knn, s->d_knn + 3 * ((size_t)n + 1), s->d_knn + 4 * ((size_t)n + 1)));
     s->n_photons = n;

@@ -103,6 +103,7 @@ struct rtu_context {
     const unsigned *tile_count = nullptr;
     unsigned tile_total = 0;
     PinnedStage stage_off, stage_tile;
+    PinnedStage stage_photon_raw, stage_photon_bal; // the host balancing's input and output (24 MB each for 10^6 photons)
     // adaptive sampling state of the frame in flight (rtu_params::adaptive_min_spp > 0): consulted by setup_frame
     unsigned char *d_tile_done = nullptr;
     int *d_tile_samples = nullptr;

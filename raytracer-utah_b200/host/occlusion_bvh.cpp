@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 #include "host_scene.h"
@@ -53,7 +54,13 @@ struct Builder {
     std::vector<Prim> prims;
     std::vector<TempNode> nodes;
     static constexpr int BINS = 16;
-    static constexpr uint32_t MAX_LEAF = 4;
+    uint32_t MAX_LEAF = 4;   // (RTU_OCC_MAX_LEAF / RTU_OCC_TRAV_COST: tuning experiments, profiles/README.md)
+    double TRAV = 1.0;
+    Builder()
+    {
+        if (const char *e = getenv("RTU_OCC_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) MAX_LEAF = (uint32_t)v; }
+        if (const char *e = getenv("RTU_OCC_TRAV_COST")) { double v = atof(e); if (v > 0) TRAV = v; }
+    }
 
     int build(uint32_t b, uint32_t e)
     {
@@ -96,7 +103,7 @@ struct Builder {
                 acc.grow(bb[k]);
                 c += cnt[k];
                 if (c == 0 || right_cnt[k + 1] == 0) continue;
-                const double cost = 1.0 + (acc.half_area() * c + right_area[k + 1] * right_cnt[k + 1]) / (area > 0 ? area : 1.0);
+                const double cost = TRAV + (acc.half_area() * c + right_area[k + 1] * right_cnt[k + 1]) / (area > 0 ? area : 1.0);
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = k; }
             }
         }

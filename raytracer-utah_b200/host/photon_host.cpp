@@ -2,7 +2,10 @@
 // photons.  The tree is stored the way the reference stores it (heap order, slot 0 unused, splitting axis in the low
 // two bits of plane_dirz), so a map balanced here can be handed to the reference and vice versa, and the device
 // gather walks the same nodes the reference's LocatePhotons walks.
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -43,7 +46,130 @@ struct Balancer {
     // Hoare-style selection around the value of the right-most element until `median` is in place (:252-267)
     void select(int axis, int start, int end, int median)
     {
+        if (team && end - start + 1 >= PAR_MIN) select_parallel(axis, start, end, median);
+        else select_from(axis, start, end, median);
+    }
+
+    // ---- the top levels.  A range of hundreds of thousands of photons is one selection on one thread in the reference, and the
+    // first three levels of a 10^6-photon map were two thirds of the build.  One PASS of that selection (Hoare partition
+    // around the last element) has a closed form: with I = the positions, ascending, where the up-scan stops (a >= pivot;
+    // the pivot's own slot ends it) and J = the positions, descending, where the down-scan stops (a <= pivot, or the range's
+    // first slot, which stops it unconditionally), the pass swaps I[k] with J[k] for every k < K, K = the first k with
+    // I[k] >= J[k] - until then the scans only see slots no swap has touched - and the pivot then goes to min(I[K], J[K-1]):
+    // the up-scan's last stop is its next original one or the slot the last swap has just filled from the other side.  Both lists are
+    // stream compactions, K is a bisection (I ascends, J descends), the swaps are independent: every step runs on all
+    // threads, and the array after the pass is the reference's, element for element.
+    struct Team {
+        unsigned n = 1;
+        std::vector<std::thread> th;
+        std::atomic<unsigned> arrived{0}, phase{0};
+        std::atomic<int> job{0}; // 0 idle, 1 run, -1 quit
+        std::function<void(unsigned)> fn;
+        void barrier()
+        {
+            const unsigned p = phase.load(std::memory_order_acquire);
+            if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+                arrived.store(0, std::memory_order_relaxed);
+                phase.store(p + 1, std::memory_order_release);
+            } else {
+                while (phase.load(std::memory_order_acquire) == p) std::this_thread::yield();
+            }
+        }
+        // runs f(t) on every member (the caller is member 0) and returns when all are done
+        void run(const std::function<void(unsigned)> &f)
+        {
+            fn = f;
+            barrier(); // release the workers
+            fn(0);
+            barrier(); // everybody done
+        }
+        void start(unsigned members)
+        {
+            n = members;
+            for (unsigned t = 1; t < n; t++)
+                th.emplace_back([this, t]() {
+                    for (;;) {
+                        barrier();
+                        if (job.load(std::memory_order_acquire) < 0) return;
+                        fn(t);
+                        barrier();
+                    }
+                });
+        }
+        void stop()
+        {
+            if (th.empty()) return;
+            job.store(-1, std::memory_order_release);
+            barrier();
+            for (auto &t : th) t.join();
+            th.clear();
+        }
+    };
+    Team *team = nullptr;
+    struct Deferred { int index, start, end; float lo[3], hi[3]; };
+    std::vector<Deferred> later;      // subtrees below PAR_MIN met while the team was busy with the top levels
+    uint32_t *ipos = nullptr, *jpos = nullptr; // the two stop lists of a pass
+    static constexpr int PAR_MIN = 1 << 17; // ranges at least this long are selected by the whole team
+
+    void select_parallel(int axis, int start, int end, int median)
+    {
+        const unsigned T = team->n;
+        std::vector<uint32_t> cnt_i(T + 1), cnt_j(T + 1);
         int left = start, right = end;
+        while (right > left) {
+            if (right - left + 1 < PAR_MIN / 4) { select_from(axis, left, right, median); return; } // the tail of the selection: one thread
+            const float pivot = work[right].position[axis];
+            const int n = right - left + 1; // slots left .. right; the up-scan may stop on any of them, the down-scan on left .. right-1
+            auto chunk = [&](unsigned t, int &a, int &b) { a = left + (int)((long long)n * t / T); b = left + (int)((long long)n * (t + 1) / T); };
+            team->run([&](unsigned t) {
+                int a, b;
+                chunk(t, a, b);
+                uint32_t ci = 0, cj = 0;
+                for (int p = a; p < b; p++) {
+                    const float v = work[p].position[axis];
+                    ci += !(v < pivot);                         // where `while (a[++i] < pivot)` stops (the pivot's own slot at the latest)
+                    cj += p < right && (!(v > pivot) || p == left); // where `while (a[--j] > pivot && j > left)` stops
+                }
+                cnt_i[t + 1] = ci;
+                cnt_j[t + 1] = cj;
+            });
+            cnt_i[0] = cnt_j[0] = 0;
+            for (unsigned t = 0; t < T; t++) { cnt_i[t + 1] += cnt_i[t]; cnt_j[t + 1] += cnt_j[t]; }
+            const uint32_t ni = cnt_i[T], nj = cnt_j[T];
+            team->run([&](unsigned t) {
+                int a, b;
+                chunk(t, a, b);
+                uint32_t oi = cnt_i[t], oj = cnt_j[t];
+                for (int p = a; p < b; p++) {
+                    const float v = work[p].position[axis];
+                    if (!(v < pivot)) ipos[oi++] = (uint32_t)p;
+                    if (p < right && (!(v > pivot) || p == left)) jpos[nj - 1 - oj++] = (uint32_t)p; // descending
+                }
+            });
+            // K = first k with I[k] >= J[k]
+            uint32_t lo = 0, hi = ni < nj ? ni : nj;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) / 2;
+                if (ipos[mid] < jpos[mid]) lo = mid + 1; else hi = mid;
+            }
+            const uint32_t K = lo;
+            team->run([&](unsigned t) {
+                const uint32_t a = (uint32_t)((unsigned long long)K * t / T), b = (uint32_t)((unsigned long long)K * (t + 1) / T);
+                for (uint32_t k = a; k < b; k++) std::swap(work[ipos[k]], work[jpos[k]]);
+            });
+            // where the up-scan stops for the last time: its next stop of the original array (I[K] exists: the pivot's slot is
+            // the last entry of I and lies above every entry of J) - or the slot the last swap filled from the other side
+            int i = (int)ipos[K];
+            if (K > 0 && (int)jpos[K - 1] < i) i = (int)jpos[K - 1];
+            std::swap(work[i], work[right]);
+            if (i >= median) right = i - 1;
+            if (i <= median) left = i + 1;
+        }
+    }
+
+    // the reference's loop from an intermediate state (left, right) of a selection
+    void select_from(int axis, int left, int right, int median)
+    {
         while (right > left) {
             const float pivot = work[right].position[axis];
             int i = left - 1, j = right;
@@ -80,6 +206,22 @@ struct Balancer {
         const bool left_rec = median > start && start < median - 1, right_rec = median < end && median + 1 < end;
         if (median > start && !left_rec) place(2 * index, work[start], -1);
         if (median < end && !right_rec) place(2 * index + 1, work[end], -1);
+        if (team && end - start + 1 >= PAR_MIN) {
+            // both sides one after the other while their selections still use the whole team; sides below PAR_MIN are put off
+            // until the team is idle (`later`), then run side by side
+            for (int side = 0; side < 2; side++) {
+                const bool rec = side == 0 ? left_rec : right_rec;
+                if (!rec) continue;
+                Deferred d;
+                d.index = side == 0 ? 2 * index : 2 * index + 1;
+                d.start = side == 0 ? start : median + 1;
+                d.end = side == 0 ? median - 1 : end;
+                for (int k = 0; k < 3; k++) { d.lo[k] = side == 0 ? lo[k] : l2[k]; d.hi[k] = side == 0 ? h2[k] : hi[k]; }
+                if (d.end - d.start + 1 >= PAR_MIN) segment(d.lo, d.hi, d.index, d.start, d.end, fork_levels);
+                else later.push_back(d);
+            }
+            return;
+        }
         if (left_rec && right_rec && fork_levels > 0 && end - start > 4096) {
             std::thread t([&]() { segment(lo, h2, 2 * index, start, median - 1, fork_levels - 1); });
             segment(l2, hi, 2 * index + 1, median + 1, end, fork_levels - 1);
@@ -140,7 +282,28 @@ extern "C" int rtu_host_balance_photons(const rtu_photon *in, uint32_t n, rtu_ph
         }
     int fork_levels = 0;
     while ((1u << (fork_levels + 1)) <= hw && fork_levels < 6) fork_levels++;
+    Balancer::Team team;
+    std::unique_ptr<uint32_t[]> lists;
+    if ((int)n >= Balancer::PAR_MIN && hw > 1 && !getenv("RTU_PHOTON_SERIAL_TOP")) {
+        team.start(hw < 32 ? hw : 32);
+        b.team = &team;
+        lists.reset(new uint32_t[2 * ((size_t)n + 1)]); // not value-initialised
+        b.ipos = lists.get();
+        b.jpos = lists.get() + (size_t)n + 1;
+    }
     b.segment(lo, hi, 1, 1, (int)n, fork_levels);
+    team.stop();
+    b.team = nullptr;
+    if (!b.later.empty()) {
+        // the put-off subtrees side by side (each forks further like the plain recursion does)
+        int fl = 0;
+        while ((b.later.size() << (fl + 1)) <= (size_t)hw && fl < 6) fl++;
+        std::vector<std::thread> pool;
+        for (size_t k = 1; k < b.later.size(); k++)
+            pool.emplace_back([&, k]() { const auto &d = b.later[k]; b.segment(d.lo, d.hi, d.index, d.start, d.end, fl); });
+        { const auto &d = b.later[0]; b.segment(d.lo, d.hi, d.index, d.start, d.end, fl); }
+        for (auto &th : pool) th.join();
+    }
     return RTU_OK;
     });
 }

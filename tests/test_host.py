@@ -204,7 +204,8 @@ def test_photon_map_balancing_sizes_and_ties(rtu):
     import oracle_py as oracle  # the checker (tests/ may use it; the product may not)
     oracle.lib()
     rng = np.random.default_rng(7)
-    for n in (1, 2, 3, 4, 5, 7, 8, 100, 4097, 70001):
+    # (from 131 072 photons on the top levels' selections run as team-parallel passes: 600 001 has three such levels)
+    for n in (1, 2, 3, 4, 5, 7, 8, 100, 4097, 70001, 131072, 600001):
         ph = np.zeros(n, dtype=rtu.PHOTON_DTYPE)
         ph["position"] = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
         ph["position"][: n // 2, 1] = 1.5
