@@ -200,6 +200,7 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
 #define XP_POOL 512
 #endif
 #define XP_LEAF 192 // one iteration of the 4-wide walk can add 128 leaves while 31 wait
+static_assert(XP_POOL >= 160, "an iteration of the 4-wide walk expands up to 32 items into 128");
 
 struct XpWarp {
     float4 o[32];                  // mesh-local origin, z of the HitInfo when the mesh was entered
