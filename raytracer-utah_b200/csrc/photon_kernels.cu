@@ -360,15 +360,15 @@ __device__ __forceinline__ size_t knn_entry(unsigned q, unsigned i) { return ((s
 
 __global__ void __launch_bounds__(KNN_THREADS, KNN_CTAS)
 k_knn_candidates(DPhotonMap PM, const float *pos, const float *normal, const unsigned *n_ptr, unsigned n_mult, unsigned n_max,
-                 unsigned q0, float radius, float norm_scale, uint2 *lists, unsigned *len, unsigned *work, unsigned *fb_count,
-                 unsigned *fb_ids)
+                 unsigned q0, unsigned chunk, float radius, float norm_scale, uint2 *lists, unsigned *len, unsigned *work,
+                 unsigned *fb_count, unsigned *fb_ids)
 {
     __shared__ unsigned hist[8 * KNN_THREADS]; // word w of this lane's 32 byte counters: hist[w * KNN_THREADS + tid]
     const unsigned tid = threadIdx.x, lane = tid & 31u, FULL = 0xffffffffu;
     unsigned n = n_max;
     if (n_ptr) { const unsigned long long m = (unsigned long long)__ldg(n_ptr) * n_mult; if (m < n) n = (unsigned)m; }
     n = n > q0 ? n - q0 : 0u;
-    if (n > KNN_CHUNK) n = KNN_CHUNK;
+    if (n > chunk) n = chunk;
     const float r2_0 = radius * radius;
     const int key_top = (int)(__float_as_uint(r2_0) >> 21);
     const bool can_shrink = key_top >= 32 && key_top < (0x7f800000 >> 21);
@@ -521,7 +521,7 @@ struct ColumnHeap {
 };
 
 __global__ void __launch_bounds__(KNN_REPLAY_WARPS * 32, 1)
-k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_mult, unsigned n_max, unsigned q0, float radius, const uint2 *lists,
+k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_mult, unsigned n_max, unsigned q0, unsigned chunk, float radius, const uint2 *lists,
              const unsigned *len, unsigned *work, float *irrad, float *direction, int *found_out)
 {
     extern __shared__ __align__(16) unsigned char knn_raw[];
@@ -532,7 +532,7 @@ k_knn_replay(DPhotonMap PM, const float *pos, const unsigned *n_ptr, unsigned n_
     unsigned n = n_max;
     if (n_ptr) { const unsigned long long m = (unsigned long long)__ldg(n_ptr) * n_mult; if (m < n) n = (unsigned)m; }
     n = n > q0 ? n - q0 : 0u;
-    if (n > KNN_CHUNK) n = KNN_CHUNK;
+    if (n > chunk) n = chunk;
     const unsigned groups = (n + 31u) >> 5;
     for (;;) {
         unsigned g = 0;
@@ -1054,11 +1054,20 @@ static cudaError_t run_estimate(cudaStream_t st, const DPhotonMap &PM, const flo
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const unsigned chunks = (n_max + KNN_CHUNK - 1) / KNN_CHUNK;
-    const size_t per_chunk = std::min<size_t>(n_max, KNN_CHUNK);
+    // the candidate lists are the big allocation (8 KB per query of a chunk): smaller chunks when the device cannot spare it
+    unsigned chunk = (unsigned)std::min<size_t>(n_max, KNN_CHUNK);
     uint2 *lists = nullptr;
     unsigned *len = nullptr, *ctr = nullptr, *fb_ids = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&lists, ((per_chunk + 31) / 32) * 32 * (size_t)KNN_CAP * sizeof(uint2), st);
+    cudaError_t e;
+    for (;;) {
+        e = cudaMallocAsync((void **)&lists, (((size_t)chunk + 31) / 32) * 32 * (size_t)KNN_CAP * sizeof(uint2), st);
+        if (e != cudaErrorMemoryAllocation || chunk <= 32768u) break;
+        cudaGetLastError();
+        lists = nullptr;
+        chunk /= 2;
+    }
+    const unsigned chunks = (n_max + chunk - 1) / chunk;
+    const size_t per_chunk = chunk;
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&len, per_chunk * sizeof(unsigned), st);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&ctr, (2 * (size_t)chunks + 1) * sizeof(unsigned), st);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&fb_ids, (size_t)n_max * sizeof(unsigned), st);
@@ -1067,10 +1076,10 @@ static cudaError_t run_estimate(cudaStream_t st, const DPhotonMap &PM, const flo
         const int sms = knn_sm_count();
         unsigned *fb_count = ctr + 2 * (size_t)chunks;
         for (unsigned c = 0; c < chunks; c++) {
-            const unsigned q0 = c * KNN_CHUNK;
-            k_knn_candidates<<<sms * KNN_CTAS, KNN_THREADS, 0, st>>>(PM, pos, normal, n_ptr, n_mult, n_max, q0, radius, norm_scale, lists, len,
+            const unsigned q0 = c * chunk;
+            k_knn_candidates<<<sms * KNN_CTAS, KNN_THREADS, 0, st>>>(PM, pos, normal, n_ptr, n_mult, n_max, q0, chunk, radius, norm_scale, lists, len,
                                                              ctr + 2 * c, fb_count, fb_ids);
-            k_knn_replay<<<sms, KNN_REPLAY_WARPS * 32, replay_smem, st>>>(PM, pos, n_ptr, n_mult, n_max, q0, radius, lists, len, ctr + 2 * c + 1,
+            k_knn_replay<<<sms, KNN_REPLAY_WARPS * 32, replay_smem, st>>>(PM, pos, n_ptr, n_mult, n_max, q0, chunk, radius, lists, len, ctr + 2 * c + 1,
                                                                          irrad, direction, found);
         }
         k_estimate_list<<<sms * 2, 128, 0, st>>>(PM, pos, normal, fb_ids, fb_count, radius, norm_scale, irrad, direction, found);
