@@ -523,10 +523,14 @@ int rtu_context_create(int32_t device, void *stream, rtu_context **out)
         return RTU_ERR_CUDA;
     };
     cudaError_t e2;
-    if ((e2 = cudaMalloc((void **)&c->zmm, 2 * sizeof(unsigned))) != cudaSuccess) return bail(e2, "cudaMalloc");
+    if ((e2 = cudaMalloc((void **)&c->zmm, (4 + 2 * rtu_context::WAVE_LOG_MAX) * sizeof(unsigned))) != cudaSuccess) return bail(e2, "cudaMalloc");
+    c->d_wave_log = c->zmm + 4;
+    if ((e2 = cudaEventCreateWithFlags(&c->wave_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e2, "cudaEventCreate");
+    if (const char *s = getenv("RTU_TAIL_RAYS")) { long long v = atoll(s); if (v >= 0) c->tail_rays = (size_t)v; }
     if ((e2 = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(e2, "cudaEventCreate");
     if ((e2 = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e2, "cudaEventCreate");
-    if ((e2 = cudaHostAlloc((void **)&c->h_flag, 64, cudaHostAllocDefault)) != cudaSuccess) return bail(e2, "cudaHostAlloc");
+    if ((e2 = cudaHostAlloc((void **)&c->h_flag, 64 + rtu_context::WAVE_LOG_MAX * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return bail(e2, "cudaHostAlloc");
+    c->h_wave_log = c->h_flag + 16;
     *out = c;
     return RTU_OK;
 }
@@ -542,6 +546,7 @@ void rtu_context_destroy(rtu_context *c)
     if (c->gi) cudaFree(c->gi);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->wave_ev) cudaEventDestroy(c->wave_ev);
     for (cudaEvent_t e : c->kt_ev) cudaEventDestroy(e);
     void *fbp[] = {c->fb.accum, c->fb.accum2, c->fb.d_rgb, c->fb.d_rgb8, c->fb.d_z, c->fb.d_z8, c->fb.d_node, c->fb.d_face, c->fb.d_offsets};
     for (void *p : fbp) if (p) cudaFree(p);
@@ -1138,7 +1143,10 @@ int wave_count(const FrameSetup &F, int tree_waves)
     return tree + (F.mode == RTU_MODE_PATH ? F.gi_bounces : 0);
 }
 
-int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_t *work_i, int tree_waves)
+// wave_log: where the rays entering each wave are noted (NULL: nowhere); tail_w0 >= 0: waves [tail_w0, n_waves) as ONE
+// cooperative launch that stops at the first empty wave (k_tail_waves)
+int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_t *work_i, int tree_waves, unsigned *wave_log = nullptr,
+              int tail_w0 = -1)
 {
     rtu_context *c = s->ctx;
     int n_waves = wave_count(F, tree_waves);
@@ -1149,7 +1157,17 @@ int run_waves(rtu_scene *s, const FrameSetup &F, float4 *accum, int out_q, size_
     s->launches++;
     int in_q = out_q;
     for (int w = 0; w < n_waves; w++) {
-        launch_reset_counts(c->stream, c->wb.q[1 - in_q].count, c->wb.aux[1 - in_q].count, c->wb.shadow.count, c->wb.hits.count);
+        if (w == tail_w0) {
+            if (launch_tail_waves(c->cfg, c->stream, s->S, F, c->wb, in_q, w, n_waves, accum, c->work + *work_i, wave_log)) {
+                *work_i += 3 * (size_t)(n_waves - w);
+                s->launches++;
+                c->tail_launches++;
+                break;
+            }
+            cudaGetLastError(); // no cooperative launch on this device: one by one
+        }
+        launch_reset_counts(c->stream, c->wb.q[1 - in_q].count, c->wb.aux[1 - in_q].count, c->wb.shadow.count, c->wb.hits.count,
+                            wave_log ? wave_log + w : nullptr, c->wb.q[in_q].count);
         kt_begin(c, 1);
         launch_extend_queue(c->cfg, c->stream, s->S, F, c->wb, in_q, accum, c->work + (*work_i)++);
         kt_end(c);
@@ -1237,9 +1255,29 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
     if (clear_accum) CU(cudaMemsetAsync(accum, 0, npix * (c->adaptive_on ? 2 : 1) * sizeof(float4), c->stream));
     s->launches = mask_launched ? 1 : 0; // k_tile_mask ran in setup_frame
     kt_reset(c, (p->flags & RTU_FLAG_TIME_KERNELS) != 0);
+    // the deep waves of a frame this shape held few rays the last time: one launch for all of them
+    rtu_context::WaveKey wkey;
+    wkey.W = W; wkey.rows = rows; wkey.mode = F.mode; wkey.shade_bounces = F.shade_bounces; wkey.gi_bounces = F.gi_bounces;
+    wkey.n_waves = wave_count(F, s->tree_waves); wkey.n_nodes = s->S.n_nodes; wkey.chunk_samples = chunk_samples;
+    const bool log_waves = wkey.n_waves > 0 && wkey.n_waves <= rtu_context::WAVE_LOG_MAX;
+    int tail_w0 = -1;
+    if (log_waves && c->tail_rays > 0 && !(p->flags & (RTU_FLAG_TIME_KERNELS | RTU_FLAG_REFERENCE_WALK)) && c->wave_log_valid &&
+        c->wave_key == wkey && cudaEventQuery(c->wave_ev) == cudaSuccess) {
+        tail_w0 = wkey.n_waves;
+        while (tail_w0 > 0 && c->h_wave_log[tail_w0 - 1] <= c->tail_rays) tail_w0--;
+        if (tail_w0 >= wkey.n_waves) tail_w0 = -1;
+    }
+    if (log_waves && !(p->flags & (RTU_FLAG_TIME_KERNELS | RTU_FLAG_REFERENCE_WALK)) && getenv("RTU_TAIL_FORCE")) tail_w0 = 0; // (tests)
+    cudaGetLastError(); // (cudaErrorNotReady of the query above is not an error)
+    if (getenv("RTU_TAIL_DEBUG") && c->wave_log_valid && c->wave_key == wkey) {
+        fprintf(stderr, "wave log:");
+        for (int w = 0; w < wkey.n_waves; w++) fprintf(stderr, " %u", c->h_wave_log[w]);
+        fprintf(stderr, " -> tail from wave %d\n", tail_w0);
+    }
     size_t wi = 0;
     for (int a = s0; a < s1; a += (int)chunk_samples) {
         int b = std::min<int>(s1, a + (int)chunk_samples);
+        unsigned *wave_log = log_waves ? c->d_wave_log + (a == s0 ? 0 : rtu_context::WAVE_LOG_MAX) : nullptr;
         launch_reset_counts(c->stream, c->wb.q[0].count, c->wb.aux[0].count, c->wb.shadow.count, c->wb.hits.count);
         kt_begin(c, 0);
         launch_extend_primary(c->cfg, c->stream, s->S, F, a, b, c->wb, accum, target, c->work + wi++);
@@ -1259,7 +1297,7 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
         }
         kt_end(c);
         s->launches += 3;
-        if ((rc = run_waves(s, F, target, 0, &wi, s->tree_waves))) return rc;
+        if ((rc = run_waves(s, F, target, 0, &wi, s->tree_waves, wave_log, tail_w0))) return rc;
         if (path_mode) {
             launch_gi_combine(c->stream, c->gi, c->wb.gi_count, c->wb.hits.cap, F.gi_bounces, accum);
             s->launches++;
@@ -1267,6 +1305,13 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     s->timed = true;
+    c->wave_log_valid = false;
+    if (log_waves && F.mode != RTU_MODE_PHOTON) {
+        CU(cudaMemcpyAsync(c->h_wave_log, c->d_wave_log, rtu_context::WAVE_LOG_MAX * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->wave_ev, c->stream));
+        c->wave_key = wkey;
+        c->wave_log_valid = true;
+    }
     CU(cudaGetLastError());
     return RTU_OK;
 }

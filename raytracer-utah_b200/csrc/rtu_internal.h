@@ -71,7 +71,11 @@ void launch_shade_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
 void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const WaveBuffers &B, float4 *accum,
                         unsigned *work_counter, bool reference_walk = false);
 void launch_gi_combine(cudaStream_t st, const float4 *gi, const unsigned *count, unsigned cap, int gi_bounces, float4 *accum);
-void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d);
+void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d, unsigned *log_dst = nullptr,
+                         const unsigned *log_src = nullptr);
+// waves [w0, n_waves) of a chunk as ONE cooperative launch (k_tail_waves); work: three zeroed counters per wave
+bool launch_tail_waves(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B, int in_q, int w0,
+                       int n_waves, float4 *target, unsigned *work, unsigned *wave_log);
 
 // pixel-centre primary visibility: z / node / face per pixel (RTU_MODE_PRIMARY, ZBuffer.png)
 void launch_primary_ids(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const DCamera &cam, float *z, int *node,

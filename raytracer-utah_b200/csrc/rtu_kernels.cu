@@ -28,6 +28,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "rtu_internal.h"
 #include "shade.cuh"
 #include "camera.cuh"
@@ -139,10 +141,11 @@ __device__ __forceinline__ void primary_miss_fast(const DScene &S, const FrameSe
 
 // ------------------------------------------------------------------ closest hit
 // Plain version: every lane walks its own meshes (used when a mesh does not fit the pooled kernel's item encoding).
-template <bool PRIMARY>
-__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
-k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
-         DCounters *counters, unsigned *work)
+// (FAST: meshes through their 4-wide hierarchies, one lane per ray - the tail kernel below; the stand-alone kernel keeps
+// the cyBVH walk whose counters book the reference's work)
+template <bool PRIMARY, bool FAST>
+__device__ __forceinline__ void extend_body(const DScene &S, const FrameSetup &F, int s0, int s1, const RayQueue &in, const AuxPool &inaux,
+                                            const HitQueue &hq, float4 *accum, float4 *target, DCounters *counters, unsigned *work)
 {
     // accum: the pixel accumulator (primary misses add the background there)
     // target: the array the rays' slots index: == accum for Whitted frames, the GI records in RTU_MODE_PATH
@@ -180,11 +183,19 @@ k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, Hit
         Best B;
         B.z = RTU_BIG; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f;
         tl.trace++;
-        scene_hit<false>(S, ray, B, tl, PRIMARY);
+        scene_hit<false, FAST>(S, ray, B, tl, PRIMARY);
 
         extend_finish<PRIMARY>(S, F, pm, in, inaux, hq, accum, target, counters, idx, ray, pixel, x, y, B);
     }
     flush_tally(tl, counters, PRIMARY ? 0 : 1);
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_extend(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
+         DCounters *counters, unsigned *work)
+{
+    extend_body<PRIMARY, false>(S, F, s0, s1, in, inaux, hq, accum, target, counters, work);
 }
 
 // Pooled version (see k_shadow_wave below for the idea): a ray that reaches a mesh whose bound box it enters is
@@ -705,8 +716,8 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
 #define SHADE_SMEM_LIGHTS 16     // scenes with no more lights / materials than this shade out of shared-memory copies
 #define SHADE_SMEM_MATERIALS 32
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WAVE_THREADS, SHADE_BLOCKS)
-k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq, WaveOut O, unsigned *work, unsigned *gi_count)
+__device__ __forceinline__ void shade_body(DScene S, const FrameSetup &F, int s0, const RayQueue &in, const AuxPool &inaux, const HitQueue &hq,
+                                           const WaveOut &O, unsigned *work, unsigned *gi_count)
 {
     const unsigned lane = threadIdx.x & 31u;
     PrimaryMap pm;
@@ -857,9 +868,15 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
     }
 }
 
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WAVE_THREADS, SHADE_BLOCKS)
+k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq, WaveOut O, unsigned *work, unsigned *gi_count)
+{
+    shade_body<PRIMARY>(S, F, s0, in, inaux, hq, O, work, gi_count);
+}
+
 // ------------------------------------------------------------------ any hit
-__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
-k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+__device__ __forceinline__ void shadow_body(const DScene &S, const ShadowQueue &Q, float4 *accum, DCounters *counters, unsigned *work)
 {
     Tally tl = {0, 0, 0, 0, 0};
     const unsigned lane = threadIdx.x & 31u;
@@ -885,6 +902,66 @@ k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters
         accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
     }
     flush_tally(tl, counters, 2);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+{
+    shadow_body(S, Q, accum, counters, work);
+}
+
+// ------------------------------------------------------------------ the tail of a frame in one launch
+// Deep waves hold few rays (the first bounces' survivors), yet each costs four launches whose floor - launch, ticket
+// atomics, a chain of dependent loads through an almost empty pipeline - is ~15 us a piece: on 1-spp frames that is most
+// of the frame.  k_tail_waves runs waves [w0, n_waves) as ONE cooperative launch of persistent threads: per wave
+// reset / extend / shade / any-hit with grid-wide barriers in between (the three bodies are the stand-alone kernels' own
+// code), and it stops at the first wave whose ray queue is empty.  It is chosen by the host from what the same frame did the
+// last time (WaveLog); whatever the waves turn out to hold, the result is the ordinary one.
+struct TailArgs {
+    RayQueue q[2];
+    AuxPool aux[2];
+    ShadowQueue shadow;
+    HitQueue hits;
+    DCounters *counters;
+    unsigned *gi_count;
+    unsigned *work;      // three counters per wave
+    unsigned *wave_log;  // rays that entered each wave (read back for the next frame's choice)
+    float4 *target;
+    int in_q, w0, n_waves;
+};
+
+__global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
+k_tail_waves(DScene S, FrameSetup F, TailArgs A)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    int in_q = A.in_q;
+    for (int w = A.w0; w < A.n_waves; w++) {
+        const unsigned n_in = *(volatile unsigned *)A.q[in_q].count;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (A.wave_log)
+                for (int k = w; k < (n_in ? w + 1 : A.n_waves); k++) A.wave_log[k] = n_in; // (an empty wave: so are all after it)
+            *A.q[1 - in_q].count = 0;
+            *A.aux[1 - in_q].count = 0;
+            *A.shadow.count = 0;
+            *A.hits.count = 0;
+        }
+        if (n_in == 0u) break; // (every thread of the grid reads the same word: nobody is left waiting at a barrier)
+        grid.sync();
+        unsigned *work = A.work + 3 * (w - A.w0);
+        extend_body<false, true>(S, F, 0, 0, A.q[in_q], A.aux[in_q], A.hits, A.target, A.target, A.counters, work);
+        grid.sync();
+        WaveOut O;
+        O.next = A.q[1 - in_q];
+        O.aux = A.aux[1 - in_q];
+        O.shadow = A.shadow;
+        O.accum = A.target;
+        O.counters = A.counters;
+        shade_body<false>(S, F, 0, A.q[in_q], A.aux[in_q], A.hits, O, work + 1, A.gi_count);
+        grid.sync();
+        shadow_body(S, A.shadow, A.target, A.counters, work + 2);
+        grid.sync(); // the next wave's reset must not overtake this wave's readers
+        in_q = 1 - in_q;
+    }
 }
 
 
@@ -1275,8 +1352,9 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
     flush_tally(tl, counters, 2);
 }
 
-__global__ void k_reset_counts(unsigned *a, unsigned *b, unsigned *c, unsigned *d)
+__global__ void k_reset_counts(unsigned *a, unsigned *b, unsigned *c, unsigned *d, unsigned *log_dst, const unsigned *log_src)
 {
+    if (log_dst) *log_dst = *log_src; // rays entering the wave that is about to start (WaveLog)
     if (a) *a = 0;
     if (b) *b = 0;
     if (c) *c = 0;
@@ -2027,9 +2105,40 @@ void launch_gi_combine(cudaStream_t st, const float4 *gi, const unsigned *count,
     k_gi_combine<<<1184, 256, 0, st>>>(gi, count, cap, gi_bounces, accum);
 }
 
-void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d)
+void launch_reset_counts(cudaStream_t st, unsigned *a, unsigned *b, unsigned *c, unsigned *d, unsigned *log_dst, const unsigned *log_src)
 {
-    k_reset_counts<<<1, 1, 0, st>>>(a, b, c, d);
+    k_reset_counts<<<1, 1, 0, st>>>(a, b, c, d, log_dst, log_src);
+}
+
+// waves [w0, n_waves) of a chunk as one cooperative launch; false: the device cannot (the caller launches them one by one)
+bool launch_tail_waves(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const FrameSetup &F, const WaveBuffers &B, int in_q, int w0,
+                       int n_waves, float4 *target, unsigned *work, unsigned *wave_log)
+{
+    static int occ = -1;
+    if (occ < 0) {
+        int n = 0, coop = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tail_waves, WAVE_THREADS, 0) != cudaSuccess || n < 1) n = 0;
+        if (n > EXT_BLOCKS) n = EXT_BLOCKS;
+        occ = n;
+    }
+    if (occ == 0) return false;
+    TailArgs A;
+    A.q[0] = B.q[0]; A.q[1] = B.q[1];
+    A.aux[0] = B.aux[0]; A.aux[1] = B.aux[1];
+    A.shadow = B.shadow;
+    A.hits = B.hits;
+    A.counters = B.counters;
+    A.gi_count = B.gi_count;
+    A.work = work;
+    A.wave_log = wave_log;
+    A.target = target;
+    A.in_q = in_q; A.w0 = w0; A.n_waves = n_waves;
+    DScene S2 = S;
+    FrameSetup F2 = F;
+    void *args[3] = {(void *)&S2, (void *)&F2, (void *)&A};
+    return cudaLaunchCooperativeKernel((const void *)k_tail_waves, dim3(cfg.sm_count * occ), dim3(WAVE_THREADS), args, 0, st) == cudaSuccess;
 }
 
 void launch_primary_ids(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, const DCamera &cam, float *z, int *node,

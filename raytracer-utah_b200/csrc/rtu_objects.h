@@ -117,6 +117,24 @@ struct rtu_context {
     size_t scount_n = 0;
     uint32_t *h_flag = nullptr;      // page-locked word the overflow flag is copied into
     uint64_t queue_retries = 0;      // frames re-rendered after a queue overflow (rtu_stats::queue_retries)
+    // Rays that entered each secondary wave of the last frame's first chunk (WaveLog).  The next frame of the same shape runs
+    // its small deep waves as one cooperative launch (k_tail_waves); a wrong guess costs time, never the result.
+    enum { WAVE_LOG_MAX = 64 };
+    unsigned *d_wave_log = nullptr;  // [0, 64): the first chunk's waves; [64, 128): scratch for the other chunks
+    uint32_t *h_wave_log = nullptr;  // page-locked copy of the first half, readable once wave_ev has passed
+    cudaEvent_t wave_ev = nullptr;
+    struct WaveKey {
+        int W = 0, rows = 0, mode = -1, shade_bounces = 0, gi_bounces = 0, n_waves = 0, n_nodes = 0;
+        size_t chunk_samples = 0;
+        bool operator==(const WaveKey &o) const
+        {
+            return W == o.W && rows == o.rows && mode == o.mode && shade_bounces == o.shade_bounces && gi_bounces == o.gi_bounces &&
+                   n_waves == o.n_waves && n_nodes == o.n_nodes && chunk_samples == o.chunk_samples;
+        }
+    } wave_key;
+    bool wave_log_valid = false;
+    size_t tail_rays = 16384;        // waves at most this large go into the tail launch (RTU_TAIL_RAYS; 0: never)
+    uint64_t tail_launches = 0;
 };
 
 struct rtu_scene {

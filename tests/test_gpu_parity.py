@@ -422,6 +422,62 @@ def test_errors_are_reported_not_swallowed(rtu, gpu_ctx):
         hs.close()
 
 
+@pytest.mark.parametrize("tag", ["p4", "p5", "p7", "teapot2", "p4_spp4", "teapot2_1080p"])
+@pytest.mark.parametrize("force", [False, True])
+def test_tail_waves_give_the_same_frame(rtu, gpu_ctx, tag, force, monkeypatch):
+    """The second frame of a shape runs the deep, small waves as ONE cooperative launch (k_tail_waves, chosen from what the
+    first frame's waves held).  It must be the frame the golden describes - same image within the Whitted bar, the same
+    set of rays - with fewer launches.  force: every secondary wave goes through the tail kernel, large ones included."""
+    g, meta = load_golden("whitted_" + tag)
+    hs = rtu.HostScene(os.path.join(SCENES, meta["scene"]))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        pattern = rtu.PATTERN_CENTER if meta["pattern"] == "center" else rtu.PATTERN_REFERENCE
+        p = rtu.default_params(width=meta["width"], height=meta["height"], spp=meta["spp"], pattern=pattern,
+                               mode=rtu.MODE_WHITTED, shade_bounces=5)
+        first = sc.render(p, want=("rgb",))["rgb"]
+        st1 = sc.stats()
+        if force:
+            monkeypatch.setenv("RTU_TAIL_FORCE", "1")
+        second = sc.render(p, want=("rgb",))["rgb"]
+        st2 = sc.stats()
+        for img in (first, second):
+            assert within_tol(img, g["rgb"]).all()
+        for st in (st1, st2):
+            assert st["trace_rays"] == meta["trace_rays"] and st["shadow_rays"] == meta["shadow_rays"]
+        if st1["kernel_launches"] > 8:  # (a scene without mirrors or glass has no secondary waves)
+            assert st2["kernel_launches"] < st1["kernel_launches"], "the second frame did not use the tail launch"
+        third = sc.render(p, want=("rgb",))["rgb"]  # (the log the tail kernel wrote itself drives this one)
+        assert within_tol(third, g["rgb"]).all()
+        assert sc.stats()["kernel_launches"] <= st2["kernel_launches"] or force
+    finally:
+        sc.close()
+        hs.close()
+
+
+def test_tail_waves_in_path_mode(rtu, gpu_ctx, monkeypatch):
+    """RTU_MODE_PATH draws its samples from counters keyed by pixel and path, so a frame does not depend on how its waves
+    were launched: one by one, or the small ones / all of them in the tail kernel."""
+    hs = rtu.HostScene(os.path.join(SCENES, "Project11/scene.xml"))
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        p = rtu.default_params(width=200, height=150, spp=4, pattern=rtu.PATTERN_REFERENCE, mode=rtu.MODE_PATH, shade_bounces=5, gi_bounces=4)
+        a = sc.render(p, want=("rgb",))["rgb"]
+        st1 = sc.stats()
+        b = sc.render(p, want=("rgb",))["rgb"]
+        st2 = sc.stats()
+        monkeypatch.setenv("RTU_TAIL_FORCE", "1")
+        c = sc.render(p, want=("rgb",))["rgb"]
+        st3 = sc.stats()
+        assert st2["kernel_launches"] < st1["kernel_launches"] and st3["kernel_launches"] < st1["kernel_launches"]
+        for st in (st2, st3):
+            assert st["trace_rays"] == st1["trace_rays"] and st["shadow_rays"] == st1["shadow_rays"]
+        assert within_tol(a, b).all() and within_tol(a, c).all()
+    finally:
+        sc.close()
+        hs.close()
+
+
 @pytest.mark.parametrize("scene", ["Project4.xml", "Project11/scene.xml", "Teapot/scene2.xml"])
 def test_path_mode_without_bounces_is_deterministic(rtu, gpu_ctx, scene):
     """gi_bounces = 0 makes MonteCarlo() return the constant 0.1 ambient (RenderFunctions.cpp:584): the frame is
