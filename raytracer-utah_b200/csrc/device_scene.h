@@ -150,6 +150,7 @@ struct DScene {
     int32_t n_top;       // nodes of the top-level hierarchy (0: not built, every node is visited linearly)
     const TopNode *top;
     const int32_t *top_items;
+    const float4 *top_bounds; // bounds[] of the items, in the order of top_items (no dependent load in a leaf)
     const int32_t *obj_rank; // per node: number of object nodes with index <= that node
     int32_t any_no_ref;  // some mesh has no cyBVH: RTU_FLAG_REFERENCE_WALK cannot be honoured
     int32_t pool_ok;     // 1: every mesh fits the item encoding of the pooled shadow kernel (<= 2^24 triangles, < 2^27 pairs)

@@ -748,8 +748,12 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     }
     TopNode *dtop = nullptr;
     int32_t *dtop_items = nullptr, *drank = nullptr;
+    float4 *dtop_bounds = nullptr;
+    std::vector<float4> top_bounds(top_items.size());
+    for (size_t k = 0; k < top_items.size(); k++) top_bounds[k] = bounds[top_items[k]];
     if ((rc = dev_upload(top_nodes, &dtop, c->stream, sc->owned))) return fail(rc);
     if ((rc = dev_upload(top_items, &dtop_items, c->stream, sc->owned))) return fail(rc);
+    if ((rc = dev_upload(top_bounds, &dtop_bounds, c->stream, sc->owned))) return fail(rc);
     if ((rc = dev_upload(obj_rank, &drank, c->stream, sc->owned))) return fail(rc);
     // meshes
     std::vector<DMesh> meshes(d->n_meshes);
@@ -841,6 +845,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.n_top = (int)top_nodes.size();
     S.top = dtop;
     S.top_items = dtop_items;
+    S.top_bounds = dtop_bounds;
     S.obj_rank = drank;
     S.any_no_ref = 0;
     for (int m = 0; m < d->n_meshes; m++) if (d->meshes[m].flags & RTU_MESH_DEVICE_BVH) S.any_no_ref = 1;

@@ -876,6 +876,7 @@ k_shade(DScene S, FrameSetup F, int s0, RayQueue in, AuxPool inaux, HitQueue hq,
 }
 
 // ------------------------------------------------------------------ any hit
+template <bool FAST>
 __device__ __forceinline__ void shadow_body(const DScene &S, const ShadowQueue &Q, float4 *accum, DCounters *counters, unsigned *work)
 {
     Tally tl = {0, 0, 0, 0, 0};
@@ -896,7 +897,7 @@ __device__ __forceinline__ void shadow_body(const DScene &S, const ShadowQueue &
         Best B;
         B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
         tl.shadow++;
-        bool occ = scene_hit<true>(S, ray, B, tl, false);
+        bool occ = scene_hit<true, FAST>(S, ray, B, tl, false);
         if (occ && B.z > 0.0f) continue;                                                // :31-35
         float4 c = Q.c[idx];
         accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
@@ -907,7 +908,26 @@ __device__ __forceinline__ void shadow_body(const DScene &S, const ShadowQueue &
 __global__ void __launch_bounds__(WAVE_THREADS, EXT_BLOCKS)
 k_shadow_wave_simple(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
 {
-    shadow_body(S, Q, accum, counters, work);
+    shadow_body<false>(S, Q, accum, counters, work);
+}
+
+// Scenes with a top-level hierarchy (hundreds to thousands of nodes): one lane per ray, each on its own ordered, pruned
+// search (scene_hit_bvh).  The k_*_top kernels further down keep the visit in scene order for RTU_FLAG_REFERENCE_WALK.
+#ifndef BVH_BLOCKS
+#define BVH_BLOCKS 3
+#endif
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WAVE_THREADS, BVH_BLOCKS)
+k_extend_bvh(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux, HitQueue hq, float4 *accum, float4 *target,
+             DCounters *counters, unsigned *work)
+{
+    extend_body<PRIMARY, true>(S, F, s0, s1, in, inaux, hq, accum, target, counters, work);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, BVH_BLOCKS)
+k_shadow_wave_bvh(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
+{
+    shadow_body<true>(S, Q, accum, counters, work);
 }
 
 // ------------------------------------------------------------------ the tail of a frame in one launch
@@ -958,7 +978,7 @@ k_tail_waves(DScene S, FrameSetup F, TailArgs A)
         O.counters = A.counters;
         shade_body<false>(S, F, 0, A.q[in_q], A.aux[in_q], A.hits, O, work + 1, A.gi_count);
         grid.sync();
-        shadow_body(S, A.shadow, A.target, A.counters, work + 2);
+        shadow_body<true>(S, A.shadow, A.target, A.counters, work + 2);
         grid.sync(); // the next wave's reset must not overtake this wave's readers
         in_q = 1 - in_q;
     }
@@ -1920,6 +1940,28 @@ template <class K> static int resident_grid(const LaunchCfg &cfg, K kernel, int 
     return cfg.sm_count * *cache;
 }
 
+// the per-lane search kernels of many-node scenes: as many CTAs as fit (BVH_BLOCKS)
+template <class K> static int bvh_grid(const LaunchCfg &cfg, K kernel, int *cache)
+{
+    if (*cache == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WAVE_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+        if (n > BVH_BLOCKS) n = BVH_BLOCKS;
+        *cache = n;
+    }
+    return cfg.sm_count * *cache;
+}
+
+static int top_mode()
+{
+    static int mode = -1;
+    if (mode < 0) { // RTU_TOP_KERNEL=list selects the nominate / sort / visit-in-order kernels (A/B measurements)
+        const char *e = getenv("RTU_TOP_KERNEL");
+        mode = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return mode;
+}
+
 // the shading kernel has its own residency (SHADE_BLOCKS), independent of the traversal kernels' cfg.blocks_per_sm
 template <class K> static int shade_grid(const LaunchCfg &cfg, K kernel, int *cache)
 {
@@ -1993,6 +2035,12 @@ void launch_extend_primary(const LaunchCfg &cfg, cudaStream_t st, const DScene &
         launch_extend_pooled<true>(cfg, st, S, F, s0, s1, B.q[1], B.aux[1], B, pixel_accum, accum, work_counter);
         return;
     }
+    if (S.n_top > 0 && extend_mode() == 1 && !(F.flags & RTU_FLAG_REFERENCE_WALK) && top_mode() == 1) {
+        static int occ_b = 0;
+        k_extend_bvh<true><<<bvh_grid(cfg, k_extend_bvh<true>, &occ_b), WAVE_THREADS, 0, st>>>(S, F, s0, s1, B.q[1], B.aux[1], B.hits, pixel_accum, accum,
+                                                                                               B.counters, work_counter);
+        return;
+    }
     if (S.n_top > 0 && extend_mode() == 1) {
         static int occ_t = 0;
         const size_t tsmem = sizeof(TopWarp) * (WAVE_THREADS / 32);
@@ -2019,6 +2067,12 @@ void launch_extend_queue(const LaunchCfg &cfg, cudaStream_t st, const DScene &S,
     static int occ = 0;
     if (extend_mode() == 1 && S.pool_ok && S.n_top == 0) { // many-node scenes: plain kernels with top-level nomination
         launch_extend_pooled<false>(cfg, st, S, F, 0, 0, B.q[in_q], B.aux[in_q], B, accum, accum, work_counter);
+        return;
+    }
+    if (S.n_top > 0 && extend_mode() == 1 && !(F.flags & RTU_FLAG_REFERENCE_WALK) && top_mode() == 1) {
+        static int occ_b = 0;
+        k_extend_bvh<false><<<bvh_grid(cfg, k_extend_bvh<false>, &occ_b), WAVE_THREADS, 0, st>>>(S, F, 0, 0, B.q[in_q], B.aux[in_q], B.hits, accum, accum,
+                                                                                                B.counters, work_counter);
         return;
     }
     if (S.n_top > 0 && extend_mode() == 1) {
@@ -2070,6 +2124,9 @@ void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
         else if (S.flat) k_shadow_wave<true, false><<<shadow_grid(cfg, k_shadow_wave<true, false>, smem, &occ[1]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
         else if (!reference_walk) k_shadow_wave<false, true><<<shadow_grid(cfg, k_shadow_wave<false, true>, smem, &occ[2]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
         else k_shadow_wave<false, false><<<shadow_grid(cfg, k_shadow_wave<false, false>, smem, &occ[3]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+    } else if (S.n_top > 0 && mode == 1 && !reference_walk && top_mode() == 1) {
+        static int occ_b = 0;
+        k_shadow_wave_bvh<<<bvh_grid(cfg, k_shadow_wave_bvh, &occ_b), WAVE_THREADS, 0, st>>>(S, B.shadow, accum, B.counters, work_counter);
     } else if (S.n_top > 0 && mode == 1) {
         static int occ_t = 0;
         const size_t tsmem = sizeof(TopWarp) * (WAVE_THREADS / 32);
