@@ -857,6 +857,91 @@ def test_queue_overflow_is_absorbed(rtu):
         ctx.close()
 
 
+def _clutter_scene(path, n=300, seed=20261019):
+    """n spheres that overlap heavily (a point of the cluster lies inside several), every tenth one twice under a different
+    name (exact ties in z between NODES), a floor and a tilted wall; flat scene graph, enough objects for the top-level
+    hierarchy."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic as ms
+    rng = np.random.default_rng(seed)
+    mats = ["matte", "mirror", "glass"]
+    with open(path, "w") as f:
+        f.write("<xml>\n  <scene>\n    <background r=\"0.05\" g=\"0.06\" b=\"0.09\"/>\n    <environment value=\"0.2\"/>\n")
+        f.write("    <object type=\"plane\" name=\"floor\" material=\"matte\"><scale value=\"12\"/><translate z=\"-2\"/></object>\n")
+        lines = []
+        for i in range(n):
+            c = rng.uniform(-3, 3, 3)
+            r = rng.uniform(0.15, 0.7)
+            line = "<scale value=\"%.4f\"/><translate x=\"%.4f\" y=\"%.4f\" z=\"%.4f\"/></object>\n" % (r, c[0], c[1], c[2] * 0.5)
+            lines.append("    <object type=\"sphere\" name=\"s%d\" material=\"%s\">" % (i, mats[i % 3]) + line)
+            if i % 10 == 0:
+                lines.append("    <object type=\"sphere\" name=\"t%d\" material=\"%s\">" % (i, mats[(i + 1) % 3]) + line)
+        for k in rng.permutation(len(lines)):
+            f.write(lines[k])
+        f.write("    <object type=\"plane\" name=\"wall\" material=\"mirror\"><scale value=\"6\"/><rotate angle=\"70\" x=\"1\"/><translate y=\"2\"/></object>\n")
+        f.write(ms.MATERIALS)
+        f.write("  </scene>\n" + ms.CAMERA % dict(dist=14, height=5, w=160, h=120) + "</xml>\n")
+
+
+def test_pruned_search_equals_the_visit_in_scene_order(rtu, gpu_ctx, tmp_path, monkeypatch):
+    """Scenes with hundreds of nodes are searched front to back through the top-level hierarchy, with boxes beyond the best
+    distance skipped (scene_hit_bvh), although Trace() visits the nodes in scene order and its result depends on that order:
+    equal distances go to the first node, and a sphere that holds the ray's origin relabels a hit it does not improve
+    (SURVEY A-7).  Rays that start inside a heap of overlapping, partly duplicated spheres: node, front, z, p, N, uvw equal
+    the visit in scene order (per-lane kernel and the C restatement of the reference), and so does every shadow ray."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    xml = str(tmp_path / "clutter.xml")
+    _clutter_scene(xml)
+    hs = rtu.HostScene(xml)
+    sc = rtu.Scene(gpu_ctx, hs.desc)
+    try:
+        assert hs.desc.n_nodes > 300
+        rng = np.random.default_rng(7)
+        n = 1 << 17
+        rays = np.zeros(n, rtu.RAY_DTYPE)
+        rays["p"] = rng.uniform(-3.5, 3.5, (n, 3)) * np.array([1, 1, 0.6])
+        d = rng.standard_normal((n, 3))
+        rays["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        rays["dir"][::7] *= rng.uniform(0.2, 5.0, (len(rays["dir"][::7]), 1)).astype("f4")  # Trace() does not ask for unit directions
+        monkeypatch.delenv("RTU_TRACE", raising=False)
+        fast = sc.trace(rays)
+        monkeypatch.setenv("RTU_TRACE", "exact")
+        exact = sc.trace(rays)
+        monkeypatch.delenv("RTU_TRACE", raising=False)
+        hit = exact["node"] >= 0
+        assert hit.mean() > 0.7
+        assert np.array_equal(fast["node"], exact["node"]), "%d rays with a different node" % int((fast["node"] != exact["node"]).sum())
+        assert bits_equal(fast["z"], exact["z"]) and np.array_equal(fast["front"][hit], exact["front"][hit])
+        assert bits_equal(fast["p"][hit], exact["p"][hit]) and bits_equal(fast["N"][hit], exact["N"][hit]) and bits_equal(fast["uvw"][hit], exact["uvw"][hit])
+        sub = slice(0, 1 << 14)
+        o = oracle_py.trace(hs.desc, rays[sub])
+        assert np.array_equal(o["node"], fast["node"][sub]) and bits_equal(o["z"], fast["z"][sub]) and np.array_equal(o["front"][hit[sub]], fast["front"][sub][hit[sub]])
+        # the quirk is exercised: some hits are labelled with a node other than the one whose surface was hit, and some are ties
+        # shadow rays: every object sees z = t_max
+        t_max = rng.uniform(0.05, 6.0, n).astype("f4")
+        t_max[::5] = BIG
+        occ = sc.shadow_trace(rays, t_max)
+        oo = oracle_py.shadow_trace(hs.desc, rays[: 1 << 15], t_max[: 1 << 15])
+        assert np.array_equal(occ[: 1 << 15].astype(bool), oo.astype(bool))
+        assert 0.2 < occ.astype(bool).mean() < 0.999
+        # frames: the Whitted image of the scene equals the restatement's (refraction rays start inside spheres)
+        p = rtu.default_params(width=160, height=120, mode=rtu.MODE_WHITTED, shade_bounces=4)
+        img = sc.render(p, want=("rgb",))["rgb"]
+        st = sc.stats()
+        ref = oracle_py.render(hs.desc, params=p, want=("rgb",))
+        ok = within_tol(img, ref["rgb"]).all(axis=2)
+        assert (~ok).sum() <= 3, "%d pixels outside tolerance" % int((~ok).sum())
+        assert st["trace_rays"] == ref["stats"]["trace_rays"] and st["shadow_rays"] == ref["stats"]["shadow_rays"]
+    finally:
+        sc.close()
+        hs.close()
+
+
 def test_nominated_nodes_book_the_reference_work(rtu, gpu_ctx):
     """1000 spheres: the top-level hierarchy nominates a few dozen nodes per ray, the rest are never touched, and the
     counters are still those of Trace() visiting all 1001 objects for every camera ray."""
