@@ -93,8 +93,10 @@ int ensure_scratch(rtu_context *c, size_t q_cap, size_t shadow_cap)
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(p, bytes);
         if (e == cudaSuccess) c->scratch.push_back(*p);
+        else if (e == cudaErrorMemoryAllocation) { c->scratch_oom = true; cudaGetLastError(); free_list(c->scratch); }
         return e;
     };
+    c->scratch_oom = false;
     unsigned *counts = nullptr;
     CU(alloc((void **)&counts, 8 * sizeof(unsigned)));
     CU(cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned), c->stream));
@@ -513,7 +515,11 @@ int rtu_context_create(int32_t device, void *stream, rtu_context **out)
     c->cfg.sm_count = sm_count;
     c->cfg.blocks_per_sm = 2;
     c->cfg.threads = 256;
-    if (const char *s = getenv("RTU_CHUNK_RAYS")) { long long v = atoll(s); if (v >= 1024) c->chunk_rays = (size_t)v; }
+    {   // 2^28 primary rays per chunk (80 GB of queues for two shadow lights) where the device is a 180 GB part with most of it free
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b >= (size_t)140 << 30) c->chunk_rays = (size_t)1 << 28;
+    }
+    if (const char *s = getenv("RTU_CHUNK_RAYS")) { long long v = atoll(s); if (v >= 1024) { c->chunk_rays = (size_t)v; c->chunk_rays_set = true; } }
     if (const char *s = getenv("RTU_QUEUE_FACTOR")) { double v = atof(s); if (v >= 1.0 && v <= 8.0) c->queue_factor = v; }
     if (const char *s = getenv("RTU_BLOCKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= 8) c->cfg.blocks_per_sm = v; }
     memset(&c->wb, 0, sizeof c->wb);
@@ -1230,20 +1236,28 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
     size_t npix = (size_t)W * H;
     int rows = F.row_end - F.row_begin;
     size_t per_sample = (size_t)((W + 7) / 8) * ((rows + 3) / 4) * 32;
-    size_t chunk_rays = c->chunk_rays;
-    if (s->chunk_limit && s->chunk_limit < chunk_rays) chunk_rays = s->chunk_limit;
-    size_t chunk_samples = std::max<size_t>(1, chunk_rays / per_sample);
-    chunk_samples = std::min<size_t>(chunk_samples, (size_t)(s1 - s0)); // queues are sized for what this call renders
-    size_t chunk_cap = std::max(per_sample, chunk_samples * per_sample);
-    if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
-    // Queue capacities: one entry per primary ray of a chunk.  A hit can spawn up to 3 rays, so no
-    // fixed factor is a bound; overflow is detected on the device (DCounters::overflow) and the frame is
-    // rendered again with larger queues / smaller chunks (render_checked).
-    s->last_chunk_cap = chunk_cap;
-    size_t q_cap = (size_t)((double)chunk_cap * c->queue_factor * s->queue_boost);
-    if (q_cap < chunk_cap) q_cap = chunk_cap;
-    size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
-    if ((rc = ensure_scratch(c, q_cap, sh_cap))) return rc;
+    size_t chunk_samples, chunk_cap;
+    for (;;) {
+        size_t chunk_rays = c->chunk_rays;
+        if (s->chunk_limit && s->chunk_limit < chunk_rays) chunk_rays = s->chunk_limit;
+        if (F.mode == RTU_MODE_PATH && !c->chunk_rays_set) chunk_rays = std::min<size_t>(chunk_rays, (size_t)1 << 27); // (+192 B of GI record per entry; no gain measured)
+        chunk_samples = std::max<size_t>(1, chunk_rays / per_sample);
+        chunk_samples = std::min<size_t>(chunk_samples, (size_t)(s1 - s0)); // queues are sized for what this call renders
+        chunk_cap = std::max(per_sample, chunk_samples * per_sample);
+        if (chunk_cap >= (1ull << 31)) { rtu::set_error("image too large for one wave; use row ranges"); return RTU_ERR_UNSUPPORTED; }
+        // Queue capacities: one entry per primary ray of a chunk.  A hit can spawn up to 3 rays, so no
+        // fixed factor is a bound; overflow is detected on the device (DCounters::overflow) and the frame is
+        // rendered again with larger queues / smaller chunks (render_checked).
+        s->last_chunk_cap = chunk_cap;
+        size_t q_cap = (size_t)((double)chunk_cap * c->queue_factor * s->queue_boost);
+        if (q_cap < chunk_cap) q_cap = chunk_cap;
+        size_t sh_cap = q_cap * (size_t)std::max(1, s->n_shadow_lights);
+        rc = ensure_scratch(c, q_cap, sh_cap);
+        if (rc == RTU_OK) break;
+        // the device cannot spare that much: smaller chunks (for this context from now on) rather than no frame
+        if (!c->scratch_oom || chunk_samples <= 1 || c->chunk_rays <= (1u << 22)) return rc;
+        c->chunk_rays = std::min(c->chunk_rays, chunk_cap) / 2;
+    }
     size_t n_chunks = ((size_t)(s1 - s0) + chunk_samples - 1) / chunk_samples;
     size_t launches_per_chunk = 3 + 3 * (size_t)wave_count(F, s->tree_waves);
     if ((rc = ensure_work(c, n_chunks * launches_per_chunk + 8))) return rc;

@@ -55,7 +55,10 @@ struct rtu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     LaunchCfg cfg;
-    size_t chunk_rays = 1u << 27;  // primary rays per wave chunk (~300 B of queue space each): a 64-spp 1080p frame is one chunk
+    size_t chunk_rays = 1u << 27;  // primary rays per wave chunk (~300 B of queue space each): a 64-spp 1080p frame is one chunk;
+                                   // 2^28 where the device has the memory (rtu_context_create), halved when an allocation fails
+    bool chunk_rays_set = false;   // RTU_CHUNK_RAYS given: used as is
+    bool scratch_oom = false;      // the last ensure_scratch failed for lack of memory
     double queue_factor = 1.0;
     // scratch (lazily sized)
     WaveBuffers wb;
