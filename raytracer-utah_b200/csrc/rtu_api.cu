@@ -1262,9 +1262,12 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
     size_t launches_per_chunk = 3 + 3 * (size_t)wave_count(F, s->tree_waves);
     if ((rc = ensure_work(c, n_chunks * launches_per_chunk + 8))) return rc;
     const bool path_mode = F.mode == RTU_MODE_PATH;
+    // primary hits of one chunk: what the per-hit buffers (GI records, photon queries) are sized for - not the hit queue's capacity,
+    // which remembers the largest frame this context ever rendered
+    const size_t frame_hits = std::min<size_t>(c->wb.hits.cap, chunk_cap);
     float4 *target = accum; // the array ray slots index: pixels, or GI records folded into pixels per chunk
     if (path_mode) {
-        if ((rc = ensure_gi(c, (size_t)c->wb.hits.cap * (size_t)(2 * (F.gi_bounces + 1) + 2)))) return rc;
+        if ((rc = ensure_gi(c, frame_hits * (size_t)(2 * (F.gi_bounces + 1) + 2)))) return rc;
         target = c->gi;
     }
     c->adaptive_totals_valid = false;
@@ -1303,22 +1306,22 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
         kt_end(c);
         if (F.mode == RTU_MODE_PHOTON) { // PhotonMapping(ray, hInfo) per hit; no secondary or shadow rays (bounceCount 0)
             kt_begin(c, 3);
-            CU(launch_photon_shade(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum));
+            CU(launch_photon_shade(c->stream, s->S, F, a, c->wb, (unsigned)frame_hits, photon_map_of(s), accum));
             kt_end(c);
-            s->launches += 3 + 3 * (((unsigned)c->wb.hits.cap + (1u << 20) - 1) >> 20);
+            s->launches += 3 + 3 * (((unsigned)frame_hits + (1u << 20) - 1) >> 20);
             continue;
         }
         kt_begin(c, 3);
         launch_shade_primary(c->cfg, c->stream, s->S, F, a, c->wb, 0, target, c->work + wi++);
         if (F.mode == RTU_MODE_PHOTON_GATHER) { // + MonteCarloPhoton per primary hit (the hit queue is still intact)
-            CU(launch_photon_gather(c->stream, s->S, F, a, c->wb, (unsigned)c->wb.hits.cap, photon_map_of(s), accum));
-            s->launches += 3 + 2 * (unsigned)((c->wb.hits.cap * (size_t)std::max(1, F.gi_bounces) + (1u << 20) - 1) >> 20);
+            CU(launch_photon_gather(c->stream, s->S, F, a, c->wb, (unsigned)frame_hits, photon_map_of(s), accum));
+            s->launches += 3 + 2 * (unsigned)((frame_hits * (size_t)std::max(1, F.gi_bounces) + (1u << 20) - 1) >> 20);
         }
         kt_end(c);
         s->launches += 3;
         if ((rc = run_waves(s, F, target, 0, &wi, s->tree_waves, wave_log, tail_w0))) return rc;
         if (path_mode) {
-            launch_gi_combine(c->stream, c->gi, c->wb.gi_count, c->wb.hits.cap, F.gi_bounces, accum);
+            launch_gi_combine(c->stream, c->gi, c->wb.gi_count, (unsigned)frame_hits, F.gi_bounces, accum);
             s->launches++;
         }
     }
