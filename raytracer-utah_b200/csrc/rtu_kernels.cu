@@ -1010,19 +1010,31 @@ k_tail_waves(DScene S, FrameSetup F, TailArgs A)
 #define SHADOW_PRUNE_TMAX 1 // any-hit walks skip boxes entered beyond the light (result-neutral, see k_shadow_wave)
 #endif
 
-struct SpWarp {
+// (OCC: the hoisted reciprocals are only needed where a stopped ray is confirmed and are recomputed there, and one pointer
+// table serves both hierarchies: 7.8 KB per warp instead of 8.6, so that two CTAs leave 124 KB instead of 92 KB of L1)
+template <bool OCC> struct SpWarpT {
     float4 o[32];                // mesh-local origin, t_max
     float4 d[32];                // mesh-local direction, InvDir::ok
-    float4 y[32];                // hoisted reciprocals (exact slab tests: cyBVH walk, ref_reaches)
+    float4 y[OCC ? 1 : 32];      // hoisted reciprocals (exact slab tests: cyBVH walk, ref_reaches)
     float4 ci[32];               // OccRay: 1/d, tlim
     float4 cn[32];               // OccRay: near-plane offsets
     float4 cf[32];               // OccRay: far-plane offsets
     const DMesh *mesh[32];
     unsigned hitslot[32];        // cyBVH slot of the triangle that (tentatively) occludes the slot's ray
-    const OccNode *nodes[32];    // the hierarchy the pool walks: the mesh's 4-wide any-hit hierarchy (OCC) ...
-    const BvhPair *pairs[32];    // ... or its cyBVH in the reference's own tests (RTU_FLAG_REFERENCE_WALK)
+    union {
+        const OccNode *nodes[32]; // the hierarchy the pool walks: the mesh's 4-wide any-hit hierarchy (OCC) ...
+        const BvhPair *pairs[32]; // ... or its cyBVH in the reference's own tests (RTU_FLAG_REFERENCE_WALK)
+    };
     const TriRec *tris[32];
     unsigned idx[32], node[32];  // shadow-queue entry and mesh node of the slot
+    // the slot's hoisted reciprocals
+    __device__ __forceinline__ float4 recip(unsigned sl, const float4 d) const
+    {
+        if constexpr (OCC) {
+            const InvDir I = make_invdir(d.x, d.y, d.z);
+            return make_float4(I.yx, I.yy, I.yz, 0.f);
+        } else return y[sl];
+    }
     unsigned pool[SP_POOL];
     unsigned leaf[SP_LEAF];
     uint2 jobs[SP_JOBS];
@@ -1035,7 +1047,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, SHADOW_BLOCKS)
 k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsigned *work)
 {
     extern __shared__ __align__(16) unsigned char sp_raw[];
-    SpWarp &W = reinterpret_cast<SpWarp *>(sp_raw)[threadIdx.x >> 5];
+    SpWarpT<OCC> &W = reinterpret_cast<SpWarpT<OCC> *>(sp_raw)[threadIdx.x >> 5];
     Tally tl = {0, 0, 0, 0, 0};
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u, FULL = 0xffffffffu, NONE = 0x7fffffffu;
     unsigned total = *Q.count;
@@ -1067,7 +1079,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 const InvDir I = mesh_invdir(M, lr);
                 W.o[lane] = make_float4(lr.px, lr.py, lr.pz, d.w);
                 W.d[lane] = make_float4(lr.dx, lr.dy, lr.dz, I.ok ? 1.f : 0.f);
-                W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
+                if constexpr (!OCC) W.y[lane] = make_float4(I.yx, I.yy, I.yz, 0.f);
                 W.idx[lane] = j.x;
                 W.node[lane] = j.y;
                 if constexpr (OCC) {
@@ -1154,7 +1166,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                         oc.fx = cf.x; oc.fy = cf.y; oc.fz = cf.z;
                         oc.ok = true;
                         if (finish) {
-                            const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
+                            const float4 o = W.o[sl], d = W.d[sl], yv = W.recip(sl, d);
                             RefWalkArgs a;
                             a.px = o.x; a.py = o.y; a.pz = o.z; a.dx = d.x; a.dy = d.y; a.dz = d.z;
                             a.yx = yv.x; a.yy = yv.y; a.yz = yv.z; a.ok = d.w != 0.f;
@@ -1202,7 +1214,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                     sl = it >> 27;
                     if (!((occl >> sl) & 1u)) {
                         const BvhPair *pairs = W.pairs[sl];
-                        const float4 o = W.o[sl], d = W.d[sl], yv = W.y[sl];
+                        const float4 o = W.o[sl], d = W.d[sl], yv = W.recip(sl, d);
                         Ray r;
                         r.px = o.x; r.py = o.y; r.pz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                         InvDir I;
@@ -1254,7 +1266,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 // one lane per ray: the triangle that stopped the ray is confirmed by the exact box test of its cyBVH leaf; a
                 // rejection (hit point within rounding of the box) hands the ray to the exact walk of the cyBVH
                 if (stopped && W.hitslot[lane] != 0xffffffffu) {
-                    const float4 o = W.o[lane], d = W.d[lane], yv = W.y[lane];
+                    const float4 o = W.o[lane], d = W.d[lane], yv = W.recip(lane, d);
                     RefWalkArgs a;
                     a.px = o.x; a.py = o.y; a.pz = o.z; a.dx = d.x; a.dy = d.y; a.dz = d.z;
                     a.yx = yv.x; a.yy = yv.y; a.yz = yv.z; a.ok = d.w != 0.f;
@@ -2117,12 +2129,12 @@ void launch_shadow_wave(const LaunchCfg &cfg, cudaStream_t st, const DScene &S, 
     }
     if (S.any_no_ref) reference_walk = false; // a mesh without cyBVH has nothing else to walk
     if (mode == 1 && S.pool_ok && S.n_top == 0) {
-        const size_t smem = sizeof(SpWarp) * (WAVE_THREADS / 32);
+        const size_t smem = sizeof(SpWarpT<false>) * (WAVE_THREADS / 32), smem_occ = sizeof(SpWarpT<true>) * (WAVE_THREADS / 32);
         // <FLAT, OCC>: OCC walks the meshes' any-hit hierarchies; the other instantiation walks the cyBVH with the reference's
         // own box tests (RTU_FLAG_REFERENCE_WALK: it books what ShadowTrace's walk tests, up to the any-hit early out)
-        if (S.flat && !reference_walk) k_shadow_wave<true, true><<<shadow_grid(cfg, k_shadow_wave<true, true>, smem, &occ[0]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        if (S.flat && !reference_walk) k_shadow_wave<true, true><<<shadow_grid(cfg, k_shadow_wave<true, true>, smem_occ, &occ[0]), WAVE_THREADS, smem_occ, st>>>(S, B.shadow, accum, B.counters, work_counter);
         else if (S.flat) k_shadow_wave<true, false><<<shadow_grid(cfg, k_shadow_wave<true, false>, smem, &occ[1]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
-        else if (!reference_walk) k_shadow_wave<false, true><<<shadow_grid(cfg, k_shadow_wave<false, true>, smem, &occ[2]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
+        else if (!reference_walk) k_shadow_wave<false, true><<<shadow_grid(cfg, k_shadow_wave<false, true>, smem_occ, &occ[2]), WAVE_THREADS, smem_occ, st>>>(S, B.shadow, accum, B.counters, work_counter);
         else k_shadow_wave<false, false><<<shadow_grid(cfg, k_shadow_wave<false, false>, smem, &occ[3]), WAVE_THREADS, smem, st>>>(S, B.shadow, accum, B.counters, work_counter);
     } else if (S.n_top > 0 && mode == 1 && !reference_walk && top_mode() == 1) {
         static int occ_b = 0;
