@@ -683,7 +683,9 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     {
         int rank = 0;
         for (int i = 0; i < d->n_nodes; i++) { if (d->nodes[i].kind != RTU_OBJ_NONE) rank++; obj_rank[i] = rank; }
-        int top_min = 256; // below that, stepping through every node in lock-step is cheaper
+        // below that, stepping through every node in lock-step is cheaper; scenes with meshes stay with the kernels that pool the
+        // mesh walks per warp much longer (100 spheres at 1080p 16 spp: 24.0 ms in lock-step, 12.9 ms searched)
+        int top_min = d->n_meshes > 0 ? 256 : 32;
         if (const char *e = getenv("RTU_TOP_MIN")) top_min = atoi(e);
         std::vector<int> objs;
         bool usable = top_min > 0 && rank >= top_min;
