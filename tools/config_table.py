@@ -44,7 +44,8 @@ for cfg, scene, W, H, mode, spps in ROWS:
         cache[key] = (hs, sc)
     hs, sc = cache[key]
     if mode in ("photon", "gather") and not getattr(sc, "_has_map", False):
-        st = sc.photon_map_generate(seed=1)
+        sc.photon_map_generate(seed=1)       # (the first call also allocates the page-locked staging and starts the host threads)
+        st = sc.photon_map_generate(seed=1)  # the same map again: steady state
         sc._has_map = True
         ph = sc.photon_map_get()
         bal = np.zeros(len(ph) + 1, R.PHOTON_DTYPE); bal[1:] = ph
