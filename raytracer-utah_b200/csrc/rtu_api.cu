@@ -1360,7 +1360,7 @@ static int render_device_once(rtu_scene *s, const rtu_params *p, float4 *accum, 
     if (getenv("RTU_TAIL_DEBUG") && c->wave_log_valid && c->wave_key == wkey) {
         fprintf(stderr, "wave log:");
         for (int w = 0; w < wkey.n_waves; w++) fprintf(stderr, " %u", c->h_wave_log[w]);
-        fprintf(stderr, " -> tail from wave %d\n", tail_w0);
+        fprintf(stderr, " -> tail from wave %d (%llu tail launches so far)\n", tail_w0, (unsigned long long)c->tail_launches);
     }
     size_t wi = 0;
     for (int a = s0; a < s1; a += (int)chunk_samples) {

@@ -719,7 +719,6 @@ template <bool PRIMARY>
 __device__ __forceinline__ void shade_body(DScene S, const FrameSetup &F, int s0, const RayQueue &in, const AuxPool &inaux, const HitQueue &hq,
                                            const WaveOut &O, unsigned *work, unsigned *gi_count)
 {
-    const unsigned lane = threadIdx.x & 31u;
     PrimaryMap pm;
     pm.init(F);
     unsigned total = *hq.count;
