@@ -280,6 +280,12 @@ int rtu_host_build_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t 
  * cyBVH there).  nodes: room for nf x 32 words, slots: nf words; *n_nodes < nf nodes are written. */
 int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f, uint32_t nf, const uint32_t *bvh_elements,
                                  float *nodes, uint32_t *n_nodes, uint32_t *root, uint32_t *slots);
+/* Light mask of mesh node `node` for light `light` (not in the reference: where, seen from a light that casts hard shadows,
+ * the mesh can stop a shadow ray at all; rtu_scene_upload builds the same masks and the any-hit kernel skips the mesh's walk
+ * for a ray whose cell is clear - lightFunctions.cpp:27-37 observes only the boolean).  rec: 20 words, bits: 2048 words
+ * (256 x 256 cells, row = second image coordinate).  RTU_ERR_UNSUPPORTED: no mask for this pair (soft light, light inside the
+ * mesh, margins not met); such rays are walked. */
+int rtu_host_build_light_mask(const rtu_scene_desc *desc, int32_t node, int32_t light, float *rec, uint32_t *bits);
 /* Result.png / ZBuffer.png writers (RenderImage::SaveImage/SaveZImage, scene.h:638-654). */
 int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels);
 

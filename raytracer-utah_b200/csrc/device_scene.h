@@ -29,7 +29,32 @@ struct __align__(16) DNode {
     int32_t kind;   // RTU_OBJ_*
     int32_t mesh;
     int32_t material;
-    int32_t pad[2];
+    int32_t mask_first; // mesh nodes: this node's LightMasks in DScene::light_masks ...
+    int32_t mask_count; // ... one per light that casts hard shadows (0: none)
+};
+
+// Where a mesh can shadow at all, as seen from one light (built by host/light_mask.cpp, which states the margins).  Every
+// shadow ray of a point light without size ends in the light (lightFunctions.cpp:76-78), every shadow ray of a directional
+// light runs against its direction (lights.h:48): seen from the light such a ray is one POINT of the perspective image around
+// the axis light -> mesh / of the orthographic image along the direction.  The mask is a MASK_RES x MASK_RES bitmap over the
+// image of the mesh, a bit set where the image of a triangle, grown by a cell, touches the cell.  A ray whose cell is clear
+// cannot meet a triangle, whatever the hierarchy walk would find: the walk is skipped (any-hit only; result-neutral; in the
+// node's local coordinates, where the walks happen).
+#define RTU_MASK_RES 256
+#define RTU_MASKS_PER_NODE 4 // scenes with more hard lights get no masks: the lookup steps through a node's masks
+struct __align__(16) LightMask {
+    float L[3];      // point light: position; directional light: direction (both node-local)
+    int32_t kind;    // RTU_LIGHT_POINT / RTU_LIGHT_DIRECT
+    float a[3];      // axis light -> mesh centre (point light only)
+    float u0;
+    float e1[3];
+    float v0;
+    float e2[3];
+    float su;        // cells per unit of u
+    float sv;
+    uint32_t bits;   // first word of this mask's bitmap in DScene::mask_bits
+    float lim;       // largest 1-norm of (origin - light) / of the origin for which the mask's margins hold
+    float pad;
 };
 
 // child word: bit31 = leaf; leaf: bits 28..30 = count-1, bits 0..27 = first triangle slot
@@ -151,6 +176,8 @@ struct DScene {
     const TopNode *top;
     const int32_t *top_items;
     const float4 *top_bounds; // bounds[] of the items, in the order of top_items (no dependent load in a leaf)
+    const LightMask *light_masks;
+    const uint32_t *mask_bits;
     const int32_t *obj_rank; // per node: number of object nodes with index <= that node
     int32_t any_no_ref;  // some mesh has no cyBVH: RTU_FLAG_REFERENCE_WALK cannot be honoured
     int32_t pool_ok;     // 1: every mesh fits the item encoding of the pooled shadow kernel (<= 2^24 triangles, < 2^27 pairs)

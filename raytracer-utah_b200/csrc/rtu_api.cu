@@ -618,8 +618,41 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
         if (n.kind < 0 || n.kind > 3) { rtu::set_error("rtu_scene_upload: bad object kind"); return fail(RTU_ERR_INVALID); }
     }
     if (d->nodes[0].kind != RTU_OBJ_NONE) { rtu::set_error("rtu_scene_upload: the root node cannot hold an object (rootNode never does)"); return fail(RTU_ERR_UNSUPPORTED); }
+    // light masks (device_scene.h LightMask, host/light_mask.cpp): per mesh node, one per light that casts hard shadows
+    std::vector<LightMask> light_masks;
+    std::vector<uint32_t> mask_bits;
+    {
+        static_assert(sizeof(LightMask) == 20 * sizeof(float), "host/light_mask.cpp writes the record as 20 words");
+        int hard = 0;
+        for (int l = 0; l < d->n_lights; l++)
+            hard += d->lights[l].kind == RTU_LIGHT_DIRECT || (d->lights[l].kind == RTU_LIGHT_POINT && d->lights[l].size == 0.f);
+        const char *e = getenv("RTU_LIGHT_MASKS");
+        const bool on = !(e && atoi(e) == 0);
+        std::vector<uint32_t> one;
+        for (int i = 0; on && hard > 0 && hard <= RTU_MASKS_PER_NODE && i < d->n_nodes && light_masks.size() < 1024; i++) {
+            if (d->nodes[i].kind != RTU_OBJ_MESH) continue;
+            const rtu_node *chain[RTU_MAX_DEPTH + 1];
+            int n_chain = nodes[i].depth + 1;
+            for (int a = i, k = n_chain - 1; k >= 0; a = d->nodes[a].parent, k--) chain[k] = &d->nodes[a];
+            nodes[i].mask_first = (int32_t)light_masks.size();
+            for (int l = 0; l < d->n_lights; l++) {
+                LightMask lm;
+                if (!rtu::build_light_mask(chain, n_chain, d->meshes[d->nodes[i].mesh], d->lights[l], reinterpret_cast<float *>(&lm), &one)) continue;
+                lm.bits = (uint32_t)mask_bits.size();
+                mask_bits.insert(mask_bits.end(), one.begin(), one.end());
+                light_masks.push_back(lm);
+                nodes[i].mask_count++;
+            }
+        }
+    }
     DNode *dn = nullptr;
     if ((rc = dev_upload(nodes, &dn, c->stream, sc->owned))) return fail(rc);
+    LightMask *dmasks = nullptr;
+    uint32_t *dmask_bits = nullptr;
+    if (!light_masks.empty()) {
+        if ((rc = dev_upload(light_masks, &dmasks, c->stream, sc->owned))) return fail(rc);
+        if ((rc = dev_upload(mask_bits, &dmask_bits, c->stream, sc->owned))) return fail(rc);
+    }
     // bounding spheres for the conservative cull (traverse.cuh), in root space, evaluated in double
     std::vector<float4> bounds(d->n_nodes);
     for (int i = 0; i < d->n_nodes; i++) {
@@ -918,6 +951,8 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.top = dtop;
     S.top_items = dtop_items;
     S.top_bounds = dtop_bounds;
+    S.light_masks = dmasks;
+    S.mask_bits = dmask_bits;
     S.obj_rank = drank;
     S.any_no_ref = 0;
     for (int m = 0; m < d->n_meshes; m++) if (d->meshes[m].flags & RTU_MESH_DEVICE_BVH) S.any_no_ref = 1;

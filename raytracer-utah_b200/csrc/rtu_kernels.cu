@@ -1362,6 +1362,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                     const InvDir I = mesh_invdir(M, lr);
                     float te;
                     if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
+                    if (OCC && light_mask_rejects(S, nd, lr, d.w)) continue; // inside the box, beside the mesh's silhouette from its light
                     park = i;
                     break;
                 }

@@ -19,6 +19,11 @@ struct OccBvh {
 };
 void build_occlusion_bvh(const float *v, const uint32_t *f, const uint32_t *elements, uint32_t nf, OccBvh *out);
 
+// Where a mesh can cast a hard shadow at all, seen from one light (light_mask.cpp): the 20 words of a device LightMask and its
+// bitmap.  chain = the nodes from the root down to the mesh's node.  false: no mask for this pair, the rays are walked.
+bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh &m, const rtu_light &light, float *rec,
+                      std::vector<uint32_t> *bits);
+
 // cyTriMesh::Mtl (cyTriMesh.h:74-103): one material of an OBJ's .mtl library, with the constructor's defaults
 struct ObjMtl {
     std::string name;

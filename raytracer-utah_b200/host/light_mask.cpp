@@ -1,0 +1,253 @@
+// Light masks: where a mesh can cast a hard shadow at all, as seen from one light (device_scene.h LightMask).
+//
+// Every shadow ray of a point light without size ends in the light (lightFunctions.cpp:76-78), every shadow ray of a
+// directional light runs against its direction (lights.h:48).  Seen from the light such a ray is ONE POINT: of the
+// perspective image of the scene around the axis light -> mesh centre, or of the orthographic image along the direction.  A
+// triangle can only stop the ray when its own image covers that point.  The mask is a RTU_MASK_RES^2 bitmap over the image
+// of the mesh; a cell is set when a triangle's image touches it or one of its 8 neighbours (rasterised row by row from
+// the triangle's edges, then dilated: the mask follows the silhouette, not the triangles' rectangles).  The any-hit kernel
+// looks a ray up after the mesh's bound-box gate (objFunctions.cpp:337) and skips the walk when the cell is clear.
+//
+// Only the boolean of ShadowTrace is observable, so the mask has to be conservative and nothing else.  What protects it:
+//  * images are evaluated here in double from the float vertices; the device evaluates the ray's image in float.  A mask is
+//    only built when a cell is at least 100 x the bound of that rounding (err_u below) ...
+//  * ... and when the deviation the device tolerates in "this ray ends in the light" (1e-5 of the distance) / "this ray is
+//    parallel to the direction" (sin < 4e-6), carried to the mesh, is below a quarter of a cell.  Both bounds grow with the
+//    distance of the ray's origin: `lim` is the largest distance (1-norm) up to which they hold; farther rays are walked.
+//  * every vertex has to lie in front of the light (perspective) by a clear margin; otherwise there is no mask.
+// Anything unusual (NaN, a flat image, a light inside the mesh's box, more than RTU_MASKS_PER_NODE hard lights) gives no
+// mask and the rays are walked as before.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "host_scene.h"
+
+namespace rtu {
+
+namespace {
+
+const int RES = 256; // RTU_MASK_RES of csrc/device_scene.h (checked there by a static_assert on the record size only)
+const double EPS = 5.96e-8; // 2^-24
+
+inline double dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+void basis(const double *a, double *e1, double *e2)
+{
+    int k = std::fabs(a[0]) <= std::fabs(a[1]) ? (std::fabs(a[0]) <= std::fabs(a[2]) ? 0 : 2) : (std::fabs(a[1]) <= std::fabs(a[2]) ? 1 : 2);
+    double t[3] = {0, 0, 0};
+    t[k] = 1;
+    e1[0] = a[1] * t[2] - a[2] * t[1]; e1[1] = a[2] * t[0] - a[0] * t[2]; e1[2] = a[0] * t[1] - a[1] * t[0];
+    double n = std::sqrt(dot(e1, e1));
+    for (int i = 0; i < 3; i++) e1[i] /= n;
+    e2[0] = a[1] * e1[2] - a[2] * e1[1]; e2[1] = a[2] * e1[0] - a[0] * e1[2]; e2[2] = a[0] * e1[1] - a[1] * e1[0];
+    n = std::sqrt(dot(e2, e2));
+    for (int i = 0; i < 3; i++) e2[i] /= n;
+}
+
+// set cells ix0 .. ix1 of row iy
+inline void set_span(uint32_t *row, int ix0, int ix1)
+{
+    for (int w = ix0 >> 5; w <= ix1 >> 5; w++) {
+        const int b0 = std::max(ix0 - w * 32, 0), b1 = std::min(ix1 - w * 32, 31);
+        row[w] |= (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
+    }
+}
+
+inline bool span_set(const uint32_t *row, int ix0, int ix1)
+{
+    for (int w = ix0 >> 5; w <= ix1 >> 5; w++) {
+        const int b0 = std::max(ix0 - w * 32, 0), b1 = std::min(ix1 - w * 32, 31);
+        const uint32_t mask = (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
+        if ((row[w] & mask) != mask) return false;
+    }
+    return true;
+}
+
+inline int ifloor(double x) { return (int)(x + 16.0) - 16; } // -16 < x < 2^31 - 16 (callers clamp)
+
+// The cells a triangle (cell coordinates) touches: row by row, the extent in x of the triangle's part inside the row
+// [iy, iy+1] (the ends of its edges clipped to the row; the intersection is convex).  The ends are widened by 1e-6 of a cell:
+// the arithmetic here is double, its rounding is far below that.
+void raster(const double (*p)[2], uint32_t *bits)
+{
+    const double big = RES + 8.0;
+    double y0 = std::min(p[0][1], std::min(p[1][1], p[2][1])), y1 = std::max(p[0][1], std::max(p[1][1], p[2][1]));
+    double xa = std::min(p[0][0], std::min(p[1][0], p[2][0])), xb = std::max(p[0][0], std::max(p[1][0], p[2][0]));
+    y0 = std::max(y0, -8.0); y1 = std::min(y1, big); xa = std::max(xa, -8.0); xb = std::min(xb, big);
+    const int iy0 = std::max(0, ifloor(y0 - 1e-6)), iy1 = std::min(RES - 1, ifloor(y1 + 1e-6));
+    const int rx0 = std::max(0, ifloor(xa - 1e-6)), rx1 = std::min(RES - 1, ifloor(xb + 1e-6));
+    if (rx0 > rx1 || iy0 > iy1) return;
+    {   // every cell of the triangle's rectangle already set (by its neighbours, by the other side of a closed surface)?
+        bool all = true;
+        for (int iy = iy0; iy <= iy1 && all; iy++) all = span_set(bits + (size_t)iy * (RES / 32), rx0, rx1);
+        if (all) return;
+    }
+    if (rx1 - rx0 <= 1 && iy1 - iy0 <= 1) { // up to 2 x 2 cells: the rectangle
+        for (int iy = iy0; iy <= iy1; iy++) set_span(bits + (size_t)iy * (RES / 32), rx0, rx1);
+        return;
+    }
+    // per edge: x(t), y(t) = a + t (b - a); the part of it inside a row lo <= y <= hi is t in [max(0, ta), min(1, tb)]
+    double ax[3], ay[3], dx[3], dy[3], inv[3];
+    for (int k = 0; k < 3; k++) {
+        ax[k] = p[k][0]; ay[k] = p[k][1];
+        dx[k] = p[(k + 1) % 3][0] - ax[k]; dy[k] = p[(k + 1) % 3][1] - ay[k];
+        inv[k] = dy[k] != 0.0 ? 1.0 / dy[k] : 0.0;
+    }
+    for (int iy = iy0; iy <= iy1; iy++) {
+        const double lo = iy - 1e-6, hi = iy + 1.0 + 1e-6;
+        double x0 = 1e300, x1 = -1e300;
+        for (int k = 0; k < 3; k++) {
+            double ta, tb;
+            if (dy[k] != 0.0) {
+                const double t0 = (lo - ay[k]) * inv[k], t1 = (hi - ay[k]) * inv[k];
+                ta = std::max(0.0, std::min(t0, t1)); tb = std::min(1.0, std::max(t0, t1));
+            } else {
+                ta = 0.0; tb = (ay[k] >= lo && ay[k] <= hi) ? 1.0 : -1.0;
+            }
+            if (ta <= tb) {
+                const double xa2 = ax[k] + ta * dx[k], xb2 = ax[k] + tb * dx[k];
+                x0 = std::min(x0, std::min(xa2, xb2)); x1 = std::max(x1, std::max(xa2, xb2));
+            }
+        }
+        if (!(x0 <= x1)) continue; // the triangle does not reach this row
+        x0 = std::max(x0, -8.0); x1 = std::min(x1, big);
+        const int ix0 = std::max(0, ifloor(x0 - 1e-6)), ix1 = std::min(RES - 1, ifloor(x1 + 1e-6));
+        if (ix0 <= ix1) set_span(bits + (size_t)iy * (RES / 32), ix0, ix1);
+    }
+}
+
+// every cell takes the OR of its 3 x 3 neighbourhood: the margin of one cell on every side that covers the device's float
+// evaluation of a ray's image and the tolerances of its ray classification (see the head of this file)
+void dilate(std::vector<uint32_t> &bits)
+{
+    const int W = RES / 32;
+    std::vector<uint32_t> h(bits.size());
+    for (int y = 0; y < RES; y++)
+        for (int w = 0; w < W; w++) {
+            const uint32_t c = bits[y * W + w];
+            uint32_t v = c | (c << 1) | (c >> 1);
+            if (w > 0) v |= bits[y * W + w - 1] >> 31;
+            if (w + 1 < W) v |= bits[y * W + w + 1] << 31;
+            h[y * W + w] = v;
+        }
+    for (int y = 0; y < RES; y++)
+        for (int w = 0; w < W; w++)
+            bits[y * W + w] = h[y * W + w] | (y > 0 ? h[(y - 1) * W + w] : 0u) | (y + 1 < RES ? h[(y + 1) * W + w] : 0u);
+}
+
+} // namespace
+
+// rec: the 20 words of a device LightMask (bits offset left 0).  Returns false when no mask can be given.
+// chain: the nodes from the root down to the mesh node (ToNodeCoords is applied in that order, RenderFunctions.cpp:186).
+bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh &m, const rtu_light &light, float *rec,
+                      std::vector<uint32_t> *bits)
+{
+    if (m.nf == 0 || !m.v || !m.f) return false;
+    const bool point = light.kind == RTU_LIGHT_POINT;
+    if (!point && light.kind != RTU_LIGHT_DIRECT) return false;
+    if (point && !(light.size == 0.f)) return false; // a soft light's rays end on its disk
+    // the light in the node's coordinates: p' = itm (p - pos), d' = itm d, level by level (column-major itm)
+    double L[3] = {light.v[0], light.v[1], light.v[2]};
+    for (int c = 0; c < n_chain; c++) {
+        const rtu_node &t = *chain[c];
+        double q[3] = {L[0], L[1], L[2]};
+        if (point) for (int k = 0; k < 3; k++) q[k] -= (double)t.pos[k];
+        for (int r = 0; r < 3; r++) L[r] = (double)t.itm[r] * q[0] + (double)t.itm[3 + r] * q[1] + (double)t.itm[6 + r] * q[2];
+    }
+    if (!(std::isfinite(L[0]) && std::isfinite(L[1]) && std::isfinite(L[2]))) return false;
+    double a[3], e1[3], e2[3];
+    if (point) {
+        for (int k = 0; k < 3; k++) a[k] = 0.5 * ((double)m.bound_min[k] + (double)m.bound_max[k]) - L[k];
+    } else {
+        for (int k = 0; k < 3; k++) a[k] = L[k];
+    }
+    const double an = std::sqrt(dot(a, a));
+    if (!(an > 0.0) || !std::isfinite(an)) return false;
+    for (int k = 0; k < 3; k++) a[k] /= an;
+    basis(a, e1, e2);
+
+    // images of the vertices
+    std::vector<double> img((size_t)m.nv * 2);
+    std::vector<uint8_t> used(m.nv, 0);
+    for (size_t k = 0; k < (size_t)m.nf * 3; k++) {
+        if (m.f[k] >= m.nv) return false;
+        used[m.f[k]] = 1;
+    }
+    double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300}, dmin = 1e300, vmax1 = 0;
+    for (uint32_t i = 0; i < m.nv; i++) {
+        if (!used[i]) continue;
+        double w[3] = {(double)m.v[3 * i], (double)m.v[3 * i + 1], (double)m.v[3 * i + 2]};
+        vmax1 = std::max(vmax1, std::fabs(w[0]) + std::fabs(w[1]) + std::fabs(w[2]));
+        double u, v;
+        if (point) {
+            for (int k = 0; k < 3; k++) w[k] -= L[k];
+            const double depth = dot(w, a);
+            if (!(depth > 0.0)) return false;
+            dmin = std::min(dmin, depth);
+            u = dot(w, e1) / depth;
+            v = dot(w, e2) / depth;
+        } else {
+            u = dot(w, e1);
+            v = dot(w, e2);
+        }
+        if (!(std::isfinite(u) && std::isfinite(v))) return false;
+        img[2 * i] = u; img[2 * i + 1] = v;
+        lo[0] = std::min(lo[0], u); hi[0] = std::max(hi[0], u);
+        lo[1] = std::min(lo[1], v); hi[1] = std::max(hi[1], v);
+    }
+    if (!(hi[0] > lo[0]) || !(hi[1] > lo[1])) return false; // flat image
+    const double cell[2] = {(hi[0] - lo[0]) / (RES - 2), (hi[1] - lo[1]) / (RES - 2)}; // the image spans cells 1 .. RES-2
+    const double cmin = std::min(cell[0], cell[1]);
+    const double umax = std::max(std::max(std::fabs(lo[0]), std::fabs(hi[0])), std::max(std::fabs(lo[1]), std::fabs(hi[1]))) + 2 * std::max(cell[0], cell[1]);
+    const double l1 = std::fabs(L[0]) + std::fabs(L[1]) + std::fabs(L[2]);
+    double lim;
+    if (point) {
+        if (!(dmin > 1e-3 * an) || umax > 4.0) return false; // the light is in or next to the mesh: too wide an image
+        // float evaluation of u = (w.e1)/(w.a), w = p - L, for an origin whose image is inside the bitmap: a component of w is off
+        // by eps (|w_k| + |L_k|), a dot product by eps (5 |w|_1 + |L|_1) incl. the rounding of the axes, |w|_1 <= sqrt(3) depth
+        // sqrt(1 + 2 umax^2), depth >= dmin for every origin behind a triangle; twice that
+        const double err_u = 2 * EPS * ((1.0 + umax) * (9.0 * std::sqrt(1.0 + 2.0 * umax * umax) + l1 / dmin) + umax);
+        if (!(100 * err_u <= cmin)) return false;
+        // a ray that passes the light at 1e-5 |w|_1 is off by that much at the mesh, i.e. by (1 + umax) / depth of it in u
+        lim = cmin * dmin / (4 * 1.0e-5 * (1.0 + umax));
+        if (!(lim > 2 * an)) return false;
+    } else {
+        // u = p.e1: rounding 4 eps |p|_1; a direction off by sin = 4e-6 drifts by that times the way to the mesh (<= |p|_1 + vmax1)
+        lim = std::min(cmin / (400 * EPS), cmin / (4 * 4.0e-6) - vmax1);
+        if (!(lim > 2 * vmax1)) return false;
+    }
+    if (!std::isfinite(lim)) return false;
+    lim = std::min(lim, 1.0e30);
+
+    const double s[2] = {1.0 / cell[0], 1.0 / cell[1]};
+    const double o[2] = {lo[0] - cell[0], lo[1] - cell[1]};
+    bits->assign((size_t)RES * RES / 32, 0u);
+    auto paint = [&](uint32_t f0, uint32_t f1, uint32_t *dst) {
+        for (uint32_t f = f0; f < f1; f++) {
+            double p[3][2];
+            for (int k = 0; k < 3; k++) {
+                const uint32_t i = m.f[3 * f + k];
+                p[k][0] = (img[2 * i] - o[0]) * s[0];
+                p[k][1] = (img[2 * i + 1] - o[1]) * s[1];
+            }
+            raster(p, dst);
+        }
+    };
+    paint(0, m.nf, bits->data());
+    dilate(*bits);
+
+    memset(rec, 0, 20 * sizeof(float));
+    const int32_t kind = light.kind;
+    for (int k = 0; k < 3; k++) { rec[k] = (float)L[k]; rec[4 + k] = (float)a[k]; rec[8 + k] = (float)e1[k]; rec[12 + k] = (float)e2[k]; }
+    memcpy(&rec[3], &kind, 4);
+    rec[7] = (float)o[0];
+    rec[11] = (float)o[1];
+    rec[15] = (float)s[0];
+    rec[16] = (float)s[1];
+    rec[18] = (float)lim;
+    return true;
+}
+
+} // namespace rtu

@@ -573,6 +573,27 @@ int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f,
     });
 }
 
+int rtu_host_build_light_mask(const rtu_scene_desc *d, int32_t node, int32_t light, float *rec, uint32_t *bits)
+{
+    if (!d || !rec || !bits) { rtu::set_error("rtu_host_build_light_mask: null argument"); return RTU_ERR_INVALID; }
+    if (node < 0 || node >= d->n_nodes || light < 0 || light >= d->n_lights || d->nodes[node].kind != RTU_OBJ_MESH ||
+        d->nodes[node].mesh < 0 || d->nodes[node].mesh >= d->n_meshes) {
+        rtu::set_error("rtu_host_build_light_mask: not a mesh node / light of this scene");
+        return RTU_ERR_INVALID;
+    }
+    return rtu::guarded("rtu_host_build_light_mask", [&]() -> int {
+        std::vector<const rtu_node *> chain;
+        for (int a = node; a >= 0 && chain.size() < 64; a = d->nodes[a].parent) chain.insert(chain.begin(), &d->nodes[a]);
+        std::vector<uint32_t> b;
+        if (!rtu::build_light_mask(chain.data(), (int)chain.size(), d->meshes[d->nodes[node].mesh], d->lights[light], rec, &b)) {
+            rtu::set_error("rtu_host_build_light_mask: no mask for this mesh and light");
+            return RTU_ERR_UNSUPPORTED;
+        }
+        memcpy(bits, b.data(), b.size() * sizeof(uint32_t));
+        return RTU_OK;
+    });
+}
+
 int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels)
 {
     std::string err;

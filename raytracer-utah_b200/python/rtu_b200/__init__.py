@@ -282,6 +282,7 @@ class Context:
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
+ERR_UNSUPPORTED = 5
 ERR_CANCELLED = 6
 
 
@@ -579,6 +580,20 @@ def balance_photons(photons):
     L.rtu_host_balance_photons.argtypes = [C.c_void_p, u32, C.c_void_p]
     _check(L.rtu_host_balance_photons(photons.ctypes.data, photons.shape[0], out.ctypes.data), "rtu_host_balance_photons")
     return out
+
+
+def build_light_mask(desc, node, light):
+    """rtu_host_build_light_mask: (rec[20] as f4, bits[256, 256] as bool) or None when the pair gets no mask."""
+    L = lib()
+    rec = np.zeros(20, "f4")
+    bits = np.zeros(2048, "u4")
+    L.rtu_host_build_light_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    rc = L.rtu_host_build_light_mask(C.byref(desc), node, light, rec.ctypes.data, bits.ctypes.data)
+    if rc == ERR_UNSUPPORTED:
+        return None
+    _check(rc, "rtu_host_build_light_mask")
+    cells = np.unpackbits(bits.view("u1"), bitorder="little").reshape(256, 256).astype(bool)
+    return rec, cells
 
 
 def build_bvh(v, f, max_per_leaf=4):

@@ -321,3 +321,107 @@ def test_two_phase_photon_estimate_algorithm_matches_the_oracle(rtu, tmp_path):
         assert np.array_equal(found[ok], ref_found[ok]), (r, e, with_n)
         assert np.array_equal(irr.view("u4")[ok], ref_irr.view("u4")[ok]), (r, e, with_n)
         assert np.array_equal(d.view("u4")[ok], ref_d.view("u4")[ok]), (r, e, with_n)
+
+
+def _mask_lookup_f32(rec, cells, p, d, t_max):
+    """light_mask_rejects (csrc/intersect.cuh) in numpy float32: True where the device skips the mesh's walk."""
+    f = np.float32
+    kind = rec[3:4].view("i4")[0]
+    L, a, e1, e2 = rec[0:3], rec[4:7], rec[8:11], rec[12:15]
+    u0, v0, su, sv, lim = rec[7], rec[11], rec[15], rec[16], rec[18]
+    dot = lambda x, y: (x[:, 0] * y[0] + x[:, 1] * y[1]).astype(f) + x[:, 2] * y[2]
+    if kind == 2:
+        w = (p - L).astype(f)
+        e = (w + d * f(t_max)).astype(f)
+        w1 = np.abs(w).sum(1, dtype=f)
+        known = np.abs(e).sum(1, dtype=f) <= f(1e-5) * w1
+        depth = dot(w, a)
+        ok = known & (w1 <= lim) & (depth > 0)
+        with np.errstate(all="ignore"):
+            u = ((dot(w, e1) / depth).astype(f) - u0) * su
+            v = ((dot(w, e2) / depth).astype(f) - v0) * sv
+    else:
+        c = np.cross(d, L).astype(f)
+        dd, ll = (d * d).sum(1, dtype=f), f((L * L).sum())
+        known = ((c * c).sum(1, dtype=f) <= f(1e-11) * dd * ll) & (dot(d, L) < 0) & (t_max > 1e29)
+        ok = known & (np.abs(p).sum(1, dtype=f) <= lim)
+        u = (dot(p, e1) - u0) * su
+        v = (dot(p, e2) - v0) * sv
+    inside = (u >= 0) & (u < 256) & (v >= 0) & (v < 256)
+    iu, iv = np.where(inside, u, 0).astype("i8"), np.where(inside, v, 0).astype("i8")
+    clear = ~cells[iv, iu]
+    return ok & np.isfinite(u) & np.isfinite(v) & (~inside | clear), known
+
+
+def _any_hit_f64(v, f, p, d, t_max, chunk=256):
+    """Does the segment p + t d, 0 < t < t_max, meet a triangle (Moeller-Trumbore in double, edges and vertices count)?"""
+    A, B, Cc = (v[f[:, k]].astype("f8") for k in range(3))
+    e1, e2 = B - A, Cc - A
+    hit = np.zeros(len(p), bool)
+    for s in range(0, len(p), chunk):
+        P, D = p[s:s + chunk].astype("f8")[:, None, :], d[s:s + chunk].astype("f8")[:, None, :]
+        h = np.cross(D, e2[None])
+        det = (e1[None] * h).sum(-1)
+        with np.errstate(all="ignore"):
+            inv = 1.0 / det
+            sv = P - A[None]
+            u = (sv * h).sum(-1) * inv
+            q = np.cross(sv, e1[None])
+            w = (D * q).sum(-1) * inv
+            t = (e2[None] * q).sum(-1) * inv
+        tol = 1e-7
+        ok = (np.abs(det) > 0) & (u >= -tol) & (w >= -tol) & (u + w <= 1 + tol) & (t > 0) & (t < t_max)
+        hit[s:s + chunk] = ok.any(1)
+    return hit
+
+
+@pytest.mark.parametrize("scene", ["Teapot/scene2.xml", "Project7/scene.xml"])
+def test_light_masks_never_hide_a_triangle(rtu, scene):
+    """host/light_mask.cpp: a shadow ray the any-hit kernel would skip for a mesh (clear cell of the light's mask) meets none of
+    its triangles.  Origins are sampled in the mesh node's coordinates behind, beside and on the mesh; the lookup is the
+    device's, evaluated in float32; the truth is a brute-force test against every triangle in double."""
+    hs = rtu.HostScene(os.path.join(SCENES, scene))
+    rng = np.random.default_rng(7)
+    built = 0
+    for node in range(hs.desc.n_nodes):
+        if hs.desc.nodes[node].kind != 3:
+            continue
+        m = hs.mesh(hs.desc.nodes[node].mesh)
+        lo, hi = m["bound"][:3].astype("f8"), m["bound"][3:].astype("f8")
+        ctr, ext = 0.5 * (lo + hi), float((hi - lo).max())
+        for light in range(hs.desc.n_lights):
+            got = rtu.build_light_mask(hs.desc, node, light)
+            if got is None:
+                continue
+            built += 1
+            rec, cells = got
+            assert 0.02 < cells.mean() < 0.9
+            kind = rec[3:4].view("i4")[0]
+            L = rec[0:3].astype("f8")
+            away = (ctr - L) / np.linalg.norm(ctr - L) if kind == 2 else L / np.linalg.norm(L)
+            n = 6000
+            # behind the mesh (where the ground is), in a slab 3 extents wide; and points of the mesh's own surface
+            side = rng.normal(size=(n, 3))
+            side -= (side @ away)[:, None] * away
+            p_far = ctr + away * ext * rng.uniform(0.3, 2.0, (n, 1)) + side * ext * 0.6
+            tri = m["f"][rng.integers(0, len(m["f"]), n // 3)]
+            bc = rng.dirichlet((1, 1, 1), n // 3)
+            p_on = (m["v"][tri].astype("f8") * bc[:, :, None]).sum(1)
+            p = np.concatenate([p_far, p_on]).astype("f4")
+            if kind == 2:
+                d = (rec[0:3] - p).astype("f4")
+                t_max = 1.0
+            else:
+                d = np.broadcast_to((-rec[0:3]).astype("f4"), p.shape).copy()
+                t_max = 3.0e38
+            rejected, known = _mask_lookup_f32(rec, cells, p, d, np.float32(t_max))
+            assert known.all()  # the rays of this light are recognised as such
+            hit = _any_hit_f64(m["v"], m["f"], p, d, t_max)
+            assert not (rejected & hit).any(), (scene, node, light, int((rejected & hit).sum()))
+            assert rejected[~hit].mean() > 0.2  # and the mask does reject: most of these miss rays start beside the silhouette
+            # a ray of another kind (not towards this light) is never judged
+            d2 = (d + np.float32(0.01) * rng.normal(size=d.shape).astype("f4") * np.abs(d).max()).astype("f4")
+            rej2, known2 = _mask_lookup_f32(rec, cells, p, d2, np.float32(t_max))
+            assert not rej2[~known2].any() and known2.mean() < 0.01
+    assert built >= 1
+    hs.close()
