@@ -134,6 +134,14 @@ typedef struct rtu_camera {
     int32_t width, height;
 } rtu_camera;
 
+/* A light mask prebuilt by rtu_host_build_light_mask / rtu_host_load_xml for mesh node `node` and light `light` (-1: the camera).
+ * It has to be rebuilt when the mesh, the transforms above the node or the light change. */
+typedef struct rtu_light_mask {
+    int32_t node, light;
+    float rec[20];
+    const uint32_t *bits; /* 2048 words */
+} rtu_light_mask;
+
 typedef struct rtu_scene_desc {
     rtu_camera camera;
     const rtu_node *nodes;         int32_t n_nodes;
@@ -143,6 +151,10 @@ typedef struct rtu_scene_desc {
     const rtu_texmap *texmaps;     int32_t n_texmaps;
     rtu_texcolor background;       /* scene.h global `background`  */
     rtu_texcolor environment;      /* scene.h global `environment` */
+    /* Optional (NULL / 0: rtu_scene_upload builds what it needs itself, about 1 ms per mesh node and light for 6 000 triangles):
+     * prebuilt light masks.  An entry is used when the position / direction of its light in the node's coordinates still is the
+     * one recorded in it; any other pair is built at upload. */
+    const rtu_light_mask *light_masks; int32_t n_light_masks;
 } rtu_scene_desc;
 
 /* ------------------------------------------------------------------ batched operator I/O */
@@ -284,7 +296,8 @@ int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f,
  * the mesh can stop a shadow ray at all; rtu_scene_upload builds the same masks and the any-hit kernel skips the mesh's walk
  * for a ray whose cell is clear - lightFunctions.cpp:27-37 observes only the boolean).  rec: 20 words, bits: 2048 words
  * (256 x 256 cells, row = second image coordinate).  RTU_ERR_UNSUPPORTED: no mask for this pair (soft light, light inside the
- * mesh, margins not met); such rays are walked. */
+ * mesh, margins not met); such rays are walked.  light = -1: the same for the camera rays of a camera without depth of field
+ * (they all start in its position; the primary wave skips the mesh for a ray beside its silhouette). */
 int rtu_host_build_light_mask(const rtu_scene_desc *desc, int32_t node, int32_t light, float *rec, uint32_t *bits);
 /* Result.png / ZBuffer.png writers (RenderImage::SaveImage/SaveZImage, scene.h:638-654). */
 int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels);

@@ -30,7 +30,7 @@ struct __align__(16) DNode {
     int32_t mesh;
     int32_t material;
     int32_t mask_first; // mesh nodes: this node's LightMasks in DScene::light_masks ...
-    int32_t mask_count; // ... one per light that casts hard shadows (0: none)
+    int32_t mask_count; // ... low byte: one per light that casts hard shadows; RTU_MASK_HAS_EYE: one more for the camera rays
 };
 
 // Where a mesh can shadow at all, as seen from one light (built by host/light_mask.cpp, which states the margins).  Every
@@ -41,10 +41,11 @@ struct __align__(16) DNode {
 // cannot meet a triangle, whatever the hierarchy walk would find: the walk is skipped (any-hit only; result-neutral; in the
 // node's local coordinates, where the walks happen).
 #define RTU_MASK_RES 256
+#define RTU_MASK_HAS_EYE 0x100
 #define RTU_MASKS_PER_NODE 4 // scenes with more hard lights get no masks: the lookup steps through a node's masks
 struct __align__(16) LightMask {
     float L[3];      // point light: position; directional light: direction (both node-local)
-    int32_t kind;    // RTU_LIGHT_POINT / RTU_LIGHT_DIRECT
+    int32_t kind;    // RTU_LIGHT_POINT / RTU_LIGHT_DIRECT / 3: rays that START in L (the camera without depth of field)
     float a[3];      // axis light -> mesh centre (point light only)
     float u0;
     float e1[3];
@@ -53,7 +54,7 @@ struct __align__(16) LightMask {
     float su;        // cells per unit of u
     float sv;
     uint32_t bits;   // first word of this mask's bitmap in DScene::mask_bits
-    float lim;       // largest 1-norm of (origin - light) / of the origin for which the mask's margins hold
+    float lim;       // largest 1-norm of (origin - light) / of the origin for which the mask's margins hold; eye: |origin - L|_1
     float pad;
 };
 

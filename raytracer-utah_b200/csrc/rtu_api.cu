@@ -623,26 +623,19 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     std::vector<uint32_t> mask_bits;
     {
         static_assert(sizeof(LightMask) == 20 * sizeof(float), "host/light_mask.cpp writes the record as 20 words");
-        int hard = 0;
-        for (int l = 0; l < d->n_lights; l++)
-            hard += d->lights[l].kind == RTU_LIGHT_DIRECT || (d->lights[l].kind == RTU_LIGHT_POINT && d->lights[l].size == 0.f);
-        const char *e = getenv("RTU_LIGHT_MASKS");
-        const bool on = !(e && atoi(e) == 0);
-        std::vector<uint32_t> one;
-        for (int i = 0; on && hard > 0 && hard <= RTU_MASKS_PER_NODE && i < d->n_nodes && light_masks.size() < 1024; i++) {
-            if (d->nodes[i].kind != RTU_OBJ_MESH) continue;
-            const rtu_node *chain[RTU_MAX_DEPTH + 1];
-            int n_chain = nodes[i].depth + 1;
-            for (int a = i, k = n_chain - 1; k >= 0; a = d->nodes[a].parent, k--) chain[k] = &d->nodes[a];
-            nodes[i].mask_first = (int32_t)light_masks.size();
-            for (int l = 0; l < d->n_lights; l++) {
-                LightMask lm;
-                if (!rtu::build_light_mask(chain, n_chain, d->meshes[d->nodes[i].mesh], d->lights[l], reinterpret_cast<float *>(&lm), &one)) continue;
-                lm.bits = (uint32_t)mask_bits.size();
-                mask_bits.insert(mask_bits.end(), one.begin(), one.end());
-                light_masks.push_back(lm);
-                nodes[i].mask_count++;
-            }
+        std::vector<rtu_light_mask> got;
+        std::vector<std::vector<uint32_t>> own;
+        rtu::collect_light_masks(*d, &got, &own); // the caller's where they fit the scene (rtu_host_load_xml builds them), else built here
+        for (const rtu_light_mask &g : got) { // ordered by node, a node's lights in order, its eye mask last
+            DNode &o = nodes[g.node];
+            if (o.mask_count == 0) o.mask_first = (int32_t)light_masks.size();
+            if (g.light < 0) o.mask_count |= RTU_MASK_HAS_EYE;
+            else o.mask_count++;
+            LightMask lm;
+            memcpy(&lm, g.rec, sizeof lm);
+            lm.bits = (uint32_t)mask_bits.size();
+            mask_bits.insert(mask_bits.end(), g.bits, g.bits + RTU_MASK_RES * RTU_MASK_RES / 32);
+            light_masks.push_back(lm);
         }
     }
     DNode *dn = nullptr;

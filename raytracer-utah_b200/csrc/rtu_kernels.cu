@@ -686,6 +686,7 @@ k_extend_pool(DScene S, FrameSetup F, int s0, int s1, RayQueue in, AuxPool inaux
                     const InvDir I = mesh_invdir(M, lr);
                     float te;
                     if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
+                    if (PRIMARY && OCC && eye_mask_rejects(S, nd, lr)) continue; // inside the box, beside the mesh's silhouette from the eye
                     parked = i;
                     break;
                 }

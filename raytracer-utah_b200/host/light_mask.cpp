@@ -15,10 +15,13 @@
 //    parallel to the direction" (sin < 4e-6), carried to the mesh, is below a quarter of a cell.  Both bounds grow with the
 //    distance of the ray's origin: `lim` is the largest distance (1-norm) up to which they hold; farther rays are walked.
 //  * every vertex has to lie in front of the light (perspective) by a clear margin; otherwise there is no mask.
+// The same for camera rays (`eye`): without depth of field they all START in one point, the image is the perspective one around
+// the axis eye -> mesh, `lim` the distance of a ray's origin from that point up to which it counts as the eye.
 // Anything unusual (NaN, a flat image, a light inside the mesh's box, more than RTU_MASKS_PER_NODE hard lights) gives no
 // mask and the rays are walked as before.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -139,24 +142,32 @@ void dilate(std::vector<uint32_t> &bits)
 
 } // namespace
 
-// rec: the 20 words of a device LightMask (bits offset left 0).  Returns false when no mask can be given.
-// chain: the nodes from the root down to the mesh node (ToNodeCoords is applied in that order, RenderFunctions.cpp:186).
-bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh &m, const rtu_light &light, float *rec,
-                      std::vector<uint32_t> *bits)
+// The light in the node's coordinates: p' = itm (p - pos), d' = itm d, level by level (column-major itm).  false: a light that
+// gets no mask (ambient, soft), or not finite.
+static bool light_in_node(const rtu_node *const *chain, int n_chain, const rtu_light &light, double *L)
 {
-    if (m.nf == 0 || !m.v || !m.f) return false;
     const bool point = light.kind == RTU_LIGHT_POINT;
     if (!point && light.kind != RTU_LIGHT_DIRECT) return false;
     if (point && !(light.size == 0.f)) return false; // a soft light's rays end on its disk
-    // the light in the node's coordinates: p' = itm (p - pos), d' = itm d, level by level (column-major itm)
-    double L[3] = {light.v[0], light.v[1], light.v[2]};
+    for (int k = 0; k < 3; k++) L[k] = light.v[k];
     for (int c = 0; c < n_chain; c++) {
         const rtu_node &t = *chain[c];
         double q[3] = {L[0], L[1], L[2]};
         if (point) for (int k = 0; k < 3; k++) q[k] -= (double)t.pos[k];
         for (int r = 0; r < 3; r++) L[r] = (double)t.itm[r] * q[0] + (double)t.itm[3 + r] * q[1] + (double)t.itm[6 + r] * q[2];
     }
-    if (!(std::isfinite(L[0]) && std::isfinite(L[1]) && std::isfinite(L[2]))) return false;
+    return std::isfinite(L[0]) && std::isfinite(L[1]) && std::isfinite(L[2]);
+}
+
+// rec: the 20 words of a device LightMask (bits offset left 0).  Returns false when no mask can be given.
+// chain: the nodes from the root down to the mesh node (ToNodeCoords is applied in that order, RenderFunctions.cpp:186).
+bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh &m, const rtu_light &light, float *rec,
+                      std::vector<uint32_t> *bits, bool eye)
+{
+    if (m.nf == 0 || !m.v || !m.f) return false;
+    const bool point = light.kind == RTU_LIGHT_POINT;
+    double L[3];
+    if (!light_in_node(chain, n_chain, light, L)) return false;
     double a[3], e1[3], e2[3];
     if (point) {
         for (int k = 0; k < 3; k++) a[k] = 0.5 * ((double)m.bound_min[k] + (double)m.bound_max[k]) - L[k];
@@ -212,7 +223,9 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
         if (!(100 * err_u <= cmin)) return false;
         // a ray that passes the light at 1e-5 |w|_1 is off by that much at the mesh, i.e. by (1 + umax) / depth of it in u
         lim = cmin * dmin / (4 * 1.0e-5 * (1.0 + umax));
-        if (!(lim > 2 * an)) return false;
+        if (!eye && !(lim > 2 * an)) return false;
+        // eye mask: rays START in the point; an origin off by t moves the image of a triangle by t (1 + umax) / depth of it
+        if (eye) lim = cmin * dmin / (4 * (1.0 + umax));
     } else {
         // u = p.e1: rounding 4 eps |p|_1; a direction off by sin = 4e-6 drifts by that times the way to the mesh (<= |p|_1 + vmax1)
         lim = std::min(cmin / (400 * EPS), cmin / (4 * 4.0e-6) - vmax1);
@@ -239,7 +252,7 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
     dilate(*bits);
 
     memset(rec, 0, 20 * sizeof(float));
-    const int32_t kind = light.kind;
+    const int32_t kind = eye ? RTU_MASK_EYE : light.kind;
     for (int k = 0; k < 3; k++) { rec[k] = (float)L[k]; rec[4 + k] = (float)a[k]; rec[8 + k] = (float)e1[k]; rec[12 + k] = (float)e2[k]; }
     memcpy(&rec[3], &kind, 4);
     rec[7] = (float)o[0];
@@ -248,6 +261,57 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
     rec[16] = (float)s[1];
     rec[18] = (float)lim;
     return true;
+}
+
+void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<std::vector<uint32_t>> *own)
+{
+    out->clear();
+    own->clear();
+    if (const char *e = getenv("RTU_LIGHT_MASKS")) if (atoi(e) == 0) return;
+    int hard = 0;
+    for (int l = 0; l < d.n_lights; l++)
+        hard += d.lights[l].kind == RTU_LIGHT_DIRECT || (d.lights[l].kind == RTU_LIGHT_POINT && d.lights[l].size == 0.f);
+    // the lookup steps through a node's masks: scenes with many hard lights get none for them
+    const bool lights_on = hard > 0 && hard <= 4, eye_on = !(d.camera.dof > 0.f);
+    if (!lights_on && !eye_on) return;
+    rtu_light eye;
+    memset(&eye, 0, sizeof eye);
+    eye.kind = RTU_LIGHT_POINT;
+    memcpy(eye.v, d.camera.pos, sizeof eye.v);
+    own->reserve(1024); // pointers into it are handed out
+    for (int i = 0; i < d.n_nodes && out->size() + 5 <= 1024; i++) {
+        if (d.nodes[i].kind != RTU_OBJ_MESH || d.nodes[i].mesh < 0 || d.nodes[i].mesh >= d.n_meshes) continue;
+        const rtu_node *chain[64];
+        int n_chain = 0;
+        for (int a = i; a >= 0 && n_chain < 64; a = d.nodes[a].parent) n_chain++;
+        if (n_chain >= 64) continue;
+        for (int a = i, k = n_chain - 1; k >= 0; a = d.nodes[a].parent, k--) chain[k] = &d.nodes[a];
+        for (int l = 0; l <= d.n_lights; l++) { // the eye's mask comes last
+            const bool is_eye = l == d.n_lights;
+            if (is_eye ? !eye_on : !lights_on) continue;
+            const rtu_light &lt = is_eye ? eye : d.lights[l];
+            double L[3];
+            if (!light_in_node(chain, n_chain, lt, L)) continue;
+            const rtu_light_mask *pre = nullptr;
+            for (int k = 0; k < d.n_light_masks && d.light_masks && !pre; k++) {
+                const rtu_light_mask &c = d.light_masks[k];
+                int32_t kind;
+                memcpy(&kind, &c.rec[3], 4);
+                if (c.node == i && c.light == (is_eye ? -1 : l) && c.bits && kind == (is_eye ? (int32_t)RTU_MASK_EYE : lt.kind) &&
+                    c.rec[0] == (float)L[0] && c.rec[1] == (float)L[1] && c.rec[2] == (float)L[2])
+                    pre = &c;
+            }
+            if (pre) { out->push_back(*pre); continue; }
+            rtu_light_mask lm;
+            std::vector<uint32_t> bits;
+            if (!build_light_mask(chain, n_chain, d.meshes[d.nodes[i].mesh], lt, lm.rec, &bits, is_eye)) continue;
+            own->push_back(std::move(bits));
+            lm.node = i;
+            lm.light = is_eye ? -1 : l;
+            lm.bits = own->back().data();
+            out->push_back(lm);
+        }
+    }
 }
 
 } // namespace rtu

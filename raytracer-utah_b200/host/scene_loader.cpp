@@ -488,6 +488,12 @@ void rtu_host_scene::finalize()
     desc.materials = materials.data(); desc.n_materials = (int32_t)materials.size();
     desc.lights = lights.data();       desc.n_lights = (int32_t)lights.size();
     desc.texmaps = texmaps.data();     desc.n_texmaps = (int32_t)texmaps.size();
+    // light masks (light_mask.cpp), once per load instead of once per rtu_scene_upload
+    desc.light_masks = nullptr;
+    desc.n_light_masks = 0;
+    rtu::collect_light_masks(desc, &light_masks, &light_mask_bits);
+    desc.light_masks = light_masks.empty() ? nullptr : light_masks.data();
+    desc.n_light_masks = (int32_t)light_masks.size();
 }
 
 extern "C" {
@@ -576,7 +582,7 @@ int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f,
 int rtu_host_build_light_mask(const rtu_scene_desc *d, int32_t node, int32_t light, float *rec, uint32_t *bits)
 {
     if (!d || !rec || !bits) { rtu::set_error("rtu_host_build_light_mask: null argument"); return RTU_ERR_INVALID; }
-    if (node < 0 || node >= d->n_nodes || light < 0 || light >= d->n_lights || d->nodes[node].kind != RTU_OBJ_MESH ||
+    if (node < 0 || node >= d->n_nodes || light < -1 || light >= d->n_lights || d->nodes[node].kind != RTU_OBJ_MESH ||
         d->nodes[node].mesh < 0 || d->nodes[node].mesh >= d->n_meshes) {
         rtu::set_error("rtu_host_build_light_mask: not a mesh node / light of this scene");
         return RTU_ERR_INVALID;
@@ -585,7 +591,12 @@ int rtu_host_build_light_mask(const rtu_scene_desc *d, int32_t node, int32_t lig
         std::vector<const rtu_node *> chain;
         for (int a = node; a >= 0 && chain.size() < 64; a = d->nodes[a].parent) chain.insert(chain.begin(), &d->nodes[a]);
         std::vector<uint32_t> b;
-        if (!rtu::build_light_mask(chain.data(), (int)chain.size(), d->meshes[d->nodes[node].mesh], d->lights[light], rec, &b)) {
+        rtu_light eye; // light -1: the camera's mask
+        memset(&eye, 0, sizeof eye);
+        eye.kind = RTU_LIGHT_POINT;
+        memcpy(eye.v, d->camera.pos, sizeof eye.v);
+        if ((light < 0 && d->camera.dof > 0.f) ||
+            !rtu::build_light_mask(chain.data(), (int)chain.size(), d->meshes[d->nodes[node].mesh], light < 0 ? eye : d->lights[light], rec, &b, light < 0)) {
             rtu::set_error("rtu_host_build_light_mask: no mask for this mesh and light");
             return RTU_ERR_UNSUPPORTED;
         }

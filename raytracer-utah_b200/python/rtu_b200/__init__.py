@@ -71,6 +71,10 @@ class Camera(C.Structure):
                 ("focaldist", f32), ("dof", f32), ("width", i32), ("height", i32)]
 
 
+class LightMask(C.Structure):
+    _fields_ = [("node", i32), ("light", i32), ("rec", f32 * 20), ("bits", C.POINTER(u32))]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("camera", Camera),
                 ("nodes", C.POINTER(Node)), ("n_nodes", i32),
@@ -78,7 +82,8 @@ class SceneDesc(C.Structure):
                 ("materials", C.POINTER(Material)), ("n_materials", i32),
                 ("lights", C.POINTER(Light)), ("n_lights", i32),
                 ("texmaps", C.POINTER(TexMap)), ("n_texmaps", i32),
-                ("background", TexColor), ("environment", TexColor)]
+                ("background", TexColor), ("environment", TexColor),
+                ("light_masks", C.POINTER(LightMask)), ("n_light_masks", i32)]
 
 
 class Params(C.Structure):

@@ -353,6 +353,23 @@ def _mask_lookup_f32(rec, cells, p, d, t_max):
     return ok & np.isfinite(u) & np.isfinite(v) & (~inside | clear), known
 
 
+def _eye_lookup_f32(rec, cells, p, d):
+    """eye_mask_rejects (csrc/intersect.cuh) in numpy float32."""
+    f = np.float32
+    L, a, e1, e2 = rec[0:3], rec[4:7], rec[8:11], rec[12:15]
+    u0, v0, su, sv, lim = rec[7], rec[11], rec[15], rec[16], rec[18]
+    dot = lambda x, y: (x[:, 0] * y[0] + x[:, 1] * y[1]).astype(f) + x[:, 2] * y[2]
+    ok = np.abs((p - L).astype(f)).sum(1, dtype=f) <= lim
+    depth = dot(d, a)
+    ok &= depth > 0
+    with np.errstate(all="ignore"):
+        u = ((dot(d, e1) / depth).astype(f) - u0) * su
+        v = ((dot(d, e2) / depth).astype(f) - v0) * sv
+    inside = (u >= 0) & (u < 256) & (v >= 0) & (v < 256)
+    iu, iv = np.where(inside, u, 0).astype("i8"), np.where(inside, v, 0).astype("i8")
+    return ok & np.isfinite(u) & np.isfinite(v) & (~inside | ~cells[iv, iu])
+
+
 def _any_hit_f64(v, f, p, d, t_max, chunk=256):
     """Does the segment p + t d, 0 < t < t_max, meet a triangle (Moeller-Trumbore in double, edges and vertices count)?"""
     A, B, Cc = (v[f[:, k]].astype("f8") for k in range(3))
@@ -423,5 +440,47 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
             d2 = (d + np.float32(0.01) * rng.normal(size=d.shape).astype("f4") * np.abs(d).max()).astype("f4")
             rej2, known2 = _mask_lookup_f32(rec, cells, p, d2, np.float32(t_max))
             assert not rej2[~known2].any() and known2.mean() < 0.01
-    assert built >= 1
+        # the camera's mask (light -1): rays that start in the eye, through and beside the mesh
+        got = rtu.build_light_mask(hs.desc, node, -1)
+        if got is not None:
+            built += 1
+            rec, cells = got
+            assert rec[3:4].view("i4")[0] == 3
+            n = 8000
+            E = rec[0:3]
+            tgt = ctr + rng.uniform(-0.75, 0.75, (n, 3)) * (hi - lo)
+            p = (E + (rng.uniform(-1, 1, (n, 3)) * rec[18] / 3.01).astype("f4")).astype("f4")  # within `lim` of the eye (1-norm)
+            d = ((tgt - p) * rng.uniform(0.01, 3.0, (n, 1))).astype("f4")
+            rejected = _eye_lookup_f32(rec, cells, p, d)
+            hit = _any_hit_f64(m["v"], m["f"], p, d, np.inf)
+            assert not (rejected & hit).any(), (scene, node, "eye", int((rejected & hit).sum()))
+            assert rejected[~hit].mean() > 0.2
+            far = (p + np.float32(4.0) * rec[18]).astype("f4")  # not the eye: never judged
+            assert not _eye_lookup_f32(rec, cells, far, d).any()
+    assert built >= 2
+    hs.close()
+
+
+def test_loader_prebuilds_the_light_masks(rtu):
+    """rtu_host_load_xml leaves the scene's masks in the description (rtu_scene_upload takes them from there instead of building
+    them at every upload): one per hard light and one for the camera, equal to what rtu_host_build_light_mask gives."""
+    hs = rtu.HostScene(os.path.join(SCENES, "Teapot/scene2.xml"))
+    d = hs.desc
+    assert d.n_light_masks == 3
+    seen = []
+    for k in range(d.n_light_masks):
+        lm = d.light_masks[k]
+        seen.append((lm.node, lm.light))
+        rec, cells = rtu.build_light_mask(d, lm.node, lm.light)
+        assert bits_equal(np.frombuffer(lm.rec, "f4"), rec)
+        bits = np.ctypeslib.as_array(lm.bits, shape=(2048,))
+        assert np.array_equal(np.unpackbits(bits.view("u1"), bitorder="little").reshape(256, 256).astype(bool), cells)
+    assert seen == [(1, 0), (1, 1), (1, -1)]
+    hs.close()
+    # soft lights and a camera with depth of field: nothing to prebuild for them
+    hs = rtu.HostScene(os.path.join(SCENES, "Project10/scene.xml"))
+    assert all(hs.desc.light_masks[k].light == -1 for k in range(hs.desc.n_light_masks))
+    hs.close()
+    hs = rtu.HostScene(os.path.join(SCENES, "Project9/scene.xml"))
+    assert all(hs.desc.light_masks[k].light >= 0 for k in range(hs.desc.n_light_masks))
     hs.close()
