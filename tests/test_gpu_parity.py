@@ -1156,3 +1156,39 @@ def test_queue_overflow_on_the_accumulate_path_never_corrupts_the_accumulator(rt
     finally:
         hs.close()
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,mode,w,h,spp", [("Teapot/scene2.xml", "whitted", 960, 540, 4), ("Teapot/scene.xml", "whitted", 640, 360, 2),
+                                                ("Project7/scene.xml", "whitted", 400, 300, 2), ("Project11/scene.xml", "path", 200, 150, 4)])
+def test_light_and_eye_masks_do_not_change_the_frame(rtu, gpu_ctx, scene, mode, w, h, spp, monkeypatch):
+    """host/light_mask.cpp: a ray beside a mesh's silhouette (seen from its hard light / from the camera) skips that mesh's
+    walk.  The frame must be the one rendered with every walk done: the same rays, the same image up to the order of the
+    accumulator's additions, and fewer triangle tests (the masks did skip something).  Three ways to get the masks: prebuilt
+    by the loader, built by rtu_scene_upload (description without them), none (RTU_LIGHT_MASKS=0)."""
+    hs = rtu.HostScene(os.path.join(SCENES, scene))
+    assert hs.desc.n_light_masks > 0
+    p = rtu.default_params(width=w, height=h, spp=spp, pattern=rtu.PATTERN_REFERENCE, shade_bounces=5, gi_bounces=4,
+                           mode=rtu.MODE_WHITTED if mode == "whitted" else rtu.MODE_PATH)
+    frames, stats = [], []
+    for how in ("prebuilt", "upload", "off"):
+        n = hs.desc.n_light_masks
+        if how != "prebuilt":
+            hs.desc.n_light_masks = 0
+        if how == "off":
+            monkeypatch.setenv("RTU_LIGHT_MASKS", "0")
+        sc = rtu.Scene(gpu_ctx, hs.desc)
+        hs.desc.n_light_masks = n
+        try:
+            frames.append(sc.render(p, want=("rgb",))["rgb"].copy())
+            stats.append(sc.stats())
+        finally:
+            sc.close()
+    hs.close()
+    for f in frames[:2]:
+        assert np.allclose(f, frames[2], rtol=1e-5, atol=1e-6), float(np.abs(f - frames[2]).max())
+    for st in stats[:2]:
+        assert st["trace_rays"] == stats[2]["trace_rays"] and st["shadow_rays"] == stats[2]["shadow_rays"]
+        assert st["tri_tests"] < stats[2]["tri_tests"]
+    # (the any-hit walks stop at whichever occluder a warp's pool reaches first: their test counts vary a little from run to run)
+    assert abs(stats[0]["tri_tests"] - stats[1]["tri_tests"]) < 0.01 * stats[2]["tri_tests"]
