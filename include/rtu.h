@@ -138,8 +138,13 @@ typedef struct rtu_camera {
  * It has to be rebuilt when the mesh, the transforms above the node or the light change. */
 typedef struct rtu_light_mask {
     int32_t node, light;
-    float rec[20];
-    const uint32_t *bits; /* 2048 words */
+    float rec[24];
+    const uint32_t *bits;       /* 2048 words */
+    /* Optional light lists (lights only; NULL / 0: none): per cell the triangles a shadow ray of that cell can meet, in the
+     * order of their distance from the light.  Such a ray tests those instead of walking the mesh's hierarchy. */
+    const uint32_t *cell_start; /* 256 * 256 + 1 offsets into items */
+    const uint32_t *items;      /* 2 words per entry: the triangle (cyBVH slot; face index for RTU_MESH_DEVICE_BVH), its least depth (float) */
+    uint32_t n_items;
 } rtu_light_mask;
 
 typedef struct rtu_scene_desc {
@@ -294,10 +299,10 @@ int rtu_host_build_occlusion_bvh(const float *v, uint32_t nv, const uint32_t *f,
                                  float *nodes, uint32_t *n_nodes, uint32_t *root, uint32_t *slots);
 /* Light mask of mesh node `node` for light `light` (not in the reference: where, seen from a light that casts hard shadows,
  * the mesh can stop a shadow ray at all; rtu_scene_upload builds the same masks and the any-hit kernel skips the mesh's walk
- * for a ray whose cell is clear - lightFunctions.cpp:27-37 observes only the boolean).  rec: 20 words, bits: 2048 words
+ * for a ray whose cell is clear - lightFunctions.cpp:27-37 observes only the boolean).  bits: 2048 words
  * (256 x 256 cells, row = second image coordinate).  RTU_ERR_UNSUPPORTED: no mask for this pair (soft light, light inside the
  * mesh, margins not met); such rays are walked.  light = -1: the same for the camera rays of a camera without depth of field
- * (they all start in its position; the primary wave skips the mesh for a ray beside its silhouette). */
+ * (they all start in its position; the primary wave skips the mesh for a ray beside its silhouette).  rec: 24 words. */
 int rtu_host_build_light_mask(const rtu_scene_desc *desc, int32_t node, int32_t light, float *rec, uint32_t *bits);
 /* Result.png / ZBuffer.png writers (RenderImage::SaveImage/SaveZImage, scene.h:638-654). */
 int rtu_write_png(const char *path, const uint8_t *pixels, int32_t width, int32_t height, int32_t channels);

@@ -55,7 +55,10 @@ struct __align__(16) LightMask {
     float sv;
     uint32_t bits;   // first word of this mask's bitmap in DScene::mask_bits
     float lim;       // largest 1-norm of (origin - light) / of the origin for which the mask's margins hold; eye: |origin - L|_1
-    float pad;
+    float zmargin;   // light lists: slack of the depth cut (rounding of the origin's depth on the device)
+    uint32_t cells;  // light lists: first of the RES * RES + 1 cell offsets in DScene::mask_bits; 0xffffffff: none
+    uint32_t items;  // ... first word of the (slot, least depth) pairs
+    float pad[2];
 };
 
 // child word: bit31 = leaf; leaf: bits 28..30 = count-1, bits 0..27 = first triangle slot

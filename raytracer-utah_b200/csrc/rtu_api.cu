@@ -622,9 +622,9 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     std::vector<LightMask> light_masks;
     std::vector<uint32_t> mask_bits;
     {
-        static_assert(sizeof(LightMask) == 20 * sizeof(float), "host/light_mask.cpp writes the record as 20 words");
+        static_assert(sizeof(LightMask) == 24 * sizeof(float), "host/light_mask.cpp writes the record as 24 words");
         std::vector<rtu_light_mask> got;
-        std::vector<std::vector<uint32_t>> own;
+        std::vector<rtu::OwnedMask> own;
         rtu::collect_light_masks(*d, &got, &own); // the caller's where they fit the scene (rtu_host_load_xml builds them), else built here
         for (const rtu_light_mask &g : got) { // ordered by node, a node's lights in order, its eye mask last
             DNode &o = nodes[g.node];
@@ -635,6 +635,24 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
             memcpy(&lm, g.rec, sizeof lm);
             lm.bits = (uint32_t)mask_bits.size();
             mask_bits.insert(mask_bits.end(), g.bits, g.bits + RTU_MASK_RES * RTU_MASK_RES / 32);
+            lm.cells = 0xffffffffu;
+            lm.items = 0;
+            const uint32_t n_tris = d->meshes[d->nodes[g.node].mesh].nf;
+            if (g.cell_start && g.items && g.n_items > 0 && g.light >= 0 && g.cell_start[RTU_MASK_RES * RTU_MASK_RES] == g.n_items &&
+                mask_bits.size() + (size_t)RTU_MASK_RES * RTU_MASK_RES + 1 + 2 * (size_t)g.n_items < 0xfffffff0u) {
+                // light lists (same buffer): the offsets of the cells, then the (slot, depth) pairs; validated like everything the device indexes with
+                bool ok = true;
+                for (int cidx = 0; cidx < RTU_MASK_RES * RTU_MASK_RES && ok; cidx++) ok = g.cell_start[cidx] <= g.cell_start[cidx + 1];
+                for (uint32_t k = 0; k < g.n_items && ok; k++) ok = g.items[2 * k] < n_tris;
+                if (ok) {
+                    lm.cells = (uint32_t)mask_bits.size();
+                    mask_bits.insert(mask_bits.end(), g.cell_start, g.cell_start + RTU_MASK_RES * RTU_MASK_RES + 1);
+                    if (mask_bits.size() & 1u) mask_bits.push_back(0u); // the pairs are read as uint2
+                    lm.items = (uint32_t)mask_bits.size();
+                    mask_bits.insert(mask_bits.end(), g.items, g.items + 2 * (size_t)g.n_items);
+                    if (mask_bits.size() & 1u) mask_bits.push_back(0u);
+                }
+            }
             light_masks.push_back(lm);
         }
     }

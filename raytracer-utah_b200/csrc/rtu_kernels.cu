@@ -268,6 +268,35 @@ static __device__ __noinline__ bool ref_reaches_ni(const DMesh *M, unsigned slot
     I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
     return ref_reaches(*M, slot, r, I, *tl);
 }
+// Light lists (host/light_mask.cpp): the triangles of one mask cell in the order of their least depth from the light, as (slot in
+// DMesh::tris, depth) pairs.  The exact triangle test on those that begin before the ray's origin; an accepting one is
+// confirmed like every candidate of the any-hit search (ref_reaches, else the exact walk of the cyBVH decides).
+static __device__ __noinline__ bool light_list_occludes_ni(const uint32_t *items, unsigned n, float zcut, const DMesh *M, const RefWalkArgs *a,
+                                                          float t_max, Tally *tl)
+{
+    Ray r;
+    r.px = a->px; r.py = a->py; r.pz = a->pz; r.dx = a->dx; r.dy = a->dy; r.dz = a->dz;
+    const uint2 *e = reinterpret_cast<const uint2 *>(items);
+    for (unsigned k = 0; k < n; k++) {
+        const uint2 it = __ldg(e + k);
+        if (__uint_as_float(it.y) > zcut) break; // this one and all behind it begin beyond the origin
+        const float4 *q = reinterpret_cast<const float4 *>(M->tris + it.x);
+        const float4 x = __ldg(q), y = __ldg(q + 1), w4 = __ldg(q + 2);
+        TriRec T;
+        T.nx = x.x; T.ny = x.y; T.nz = x.z; T.ax = x.w;
+        T.ay = y.x; T.az = y.y; T.area = y.z; T.fbits = y.w;
+        T.cau = w4.x; T.cav = w4.y; T.bau = w4.z; T.bav = w4.w;
+        tl->tri++;
+        float z = t_max, b1, b2, b3;
+        int fr;
+        if (!tri_hit(T, r, z, fr, b1, b2, b3)) continue;
+        InvDir I;
+        I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
+        if (ref_reaches(*M, it.x, r, I, *tl)) return true;
+        return bvh_walk_any_fallback(*M, r, I, t_max, *tl);
+    }
+    return false;
+}
 static __device__ __noinline__ bool occ_walk_ni(const DMesh *M, unsigned start, const RefWalkArgs *a, const OccRay *oc, float t_max, Tally *tl)
 {
     Ray r;
@@ -1333,7 +1362,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
             B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
             const Ray r0 = to_node(root.itm, root.pos, ray);
             const float dd = dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz);
-            bool occ = false;
+            bool occ = false, mesh_occ = false;
             Ray lvl[FLAT ? 1 : RTU_MAX_DEPTH]; // hierarchies: the ray at every depth of the current branch
             if (!FLAT) {
                 lvl[0] = r0;
@@ -1363,13 +1392,30 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                     const InvDir I = mesh_invdir(M, lr);
                     float te;
                     if (!slab_fast(lr, I, M.bmin[0], M.bmin[1], M.bmin[2], M.bmax[0], M.bmax[1], M.bmax[2], RTU_BIG, te)) continue;
-                    if (OCC && light_mask_rejects(S, nd, lr, d.w)) continue; // inside the box, beside the mesh's silhouette from its light
+                    if constexpr (OCC) {
+                        // the light's mask: beside the mesh's silhouette from its light -> skipped; with light lists the ray
+                        // tests the few triangles of its cell that lie before its origin instead of walking the hierarchy
+                        unsigned it0, it1;
+                        float zcut;
+                        const int lk = light_mask_lookup(S, nd, lr, d.w, it0, it1, zcut);
+                        if (lk == 1) continue;
+                        if (lk == 2) {
+                            RefWalkArgs a;
+                            a.px = lr.px; a.py = lr.py; a.pz = lr.pz; a.dx = lr.dx; a.dy = lr.dy; a.dz = lr.dz;
+                            a.yx = I.yx; a.yy = I.yy; a.yz = I.yz; a.ok = I.ok;
+                            Tally t2 = {0, 0, 0, 0, 0};
+                            const bool stop = light_list_occludes_ni(S.mask_bits + it0, (it1 - it0) >> 1, zcut, &M, &a, d.w, &t2);
+                            tl.box += t2.box; tl.tri += t2.tri;
+                            if (stop) { mesh_occ = true; break; }
+                            continue;
+                        }
+                    }
                     park = i;
                     break;
                 }
                 if (sphere_or_plane_hit(nd, i, lr, B, tl)) { occ = true; break; }
             }
-            if (!park && !(occ && B.z > 0.0f)) {                                          // :31-35
+            if (!park && !mesh_occ && !(occ && B.z > 0.0f)) {                             // :31-35
                 float4 c = Q.c[idx];
                 accum_add(accum, __float_as_int(o.w), mk(c.x, c.y, c.z));
             }

@@ -23,12 +23,17 @@ void build_occlusion_bvh(const float *v, const uint32_t *f, const uint32_t *elem
 // bitmap.  chain = the nodes from the root down to the mesh's node.  false: no mask for this pair, the rays are walked.
 // eye: `light` is a point light standing in for the camera position; the mask is for rays that start there (kind RTU_MASK_EYE).
 enum { RTU_MASK_EYE = 3 };
+struct LightLists {
+    std::vector<uint32_t> cell_start; // 256 * 256 + 1 offsets, empty: no lists for this pair
+    std::vector<uint32_t> items;      // (slot, least depth) pairs, per cell in the order of depth
+};
 bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh &m, const rtu_light &light, float *rec,
-                      std::vector<uint32_t> *bits, bool eye = false);
+                      std::vector<uint32_t> *bits, bool eye = false, LightLists *lists = nullptr);
 // Every mask of a scene, in the order rtu_scene_upload lays them out (by node; per node the lights in their order, the
 // camera last): entries of d.light_masks that still fit the scene are taken as they are, the others are built into `own`.
 // RTU_LIGHT_MASKS=0 in the environment: none.
-void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<std::vector<uint32_t>> *own);
+struct OwnedMask { std::vector<uint32_t> bits; LightLists lists; };
+void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<OwnedMask> *own);
 
 // cyTriMesh::Mtl (cyTriMesh.h:74-103): one material of an OBJ's .mtl library, with the constructor's defaults
 struct ObjMtl {
@@ -112,6 +117,6 @@ struct rtu_host_scene {
     std::vector<std::unique_ptr<rtu::HostTexture>> textures; // TextureList (scene.h:368)
     std::vector<rtu_texmap> texmaps;
     std::vector<rtu_light_mask> light_masks; // light_mask.cpp: built once here, rtu_scene_upload takes them from desc
-    std::vector<std::vector<uint32_t>> light_mask_bits;
+    std::vector<rtu::OwnedMask> light_mask_data;
     void finalize(); // points desc at the vectors
 };

@@ -73,24 +73,26 @@ inline int ifloor(double x) { return (int)(x + 16.0) - 16; } // -16 < x < 2^31 -
 // The cells a triangle (cell coordinates) touches: row by row, the extent in x of the triangle's part inside the row
 // [iy, iy+1] (the ends of its edges clipped to the row; the intersection is convex).  The ends are widened by 1e-6 of a cell:
 // the arithmetic here is double, its rounding is far below that.
-void raster(const double (*p)[2], uint32_t *bits)
+struct Rows {
+    int iy0, iy1;           // rows the triangle reaches (clamped to the bitmap); iy0 > iy1: none
+    int rx0, rx1;           // columns of its rectangle
+    int lo[RES], hi[RES];   // per row iy the cells lo[iy] .. hi[iy]; hi < lo: none
+};
+
+void tri_rect(const double (*p)[2], Rows &R)
 {
     const double big = RES + 8.0;
     double y0 = std::min(p[0][1], std::min(p[1][1], p[2][1])), y1 = std::max(p[0][1], std::max(p[1][1], p[2][1]));
     double xa = std::min(p[0][0], std::min(p[1][0], p[2][0])), xb = std::max(p[0][0], std::max(p[1][0], p[2][0]));
     y0 = std::max(y0, -8.0); y1 = std::min(y1, big); xa = std::max(xa, -8.0); xb = std::min(xb, big);
-    const int iy0 = std::max(0, ifloor(y0 - 1e-6)), iy1 = std::min(RES - 1, ifloor(y1 + 1e-6));
-    const int rx0 = std::max(0, ifloor(xa - 1e-6)), rx1 = std::min(RES - 1, ifloor(xb + 1e-6));
-    if (rx0 > rx1 || iy0 > iy1) return;
-    {   // every cell of the triangle's rectangle already set (by its neighbours, by the other side of a closed surface)?
-        bool all = true;
-        for (int iy = iy0; iy <= iy1 && all; iy++) all = span_set(bits + (size_t)iy * (RES / 32), rx0, rx1);
-        if (all) return;
-    }
-    if (rx1 - rx0 <= 1 && iy1 - iy0 <= 1) { // up to 2 x 2 cells: the rectangle
-        for (int iy = iy0; iy <= iy1; iy++) set_span(bits + (size_t)iy * (RES / 32), rx0, rx1);
-        return;
-    }
+    R.iy0 = std::max(0, ifloor(y0 - 1e-6)); R.iy1 = std::min(RES - 1, ifloor(y1 + 1e-6));
+    R.rx0 = std::max(0, ifloor(xa - 1e-6)); R.rx1 = std::min(RES - 1, ifloor(xb + 1e-6));
+    if (R.rx0 > R.rx1) R.iy1 = R.iy0 - 1;
+}
+
+void tri_rows(const double (*p)[2], Rows &R)
+{
+    const double big = RES + 8.0;
     // per edge: x(t), y(t) = a + t (b - a); the part of it inside a row lo <= y <= hi is t in [max(0, ta), min(1, tb)]
     double ax[3], ay[3], dx[3], dy[3], inv[3];
     for (int k = 0; k < 3; k++) {
@@ -98,7 +100,7 @@ void raster(const double (*p)[2], uint32_t *bits)
         dx[k] = p[(k + 1) % 3][0] - ax[k]; dy[k] = p[(k + 1) % 3][1] - ay[k];
         inv[k] = dy[k] != 0.0 ? 1.0 / dy[k] : 0.0;
     }
-    for (int iy = iy0; iy <= iy1; iy++) {
+    for (int iy = R.iy0; iy <= R.iy1; iy++) {
         const double lo = iy - 1e-6, hi = iy + 1.0 + 1e-6;
         double x0 = 1e300, x1 = -1e300;
         for (int k = 0; k < 3; k++) {
@@ -114,10 +116,43 @@ void raster(const double (*p)[2], uint32_t *bits)
                 x0 = std::min(x0, std::min(xa2, xb2)); x1 = std::max(x1, std::max(xa2, xb2));
             }
         }
+        R.lo[iy] = 1; R.hi[iy] = 0;
         if (!(x0 <= x1)) continue; // the triangle does not reach this row
         x0 = std::max(x0, -8.0); x1 = std::min(x1, big);
-        const int ix0 = std::max(0, ifloor(x0 - 1e-6)), ix1 = std::min(RES - 1, ifloor(x1 + 1e-6));
-        if (ix0 <= ix1) set_span(bits + (size_t)iy * (RES / 32), ix0, ix1);
+        R.lo[iy] = std::max(0, ifloor(x0 - 1e-6)); R.hi[iy] = std::min(RES - 1, ifloor(x1 + 1e-6));
+    }
+}
+
+void raster(const double (*p)[2], uint32_t *bits, Rows &R)
+{
+    tri_rect(p, R);
+    if (R.iy0 > R.iy1) return;
+    {   // every cell of the triangle's rectangle already set (by its neighbours, by the other side of a closed surface)?
+        bool all = true;
+        for (int iy = R.iy0; iy <= R.iy1 && all; iy++) all = span_set(bits + (size_t)iy * (RES / 32), R.rx0, R.rx1);
+        if (all) return;
+    }
+    if (R.rx1 - R.rx0 <= 1 && R.iy1 - R.iy0 <= 1) { // up to 2 x 2 cells: the rectangle
+        for (int iy = R.iy0; iy <= R.iy1; iy++) set_span(bits + (size_t)iy * (RES / 32), R.rx0, R.rx1);
+        return;
+    }
+    tri_rows(p, R);
+    for (int iy = R.iy0; iy <= R.iy1; iy++)
+        if (R.lo[iy] <= R.hi[iy]) set_span(bits + (size_t)iy * (RES / 32), R.lo[iy], R.hi[iy]);
+}
+
+// The cells whose 3 x 3 neighbourhood the triangle touches (what dilate() makes of its own cells), row by row: fn(iy, ix0, ix1)
+template <class F> void dilated_rows(const double (*p)[2], Rows &R, F fn)
+{
+    tri_rect(p, R);
+    if (R.iy0 > R.iy1) return;
+    tri_rows(p, R);
+    for (int r = std::max(0, R.iy0 - 1); r <= std::min(RES - 1, R.iy1 + 1); r++) {
+        int lo = RES, hi = -1;
+        for (int q = std::max(R.iy0, r - 1); q <= std::min(R.iy1, r + 1); q++)
+            if (R.lo[q] <= R.hi[q]) { lo = std::min(lo, R.lo[q]); hi = std::max(hi, R.hi[q]); }
+        if (hi < lo) continue;
+        fn(r, std::max(0, lo - 1), std::min(RES - 1, hi + 1));
     }
 }
 
@@ -159,11 +194,12 @@ static bool light_in_node(const rtu_node *const *chain, int n_chain, const rtu_l
     return std::isfinite(L[0]) && std::isfinite(L[1]) && std::isfinite(L[2]);
 }
 
-// rec: the 20 words of a device LightMask (bits offset left 0).  Returns false when no mask can be given.
+// rec: the 24 words of a device LightMask (bits / lists offsets left 0).  Returns false when no mask can be given.
 // chain: the nodes from the root down to the mesh node (ToNodeCoords is applied in that order, RenderFunctions.cpp:186).
 bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh &m, const rtu_light &light, float *rec,
-                      std::vector<uint32_t> *bits, bool eye)
+                      std::vector<uint32_t> *bits, bool eye, LightLists *lists)
 {
+    if (lists) { lists->cell_start.clear(); lists->items.clear(); }
     if (m.nf == 0 || !m.v || !m.f) return false;
     const bool point = light.kind == RTU_LIGHT_POINT;
     double L[3];
@@ -180,7 +216,7 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
     basis(a, e1, e2);
 
     // images of the vertices
-    std::vector<double> img((size_t)m.nv * 2);
+    std::vector<double> img((size_t)m.nv * 2), dep(m.nv, 0.0);
     std::vector<uint8_t> used(m.nv, 0);
     for (size_t k = 0; k < (size_t)m.nf * 3; k++) {
         if (m.f[k] >= m.nv) return false;
@@ -197,9 +233,11 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
             const double depth = dot(w, a);
             if (!(depth > 0.0)) return false;
             dmin = std::min(dmin, depth);
+            dep[i] = depth;
             u = dot(w, e1) / depth;
             v = dot(w, e2) / depth;
         } else {
+            dep[i] = dot(w, a); // along the light's direction: a point between p and the light has a smaller one
             u = dot(w, e1);
             v = dot(w, e2);
         }
@@ -237,21 +275,83 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
     const double s[2] = {1.0 / cell[0], 1.0 / cell[1]};
     const double o[2] = {lo[0] - cell[0], lo[1] - cell[1]};
     bits->assign((size_t)RES * RES / 32, 0u);
-    auto paint = [&](uint32_t f0, uint32_t f1, uint32_t *dst) {
-        for (uint32_t f = f0; f < f1; f++) {
-            double p[3][2];
-            for (int k = 0; k < 3; k++) {
-                const uint32_t i = m.f[3 * f + k];
-                p[k][0] = (img[2 * i] - o[0]) * s[0];
-                p[k][1] = (img[2 * i + 1] - o[1]) * s[1];
-            }
-            raster(p, dst);
+    Rows R;
+    auto image_of = [&](uint32_t f, double (*p)[2]) {
+        for (int k = 0; k < 3; k++) {
+            const uint32_t i = m.f[3 * f + k];
+            p[k][0] = (img[2 * i] - o[0]) * s[0];
+            p[k][1] = (img[2 * i + 1] - o[1]) * s[1];
         }
     };
-    paint(0, m.nf, bits->data());
+    for (uint32_t f = 0; f < m.nf; f++) {
+        double p[3][2];
+        image_of(f, p);
+        raster(p, bits->data(), R);
+    }
     dilate(*bits);
 
-    memset(rec, 0, 20 * sizeof(float));
+    // Light lists: per cell the triangles whose image touches its 3 x 3 neighbourhood, as (slot in DMesh::tris, least depth of the
+    // triangle) pairs in the order of that depth.  A recognised shadow ray tests the triangles of its cell that begin before
+    // its own origin instead of walking the mesh's hierarchy (k_shadow_wave); every triangle the exact test could accept is
+    // among them by the argument that makes the bitmap conservative.  Only where the lists stay short (triangles that are
+    // not much smaller than a cell) and the mesh has a slot order the host knows.
+    double zmargin = 0.0;
+    if (lists && !eye && m.nf <= (1u << 24)) {
+        std::vector<uint32_t> slot_of(m.nf);
+        bool have = true;
+        if (m.flags & RTU_MESH_DEVICE_BVH) for (uint32_t f = 0; f < m.nf; f++) slot_of[f] = f;
+        else if (m.bvh_elements) {
+            for (uint32_t k = 0; k < m.nf && have; k++) { have = m.bvh_elements[k] < m.nf; if (have) slot_of[m.bvh_elements[k]] = k; }
+        } else have = false;
+        std::vector<uint32_t> count((size_t)RES * RES + 1, 0u);
+        uint64_t total = 0;
+        for (uint32_t f = 0; f < m.nf && have; f++) {
+            double p[3][2];
+            image_of(f, p);
+            dilated_rows(p, R, [&](int iy, int ix0, int ix1) { for (int ix = ix0; ix <= ix1; ix++) count[(size_t)iy * RES + ix + 1]++; total += (uint64_t)(ix1 - ix0 + 1); });
+        }
+        size_t cells_set = 0;
+        for (size_t c = 1; c < count.size(); c++) cells_set += count[c] != 0;
+        if (have && total > 0 && total <= 24 * (uint64_t)cells_set && total < (1u << 26)) {
+            for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
+            lists->cell_start = count; // RES * RES + 1 offsets
+            std::vector<uint32_t> fill(count.begin(), count.end() - 1);
+            lists->items.assign((size_t)total * 2, 0u);
+            double zabs = 0;
+            for (uint32_t f = 0; f < m.nf; f++) {
+                double p[3][2];
+                image_of(f, p);
+                const double z = std::min(dep[m.f[3 * f]], std::min(dep[m.f[3 * f + 1]], dep[m.f[3 * f + 2]]));
+                zabs = std::max(zabs, std::fabs(z));
+                float zf = (float)z;
+                if ((double)zf > z) zf = std::nextafterf(zf, -3.0e38f); // rounded down
+                uint32_t zb;
+                memcpy(&zb, &zf, 4);
+                dilated_rows(p, R, [&](int iy, int ix0, int ix1) {
+                    for (int ix = ix0; ix <= ix1; ix++) {
+                        const size_t at = fill[(size_t)iy * RES + ix]++;
+                        lists->items[2 * at] = slot_of[f];
+                        lists->items[2 * at + 1] = zb;
+                    }
+                });
+            }
+            // per cell in the order of depth (ties by slot: the same lists whatever the order of the faces)
+            std::vector<std::pair<float, uint32_t>> seg;
+            for (size_t c = 0; c + 1 < lists->cell_start.size(); c++) {
+                const size_t b0 = lists->cell_start[c], b1 = lists->cell_start[c + 1];
+                if (b1 - b0 < 2) continue;
+                seg.clear();
+                for (size_t k = b0; k < b1; k++) { float zf; memcpy(&zf, &lists->items[2 * k + 1], 4); seg.emplace_back(zf, lists->items[2 * k]); }
+                std::sort(seg.begin(), seg.end());
+                for (size_t k = b0; k < b1; k++) { lists->items[2 * k] = seg[k - b0].second; memcpy(&lists->items[2 * k + 1], &seg[k - b0].first, 4); }
+            }
+            // the device's depth of a ray's origin: a dot product of (p - L) / p with a unit axis in float, rounding
+            // <= eps (5 |p - L|_1 + |L|_1) (see err_u); |p - L|_1 <= lim by the lookup's own check.  Far more than that:
+            zmargin = 1.0e-4 * (zabs + l1 + vmax1 + 1.0e-30) + 64 * EPS * lim;
+        }
+    }
+
+    memset(rec, 0, 24 * sizeof(float));
     const int32_t kind = eye ? RTU_MASK_EYE : light.kind;
     for (int k = 0; k < 3; k++) { rec[k] = (float)L[k]; rec[4 + k] = (float)a[k]; rec[8 + k] = (float)e1[k]; rec[12 + k] = (float)e2[k]; }
     memcpy(&rec[3], &kind, 4);
@@ -260,14 +360,17 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
     rec[15] = (float)s[0];
     rec[16] = (float)s[1];
     rec[18] = (float)lim;
+    rec[19] = (float)zmargin; // words 20 / 21: where the lists are (rtu_scene_upload)
     return true;
 }
 
-void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<std::vector<uint32_t>> *own)
+void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<OwnedMask> *own)
 {
     out->clear();
     own->clear();
     if (const char *e = getenv("RTU_LIGHT_MASKS")) if (atoi(e) == 0) return;
+    bool lists_on = true;
+    if (const char *e = getenv("RTU_LIGHT_LISTS")) lists_on = atoi(e) != 0;
     int hard = 0;
     for (int l = 0; l < d.n_lights; l++)
         hard += d.lights[l].kind == RTU_LIGHT_DIRECT || (d.lights[l].kind == RTU_LIGHT_POINT && d.lights[l].size == 0.f);
@@ -303,12 +406,19 @@ void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *o
             }
             if (pre) { out->push_back(*pre); continue; }
             rtu_light_mask lm;
-            std::vector<uint32_t> bits;
-            if (!build_light_mask(chain, n_chain, d.meshes[d.nodes[i].mesh], lt, lm.rec, &bits, is_eye)) continue;
-            own->push_back(std::move(bits));
+            memset(&lm, 0, sizeof lm);
+            OwnedMask om;
+            if (!build_light_mask(chain, n_chain, d.meshes[d.nodes[i].mesh], lt, lm.rec, &om.bits, is_eye, lists_on ? &om.lists : nullptr)) continue;
+            own->push_back(std::move(om));
+            const OwnedMask &k = own->back();
             lm.node = i;
             lm.light = is_eye ? -1 : l;
-            lm.bits = own->back().data();
+            lm.bits = k.bits.data();
+            if (!k.lists.cell_start.empty()) {
+                lm.cell_start = k.lists.cell_start.data();
+                lm.items = k.lists.items.data();
+                lm.n_items = (uint32_t)(k.lists.items.size() / 2);
+            }
             out->push_back(lm);
         }
     }

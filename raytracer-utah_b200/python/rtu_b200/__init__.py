@@ -72,7 +72,8 @@ class Camera(C.Structure):
 
 
 class LightMask(C.Structure):
-    _fields_ = [("node", i32), ("light", i32), ("rec", f32 * 20), ("bits", C.POINTER(u32))]
+    _fields_ = [("node", i32), ("light", i32), ("rec", f32 * 24), ("bits", C.POINTER(u32)),
+                ("cell_start", C.POINTER(u32)), ("items", C.POINTER(u32)), ("n_items", u32)]
 
 
 class SceneDesc(C.Structure):
@@ -590,7 +591,7 @@ def balance_photons(photons):
 def build_light_mask(desc, node, light):
     """rtu_host_build_light_mask: (rec[20] as f4, bits[256, 256] as bool) or None when the pair gets no mask."""
     L = lib()
-    rec = np.zeros(20, "f4")
+    rec = np.zeros(24, "f4")
     bits = np.zeros(2048, "u4")
     L.rtu_host_build_light_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     rc = L.rtu_host_build_light_mask(C.byref(desc), node, light, rec.ctypes.data, bits.ctypes.data)

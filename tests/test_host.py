@@ -350,6 +350,8 @@ def _mask_lookup_f32(rec, cells, p, d, t_max):
     inside = (u >= 0) & (u < 256) & (v >= 0) & (v < 256)
     iu, iv = np.where(inside, u, 0).astype("i8"), np.where(inside, v, 0).astype("i8")
     clear = ~cells[iv, iu]
+    _mask_lookup_f32.cell = np.where(ok & inside, iv * 256 + iu, -1)  # (for the light lists: the cell and the origin's depth)
+    _mask_lookup_f32.depth = (depth if kind == 2 else dot(p, a)).astype(f)
     return ok & np.isfinite(u) & np.isfinite(v) & (~inside | clear), known
 
 
@@ -370,8 +372,9 @@ def _eye_lookup_f32(rec, cells, p, d):
     return ok & np.isfinite(u) & np.isfinite(v) & (~inside | ~cells[iv, iu])
 
 
-def _any_hit_f64(v, f, p, d, t_max, chunk=256):
-    """Does the segment p + t d, 0 < t < t_max, meet a triangle (Moeller-Trumbore in double, edges and vertices count)?"""
+def _any_hit_f64(v, f, p, d, t_max, chunk=256, each=None):
+    """Does the segment p + t d, 0 < t < t_max, meet a triangle (Moeller-Trumbore in double, edges and vertices count)?
+    each: a callback (first ray of the chunk, rays x triangles matrix of hits)."""
     A, B, Cc = (v[f[:, k]].astype("f8") for k in range(3))
     e1, e2 = B - A, Cc - A
     hit = np.zeros(len(p), bool)
@@ -389,6 +392,8 @@ def _any_hit_f64(v, f, p, d, t_max, chunk=256):
         tol = 1e-7
         ok = (np.abs(det) > 0) & (u >= -tol) & (w >= -tol) & (u + w <= 1 + tol) & (t > 0) & (t < t_max)
         hit[s:s + chunk] = ok.any(1)
+        if each is not None:
+            each(s, ok)
     return hit
 
 
@@ -399,7 +404,8 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
     device's, evaluated in float32; the truth is a brute-force test against every triangle in double."""
     hs = rtu.HostScene(os.path.join(SCENES, scene))
     rng = np.random.default_rng(7)
-    built = 0
+    built = lists_seen = 0
+    lengths = []
     for node in range(hs.desc.n_nodes):
         if hs.desc.nodes[node].kind != 3:
             continue
@@ -433,7 +439,36 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
                 t_max = 3.0e38
             rejected, known = _mask_lookup_f32(rec, cells, p, d, np.float32(t_max))
             assert known.all()  # the rays of this light are recognised as such
-            hit = _any_hit_f64(m["v"], m["f"], p, d, t_max)
+            cell, depth = _mask_lookup_f32.cell.copy(), _mask_lookup_f32.depth.copy()
+            # light lists of the loader's mask for this pair: every triangle a ray meets is among the entries of its cell that
+            # begin before the origin (what k_shadow_wave tests instead of walking the hierarchy)
+            pre = [hs.desc.light_masks[k] for k in range(hs.desc.n_light_masks)
+                   if hs.desc.light_masks[k].node == node and hs.desc.light_masks[k].light == light]
+            missing = []
+            if pre and pre[0].cell_start:
+                lists_seen += 1
+                start = np.ctypeslib.as_array(pre[0].cell_start, shape=(65537,))
+                items = np.ctypeslib.as_array(pre[0].items, shape=(pre[0].n_items, 2))
+                slot_of = np.empty(len(m["f"]), "i8")
+                slot_of[m["bvh_elements"]] = np.arange(len(m["f"]))
+                zmargin = np.frombuffer(pre[0].rec, "f4")[19]
+                assert zmargin > 0 and (start[1:] >= start[:-1]).all()
+                lengths.append((start[1:] - start[:-1])[cells.ravel()].mean())
+
+                def each(s0, ok):
+                    for r, t in zip(*np.nonzero(ok)):
+                        c = cell[s0 + r]
+                        if c < 0:
+                            continue  # (not judged by the mask: walked)
+                        seg = items[start[c]:start[c + 1]]
+                        z = seg[:, 1].copy().view("f4")
+                        assert (np.diff(z) >= 0).all()
+                        if slot_of[t] not in seg[z <= depth[s0 + r] + zmargin, 0]:
+                            missing.append((s0 + r, t))
+            else:
+                each = None
+            hit = _any_hit_f64(m["v"], m["f"], p, d, t_max, each=each)
+            assert not missing, (scene, node, light, missing[:5])
             assert not (rejected & hit).any(), (scene, node, light, int((rejected & hit).sum()))
             assert rejected[~hit].mean() > 0.2  # and the mask does reject: most of these miss rays start beside the silhouette
             # a ray of another kind (not towards this light) is never judged
@@ -457,7 +492,7 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
             assert rejected[~hit].mean() > 0.2
             far = (p + np.float32(4.0) * rec[18]).astype("f4")  # not the eye: never judged
             assert not _eye_lookup_f32(rec, cells, far, d).any()
-    assert built >= 2
+    assert built >= 2 and lists_seen >= 1 and max(lengths) < 24
     hs.close()
 
 
@@ -472,7 +507,8 @@ def test_loader_prebuilds_the_light_masks(rtu):
         lm = d.light_masks[k]
         seen.append((lm.node, lm.light))
         rec, cells = rtu.build_light_mask(d, lm.node, lm.light)
-        assert bits_equal(np.frombuffer(lm.rec, "f4"), rec)
+        assert bits_equal(np.frombuffer(lm.rec, "f4")[:19], rec[:19])  # (word 19: the depth slack of the light lists, only with lists)
+        assert bool(lm.cell_start) == (lm.light >= 0) and (not lm.cell_start or lm.cell_start[65536] == lm.n_items)
         bits = np.ctypeslib.as_array(lm.bits, shape=(2048,))
         assert np.array_equal(np.unpackbits(bits.view("u1"), bitorder="little").reshape(256, 256).astype(bool), cells)
     assert seen == [(1, 0), (1, 1), (1, -1)]
