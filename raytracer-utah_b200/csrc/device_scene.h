@@ -56,7 +56,7 @@ struct __align__(16) LightMask {
     uint32_t bits;   // first word of this mask's bitmap in DScene::mask_bits
     float lim;       // largest 1-norm of (origin - light) / of the origin for which the mask's margins hold; eye: |origin - L|_1
     float zmargin;   // light lists: slack of the depth cut (rounding of the origin's depth on the device)
-    uint32_t cells;  // light lists: first of the RES * RES + 1 cell offsets in DScene::mask_bits; 0xffffffff: none
+    uint32_t cells;  // light lists: first of the RES * RES + 1 cell offsets in DScene::mask_lists; 0xffffffff: none
     uint32_t items;  // ... first word of the (slot, least depth) pairs
     float pad[2];
 };
@@ -182,6 +182,7 @@ struct DScene {
     const float4 *top_bounds; // bounds[] of the items, in the order of top_items (no dependent load in a leaf)
     const LightMask *light_masks;
     const uint32_t *mask_bits;
+    const uint32_t *mask_lists; // light lists of the masks that have them: cell offsets and (slot, depth) pairs (LightMask::cells / items)
     const int32_t *obj_rank; // per node: number of object nodes with index <= that node
     int32_t any_no_ref;  // some mesh has no cyBVH: RTU_FLAG_REFERENCE_WALK cannot be honoured
     int32_t pool_ok;     // 1: every mesh fits the item encoding of the pooled shadow kernel (<= 2^24 triangles, < 2^27 pairs)

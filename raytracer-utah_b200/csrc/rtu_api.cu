@@ -621,10 +621,13 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     // light masks (device_scene.h LightMask, host/light_mask.cpp): per mesh node, one per light that casts hard shadows
     std::vector<LightMask> light_masks;
     std::vector<uint32_t> mask_bits;
+    uint32_t *dmask_lists = nullptr;
     {
         static_assert(sizeof(LightMask) == 24 * sizeof(float), "host/light_mask.cpp writes the record as 24 words");
         std::vector<rtu_light_mask> got;
         std::vector<rtu::OwnedMask> own;
+        std::vector<const rtu_light_mask *> list_src; // masks with light lists, in the order of their device offsets
+        size_t list_words = 0;
         rtu::collect_light_masks(*d, &got, &own); // the caller's where they fit the scene (rtu_host_load_xml builds them), else built here
         for (const rtu_light_mask &g : got) { // ordered by node, a node's lights in order, its eye mask last
             DNode &o = nodes[g.node];
@@ -639,21 +642,36 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
             lm.items = 0;
             const uint32_t n_tris = d->meshes[d->nodes[g.node].mesh].nf;
             if (g.cell_start && g.items && g.n_items > 0 && g.light >= 0 && g.cell_start[RTU_MASK_RES * RTU_MASK_RES] == g.n_items &&
-                mask_bits.size() + (size_t)RTU_MASK_RES * RTU_MASK_RES + 1 + 2 * (size_t)g.n_items < 0xfffffff0u) {
-                // light lists (same buffer): the offsets of the cells, then the (slot, depth) pairs; validated like everything the device indexes with
+                list_words + (size_t)RTU_MASK_RES * RTU_MASK_RES + 2 + 2 * (size_t)g.n_items < 0xfffffff0u) {
+                // light lists: the offsets of the cells, then the (slot, depth) pairs; validated like everything the device indexes
+                // with, copied to the device straight from the caller's arrays (several MB: no second copy on the host)
                 bool ok = true;
-                for (int cidx = 0; cidx < RTU_MASK_RES * RTU_MASK_RES && ok; cidx++) ok = g.cell_start[cidx] <= g.cell_start[cidx + 1];
-                for (uint32_t k = 0; k < g.n_items && ok; k++) ok = g.items[2 * k] < n_tris;
+                for (int cidx = 0; cidx < RTU_MASK_RES * RTU_MASK_RES; cidx++) ok &= g.cell_start[cidx] <= g.cell_start[cidx + 1];
+                for (uint32_t k = 0; k < g.n_items; k++) ok &= g.items[2 * k] < n_tris;
                 if (ok) {
-                    lm.cells = (uint32_t)mask_bits.size();
-                    mask_bits.insert(mask_bits.end(), g.cell_start, g.cell_start + RTU_MASK_RES * RTU_MASK_RES + 1);
-                    if (mask_bits.size() & 1u) mask_bits.push_back(0u); // the pairs are read as uint2
-                    lm.items = (uint32_t)mask_bits.size();
-                    mask_bits.insert(mask_bits.end(), g.items, g.items + 2 * (size_t)g.n_items);
-                    if (mask_bits.size() & 1u) mask_bits.push_back(0u);
+                    lm.cells = (uint32_t)list_words;
+                    list_words += (size_t)RTU_MASK_RES * RTU_MASK_RES + 1;
+                    list_words += list_words & 1u; // the pairs are read as uint2
+                    lm.items = (uint32_t)list_words;
+                    list_words += 2 * (size_t)g.n_items;
+                    list_src.push_back(&g);
                 }
             }
             light_masks.push_back(lm);
+        }
+        if (list_words) {
+            g_upload_bytes += list_words * sizeof(uint32_t);
+            cudaError_t e = cudaMallocAsync((void **)&dmask_lists, list_words * sizeof(uint32_t), c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(light lists)");
+            sc->owned.push_back(dmask_lists);
+            size_t li = 0;
+            for (const LightMask &lm : light_masks) {
+                if (lm.cells == 0xffffffffu) continue;
+                const rtu_light_mask &g = *list_src[li++];
+                if ((e = cudaMemcpyAsync(dmask_lists + lm.cells, g.cell_start, ((size_t)RTU_MASK_RES * RTU_MASK_RES + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+                    (e = cudaMemcpyAsync(dmask_lists + lm.items, g.items, 2 * (size_t)g.n_items * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+                    return cuda_fail(e, "cudaMemcpyAsync(light lists)");
+            }
         }
     }
     DNode *dn = nullptr;
@@ -964,6 +982,7 @@ int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
     S.top_bounds = dtop_bounds;
     S.light_masks = dmasks;
     S.mask_bits = dmask_bits;
+    S.mask_lists = dmask_lists;
     S.obj_rank = drank;
     S.any_no_ref = 0;
     for (int m = 0; m < d->n_meshes; m++) if (d->meshes[m].flags & RTU_MESH_DEVICE_BVH) S.any_no_ref = 1;

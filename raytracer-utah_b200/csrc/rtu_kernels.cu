@@ -1404,7 +1404,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                             a.px = lr.px; a.py = lr.py; a.pz = lr.pz; a.dx = lr.dx; a.dy = lr.dy; a.dz = lr.dz;
                             a.yx = I.yx; a.yy = I.yy; a.yz = I.yz; a.ok = I.ok;
                             Tally t2 = {0, 0, 0, 0, 0};
-                            const bool stop = light_list_occludes_ni(S.mask_bits + it0, (it1 - it0) >> 1, zcut, &M, &a, d.w, &t2);
+                            const bool stop = light_list_occludes_ni(S.mask_lists + it0, (it1 - it0) >> 1, zcut, &M, &a, d.w, &t2);
                             tl.box += t2.box; tl.tri += t2.tri;
                             if (stop) { mesh_occ = true; break; }
                             continue;
