@@ -182,6 +182,7 @@ struct DScene {
     const float4 *top_bounds; // bounds[] of the items, in the order of top_items (no dependent load in a leaf)
     const LightMask *light_masks;
     const uint32_t *mask_bits;
+    int32_t scan_min;           // lanes that must reach a light list together for it to be scanned in the node loop (else: with a batch)
     const uint32_t *mask_lists; // light lists of the masks that have them: cell offsets and (slot, depth) pairs (LightMask::cells / items)
     const int32_t *obj_rank; // per node: number of object nodes with index <= that node
     int32_t any_no_ref;  // some mesh has no cyBVH: RTU_FLAG_REFERENCE_WALK cannot be honoured

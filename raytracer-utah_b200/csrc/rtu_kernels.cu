@@ -1097,6 +1097,8 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
             bool decided = false; // occluded before the pool starts (rays that do not use the hierarchy)
             if (lane < take) {
                 uint2 j = W.jobs[njobs + lane];
+                const bool scan = (j.y >> 31) != 0u;
+                j.y &= 0x7fffffffu;
                 float4 o = Q.o[j.x], d = Q.d[j.x];
                 Ray ray;
                 ray.px = o.x; ray.py = o.y; ray.pz = o.z;
@@ -1112,18 +1114,37 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                 W.idx[lane] = j.x;
                 W.node[lane] = j.y;
                 if constexpr (OCC) {
+                W.hitslot[lane] = 0xffffffffu;
+                bool scanned = false;
+                if (scan) {
+                    // a shadow ray of a light with light lists (host/light_mask.cpp): the exact test on the triangles of its mask
+                    // cell that begin before its origin decides; the hierarchy is not walked.  (The lookup is the node loop's,
+                    // on the same local ray: it says 2 again.)
+                    unsigned it0, it1;
+                    float zcut;
+                    if (light_mask_lookup(S, nd, lr, d.w, it0, it1, zcut) == 2) {
+                        RefWalkArgs a;
+                        a.px = lr.px; a.py = lr.py; a.pz = lr.pz; a.dx = lr.dx; a.dy = lr.dy; a.dz = lr.dz;
+                        a.yx = I.yx; a.yy = I.yy; a.yz = I.yz; a.ok = I.ok;
+                        Tally t2 = {0, 0, 0, 0, 0};
+                        decided = light_list_occludes_ni(S.mask_lists + it0, (it1 - it0) >> 1, zcut, &M, &a, d.w, &t2);
+                        tl.box += t2.box; tl.tri += t2.tri;
+                        scanned = true;
+                    }
+                }
+                if (!scanned) {
                 const OccRay oc = occ_setup(lr, M.occ_scale, d.w);
                 W.ci[lane] = make_float4(oc.ix, oc.iy, oc.iz, oc.tlim);
                 W.cn[lane] = make_float4(oc.nx, oc.ny, oc.nz, 0.f);
                 W.cf[lane] = make_float4(oc.fx, oc.fy, oc.fz, 0.f);
                 W.mesh[lane] = &M;
-                W.hitslot[lane] = 0xffffffffu;
                 W.nodes[lane] = M.occ_nodes;
                 W.tris[lane] = M.occ_tris;
                 rootw = M.occ_root;
                 if (!oc.ok) { // non-finite / huge components: the exact walk of the cyBVH decides
                     decided = bvh_walk_any_fallback(M, lr, I, d.w, tl);
                     rootw = NONE;
+                }
                 }
                 } else {
                 W.pairs[lane] = M.pairs;
@@ -1353,6 +1374,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
         }
         nres -= k;
         int park = 0; // mesh node whose walk this lane's ray has to wait for
+        unsigned scan = 0; // ... bit 31: not a walk, the scan of a light list (light_mask_lookup said 2)
         if (have) {
             float4 o = Q.o[idx], d = Q.d[idx];
             Ray ray;
@@ -1362,7 +1384,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
             B.z = d.w; B.node = -1; B.front = 1; B.slot = 0; B.bc1 = B.bc2 = B.bc3 = 0.f; // h.z = t_max (lightFunctions.cpp:29)
             const Ray r0 = to_node(root.itm, root.pos, ray);
             const float dd = dot3(r0.dx, r0.dy, r0.dz, r0.dx, r0.dy, r0.dz);
-            bool occ = false, mesh_occ = false;
+            bool occ = false, mesh_occ = false; // (mesh_occ: stopped by a triangle of a light list)
             Ray lvl[FLAT ? 1 : RTU_MAX_DEPTH]; // hierarchies: the ray at every depth of the current branch
             if (!FLAT) {
                 lvl[0] = r0;
@@ -1400,14 +1422,19 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
                         const int lk = light_mask_lookup(S, nd, lr, d.w, it0, it1, zcut);
                         if (lk == 1) continue;
                         if (lk == 2) {
-                            RefWalkArgs a;
-                            a.px = lr.px; a.py = lr.py; a.pz = lr.pz; a.dx = lr.dx; a.dy = lr.dy; a.dz = lr.dz;
-                            a.yx = I.yx; a.yy = I.yy; a.yz = I.yz; a.ok = I.ok;
-                            Tally t2 = {0, 0, 0, 0, 0};
-                            const bool stop = light_list_occludes_ni(S.mask_lists + it0, (it1 - it0) >> 1, zcut, &M, &a, d.w, &t2);
-                            tl.box += t2.box; tl.tri += t2.tri;
-                            if (stop) { mesh_occ = true; break; }
-                            continue;
+                            // Its list is scanned here when enough lanes of the warp arrived together with one (rays of one
+                            // surface: a scan is 2-10 triangle tests), else with the next batch of mesh jobs, where all lanes are busy.
+                            if (__popc(__activemask()) < S.scan_min) scan = 0x80000000u;
+                            else {
+                                RefWalkArgs a;
+                                a.px = lr.px; a.py = lr.py; a.pz = lr.pz; a.dx = lr.dx; a.dy = lr.dy; a.dz = lr.dz;
+                                a.yx = I.yx; a.yy = I.yy; a.yz = I.yz; a.ok = I.ok;
+                                Tally t2 = {0, 0, 0, 0, 0};
+                                const bool stop = light_list_occludes_ni(S.mask_lists + it0, (it1 - it0) >> 1, zcut, &M, &a, d.w, &t2);
+                                tl.box += t2.box; tl.tri += t2.tri;
+                                if (stop) { mesh_occ = true; break; }
+                                continue;
+                            }
                         }
                     }
                     park = i;
@@ -1421,7 +1448,7 @@ k_shadow_wave(DScene S, ShadowQueue Q, float4 *accum, DCounters *counters, unsig
             }
         }
         const unsigned m = __ballot_sync(FULL, park != 0);
-        if (park) W.jobs[njobs + __popc(m & lt)] = make_uint2(idx, (unsigned)park);
+        if (park) W.jobs[njobs + __popc(m & lt)] = make_uint2(idx, (unsigned)park | scan);
         njobs += __popc(m);
 #ifdef RTU_DEBUG_BOUNDS
         if (njobs > SP_JOBS) counters->overflow = 0xBAD6;
