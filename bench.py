@@ -231,14 +231,25 @@ def ncu_entry(scene, mode, kernel):
     return table.get("%s:%s" % (scene, mode), {}).get(kernel)
 
 
-def roofline(ks, clocks, scene, mode, scene_bytes):
+def roofline(ks, clocks, scene, mode, scene_bytes, ref=None):
     peaks, peak_src = measured_peaks()
-    classes = {"k_extend<primary>": ks["primary_wave"], "k_extend<queue>": ks["secondary_waves"], "k_shadow_wave": ks["shadow_waves"],
-               "k_shade": ks["shade_kernels"]}
+    names = {"k_extend<primary>": "primary_wave", "k_extend<queue>": "secondary_waves", "k_shadow_wave": "shadow_waves", "k_shade": "shade_kernels"}
+    classes = {k: ks[v] for k, v in names.items()}
     name, dom = max(((k, v) for k, v in classes.items() if k != "k_shade"), key=lambda kv: kv[1]["ms"])
     nl = max(1, dom["launches"])
-    # algorithmic bytes: 28 B per child-box test, 52 B per triangle test, 48 B per node transform
-    alg_bytes = 28 * dom["box_tests"] + 52 * dom["tri_tests"] + 48 * dom["node_visits"]
+    # bytes of the tests the kernel executed (its own counters): 28 B per child-box test, 52 B per triangle test, 48 B per node transform
+    exe_bytes = 28 * dom["box_tests"] + 52 * dom["tri_tests"] + 48 * dom["node_visits"]
+    exe = exe_bytes / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+    # algorithmic bytes: the same formula on the reference's own walk, per ray of this scene, x the rays of the step
+    rc = ref[names[name]] if ref else None
+    if rc and rc["rays"] > 0:
+        per_ray = (28 * rc["box_tests"] + 52 * rc["tri_tests"] + 48 * rc["node_visits"]) / rc["rays"]
+        alg_bytes = per_ray * dom["rays"]
+        alg_src = "reference walk (RTU_FLAG_REFERENCE_WALK counters of %d rays) x rays of the step" % rc["rays"]
+    else:
+        per_ray = exe_bytes / max(1, dom["rays"])
+        alg_bytes = exe_bytes
+        alg_src = "the kernel's own counters (no reference walk for this scene)"
     ach = alg_bytes / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     sm_mhz = (clocks or {}).get("sm_mhz") or 1500.0
     flops = 21 * dom["box_tests"] + 70 * dom["tri_tests"] + 36 * dom["node_visits"]
@@ -262,7 +273,11 @@ def roofline(ks, clocks, scene, mode, scene_bytes):
     roof = {"bound": bound, "bound_source": bound_source, "kernel": name, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / peaks["hbm_gbs"], "peak_source": peak_src, "alg_gbs": ach,
             "traffic": traffic,
-            "alg_bytes_per_launch": alg_bytes / nl, "launches_per_step": dom["launches"], "kernel_ms_per_step": dom["ms"],
+            "alg_bytes_per_launch": alg_bytes / nl, "alg_bytes_per_ray": per_ray, "alg_source": alg_src,
+            "executed_gbs": exe, "executed_bytes_per_ray": exe_bytes / max(1, dom["rays"]),
+            "note": "achieved = the reference algorithm's bytes per ray x rays / kernel time; the kernel reaches the same answers with "
+                    "fewer tests (executed_*), from caches (traffic = DRAM bytes per launch under ncu): frac can pass 1, the binding limit is `bound`",
+            "launches_per_step": dom["launches"], "kernel_ms_per_step": dom["ms"],
             "kernel_share_of_step": dom["ms"] / max(1e-9, sum(c["ms"] for c in classes.values())),
             "rays_per_step": dom["rays"], "kernel_mrays_per_s": dom["rays"] / (dom["ms"] * 1e-3) * 1e-6 if dom["ms"] > 0 else 0.0,
             "issue": ({"issue_slot_frac": cap.get("issue_pct", 0) / 100.0, "lanes_per_inst": cap.get("threads_per_inst"),
@@ -439,6 +454,18 @@ def ours(args):
                           pattern=R.PATTERN_REFERENCE, mode=_mode_id(R), shade_bounces=5, gi_bounces=4, flags=R.FLAG_TIME_KERNELS)
     job.sc.render_device(pk, 0, clear=True)
     ks = job.sc.stats()
+    # ... and a few samples with RTU_FLAG_REFERENCE_WALK: that mode books the reference's own work (every node visit, child-box test
+    # and triangle test of Trace / ShadowTrace), i.e. SURVEY 8d's algorithmic bytes per ray of this scene.  The frame kernels
+    # find the same answers with less work (pruning, light masks and lists), so their own counters say what they executed, not
+    # what the path costs per unit.
+    rs = None
+    try:
+        pr = R.default_params(width=W, height=H, spp=spp_total, sample_begin=0, sample_end=min(4, spp_total), pattern=R.PATTERN_REFERENCE,
+                              mode=_mode_id(R), shade_bounces=5, gi_bounces=4, flags=R.FLAG_REFERENCE_WALK)
+        job.sc.render_device(pr, 0, clear=True)
+        rs = job.sc.stats()
+    except R.RtuError:
+        rs = None  # (a mesh without a cyBVH: there is no reference walk to count)
 
     # ---- BASELINE config 4: the GI scene with the same sample budget, same slicing
     gi = None
@@ -475,7 +502,7 @@ def ours(args):
         gjob.close()
 
     if rank == 0:
-        roof = roofline(ks, clocks, SCENE, MODE, ks["scene_device_bytes"])
+        roof = roofline(ks, clocks, SCENE, MODE, ks["scene_device_bytes"], rs)
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
