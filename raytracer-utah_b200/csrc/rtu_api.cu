@@ -489,7 +489,7 @@ void rtu_params_default(rtu_params *p)
     p->gi_bounces = 4;    // RenderFunctions.cpp:31
 }
 
-int rtu_context_create(int32_t device, void *stream, rtu_context **out)
+static int context_create_impl(int32_t device, void *stream, rtu_context **out)
 {
     if (!out) { rtu::set_error("rtu_context_create: null out"); return RTU_ERR_INVALID; }
     int n = 0;
@@ -573,7 +573,7 @@ int rtu_synchronize(rtu_context *c)
     return RTU_OK;
 }
 
-int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
+static int scene_upload_impl(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
 {
     if (!c || !d || !out) { rtu::set_error("rtu_scene_upload: null argument"); return RTU_ERR_INVALID; }
     if (d->n_nodes < 1 || !d->nodes) { rtu::set_error("rtu_scene_upload: scene has no root node"); return RTU_ERR_INVALID; }
@@ -1775,7 +1775,7 @@ int rtu_get_stats(const rtu_scene *s, rtu_stats *out)
     return RTU_OK;
 }
 
-int rtu_trace(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
+static int trace_impl(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
 {
     if (!s || (n > 0 && (!rays || !hits)) || n < 0) { rtu::set_error("rtu_trace: bad argument"); return RTU_ERR_INVALID; }
     if (n == 0) return RTU_OK;
@@ -1819,7 +1819,7 @@ int rtu_trace(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
     return RTU_OK;
 }
 
-int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int64_t n, uint8_t *occluded)
+static int shadow_trace_impl(rtu_scene *s, const rtu_ray *rays, const float *t_max, int64_t n, uint8_t *occluded)
 {
     if (!s || (n > 0 && (!rays || !t_max || !occluded)) || n < 0) { rtu::set_error("rtu_shadow_trace: bad argument"); return RTU_ERR_INVALID; }
     if (n == 0) return RTU_OK;
@@ -1864,7 +1864,7 @@ int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int6
     return RTU_OK;
 }
 
-int rtu_selftest_division(rtu_context *c, uint32_t numerators_per_divisor, uint64_t seed, uint64_t *tested, uint64_t *mismatches)
+static int selftest_division_impl(rtu_context *c, uint32_t numerators_per_divisor, uint64_t seed, uint64_t *tested, uint64_t *mismatches)
 {
     if (!c || !tested || !mismatches) { rtu::set_error("rtu_selftest_division: null argument"); return RTU_ERR_INVALID; }
     CU(cudaSetDevice(c->device));
@@ -1885,7 +1885,7 @@ int rtu_selftest_division(rtu_context *c, uint32_t numerators_per_divisor, uint6
     return RTU_OK;
 }
 
-int rtu_camera_rays(rtu_scene *s, const rtu_params *p, int32_t sample, rtu_ray *rays)
+static int camera_rays_impl(rtu_scene *s, const rtu_params *p, int32_t sample, rtu_ray *rays)
 {
     if (!s || !p || !rays) { rtu::set_error("rtu_camera_rays: null argument"); return RTU_ERR_INVALID; }
     rtu_context *c = s->ctx;
@@ -1914,7 +1914,7 @@ int rtu_camera_rays(rtu_scene *s, const rtu_params *p, int32_t sample, rtu_ray *
     return RTU_OK;
 }
 
-int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n, int32_t bounces, float *rgb)
+static int shade_impl(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n, int32_t bounces, float *rgb)
 {
     if (!s || (n > 0 && (!rays || !hits || !rgb)) || n < 0 || bounces < 0 || bounces > 15) { rtu::set_error("rtu_shade: bad argument"); return RTU_ERR_INVALID; }
     if (n == 0) return RTU_OK;
@@ -2014,7 +2014,7 @@ int install_photon_map(rtu_scene *s, const rtu_photon *d_raw, const rtu_photon *
 
 extern "C" {
 
-int rtu_photon_map_set(rtu_scene *s, const rtu_photon *photons, uint32_t n, const rtu_photon_params *params)
+static int photon_map_set_impl(rtu_scene *s, const rtu_photon *photons, uint32_t n, const rtu_photon_params *params)
 {
     if (!s || (n && !photons)) { rtu::set_error("rtu_photon_map_set: null argument"); return RTU_ERR_INVALID; }
     CU(cudaSetDevice(s->ctx->device));
@@ -2041,7 +2041,7 @@ int rtu_photon_map_info(const rtu_scene *s, uint32_t *n_photons, uint32_t *devic
     return RTU_OK;
 }
 
-int rtu_photon_map_get(rtu_scene *s, rtu_photon *out, uint32_t cap, uint32_t *n)
+static int photon_map_get_impl(rtu_scene *s, rtu_photon *out, uint32_t cap, uint32_t *n)
 {
     if (!s || !n) { rtu::set_error("rtu_photon_map_get: null argument"); return RTU_ERR_INVALID; }
     *n = s->n_photons;
@@ -2053,7 +2053,7 @@ int rtu_photon_map_get(rtu_scene *s, rtu_photon *out, uint32_t cap, uint32_t *n)
     return RTU_OK;
 }
 
-int rtu_estimate_irradiance(rtu_scene *s, const float *pos, const float *normal, int64_t n, float radius, float ellipticity,
+static int estimate_irradiance_impl(rtu_scene *s, const float *pos, const float *normal, int64_t n, float radius, float ellipticity,
                             float *irrad, float *direction, int32_t *found)
 {
     if (!s || !pos || !irrad || !direction || n < 0) { rtu::set_error("rtu_estimate_irradiance: bad argument"); return RTU_ERR_INVALID; }
@@ -2085,7 +2085,7 @@ int rtu_estimate_irradiance(rtu_scene *s, const float *pos, const float *normal,
     return RTU_OK;
 }
 
-int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_photon_stats *stats)
+static int photon_map_generate_impl(rtu_scene *s, const rtu_photon_params *params, rtu_photon_stats *stats)
 {
     if (!s) { rtu::set_error("rtu_photon_map_generate: null scene"); return RTU_ERR_INVALID; }
     rtu_context *c = s->ctx;
@@ -2182,6 +2182,63 @@ int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_p
         stats->device_build = s->photon_device_build ? 1u : 0u;
     }
     return RTU_OK;
+}
+
+// The entry points above that build std containers, behind the exception barrier of the ABI (a bad_alloc becomes an error code)
+int rtu_context_create(int32_t device, void *stream, rtu_context **out)
+{
+    return rtu::guarded("rtu_context_create", [&]() -> int { return context_create_impl(device, stream, out); });
+}
+
+int rtu_scene_upload(rtu_context *c, const rtu_scene_desc *d, rtu_scene **out)
+{
+    return rtu::guarded("rtu_scene_upload", [&]() -> int { return scene_upload_impl(c, d, out); });
+}
+
+int rtu_trace(rtu_scene *s, const rtu_ray *rays, int64_t n, rtu_hit *hits)
+{
+    return rtu::guarded("rtu_trace", [&]() -> int { return trace_impl(s, rays, n, hits); });
+}
+
+int rtu_shadow_trace(rtu_scene *s, const rtu_ray *rays, const float *t_max, int64_t n, uint8_t *occluded)
+{
+    return rtu::guarded("rtu_shadow_trace", [&]() -> int { return shadow_trace_impl(s, rays, t_max, n, occluded); });
+}
+
+int rtu_selftest_division(rtu_context *c, uint32_t numerators_per_divisor, uint64_t seed, uint64_t *tested, uint64_t *mismatches)
+{
+    return rtu::guarded("rtu_selftest_division", [&]() -> int { return selftest_division_impl(c, numerators_per_divisor, seed, tested, mismatches); });
+}
+
+int rtu_camera_rays(rtu_scene *s, const rtu_params *p, int32_t sample, rtu_ray *rays)
+{
+    return rtu::guarded("rtu_camera_rays", [&]() -> int { return camera_rays_impl(s, p, sample, rays); });
+}
+
+int rtu_shade(rtu_scene *s, const rtu_ray *rays, const rtu_hit *hits, int64_t n, int32_t bounces, float *rgb)
+{
+    return rtu::guarded("rtu_shade", [&]() -> int { return shade_impl(s, rays, hits, n, bounces, rgb); });
+}
+
+int rtu_photon_map_set(rtu_scene *s, const rtu_photon *photons, uint32_t n, const rtu_photon_params *params)
+{
+    return rtu::guarded("rtu_photon_map_set", [&]() -> int { return photon_map_set_impl(s, photons, n, params); });
+}
+
+int rtu_photon_map_get(rtu_scene *s, rtu_photon *out, uint32_t cap, uint32_t *n)
+{
+    return rtu::guarded("rtu_photon_map_get", [&]() -> int { return photon_map_get_impl(s, out, cap, n); });
+}
+
+int rtu_estimate_irradiance(rtu_scene *s, const float *pos, const float *normal, int64_t n, float radius, float ellipticity,
+                            float *irrad, float *direction, int32_t *found)
+{
+    return rtu::guarded("rtu_estimate_irradiance", [&]() -> int { return estimate_irradiance_impl(s, pos, normal, n, radius, ellipticity, irrad, direction, found); });
+}
+
+int rtu_photon_map_generate(rtu_scene *s, const rtu_photon_params *params, rtu_photon_stats *stats)
+{
+    return rtu::guarded("rtu_photon_map_generate", [&]() -> int { return photon_map_generate_impl(s, params, stats); });
 }
 
 } // extern "C"
