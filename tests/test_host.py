@@ -397,7 +397,7 @@ def _any_hit_f64(v, f, p, d, t_max, chunk=256, each=None):
     return hit
 
 
-@pytest.mark.parametrize("scene", ["Teapot/scene2.xml", "Project7/scene.xml"])
+@pytest.mark.parametrize("scene", ["Teapot/scene2.xml", "Project7/scene.xml", "Project11/scene.xml"])
 def test_light_masks_never_hide_a_triangle(rtu, scene):
     """host/light_mask.cpp: a shadow ray the any-hit kernel would skip for a mesh (clear cell of the light's mask) meets none of
     its triangles.  Origins are sampled in the mesh node's coordinates behind, beside and on the mesh; the lookup is the
