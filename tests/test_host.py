@@ -520,3 +520,39 @@ def test_loader_prebuilds_the_light_masks(rtu):
     hs = rtu.HostScene(os.path.join(SCENES, "Project9/scene.xml"))
     assert all(hs.desc.light_masks[k].light >= 0 for k in range(hs.desc.n_light_masks))
     hs.close()
+
+
+def test_light_mask_records_hold_the_light_in_node_coordinates(rtu):
+    """A mask is looked up with the node-local ray, so its record holds the light's position (direction) carried through
+    ToNodeCoords of every node from the root down to the mesh's (RenderFunctions.cpp:186-198: p' = itm (p - pos), d' = itm d).
+    The shipped scenes hang their meshes below the root; here a teapot of Project5 is moved below the scene's transformed
+    "box" node first (still pre-order), and Project9 supplies a directional light."""
+    for scene, node, parent in (("Project5/scene.xml", 7, 1), ("Project5/scene.xml", 8, 0), ("Project9/scene.xml", 2, 0)):
+        hs = rtu.HostScene(os.path.join(SCENES, scene))
+        hs.desc.nodes[node].parent = parent
+        n = hs.nodes()
+        lights = hs.lights()
+        chain = []
+        a = node
+        while a >= 0:
+            chain.insert(0, a)
+            a = int(n["meta"][a][0])
+        assert len(chain) == (3 if parent else 2)
+        seen = 0
+        for light in list(range(hs.desc.n_lights)) + [-1]:
+            got = rtu.build_light_mask(hs.desc, node, light)
+            if got is None:
+                continue
+            seen += 1
+            rec = got[0]
+            if light >= 0:
+                kind, L = int(lights[light][0]), lights[light][4:7].astype("f8")
+            else:
+                kind, L = 2, hs.camera()[0:3].astype("f8")
+            for a in chain:
+                M = n["itm"][a].astype("f8").reshape(3, 3).T  # column-major (cyMatrix3)
+                L = M @ (L - n["pos"][a].astype("f8") if kind == 2 else L)
+            assert np.allclose(rec[0:3], L, rtol=1e-6, atol=1e-6), (scene, node, light, rec[0:3], L)
+            assert rec[3:4].view("i4")[0] == (3 if light < 0 else kind)
+        assert seen >= (1 if parent else 2)  # (below the box node the light ends up too close to the teapot for a mask)
+        hs.close()
