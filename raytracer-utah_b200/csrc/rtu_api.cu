@@ -628,7 +628,8 @@ static int scene_upload_impl(rtu_context *c, const rtu_scene_desc *d, rtu_scene 
         std::vector<rtu::OwnedMask> own;
         std::vector<const rtu_light_mask *> list_src; // masks with light lists, in the order of their device offsets
         size_t list_words = 0;
-        rtu::collect_light_masks(*d, &got, &own); // the caller's where they fit the scene (rtu_host_load_xml builds them), else built here
+        // the caller's where they fit the scene (rtu_host_load_xml builds them), else built here within ~0.3 s of host time
+        rtu::collect_light_masks(*d, &got, &own, 2u << 20);
         for (const rtu_light_mask &g : got) { // ordered by node, a node's lights in order, its eye mask last
             DNode &o = nodes[g.node];
             if (o.mask_count == 0) o.mask_first = (int32_t)light_masks.size();

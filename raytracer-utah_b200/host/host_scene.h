@@ -33,7 +33,7 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
 // camera last): entries of d.light_masks that still fit the scene are taken as they are, the others are built into `own`.
 // RTU_LIGHT_MASKS=0 in the environment: none.
 struct OwnedMask { std::vector<uint32_t> bits; LightLists lists; };
-void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<OwnedMask> *own);
+void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<OwnedMask> *own, uint64_t budget);
 
 // cyTriMesh::Mtl (cyTriMesh.h:74-103): one material of an OBJ's .mtl library, with the constructor's defaults
 struct ObjMtl {

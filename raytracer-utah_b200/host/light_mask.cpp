@@ -364,7 +364,10 @@ bool build_light_mask(const rtu_node *const *chain, int n_chain, const rtu_mesh 
     return true;
 }
 
-void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<OwnedMask> *own)
+// budget: triangles this call may rasterise (a bitmap costs a mesh's faces once, ~0.15 us each; its lists 8 times that).  The
+// loader spends what a scene takes; rtu_scene_upload, for a description that comes without masks, stays within a few tenths
+// of a second and leaves the pairs beyond that without mask / without lists.
+void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *out, std::vector<OwnedMask> *own, uint64_t budget)
 {
     out->clear();
     own->clear();
@@ -408,7 +411,11 @@ void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *o
             rtu_light_mask lm;
             memset(&lm, 0, sizeof lm);
             OwnedMask om;
-            if (!build_light_mask(chain, n_chain, d.meshes[d.nodes[i].mesh], lt, lm.rec, &om.bits, is_eye, lists_on ? &om.lists : nullptr)) continue;
+            const uint64_t nf = d.meshes[d.nodes[i].mesh].nf;
+            if (nf > budget) continue;
+            const bool with_lists = lists_on && !is_eye && 9 * nf <= budget;
+            if (!build_light_mask(chain, n_chain, d.meshes[d.nodes[i].mesh], lt, lm.rec, &om.bits, is_eye, with_lists ? &om.lists : nullptr)) continue;
+            budget -= with_lists ? 9 * nf : nf;
             own->push_back(std::move(om));
             const OwnedMask &k = own->back();
             lm.node = i;

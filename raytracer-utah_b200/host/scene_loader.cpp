@@ -491,7 +491,7 @@ void rtu_host_scene::finalize()
     // light masks (light_mask.cpp), once per load instead of once per rtu_scene_upload
     desc.light_masks = nullptr;
     desc.n_light_masks = 0;
-    rtu::collect_light_masks(desc, &light_masks, &light_mask_data);
+    rtu::collect_light_masks(desc, &light_masks, &light_mask_data, 1ull << 28);
     desc.light_masks = light_masks.empty() ? nullptr : light_masks.data();
     desc.n_light_masks = (int32_t)light_masks.size();
 }
