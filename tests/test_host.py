@@ -324,7 +324,7 @@ def test_two_phase_photon_estimate_algorithm_matches_the_oracle(rtu, tmp_path):
 
 
 def _mask_lookup_f32(rec, cells, p, d, t_max):
-    """light_mask_rejects (csrc/intersect.cuh) in numpy float32: True where the device skips the mesh's walk."""
+    """light_mask_lookup (csrc/intersect.cuh) in numpy float32: True where it answers 1 and the device skips the mesh's walk."""
     f = np.float32
     kind = rec[3:4].view("i4")[0]
     L, a, e1, e2 = rec[0:3], rec[4:7], rec[8:11], rec[12:15]
