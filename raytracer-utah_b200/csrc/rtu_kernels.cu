@@ -277,11 +277,25 @@ static __device__ __noinline__ bool light_list_occludes_ni(const uint32_t *items
     Ray r;
     r.px = a->px; r.py = a->py; r.pz = a->pz; r.dx = a->dx; r.dy = a->dy; r.dz = a->dz;
     const uint2 *e = reinterpret_cast<const uint2 *>(items);
-    for (unsigned k = 0; k < n; k++) {
-        const uint2 it = __ldg(e + k);
-        if (__uint_as_float(it.y) > zcut) break; // this one and all behind it begin beyond the origin
-        const float4 *q = reinterpret_cast<const float4 *>(M->tris + it.x);
-        const float4 x = __ldg(q), y = __ldg(q + 1), w4 = __ldg(q + 2);
+    if (n == 0u) return false;
+    uint2 it = __ldg(e);
+    if (__uint_as_float(it.y) > zcut) return false; // this one and all behind it begin beyond the origin
+    const float4 *q = reinterpret_cast<const float4 *>(M->tris + it.x);
+    float4 x = __ldg(q), y = __ldg(q + 1), w4 = __ldg(q + 2);
+    for (unsigned k = 0;; k++) {
+        // the next entry and its record are fetched before this one is tested: entry -> record -> test is a chain of two
+        // dependent loads per triangle, and the scan is bound by their latency (L2: the lists of a mask are 3 MB)
+        uint2 nit = make_uint2(0u, 0u);
+        float4 nx = x, ny = y, nw = w4;
+        bool more = k + 1u < n;
+        if (more) {
+            nit = __ldg(e + k + 1u);
+            more = !(__uint_as_float(nit.y) > zcut);
+            if (more) {
+                const float4 *nq = reinterpret_cast<const float4 *>(M->tris + nit.x);
+                nx = __ldg(nq); ny = __ldg(nq + 1); nw = __ldg(nq + 2);
+            }
+        }
         TriRec T;
         T.nx = x.x; T.ny = x.y; T.nz = x.z; T.ax = x.w;
         T.ay = y.x; T.az = y.y; T.area = y.z; T.fbits = y.w;
@@ -289,13 +303,15 @@ static __device__ __noinline__ bool light_list_occludes_ni(const uint32_t *items
         tl->tri++;
         float z = t_max, b1, b2, b3;
         int fr;
-        if (!tri_hit(T, r, z, fr, b1, b2, b3)) continue;
-        InvDir I;
-        I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
-        if (ref_reaches(*M, it.x, r, I, *tl)) return true;
-        return bvh_walk_any_fallback(*M, r, I, t_max, *tl);
+        if (tri_hit(T, r, z, fr, b1, b2, b3)) {
+            InvDir I;
+            I.yx = a->yx; I.yy = a->yy; I.yz = a->yz; I.ok = a->ok != 0;
+            if (ref_reaches(*M, it.x, r, I, *tl)) return true;
+            return bvh_walk_any_fallback(*M, r, I, t_max, *tl);
+        }
+        if (!more) return false;
+        it = nit; x = nx; y = ny; w4 = nw;
     }
-    return false;
 }
 static __device__ __noinline__ bool occ_walk_ni(const DMesh *M, unsigned start, const RefWalkArgs *a, const OccRay *oc, float t_max, Tally *tl)
 {
