@@ -282,20 +282,20 @@ static __device__ __noinline__ bool light_list_occludes_ni(const uint32_t *items
     if (__uint_as_float(it.y) > zcut) return false; // this one and all behind it begin beyond the origin
     const float4 *q = reinterpret_cast<const float4 *>(M->tris + it.x);
     float4 x = __ldg(q), y = __ldg(q + 1), w4 = __ldg(q + 2);
+    bool have1 = n > 1u;
+    uint2 it1 = have1 ? __ldg(e + 1) : make_uint2(0u, 0u);
     for (unsigned k = 0;; k++) {
-        // the next entry and its record are fetched before this one is tested: entry -> record -> test is a chain of two
-        // dependent loads per triangle, and the scan is bound by their latency (L2: the lists of a mask are 3 MB)
-        uint2 nit = make_uint2(0u, 0u);
+        // entry -> record -> test is a chain of two dependent loads per triangle, and the scan is bound by their latency (L2: the
+        // lists of a mask are 3 MB).  Two steps ahead: while triangle k is tested, the record of entry k+1 (whose entry came
+        // with the last step) and entry k+2 are in flight.
+        const bool more = have1 && !(__uint_as_float(it1.y) > zcut);
         float4 nx = x, ny = y, nw = w4;
-        bool more = k + 1u < n;
         if (more) {
-            nit = __ldg(e + k + 1u);
-            more = !(__uint_as_float(nit.y) > zcut);
-            if (more) {
-                const float4 *nq = reinterpret_cast<const float4 *>(M->tris + nit.x);
-                nx = __ldg(nq); ny = __ldg(nq + 1); nw = __ldg(nq + 2);
-            }
+            const float4 *nq = reinterpret_cast<const float4 *>(M->tris + it1.x);
+            nx = __ldg(nq); ny = __ldg(nq + 1); nw = __ldg(nq + 2);
         }
+        const bool have2 = more && k + 2u < n;
+        const uint2 it2 = have2 ? __ldg(e + k + 2u) : make_uint2(0u, 0u);
         TriRec T;
         T.nx = x.x; T.ny = x.y; T.nz = x.z; T.ax = x.w;
         T.ay = y.x; T.az = y.y; T.area = y.z; T.fbits = y.w;
@@ -310,7 +310,8 @@ static __device__ __noinline__ bool light_list_occludes_ni(const uint32_t *items
             return bvh_walk_any_fallback(*M, r, I, t_max, *tl);
         }
         if (!more) return false;
-        it = nit; x = nx; y = ny; w4 = nw;
+        it = it1; x = nx; y = ny; w4 = nw;
+        it1 = it2; have1 = have2;
     }
 }
 static __device__ __noinline__ bool occ_walk_ni(const DMesh *M, unsigned start, const RefWalkArgs *a, const OccRay *oc, float t_max, Tally *tl)
