@@ -407,7 +407,11 @@ void collect_light_masks(const rtu_scene_desc &d, std::vector<rtu_light_mask> *o
                     c.rec[0] == (float)L[0] && c.rec[1] == (float)L[1] && c.rec[2] == (float)L[2])
                     pre = &c;
             }
-            if (pre) { out->push_back(*pre); continue; }
+            if (pre) {
+                out->push_back(*pre);
+                if (!lists_on) { out->back().cell_start = nullptr; out->back().items = nullptr; out->back().n_items = 0; }
+                continue;
+            }
             rtu_light_mask lm;
             memset(&lm, 0, sizeof lm);
             OwnedMask om;
