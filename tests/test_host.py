@@ -402,7 +402,47 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
     """host/light_mask.cpp: a shadow ray the any-hit kernel would skip for a mesh (clear cell of the light's mask) meets none of
     its triangles.  Origins are sampled in the mesh node's coordinates behind, beside and on the mesh; the lookup is the
     device's, evaluated in float32; the truth is a brute-force test against every triangle in double."""
-    hs = rtu.HostScene(os.path.join(SCENES, scene))
+    _check_light_masks(rtu, rtu.HostScene(os.path.join(SCENES, scene)), scene)
+
+
+def test_light_masks_on_a_triangle_soup(rtu, tmp_path):
+    """The same on triangles no modeller would make: needles, specks far smaller than a mask cell, sheets that span the whole
+    image, degenerate (zero-area) faces, all jumbled in depth."""
+    rng = np.random.default_rng(11)
+    tris = []
+    for k in range(700):
+        c = rng.uniform(-4, 4, 3)
+        kind = k % 5
+        if kind == 0:    # needle
+            e1, e2 = rng.normal(size=3) * 3.0, rng.normal(size=3) * 0.004
+        elif kind == 1:  # speck
+            e1, e2 = rng.normal(size=3) * 0.003, rng.normal(size=3) * 0.003
+        elif kind == 2:  # sheet
+            e1, e2 = rng.normal(size=3) * 4.0, rng.normal(size=3) * 4.0
+        elif kind == 3:  # ordinary
+            e1, e2 = rng.normal(size=3) * 0.4, rng.normal(size=3) * 0.4
+        else:            # degenerate: three points of one line
+            e1 = rng.normal(size=3) * 0.5
+            e2 = 0.3 * e1
+        tris.append((c, c + e1, c + e2))
+    with open(tmp_path / "soup.obj", "w") as f:
+        for t in tris:
+            for v in t:
+                f.write("v %.7g %.7g %.7g\n" % tuple(v))
+        for k in range(len(tris)):
+            f.write("f %d %d %d\n" % (3 * k + 1, 3 * k + 2, 3 * k + 3))
+    with open(tmp_path / "soup.xml", "w") as f:
+        f.write("""<xml><scene>
+  <object type="obj" name="soup.obj" material="m"><rotate angle="25" x="1"/><scale value="1.3"/><translate x="0.5" y="1" z="2"/></object>
+  <material type="blinn" name="m"><diffuse value="0.7"/></material>
+  <light type="direct" name="sun"><intensity value="0.8"/><direction x="-0.4" y="0.5" z="-1"/></light>
+  <light type="point" name="lamp"><intensity value="300"/><position x="6" y="-8" z="40"/></light>
+</scene>
+<camera><position x="1.7" y="-42" z="12"/><target x="0.3" y="0" z="0"/><up x="0" y="0" z="1"/><fov value="40"/><width value="64"/><height value="48"/></camera></xml>""")
+    _check_light_masks(rtu, rtu.HostScene(str(tmp_path / "soup.xml"), asset_root=str(tmp_path)), "soup", fill=(0.02, 1.01), useful=0.0, longest=1e9)
+
+
+def _check_light_masks(rtu, hs, scene, fill=(0.02, 0.9), useful=0.2, longest=24):
     rng = np.random.default_rng(7)
     built = lists_seen = 0
     lengths = []
@@ -418,7 +458,7 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
                 continue
             built += 1
             rec, cells = got
-            assert 0.02 < cells.mean() < 0.9
+            assert fill[0] < cells.mean() < fill[1]
             kind = rec[3:4].view("i4")[0]
             L = rec[0:3].astype("f8")
             away = (ctr - L) / np.linalg.norm(ctr - L) if kind == 2 else L / np.linalg.norm(L)
@@ -470,7 +510,7 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
             hit = _any_hit_f64(m["v"], m["f"], p, d, t_max, each=each)
             assert not missing, (scene, node, light, missing[:5])
             assert not (rejected & hit).any(), (scene, node, light, int((rejected & hit).sum()))
-            assert rejected[~hit].mean() > 0.2  # and the mask does reject: most of these miss rays start beside the silhouette
+            assert rejected[~hit].mean() >= useful  # and the mask does reject: most of these miss rays start beside the silhouette
             # a ray of another kind (not towards this light) is never judged
             d2 = (d + np.float32(0.01) * rng.normal(size=d.shape).astype("f4") * np.abs(d).max()).astype("f4")
             rej2, known2 = _mask_lookup_f32(rec, cells, p, d2, np.float32(t_max))
@@ -489,11 +529,12 @@ def test_light_masks_never_hide_a_triangle(rtu, scene):
             rejected = _eye_lookup_f32(rec, cells, p, d)
             hit = _any_hit_f64(m["v"], m["f"], p, d, np.inf)
             assert not (rejected & hit).any(), (scene, node, "eye", int((rejected & hit).sum()))
-            assert rejected[~hit].mean() > 0.2
+            assert rejected[~hit].mean() >= useful
             far = (p + np.float32(4.0) * rec[18]).astype("f4")  # not the eye: never judged
             assert not _eye_lookup_f32(rec, cells, far, d).any()
-    assert built >= 2 and lists_seen >= 1 and max(lengths) < 24
+    assert built >= 2 and (longest > 1e8 or (lists_seen >= 1 and max(lengths) < longest))
     hs.close()
+    return built, lists_seen
 
 
 def test_loader_prebuilds_the_light_masks(rtu):
