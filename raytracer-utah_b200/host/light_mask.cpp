@@ -19,6 +19,9 @@
 // the axis eye -> mesh, `lim` the distance of a ray's origin from that point up to which it counts as the eye.
 // Anything unusual (NaN, a flat image, a light inside the mesh's box, more than RTU_MASKS_PER_NODE hard lights) gives no
 // mask and the rays are walked as before.
+// Light lists (build_light_mask, second half): the same image also says WHICH triangles a ray of a cell can meet; with the
+// triangles of every cell listed in the order of their distance from the light, a shadow ray tests a handful of them and
+// walks no hierarchy at all.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
